@@ -1,0 +1,282 @@
+// Warp-specialised, persistent tcgen05 GEMM main loop for sm_100a, shared by every dense contraction on the
+// loop-closure path (SDA encoder layers, SDAV Gram/score, query x database similarity, conv-as-GEMM).
+//
+//   D[128 x n_tile] (TMEM, fp32) = sum over products of  A_p[128 x K] * B_p[n_tile x K]^T     (both K-major)
+//
+// NPROD = 1 : one fp16 (or bf16) product.
+// NPROD = 3 : error-compensated fp16 split, A ~= A_hi + A_lo, B ~= B_hi + B_lo,
+//             D = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (the dropped lo*lo term is ~2^-22 relative).
+//
+// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
+// warps 2..5 = epilogue (each owns the 32 TMEM lanes of its quarter: quarter = warp_idx % 4).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
+// What happens to an accumulator tile is decided by the Policy's Epilogue (bias+sigmoid+re-split, argmin/score,
+// running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
+#pragma once
+#include "ptx.cuh"
+
+namespace dlc {
+
+constexpr int kTileM = 128;
+constexpr int kMaxTileN = 256;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
+constexpr int kEpiScratchBytes = 4096;
+
+struct TileCoord {
+  int mt;
+  int nt;
+};
+
+template <int BK_, int NPROD_>
+struct GemmCfg {
+  static constexpr int BK = BK_;
+  static constexpr int NPROD = NPROD_;
+  static_assert(BK == 64 || BK == 32, "BK is one swizzle span: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B) fp16");
+  static_assert(NPROD == 1 || NPROD == 3, "1 product or the 3-product fp16 split");
+  static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
+  static constexpr int kABytes = kTileM * BK * 2;     // one A plane tile
+  static constexpr int kBBytes = kMaxTileN * BK * 2;  // one B plane tile, sized for n_tile = 256
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr uint32_t kSwizzleMode = BK == 64 ? 2u : 4u;  // UMMA layout code: 2 = 128B, 4 = 64B
+  static constexpr uint32_t kSBO = 8 * BK * 2;                  // bytes between 8-row groups
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBarrierBytes + kEpiScratchBytes;
+  static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert((2 * kStages + 4) * 8 + 8 <= kBarrierBytes, "barrier block too small");
+  static_assert(kSmemBytes <= 227 * 1024, "exceeds the 227 KB per-CTA shared memory limit");
+};
+
+// Policy contract:
+//   using Cfg = GemmCfg<BK, NPROD>;
+//   struct Params { int n_tile; int k_blocks; int ab_fmt; ... };            (POD, passed by value)
+//   static __device__ int  num_tiles(const Params&, int cta, int ncta);
+//   static __device__ TileCoord tile(const Params&, int cta, int ncta, int i);
+//   struct Epilogue { __device__ Epilogue(const Params&, int quarter, int lane, void* scratch);
+//                     __device__ void tile(TileCoord, uint32_t tmem_acc /*lane quarter already applied*/);
+//                     __device__ void finish(); };
+template <class Policy>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const typename Policy::Params p) {
+  using Cfg = typename Policy::Cfg;
+  constexpr int BK = Cfg::BK;
+  constexpr int S = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tfull = bars + 2 * S;
+  uint64_t* tempty = bars + 2 * S + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  void* scratch = smem + S * Cfg::kStageBytes + Cfg::kBarrierBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int ncta = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+    if (Cfg::NPROD == 3) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull[a], 1);
+        mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_tiles = Policy::num_tiles(p, cta, ncta);
+  const int n_tile = p.n_tile;
+  const int k_blocks = p.k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kABytes + n_tile * BK * 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const TileCoord tc = Policy::tile(p, cta, ncta, i);
+        const int m0 = tc.mt * kTileM;
+        const int n0 = tc.nt * n_tile;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u, 1);
+          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
+          if (Cfg::NPROD == 3) tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
+          uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+          tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
+          if (Cfg::NPROD == 3) tma_load_2d(sb + Cfg::kBBytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc_f16(kTileM, n_tile, p.ab_fmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxTileN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kABytes;
+          const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t koff = k * 32;  // 16 fp16 along K inside the swizzle span
+            const uint64_t dah = make_smem_desc(a_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+            const uint64_t dbh = make_smem_desc(b_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+            if (Cfg::NPROD == 3) {
+              // small cross terms first, dominant term last
+              const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+              const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+              umma_f16(d_tmem, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, dah, dbl, idesc, 1u);
+              umma_f16(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    typename Policy::Epilogue epi(p, quarter, lane, scratch);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const TileCoord tc = Policy::tile(p, cta, ncta, i);
+      mbar_wait(&tfull[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) + (static_cast<uint32_t>(quarter * 32) << 16);
+      epi.tile(tc, taddr);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    epi.finish();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+// Row-major [rows, inner] 16-bit matrix with `pitch_elems` elements per row; box = [box_rows, bk] with the swizzle
+// span equal to bk*2 bytes. Out-of-range rows/columns are zero-filled by the TMA unit.
+inline bool make_tmap_k_major(CUtensorMap* m, const void* base, int ab_fmt, uint64_t inner, uint64_t rows,
+                              uint64_t pitch_elems, int bk, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapDataType dt = ab_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <class Policy>
+inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                               const CUtensorMap& b1, const typename Policy::Params& p, int grid,
+                               cudaStream_t stream) {
+  using Cfg = typename Policy::Cfg;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_tc_kernel<Policy><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  return cudaGetLastError();
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace dlc

@@ -1,0 +1,329 @@
+// Operand planes (fp16 hi/lo split, K-major, zero padded) and the generic fused contraction
+//   out = act(A * B^T + bias)
+// on tcgen05 tensor cores. Replaces the reference's float64 `x.matmul(W).add(b).sigmoid()` chain
+// (src/utils/TensorflowWrapper.py:57-78, used at src/sdav/network/SDAV.py:129,136,143,150,157 and
+// src/sdav/network/DenoisingAutoencoderVariant.py:119) and the matmul core of tf.layers.conv2d
+// (src/cnn_vtl/network/cnn_vtl.py:33-93).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "gemm_sm100.cuh"
+#include "util.h"
+
+namespace dlc {
+
+// ------------------------------------------------------------------------------------------------
+// split: [rows, cols] f32/f64 -> hi/lo planes, regrouping rows (group_in -> group_out)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void split_planes_kernel(const T* __restrict__ src, int rows, int cols, int src_ld, int group_in,
+                                    int group_out, int rows_out, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    int ld) {
+  const int chunks = ld >> 3;
+  const int64_t total = static_cast<int64_t>(rows_out) * chunks;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int pr = static_cast<int>(t / chunks);
+    const int c0 = static_cast<int>(t % chunks) << 3;
+    const int g = pr / group_out;
+    const int w = pr - g * group_out;
+    const int r = g * group_in + w;
+    const bool row_ok = (w < group_in) && (r < rows);
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      if (row_ok && c < cols) {
+        const T x = src[static_cast<int64_t>(r) * src_ld + c];
+        if (sizeof(T) == 8) split_f64(static_cast<double>(x), h[j], l[j]);
+        else split_f32(static_cast<float>(x), h[j], l[j]);
+      } else {
+        h[j] = __float2half_rn(0.f);
+        l[j] = __float2half_rn(0.f);
+      }
+    }
+    const int64_t o = static_cast<int64_t>(pr) * ld + c0;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// W [k, n] row-major -> Wt planes [n_pad, ld]: Wt[j][i] = W[i][j]
+template <typename T>
+__global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_pad, __half* __restrict__ hi,
+                                   __half* __restrict__ lo, int ld) {
+  const int chunks = ld >> 3;
+  const int64_t total = static_cast<int64_t>(n_pad) * chunks;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(t % n_pad);  // output row (fastest across threads -> coalesced reads of W)
+    const int i0 = static_cast<int>(t / n_pad) << 3;
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q;
+      if (j < n && i < k) {
+        const T x = w[static_cast<int64_t>(i) * n + j];
+        if (sizeof(T) == 8) split_f64(static_cast<double>(x), h[q], l[q]);
+        else split_f32(static_cast<float>(x), h[q], l[q]);
+      } else {
+        h[q] = __float2half_rn(0.f);
+        l[q] = __float2half_rn(0.f);
+      }
+    }
+    const int64_t o = static_cast<int64_t>(j) * ld + i0;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias + activation epilogue
+// ------------------------------------------------------------------------------------------------
+struct BiasActParams {
+  int n_tile, k_blocks, ab_fmt;
+  int m_tiles, n_tiles;
+  int M, N;
+  const float* bias;
+  int act;
+  float* out_f32;
+  int out_ld;
+  void* out_hi;
+  void* out_lo;
+  int out_plane_ld;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat16 x = __float2bfloat16_rn(a), y = __float2bfloat16_rn(b);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(y)) << 16);
+}
+
+template <int BK, int NPROD>
+struct BiasActPolicy {
+  using Cfg = GemmCfg<BK, NPROD>;
+  using Params = BiasActParams;
+  static constexpr uint64_t kHintA = kEvictNormal;
+  static constexpr uint64_t kHintB = kEvictLast;  // weights are re-read by every M tile: keep them in L2
+
+  static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
+    const int total = p.m_tiles * p.n_tiles;
+    return cta < total ? (total - cta + ncta - 1) / ncta : 0;
+  }
+  // N fastest: the CTAs running concurrently share one A row-block (read from HBM once, then L2).
+  static __device__ __forceinline__ TileCoord tile(const Params& p, int cta, int ncta, int i) {
+    const int t = cta + i * ncta;
+    TileCoord tc;
+    tc.mt = t / p.n_tiles;
+    tc.nt = t - tc.mt * p.n_tiles;
+    return tc;
+  }
+
+  struct Epilogue {
+    const Params& p;
+    const int quarter, lane;
+    __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
+
+    __device__ __forceinline__ void tile(TileCoord tc, uint32_t taddr) {
+      const int row = tc.mt * kTileM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int chunks = p.n_tile >> 5;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = tc.nt * p.n_tile + c * 32;
+        float h[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float z = __uint_as_float(v[j]);
+          if (p.bias) z += __ldg(p.bias + col0 + j);
+          if (p.act == DLC_ACT_SIGMOID) z = 1.0f / (1.0f + expf(-z));
+          else if (p.act == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
+          h[j] = (col0 + j < p.N) ? z : 0.0f;
+        }
+        if (!row_ok) continue;
+        if (p.out_f32) {
+          float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
+          const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (vec_ok && col0 + j + 3 < p.N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + j + q < p.N) o[j + q] = h[j + q];
+            }
+          }
+        }
+        if (p.out_hi && col0 < p.out_plane_ld) {
+          const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
+          if (p.ab_fmt == 1) {  // bf16 planes (single plane)
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf2(h[2 * j], h[2 * j + 1]);
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          } else {
+            uint32_t wh[16], wl[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __half h0, l0, h1, l1;
+              split_f32(h[2 * j], h0, l0);
+              split_f32(h[2 * j + 1], h1, l1);
+              wh[j] = pack_h2(h0, h1);
+              wl[j] = pack_h2(l0, l1);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
+            if (p.out_lo) {
+              uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_lo) + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+            }
+          }
+        }
+      }
+    }
+    __device__ __forceinline__ void finish() {}
+  };
+};
+
+static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
+
+template <class Policy>
+static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int m, int n_pad,
+                        int ld, BiasActParams p, cudaStream_t stream) {
+  constexpr int BK = Policy::Cfg::BK;
+  CUtensorMap ta0, ta1, tb0, tb1;
+  const bool split = Policy::Cfg::NPROD == 3;
+  if (!make_tmap_k_major(&ta0, a_hi, p.ab_fmt, ld, m, ld, BK, kTileM) ||
+      !make_tmap_k_major(&tb0, b_hi, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile))
+    return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed");
+  ta1 = ta0;
+  tb1 = tb0;
+  if (split) {
+    if (!make_tmap_k_major(&ta1, a_lo, p.ab_fmt, ld, m, ld, BK, kTileM) ||
+        !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile))
+      return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (lo planes)");
+  }
+  p.k_blocks = ld / BK;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_gemm_planes: launch failed: %s", cudaGetErrorString(e));
+  return DLC_OK;
+}
+
+}  // namespace dlc
+
+using namespace dlc;
+
+extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 * 64; }
+
+extern "C" int dlc_debug_set(int key, int value) {
+  if (key == 0 && (value == 32 || value == 64)) {
+    g_split_bk = value;
+    return DLC_OK;
+  }
+  return fail(DLC_EINVAL, "dlc_debug_set: unknown key/value %d/%d", key, value);
+}
+
+extern "C" int dlc_split_planes(const void* src_dev, int src_dtype, int rows, int cols, int src_ld, int group_in,
+                                int group_out, void* hi_dev, void* lo_dev, int ld, void* stream) {
+  DLC_CHECK_ARG(src_dev && hi_dev);
+  DLC_CHECK_ARG(src_dtype == DLC_F32 || src_dtype == DLC_F64);
+  DLC_CHECK_ARG(rows >= 0 && cols > 0 && src_ld >= cols);
+  DLC_CHECK_ARG(group_in >= 1 && group_out >= group_in);
+  DLC_CHECK_ARG(ld >= cols && ld % 8 == 0);
+  if (rows == 0) return DLC_OK;
+  const int rows_out = ceil_div(rows, group_in) * group_out;
+  const int64_t total = static_cast<int64_t>(rows_out) * (ld / 8);
+  const int block = 256;
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, block), static_cast<int64_t>(sm_count()) * 16));
+  if (src_dtype == DLC_F64)
+    split_planes_kernel<double><<<grid, block, 0, as_stream(stream)>>>(
+        static_cast<const double*>(src_dev), rows, cols, src_ld, group_in, group_out, rows_out,
+        static_cast<__half*>(hi_dev), static_cast<__half*>(lo_dev), ld);
+  else
+    split_planes_kernel<float><<<grid, block, 0, as_stream(stream)>>>(
+        static_cast<const float*>(src_dev), rows, cols, src_ld, group_in, group_out, rows_out,
+        static_cast<__half*>(hi_dev), static_cast<__half*>(lo_dev), ld);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+extern "C" int dlc_pack_weight_planes(const void* w_dev, int src_dtype, int k, int n, int n_pad, void* wt_hi_dev,
+                                      void* wt_lo_dev, int ld, void* stream) {
+  DLC_CHECK_ARG(w_dev && wt_hi_dev);
+  DLC_CHECK_ARG(src_dtype == DLC_F32 || src_dtype == DLC_F64);
+  DLC_CHECK_ARG(k > 0 && n > 0 && n_pad >= n);
+  DLC_CHECK_ARG(ld >= k && ld % 8 == 0);
+  const int64_t total = static_cast<int64_t>(n_pad) * (ld / 8);
+  const int block = 256;
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, block), static_cast<int64_t>(sm_count()) * 16));
+  if (src_dtype == DLC_F64)
+    pack_weight_kernel<double><<<grid, block, 0, as_stream(stream)>>>(static_cast<const double*>(w_dev), k, n, n_pad,
+                                                                      static_cast<__half*>(wt_hi_dev),
+                                                                      static_cast<__half*>(wt_lo_dev), ld);
+  else
+    pack_weight_kernel<float><<<grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(w_dev), k, n, n_pad,
+                                                                     static_cast<__half*>(wt_hi_dev),
+                                                                     static_cast<__half*>(wt_lo_dev), ld);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+extern "C" int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const void* b_hi_dev, const void* b_lo_dev,
+                               int m, int n, int n_pad, int ld, const float* bias_dev, int act, int precision,
+                               float* out_f32_dev, int out_ld, void* out_hi_dev, void* out_lo_dev, int out_plane_ld,
+                               void* stream) {
+  DLC_CHECK_ARG(a_hi_dev && b_hi_dev);
+  DLC_CHECK_ARG(m > 0 && n > 0 && n_pad >= n && n_pad % 32 == 0);
+  DLC_CHECK_ARG(ld > 0 && ld % 64 == 0);
+  DLC_CHECK_ARG(act == DLC_ACT_NONE || act == DLC_ACT_SIGMOID || act == DLC_ACT_RELU);
+  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2 || precision == DLC_PREC_BF16);
+  DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || (a_lo_dev && b_lo_dev));
+  DLC_CHECK_ARG(out_f32_dev || out_hi_dev);
+  DLC_CHECK_ARG(!out_f32_dev || out_ld >= n);
+  DLC_CHECK_ARG(!out_hi_dev || (out_plane_ld >= 32 && out_plane_ld % 8 == 0));
+  DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi_dev) & 15) == 0);
+
+  BiasActParams p{};
+  // largest accumulator width (multiple of 32, <= 256) that divides the padded N
+  int n_tile = 0;
+  for (int cand = 256; cand >= 32; cand -= 32)
+    if (n_pad % cand == 0) {
+      n_tile = cand;
+      break;
+    }
+  DLC_CHECK_ARG(n_tile > 0);
+  p.n_tile = n_tile;
+  p.ab_fmt = precision == DLC_PREC_BF16 ? 1 : 0;
+  p.m_tiles = ceil_div(m, kTileM);
+  p.n_tiles = n_pad / n_tile;
+  p.M = m;
+  p.N = n;
+  p.bias = bias_dev;
+  p.act = act;
+  p.out_f32 = out_f32_dev;
+  p.out_ld = out_ld;
+  p.out_hi = out_hi_dev;
+  p.out_lo = precision == DLC_PREC_FP16X2 ? out_lo_dev : nullptr;
+  p.out_plane_ld = out_plane_ld;
+  cudaStream_t s = as_stream(stream);
+  if (precision == DLC_PREC_FP16X2) {
+    if (g_split_bk == 64)
+      return run_bias_act<BiasActPolicy<64, 3>>(a_hi_dev, a_lo_dev, b_hi_dev, b_lo_dev, m, n_pad, ld, p, s);
+    return run_bias_act<BiasActPolicy<32, 3>>(a_hi_dev, a_lo_dev, b_hi_dev, b_lo_dev, m, n_pad, ld, p, s);
+  }
+  return run_bias_act<BiasActPolicy<64, 1>>(a_hi_dev, a_lo_dev, b_hi_dev, b_lo_dev, m, n_pad, ld, p, s);
+}

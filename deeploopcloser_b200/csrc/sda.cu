@@ -1,0 +1,150 @@
+// SDA encoder forward: H_0 = sigmoid(X W_0 + b_0), H_l = sigmoid(H_{l-1} W_l + b_l).
+// Replaces SDAV._define_model + SDAV.transform (src/sdav/network/SDAV.py:120-163, 293-302; weights :188-217)
+// and DA._define_transforming_model + DA.transform (src/sdav/network/DenoisingAutoencoderVariant.py:116-119, 254-259).
+// Each layer is ONE fused tcgen05 kernel (dlc_gemm_planes): GEMM + bias + sigmoid + re-split of the activations into
+// the next layer's fp16 operand planes; only the last layer writes float32 descriptors.
+#include <algorithm>
+#include <vector>
+
+#include "util.h"
+
+struct dlc_sda {
+  int n_layers = 0;
+  int precision = DLC_PREC_FP16X2;
+  std::vector<int> dims;     // n_layers + 1
+  std::vector<int> ld;       // plane ld of each layer's input  (dlc_plane_ld(dims[l]))
+  std::vector<int> n_pad;    // padded output width of each layer (= ld of the next layer's input)
+  std::vector<void*> w_hi;   // [n_pad[l], ld[l]] fp16 (or bf16)
+  std::vector<void*> w_lo;
+  std::vector<float*> bias;  // [n_pad[l]]
+  std::vector<bool> is_set;
+};
+
+using namespace dlc;
+
+namespace {
+int out_pad(int n) {
+  // Output width padded so that (a) it is the next layer's K (multiple of 64) and (b) a 32-multiple accumulator
+  // width <= 256 divides it with little waste: multiples of 256 when n > 256, else multiples of 64.
+  if (n > 256) return (n + 255) / 256 * 256;
+  return (n + 63) / 64 * 64;
+}
+}  // namespace
+
+extern "C" int dlc_sda_create(dlc_sda** h, int n_layers, const int* dims, int precision) {
+  DLC_CHECK_ARG(h && dims);
+  DLC_CHECK_ARG(n_layers >= 1 && n_layers <= 64);
+  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2 || precision == DLC_PREC_BF16);
+  for (int i = 0; i <= n_layers; ++i) DLC_CHECK_ARG(dims[i] > 0);
+  if (int rc = dlc_device_check()) return rc;
+  dlc_sda* s = new dlc_sda();
+  s->n_layers = n_layers;
+  s->precision = precision;
+  s->dims.assign(dims, dims + n_layers + 1);
+  s->ld.resize(n_layers);
+  s->n_pad.resize(n_layers);
+  s->w_hi.assign(n_layers, nullptr);
+  s->w_lo.assign(n_layers, nullptr);
+  s->bias.assign(n_layers, nullptr);
+  s->is_set.assign(n_layers, false);
+  for (int l = 0; l < n_layers; ++l) {
+    s->n_pad[l] = out_pad(dims[l + 1]);
+    s->ld[l] = l == 0 ? dlc_plane_ld(dims[0]) : s->n_pad[l - 1];
+  }
+  for (int l = 0; l < n_layers; ++l) {
+    const size_t plane = static_cast<size_t>(s->n_pad[l]) * s->ld[l] * 2;
+    cudaError_t e = cudaMalloc(&s->w_hi[l], plane);
+    if (e == cudaSuccess && precision == DLC_PREC_FP16X2) e = cudaMalloc(&s->w_lo[l], plane);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bias[l]), sizeof(float) * s->n_pad[l]);
+    if (e != cudaSuccess) {
+      dlc_sda_destroy(s);
+      return fail(DLC_ENOMEM, "dlc_sda_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *h = s;
+  return DLC_OK;
+}
+
+extern "C" int dlc_sda_destroy(dlc_sda* h) {
+  if (!h) return DLC_OK;
+  for (int l = 0; l < h->n_layers; ++l) {
+    if (h->w_hi[l]) cudaFree(h->w_hi[l]);
+    if (h->w_lo[l]) cudaFree(h->w_lo[l]);
+    if (h->bias[l]) cudaFree(h->bias[l]);
+  }
+  delete h;
+  return DLC_OK;
+}
+
+extern "C" int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const double* b_host) {
+  DLC_CHECK_ARG(h && w_host && b_host);
+  DLC_CHECK_ARG(l >= 0 && l < h->n_layers);
+  const int k = h->dims[l], n = h->dims[l + 1];
+  double* w_dev = nullptr;
+  const size_t wbytes = sizeof(double) * static_cast<size_t>(k) * n;
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&w_dev), wbytes));
+  cudaError_t e = cudaMemcpy(w_dev, w_host, wbytes, cudaMemcpyHostToDevice);
+  int rc = DLC_OK;
+  if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_sda_set_layer: H2D copy failed: %s", cudaGetErrorString(e));
+  if (rc == DLC_OK) {
+    if (h->precision == DLC_PREC_BF16)
+      rc = fail(DLC_EUNSUPPORTED, "dlc_sda_set_layer: bf16 weight packing is not implemented for the encoder");
+    else
+      rc = dlc_pack_weight_planes(w_dev, DLC_F64, k, n, h->n_pad[l], h->w_hi[l], h->w_lo[l], h->ld[l], nullptr);
+  }
+  if (rc == DLC_OK) {
+    std::vector<float> b(h->n_pad[l], 0.0f);
+    for (int i = 0; i < n; ++i) b[i] = static_cast<float>(b_host[i]);
+    e = cudaMemcpy(h->bias[l], b.data(), sizeof(float) * b.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_sda_set_layer: bias copy failed: %s", cudaGetErrorString(e));
+  }
+  e = cudaDeviceSynchronize();
+  if (rc == DLC_OK && e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_sda_set_layer: %s", cudaGetErrorString(e));
+  cudaFree(w_dev);
+  if (rc == DLC_OK) h->is_set[l] = true;
+  return rc;
+}
+
+extern "C" size_t dlc_sda_workspace_bytes(const dlc_sda* h, int rows) {
+  if (!h || rows <= 0 || h->n_layers < 2) return 0;
+  int max_pad = 0;
+  for (int l = 0; l + 1 < h->n_layers; ++l) max_pad = std::max(max_pad, h->n_pad[l]);
+  const size_t plane = align_up(static_cast<size_t>(rows) * max_pad * 2, 256);
+  const int planes_per_buf = h->precision == DLC_PREC_FP16X2 ? 2 : 1;
+  const int bufs = h->n_layers >= 3 ? 2 : 1;
+  return plane * planes_per_buf * bufs + 256;
+}
+
+extern "C" int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int rows, float* out_dev,
+                              void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(h && x_hi_dev && out_dev);
+  DLC_CHECK_ARG(rows > 0);
+  DLC_CHECK_ARG(h->precision != DLC_PREC_FP16X2 || x_lo_dev);
+  for (int l = 0; l < h->n_layers; ++l)
+    if (!h->is_set[l]) return fail(DLC_EINVAL, "dlc_sda_encode: layer %d has no weights (dlc_sda_set_layer)", l);
+  if (ws_bytes < dlc_sda_workspace_bytes(h, rows) || (h->n_layers > 1 && !ws_dev))
+    return fail(DLC_ENOMEM, "dlc_sda_encode: workspace of %zu bytes needed, %zu given",
+                dlc_sda_workspace_bytes(h, rows), ws_bytes);
+  const bool split = h->precision == DLC_PREC_FP16X2;
+  int max_pad = 0;
+  for (int l = 0; l + 1 < h->n_layers; ++l) max_pad = std::max(max_pad, h->n_pad[l]);
+  const size_t plane = align_up(static_cast<size_t>(rows) * max_pad * 2, 256);
+  char* base = static_cast<char*>(ws_dev);
+  void* buf_hi[2] = {base, base + plane * (split ? 2 : 1)};
+  void* buf_lo[2] = {split ? base + plane : nullptr, split ? base + plane * 3 : nullptr};
+
+  const void* a_hi = x_hi_dev;
+  const void* a_lo = x_lo_dev;
+  for (int l = 0; l < h->n_layers; ++l) {
+    const bool last = l + 1 == h->n_layers;
+    void* o_hi = last ? nullptr : buf_hi[l & 1];
+    void* o_lo = last ? nullptr : buf_lo[l & 1];
+    int rc = dlc_gemm_planes(a_hi, a_lo, h->w_hi[l], h->w_lo[l], rows, h->dims[l + 1], h->n_pad[l], h->ld[l],
+                             h->bias[l], DLC_ACT_SIGMOID, h->precision, last ? out_dev : nullptr, h->dims[l + 1], o_hi,
+                             o_lo, h->n_pad[l], stream);
+    if (rc != DLC_OK) return rc;
+    a_hi = o_hi;
+    a_lo = o_lo;
+  }
+  return DLC_OK;
+}

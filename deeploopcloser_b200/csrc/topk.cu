@@ -1,0 +1,125 @@
+// Row-wise candidate selection: per-row top-k of a dense score matrix (loop candidates from the SDAV score
+// matrix) and the deterministic k-way merge of partial top-k lists (per-CTA partials of the matcher, per-rank
+// partials of the sharded matcher). New capability (north star); nearest reference analogue is the first-minimum
+// np.argmin of src/sdav/similarity/SimilarityCalculator.py:33-35.
+// Order: best score first; ties -> lowest reported index (so results do not depend on how the work was split).
+// HBM/L2-bound integer/compare work: one warp per row, k selection passes with warp-shuffle arg-reduction.
+#include <math.h>
+
+#include "topk.h"
+#include "util.h"
+
+namespace dlc {
+
+struct Cand {
+  float s;
+  int64_t i;
+};
+
+// strict "a is better than b"
+template <bool LARGEST>
+__device__ __forceinline__ bool better(float as, int64_t ai, float bs, int64_t bi) {
+  if (LARGEST) return as > bs || (as == bs && ai < bi);
+  return as < bs || (as == bs && ai < bi);
+}
+
+template <bool LARGEST>
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float* __restrict__ scores, const int64_t* __restrict__ cand_idx, int rows, int cols, int ld,
+                 int k, int exclude_band, const float* __restrict__ row_add, float scale,
+                 float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int row = warp;
+  const float* srow = scores + static_cast<int64_t>(row) * ld;
+  const int64_t* irow = cand_idx ? cand_idx + static_cast<int64_t>(row) * ld : nullptr;
+  const float worst = LARGEST ? -INFINITY : INFINITY;
+  float prev_s = LARGEST ? INFINITY : -INFINITY;
+  int64_t prev_i = -2;  // (prev_s, prev_i) is better than every real candidate before the first pass
+  bool have_prev = false;
+  for (int sel = 0; sel < k; ++sel) {
+    float bs = worst;
+    int64_t bi = INT64_MAX;
+    bool found = false;
+    for (int c = lane; c < cols; c += 32) {
+      if (exclude_band >= 0) {
+        const int d = c - row;
+        if ((d < 0 ? -d : d) <= exclude_band) continue;
+      }
+      const float s = srow[c];
+      if (s != s) continue;  // NaN never selected
+      const int64_t id = irow ? irow[c] : static_cast<int64_t>(c);
+      if (id < 0) continue;  // padding entry of a partial list
+      if (have_prev && !better<LARGEST>(prev_s, prev_i, s, id)) continue;  // already emitted (or equal to it)
+      if (!found || better<LARGEST>(s, id, bs, bi)) {
+        bs = s;
+        bi = id;
+        found = true;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      const int of = __shfl_xor_sync(0xffffffffu, static_cast<int>(found), off);
+      if (of && (!found || better<LARGEST>(os, oi, bs, bi))) {
+        bs = os;
+        bi = oi;
+        found = true;
+      }
+    }
+    if (lane == 0) {
+      const int64_t o = static_cast<int64_t>(row) * k + sel;
+      if (found) {
+        out_scores[o] = (row_add ? row_add[row] : 0.0f) + scale * bs;
+        out_idx[o] = bi;
+      } else {
+        out_scores[o] = worst;
+        out_idx[o] = -1;
+      }
+    }
+    if (!found) {  // pad the rest of the row
+      if (lane == 0)
+        for (int t = sel + 1; t < k; ++t) {
+          out_scores[static_cast<int64_t>(row) * k + t] = worst;
+          out_idx[static_cast<int64_t>(row) * k + t] = -1;
+        }
+      break;
+    }
+    prev_s = bs;
+    prev_i = bi;
+    have_prev = true;
+  }
+}
+
+int topk_rows_impl(const float* scores, const int64_t* cand_idx, int rows, int cols, int ld, int k, int largest,
+                   int exclude_band, const float* row_add, float scale, float* out_scores, int64_t* out_idx,
+                   cudaStream_t stream) {
+  if (rows == 0) return DLC_OK;
+  const int block = 256;
+  const int grid = ceil_div(rows, block / 32);
+  if (largest)
+    topk_rows_kernel<true><<<grid, block, 0, stream>>>(scores, cand_idx, rows, cols, ld, k, exclude_band, row_add,
+                                                       scale, out_scores, out_idx);
+  else
+    topk_rows_kernel<false><<<grid, block, 0, stream>>>(scores, cand_idx, rows, cols, ld, k, exclude_band, row_add,
+                                                        scale, out_scores, out_idx);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_topk_rows: launch failed: %s", cudaGetErrorString(e));
+  return DLC_OK;
+}
+
+}  // namespace dlc
+
+using namespace dlc;
+
+extern "C" int dlc_topk_rows(const float* scores_dev, const int64_t* cand_idx_dev, int rows, int cols, int ld, int k,
+                             int largest, int exclude_band, float* out_scores_dev, int64_t* out_idx_dev,
+                             void* stream) {
+  DLC_CHECK_ARG(scores_dev && out_scores_dev && out_idx_dev);
+  DLC_CHECK_ARG(rows >= 0 && cols >= 0 && ld >= cols);
+  DLC_CHECK_ARG(k >= 1);
+  return topk_rows_impl(scores_dev, cand_idx_dev, rows, cols, ld, k, largest, exclude_band, nullptr, 1.0f,
+                        out_scores_dev, out_idx_dev, as_stream(stream));
+}

@@ -1,0 +1,195 @@
+/* libdlc - C ABI of the B200-native loop-closure hot path (descriptor extraction + keyframe matching).
+ *
+ * This header is the drop-in boundary. The reference (nschejtman/deepLoopCloser) has no FFI of its own: its hot
+ * path is a handful of Python methods that hand NumPy arrays to TensorFlow-1 / NumPy / CPython loops. Each entry
+ * point below names the reference call it replaces (file:line relative to the reference tree); INTEGRATION.md
+ * shows the ctypes stub a maintainer of the reference would add for each.
+ *
+ * Conventions
+ *  - every function returns 0 (DLC_OK) or a negative DLC_E* code; dlc_last_error() gives a thread-local message;
+ *  - pointers named *_dev are DEVICE pointers owned by the caller, pointers named *_host are host pointers;
+ *  - every launch goes on the cudaStream_t passed in (as void*; 0 = legacy default stream); no hidden syncs,
+ *    no allocations on the hot path: scratch memory is caller-provided (`ws_dev`, size from *_workspace_bytes);
+ *  - a handle is not thread-safe; distinct handles may be used from distinct threads; one process per GPU;
+ *  - sm_100a only. There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef DLC_H_
+#define DLC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLC_OK 0
+#define DLC_EINVAL (-1)       /* bad argument */
+#define DLC_ECUDA (-2)        /* CUDA runtime / driver error (message has the CUDA string) */
+#define DLC_ENOMEM (-3)       /* workspace too small or allocation failed */
+#define DLC_EUNSUPPORTED (-4) /* device is not sm_100 or shape outside the supported envelope */
+
+/* Arithmetic modes of the tensor-core contractions (fp32 accumulation in TMEM in all of them). */
+#define DLC_PREC_FP16 0   /* one fp16 product                           (~1e-3 on well-scaled weights)          */
+#define DLC_PREC_FP16X2 1 /* fp16 hi/lo split, 3 products, ~22-bit operands (meets 1e-3 on N(0,1) weights too) */
+#define DLC_PREC_BF16 2   /* one bf16 product (matcher databases stored as bf16)                                */
+
+/* dtypes for untyped buffers */
+#define DLC_F32 0
+#define DLC_F64 1
+#define DLC_F16 2
+#define DLC_BF16 3
+#define DLC_U8 4
+
+/* activations of dlc_gemm_planes */
+#define DLC_ACT_NONE 0
+#define DLC_ACT_SIGMOID 1
+#define DLC_ACT_RELU 2
+
+/* matcher metrics */
+#define DLC_METRIC_COS 0 /* cosine similarity, larger = closer  */
+#define DLC_METRIC_DOT 1 /* inner product, larger = closer      */
+#define DLC_METRIC_L2 2  /* squared L2 distance, smaller = closer; reported score is the distance */
+
+const char* dlc_last_error(void);
+int dlc_version(void);
+/* 0 when the current CUDA device can run this library (compute capability 10.x), DLC_EUNSUPPORTED otherwise. */
+int dlc_device_check(void);
+int dlc_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Operand planes. Every tensor-core contraction consumes K-major fp16 "planes": a row-major [rows, ld] fp16
+ * matrix with ld a multiple of 64 (zero padded), optionally accompanied by a second plane holding the fp16
+ * rounding residual (DLC_PREC_FP16X2).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ld (in elements) of a plane holding `cols` valid columns: cols rounded up to a multiple of 64. */
+int dlc_plane_ld(int cols);
+
+/* src_dev [rows, cols] (DLC_F32 or DLC_F64, row pitch src_ld elements) -> hi_dev / lo_dev [rows_out, ld] fp16.
+ * Rows are regrouped on the way: source row r goes to plane row (r / group_in) * group_out + r % group_in
+ * (group_in = group_out = 1 for a plain copy). Pad rows/columns are written as zeros. lo_dev may be NULL.
+ * Replaces: the float64 feed of tf.Session.run (src/sdav/network/SDAV.py:297-302). */
+int dlc_split_planes(const void* src_dev, int src_dtype, int rows, int cols, int src_ld, int group_in, int group_out,
+                     void* hi_dev, void* lo_dev, int ld, void* stream);
+
+/* W_dev [k, n] row-major (DLC_F32/DLC_F64; the reference's weight layout, SDAV.py:189-217) -> transposed K-major
+ * planes wt_hi_dev / wt_lo_dev [n_pad, ld] with ld = dlc_plane_ld(k); rows n..n_pad-1 and columns k..ld-1 zero. */
+int dlc_pack_weight_planes(const void* w_dev, int src_dtype, int k, int n, int n_pad, void* wt_hi_dev,
+                           void* wt_lo_dev, int ld, void* stream);
+
+/* out = act(A * B^T + bias):  A planes [m, ld] , B planes [n_pad, ld] (n_pad multiple of n_tile), k = ld.
+ * Outputs (each optional): out_f32_dev [m, n] with pitch out_ld; out_hi/out_lo planes [m, out_plane_ld] whose
+ * columns >= n are written as zero (so they can feed the next contraction directly).
+ * precision: DLC_PREC_FP16 (lo planes ignored), DLC_PREC_FP16X2, DLC_PREC_BF16 (planes hold bf16).
+ * Replaces: TensorWrapper.matmul/add/sigmoid (src/utils/TensorflowWrapper.py:57-78) and tf.layers.conv2d's
+ * matmul core (src/cnn_vtl/network/cnn_vtl.py:33-93). */
+int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const void* b_hi_dev, const void* b_lo_dev, int m,
+                    int n, int n_pad, int ld, const float* bias_dev, int act, int precision, float* out_f32_dev,
+                    int out_ld, void* out_hi_dev, void* out_lo_dev, int out_plane_ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a1  patch gather + normalise.   Replaces get_vectorized_patches_from_key_points + get_1d/2d_boundaries + /255.0
+ *     (src/sdav/input/CvInputParser.py:100-123, 49-97, 27).
+ * img_dev uint8 [B,H,W]; xy_dev float32 [B,P,2] keypoint (x = column, y = row) centres, rounded half-to-even
+ * like Python's round(); patch is odd. swap_xy_quirk = 1 reproduces the reference (rows are indexed by x and
+ * clamped against H, columns by y against W); 0 is the geometrically intended behaviour.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* fp16 planes [B*P, ld] (ld = dlc_plane_ld(patch*patch)), value = pixel/255 split into hi/lo. lo may be NULL. */
+int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
+                     int swap_xy_quirk, void* out_hi_dev, void* out_lo_dev, int ld, void* stream);
+/* float64 [B*P, patch*patch], bit-identical to the reference's ndarray. */
+int dlc_patch_gather_f64(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
+                         int swap_xy_quirk, double* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a3/a4  SDA encoder forward: H_l = sigmoid(H_{l-1} W_l + b_l).
+ *        Replaces SDAV.transform (src/sdav/network/SDAV.py:120-163, 293-302) and DA.transform
+ *        (src/sdav/network/DenoisingAutoencoderVariant.py:116-119, 254-259).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct dlc_sda dlc_sda;
+/* dims has n_layers+1 entries (1681,2500,2500,2500,2500,2500 for SDAV; in,hidden for one DA). */
+int dlc_sda_create(dlc_sda** h, int n_layers, const int* dims, int precision);
+int dlc_sda_destroy(dlc_sda* h);
+/* W_host [dims[l], dims[l+1]] row-major float64, b_host [dims[l+1]] float64 (the reference's variable layout). */
+int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const double* b_host);
+/* bytes of scratch needed to encode `rows` patch rows */
+size_t dlc_sda_workspace_bytes(const dlc_sda* h, int rows);
+/* x planes [rows, dlc_plane_ld(dims[0])] (from dlc_patch_gather or dlc_split_planes); out_dev float32
+ * [rows, dims[n_layers]] dense (the reference's flat [B*30, 2500] result, SDAV.py:163). */
+int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int rows, float* out_dev, void* ws_dev,
+                   size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a5/a6  SDAV frame-pair similarity matrix.  Replaces SimilarityCalculator.similarity_score and the i<j double
+ *        loop around it (src/sdav/similarity/SimilarityCalculator.py:12-49, src/sdav/create_similarity_matrix.py:31-38).
+ * desc_dev float32 [N, P, D] descriptors (P <= 32). S_dev float32 [N, N]: S[i][j] = S[j][i] = score(i, j) for i < j
+ * (the reference evaluates only i < j and mirrors), diagonal = -1 (the reference's fill value).
+ * full_asymmetric = 1 instead evaluates score(i, j) for every ordered pair i != j.
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D);
+int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
+                        int precision, int full_asymmetric, float* S_dev, void* ws_dev, size_t ws_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Row-wise candidate selection on a dense score matrix (loop candidates from S, or a k-way merge of partial
+ * top-k lists). New capability (north star); nearest reference analogue: np.argmin in
+ * src/sdav/similarity/SimilarityCalculator.py:33-35. Order: best score first, ties -> lowest index.
+ * cand_idx_dev (optional, int64 [rows, cols]) maps a column to the index reported; NULL reports the column.
+ * Columns with |col - row| <= exclude_band are skipped when exclude_band >= 0 (temporal neighbours / diagonal).
+ * Rows with fewer than k candidates are padded with idx = -1 and score = -inf (+inf when smallest-first).
+ * ------------------------------------------------------------------------------------------------------------ */
+int dlc_topk_rows(const float* scores_dev, const int64_t* cand_idx_dev, int rows, int cols, int ld, int k,
+                  int largest, int exclude_band, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Keyframe database + global matcher (cosine / dot / L2 similarity matrix with fused per-row top-k). New capability.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct dlc_db dlc_db;
+/* dtype: DLC_F16 or DLC_BF16 storage. Device memory for `capacity_rows` rows is allocated once here. */
+int dlc_db_create(dlc_db** db, int dim, int64_t capacity_rows, int metric, int dtype);
+int dlc_db_destroy(dlc_db* db);
+int64_t dlc_db_size(const dlc_db* db);
+int dlc_db_clear(dlc_db* db);
+/* rows_dev [n, dim] (DLC_F32, DLC_F16 or DLC_BF16). COS: rows are L2-normalised before storage. */
+int dlc_db_append(dlc_db* db, const void* rows_dev, int src_dtype, int64_t n, void* stream);
+size_t dlc_match_workspace_bytes(const dlc_db* db, int B, int k);
+/* q_dev float32 [B, dim]; out scores [B,k] / idx [B,k] (database row + idx_offset). k <= 32. */
+int dlc_match_topk(dlc_db* db, const float* q_dev, int B, int k, int64_t idx_offset, float* scores_dev,
+                   int64_t* idx_dev, void* ws_dev, size_t ws_bytes, void* stream);
+/* Threshold selection: counts_dev[b] = number of database rows whose score passes `thr` (>= for COS/DOT, <= for L2);
+ * the best min(count, max_per_row) of them are listed (max_per_row <= 32), the rest of the row is padded. */
+int dlc_match_threshold(dlc_db* db, const float* q_dev, int B, float thr, int max_per_row, int64_t idx_offset,
+                        int32_t* counts_dev, float* scores_dev, int64_t* idx_dev, void* ws_dev, size_t ws_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a9/a10  cnn_vtl Hamming matrix.  Replaces DistanceCalculator.calculate_distance and the N x N loop around it
+ *         (src/cnn_vtl/similarity/DistanceCalculator.py:4-12, src/cnn_vtl/create_distance_matrix.py:31-36).
+ * desc_dev int8 [N, M]; D_dev int32 [N, N]. signed_bin_quirk = 1 reproduces the reference exactly
+ * (bin() of the signed XOR: popcount of |int8(a ^ b)|); 0 = plain two's-complement popcount.
+ * ------------------------------------------------------------------------------------------------------------ */
+int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quirk, int32_t* D_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a7  cnn_vtl conv head building blocks (src/cnn_vtl/network/cnn_vtl.py:28-128). The convolutions run as
+ *     im2col planes + dlc_gemm_planes (bias + ReLU fused), NHWC throughout.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* x planes NHWC [N,H,W,C] (row = pixel, ld_in >= C) -> im2col planes [N*OH*OW, ld] with column (kh*KW + kw)*C + c,
+ * zero padding of pad_t/pad_l pixels (TF 'SAME' puts the extra pixel at the bottom/right). */
+int dlc_im2col_planes(const void* x_hi_dev, const void* x_lo_dev, int N, int H, int W, int C, int ld_in, int KH,
+                      int KW, int stride, int pad_t, int pad_l, int OH, int OW, void* out_hi_dev, void* out_lo_dev,
+                      int ld, void* stream);
+/* 3x3/2 VALID max-pool on NHWC float32 -> planes [N*OH*OW, ld] (cnn_vtl.py:42-45, 58-61). */
+int dlc_maxpool_planes(const float* x_dev, int N, int H, int W, int C, int window, int stride, int OH, int OW,
+                       void* out_hi_dev, void* out_lo_dev, int ld, void* stream);
+/* Per-image min/max over `n_seg` NHWC float32 segments (the concatenated descriptor of cnn_vtl.py:96-111), then
+ * q = int8(trunc((d - min) * (255 / (max - min)))) with two's-complement wrap, evaluated only at the kept columns
+ * keep_cols_dev[M] (indices into the concatenated descriptor; cnn_vtl.py:113-128). minmax_dev float32 [N,2] scratch. */
+int dlc_cnnvtl_quantise(const float* const* seg_ptrs_host, const int64_t* seg_sizes_host, int n_seg, int N,
+                        const int64_t* keep_cols_dev, int M, float* minmax_dev, int8_t* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLC_H_ */

@@ -1,0 +1,95 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own importable code (authoring container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [/root/reference]
+
+Imports (unmodified, from the read-only mount): src.sdav.similarity.SimilarityCalculator,
+src.cnn_vtl.similarity.DistanceCalculator, src.sdav.input.CvInputParser (patch functions; SURF detection is not
+available, keypoints are seeded), src.utils.MathUtils. The TensorFlow classes cannot be imported here.
+The fixtures travel with the repo; nothing at test time reads /root/reference.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class FakeKeyPoint:  # the only attribute the reference reads is .pt (CvInputParser.py:111)
+    def __init__(self, x, y):
+        self.pt = (float(x), float(y))
+
+
+def golden_patches():
+    import cv2
+    from src.sdav.input.CvInputParser import get_vectorized_patches_from_key_points
+    rng = np.random.default_rng(0)
+    imgs, kps, outs = [], [], []
+    for f in ("outdoor_kennedylong_000000.ppm", "outdoor_kennedylong_000007.ppm"):
+        img = cv2.imread(os.path.join(REF, "datasets/test", f), cv2.IMREAD_GRAYSCALE)
+        h, w = img.shape
+        xy = np.stack([rng.uniform(0, w, 30), rng.uniform(0, h, 30)], axis=1).astype(np.float32)
+        # edge cases: corners, half-integers (banker's rounding), x beyond H (the x/y swap quirk clamps it)
+        xy[:6] = [[0, 0], [w - 1, h - 1], [230.5, 10.5], [20.5, 21.5], [239.49, 0.5], [100.5, 191.0]]
+        pts = [FakeKeyPoint(x, y) for x, y in xy]
+        out = get_vectorized_patches_from_key_points(img, pts, 41) / 255.0   # parse(): CvInputParser.py:26-27
+        imgs.append(img); kps.append(xy); outs.append(out)
+    np.savez_compressed(os.path.join(HERE, "patches.npz"), img=np.stack(imgs), xy=np.stack(kps),
+                        out=np.stack(outs).astype(np.float64))
+
+
+def golden_similarity():
+    from src.sdav.similarity.SimilarityCalculator import SimilarityCalculator
+    rng = np.random.default_rng(1)
+    cases = {}
+    # (a) sigmoid-like descriptors, small D;  (b) saturated 0/1-ish descriptors like N(0,1)-weight SDA outputs
+    for name, n, p, d, sat in (("a", 5, 30, 96, False), ("b", 4, 30, 200, True), ("c", 3, 7, 64, False)):
+        x = rng.standard_normal((n, p, d)) * (8.0 if sat else 1.0)
+        desc = (1.0 / (1.0 + np.exp(-x))).astype(np.float32).astype(np.float64)  # float32-representable
+        calc = SimilarityCalculator(desc)
+        S = np.full((n, n), np.nan)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(n):
+                for j in range(n):
+                    if i != j:
+                        S[i, j] = calc.similarity_score(desc[i], desc[j])
+        cases["desc_" + name] = desc
+        cases["S_" + name] = S
+    np.savez_compressed(os.path.join(HERE, "similarity.npz"), **cases)
+
+
+def golden_hamming():
+    from src.cnn_vtl.similarity.DistanceCalculator import DistanceCalculator
+    rng = np.random.default_rng(2)
+    desc = rng.integers(-128, 128, size=(9, 203)).astype(np.int8)
+    desc[0, :4] = [-128, 127, -1, 0]
+    desc[1, :4] = [127, -128, 0, -1]
+    D = np.array([[DistanceCalculator.calculate_distance(a, b) for b in desc] for a in desc], dtype=np.int64)
+    # basic_example.py recipe: change one element to 23
+    y1 = desc[2].copy(); y2 = y1.copy(); y2[0] = 23
+    ex = DistanceCalculator.calculate_distance(y1, y2)
+    np.savez_compressed(os.path.join(HERE, "hamming.npz"), desc=desc, D=D, ex_y1=y1, ex_y2=y2, ex_d=np.int64(ex))
+
+
+def golden_misc():
+    from src.utils.MathUtils import MathUtils
+    vals = np.array([256128, 157696, 49920, 49920, 33280, 290400, 186624, 64896, 43264, 1, 1000], dtype=np.int64)
+    comp = np.array([MathUtils.compressed_size(int(v), 99.59) for v in vals], dtype=np.int64)
+    # the reference's only test vector (test/TensorflowWrapperTest.py:12-14)
+    x = np.array([[[1, 2], [3, 4]], [[5, 6], [7, 8]], [[9, 10], [11, 12]]], dtype=np.float64)
+    w = np.array([[2, 2], [2, 2]], dtype=np.float64)
+    expected = np.array([[[6, 6], [14, 14]], [[22, 22], [30, 30]], [[38, 38], [46, 46]]], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "misc.npz"), vals=vals, compressed=comp, tw_x=x, tw_w=w,
+                        tw_expected=expected)
+
+
+if __name__ == "__main__":
+    golden_patches(); golden_similarity(); golden_hamming(); golden_misc()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
