@@ -225,14 +225,37 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
 
 using namespace dlc;
 
+// Developer switch (dlc_debug_set key 1): launch only the Gram/score kernel, reusing the operand planes, statistics
+// and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
+static int g_gram_only = 0;
+extern "C" int dlc_sdav_debug_gram_only(int on) {
+  g_gram_only = on ? 1 : 0;
+  return DLC_OK;
+}
+
 extern "C" size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D) {
   if (N <= 0 || P <= 0 || D <= 0) return 0;
   return sim_layout(N, P, D).total;
 }
 
+extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, double sigma, double* w_dev,
+                                void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(desc_dev && w_dev && ws_dev);
+  DLC_CHECK_ARG(N >= 1 && P >= 1 && D >= 1 && sigma != 0.0);
+  if (ws_bytes < sizeof(double) * kColSumSlabs * D)
+    return fail(DLC_ENOMEM, "dlc_sdav_weights: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * D);
+  cudaStream_t s = as_stream(stream);
+  double* part = static_cast<double*>(ws_dev);
+  const int64_t rows = static_cast<int64_t>(N) * P;
+  colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
+  weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
 extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
-                                   double b, int precision, int full_asymmetric, float* S_dev, void* ws_dev,
-                                   size_t ws_bytes, void* stream) {
+                                   double b, const double* w_dev, int precision, int full_asymmetric,
+                                   float* S_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(desc_dev && S_dev && ws_dev);
   DLC_CHECK_ARG(N >= 1 && N <= (1 << 20));
   DLC_CHECK_ARG(P >= 1 && P <= kFrameRows);
@@ -247,24 +270,30 @@ extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, d
   char* ws = static_cast<char*>(ws_dev);
   const int64_t rows = static_cast<int64_t>(N) * P;
 
+  double* part = reinterpret_cast<double*>(ws + L.off_part);
+  double* w = reinterpret_cast<double*>(ws + L.off_w);
+  float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
+  double* pw = reinterpret_cast<double*>(ws + L.off_pw);
+  static thread_local std::vector<int2> tiles;
+  if (!g_gram_only) {
   // 1. operand planes: frames padded P -> 32 rows, K padded to a multiple of 64 (zeros)
   if (int rc = dlc_split_planes(desc_dev, DLC_F32, static_cast<int>(rows), D, D, P, kFrameRows, ws + L.off_hi,
                                 ws + L.off_lo, L.ld, stream))
     return rc;
   // 2. dataset mean -> distinctive weights w; 3. per-row squared norms and projections p = h . w
-  double* part = reinterpret_cast<double*>(ws + L.off_part);
-  double* w = reinterpret_cast<double*>(ws + L.off_w);
-  float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
-  double* pw = reinterpret_cast<double*>(ws + L.off_pw);
-  colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
-  weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w);
+  if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
+    w = const_cast<double*>(w_dev);
+  } else {
+    colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
+    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w);
+  }
   rowstats_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(desc_dev, N, P, D, w, sqn, pw);
   DLC_CUDA(cudaGetLastError());
 
   // 4. tile work list (host-built, tiny) -> device
-  static thread_local std::vector<int2> tiles;
   build_tile_list(N, full_asymmetric, tiles);
   DLC_CUDA(cudaMemcpyAsync(ws + L.off_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
+  }  // !g_gram_only
 
   // 5. Gram + argmin + score
   GramParams p{};

@@ -1,0 +1,242 @@
+"""Python faces of the C-ABI entry points (include/dlc.h). Inputs/outputs are CUDA torch tensors used purely as
+device buffers; every function launches hand-written sm_100a kernels from libdlc.so on torch's current stream.
+There is no fallback path: without the library or a B200 these raise."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._cuda import Workspace, ptr, stream_ptr
+
+PRECISIONS = {"fp16": _lib.PREC_FP16, "fp16x2": _lib.PREC_FP16X2, "bf16": _lib.PREC_BF16}
+METRICS = {"cos": _lib.METRIC_COS, "cosine": _lib.METRIC_COS, "dot": _lib.METRIC_DOT, "l2": _lib.METRIC_L2}
+_DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+_ws = Workspace()
+
+
+def precision_code(p):
+    if isinstance(p, str):
+        return PRECISIONS[p]
+    return int(p)
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("expected contiguous CUDA tensors")
+
+
+# ------------------------------------------------------------------------------------------------ planes
+def split_planes(src, group_in=1, group_out=1, need_lo=True):
+    """[rows, cols] f32/f64 -> (hi, lo) fp16 planes [rows_out, ld]."""
+    _check_cuda(src)
+    rows, cols = src.shape
+    ld = _lib.plane_ld(cols)
+    rows_out = -(-rows // group_in) * group_out
+    hi = torch.empty((rows_out, ld), dtype=torch.float16, device=src.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    _lib.call("dlc_split_planes", ptr(src), _DT[src.dtype], rows, cols, src.stride(0), group_in, group_out, ptr(hi),
+              ptr(lo), ld, stream_ptr())
+    return hi, lo
+
+
+def pack_weight_planes(w, n_pad=None, need_lo=True):
+    """W [k, n] f32/f64 -> transposed planes [n_pad, ld(k)]."""
+    _check_cuda(w)
+    k, n = w.shape
+    n_pad = n_pad or (-(-n // 32) * 32)
+    ld = _lib.plane_ld(k)
+    hi = torch.empty((n_pad, ld), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    _lib.call("dlc_pack_weight_planes", ptr(w), _DT[w.dtype], k, n, n_pad, ptr(hi), ptr(lo), ld, stream_ptr())
+    return hi, lo
+
+
+def gemm_planes(a_hi, a_lo, b_hi, b_lo, m, n, bias=None, act="none", precision="fp16x2", want_f32=True,
+                want_planes=False):
+    """act(A B^T + bias). Returns (out_f32 [m, n] or None, (out_hi, out_lo) or None)."""
+    _check_cuda(a_hi, a_lo, b_hi, b_lo, bias)
+    n_pad, ld = b_hi.shape
+    assert a_hi.shape[1] == ld and a_hi.shape[0] >= m
+    prec = precision_code(precision)
+    out = torch.empty((m, n), dtype=torch.float32, device=a_hi.device) if want_f32 else None
+    o_hi = o_lo = None
+    pld = 0
+    if want_planes:
+        pld = max(_lib.plane_ld(n), n_pad)
+        o_hi = torch.zeros((m, pld), dtype=torch.float16, device=a_hi.device)
+        o_lo = torch.zeros_like(o_hi) if prec == _lib.PREC_FP16X2 else None
+    acts = {"none": _lib.ACT_NONE, "sigmoid": _lib.ACT_SIGMOID, "relu": _lib.ACT_RELU}
+    _lib.call("dlc_gemm_planes", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), m, n, n_pad, ld, ptr(bias), acts[act],
+              prec, ptr(out), n, ptr(o_hi), ptr(o_lo), pld, stream_ptr())
+    return out, ((o_hi, o_lo) if want_planes else None)
+
+
+def matmul(a, b, bias=None, act="none", precision="fp16x2"):
+    """a [m, k] @ b [k, n] (+ bias, activation) for f32/f64 CUDA tensors -> float32 [m, n] (tensor cores)."""
+    _check_cuda(a, b)
+    m, k = a.shape
+    k2, n = b.shape
+    assert k == k2
+    split = precision_code(precision) == _lib.PREC_FP16X2
+    a_hi, a_lo = split_planes(a, need_lo=split)
+    b_hi, b_lo = pack_weight_planes(b, need_lo=split)
+    bias_f = None
+    if bias is not None:
+        bias_f = torch.zeros(b_hi.shape[0], dtype=torch.float32, device=a.device)
+        bias_f[:n] = bias.to(torch.float32)
+    out, _ = gemm_planes(a_hi, a_lo, b_hi, b_lo, m, n, bias_f, act, precision)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ patches
+def patch_gather(img, xy, patch=41, swap_xy_quirk=True, need_lo=True):
+    """img uint8 [B,H,W], xy float32 [B,P,2] -> (hi, lo) planes [B*P, ld(patch^2)]."""
+    _check_cuda(img, xy)
+    B, H, W = img.shape
+    P = xy.shape[1]
+    ld = _lib.plane_ld(patch * patch)
+    hi = torch.empty((B * P, ld), dtype=torch.float16, device=img.device)
+    lo = torch.empty_like(hi) if need_lo else None
+    _lib.call("dlc_patch_gather", ptr(img), B, H, W, ptr(xy), P, patch, int(bool(swap_xy_quirk)), ptr(hi), ptr(lo), ld,
+              stream_ptr())
+    return hi, lo
+
+
+def patch_gather_f64(img, xy, patch=41, swap_xy_quirk=True):
+    _check_cuda(img, xy)
+    B, H, W = img.shape
+    P = xy.shape[1]
+    out = torch.empty((B * P, patch * patch), dtype=torch.float64, device=img.device)
+    _lib.call("dlc_patch_gather_f64", ptr(img), B, H, W, ptr(xy), P, patch, int(bool(swap_xy_quirk)), ptr(out),
+              stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ SDA encoder
+class SdaEncoder:
+    """Owner of a dlc_sda handle (packed weights live on the device)."""
+
+    def __init__(self, dims, precision="fp16x2"):
+        self.dims = [int(d) for d in dims]
+        self.precision = precision
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(self.dims))(*self.dims)
+        _lib.call("dlc_sda_create", C.byref(self._h), len(self.dims) - 1, arr, precision_code(precision))
+        self._ws = Workspace()
+
+    def set_layer(self, l, w, b):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        if w.shape != (self.dims[l], self.dims[l + 1]) or b.shape != (self.dims[l + 1],):
+            raise ValueError("layer %d expects W %s and b %s" % (l, (self.dims[l], self.dims[l + 1]), (self.dims[l + 1],)))
+        _lib.call("dlc_sda_set_layer", self._h, l, w.ctypes.data, b.ctypes.data)
+
+    def encode_planes(self, x_hi, x_lo, rows, out=None):
+        _check_cuda(x_hi, x_lo)
+        if out is None:
+            out = torch.empty((rows, self.dims[-1]), dtype=torch.float32, device=x_hi.device)
+        need = _lib.call("dlc_sda_workspace_bytes", self._h, rows)
+        ws, ws_bytes = self._ws.get(need)
+        _lib.call("dlc_sda_encode", self._h, ptr(x_hi), ptr(x_lo), rows, ptr(out), ws, ws_bytes, stream_ptr())
+        return out
+
+    def encode(self, x):
+        """x [rows, in] f32/f64 CUDA -> float32 [rows, out]."""
+        split = precision_code(self.precision) == _lib.PREC_FP16X2
+        hi, lo = split_planes(x, need_lo=split)
+        return self.encode_planes(hi, lo, x.shape[0])
+
+    def close(self):
+        if self._h:
+            _lib.call("dlc_sda_destroy", self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ SDAV similarity
+def sdav_weights(desc, mu=0.5, sigma=0.2):
+    """desc float32 [N,P,D] -> float64 [D] distinctive weights."""
+    _check_cuda(desc)
+    N, P, D = desc.shape
+    w = torch.empty(D, dtype=torch.float64, device=desc.device)
+    ws, ws_bytes = _ws.get(_lib.call("dlc_sdav_similarity_workspace_bytes", N, P, D))
+    _lib.call("dlc_sdav_weights", ptr(desc), N, P, D, float(mu), float(sigma), ptr(w), ws, ws_bytes, stream_ptr())
+    return w
+
+
+def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="fp16x2",
+                    full_asymmetric=False, out=None):
+    """desc float32 [N,P,D] -> float32 [N,N] score matrix (reference order: i<j mirrored, diagonal -1)."""
+    _check_cuda(desc, weights)
+    N, P, D = desc.shape
+    if out is None:
+        out = torch.empty((N, N), dtype=torch.float32, device=desc.device)
+    ws, ws_bytes = _ws.get(_lib.call("dlc_sdav_similarity_workspace_bytes", N, P, D))
+    _lib.call("dlc_sdav_similarity", ptr(desc), N, P, D, float(mu), float(sigma), float(a), float(b), ptr(weights),
+              precision_code(precision), int(bool(full_asymmetric)), ptr(out), ws, ws_bytes, stream_ptr())
+    return out
+
+
+def topk_rows(scores, k, largest=True, exclude_band=-1, cand_idx=None):
+    """Per-row top-k of a dense [rows, cols] float32 matrix -> (scores [rows,k] f32, idx [rows,k] i64)."""
+    _check_cuda(scores, cand_idx)
+    rows, cols = scores.shape
+    o_s = torch.empty((rows, k), dtype=torch.float32, device=scores.device)
+    o_i = torch.empty((rows, k), dtype=torch.int64, device=scores.device)
+    _lib.call("dlc_topk_rows", ptr(scores), ptr(cand_idx), rows, cols, scores.stride(0), k, int(bool(largest)),
+              int(exclude_band), ptr(o_s), ptr(o_i), stream_ptr())
+    return o_s, o_i
+
+
+# ------------------------------------------------------------------------------------------------ Hamming
+def hamming_matrix(desc, signed_bin_quirk=True):
+    """desc int8 [N,M] -> int32 [N,N]."""
+    _check_cuda(desc)
+    assert desc.dtype == torch.int8
+    N, M = desc.shape
+    out = torch.empty((N, N), dtype=torch.int32, device=desc.device)
+    _lib.call("dlc_hamming_matrix", ptr(desc), N, M, int(bool(signed_bin_quirk)), ptr(out), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ conv blocks
+def im2col_planes(x_hi, x_lo, N, H, W, C_, KH, KW, stride, pad_t, pad_l, OH, OW):
+    _check_cuda(x_hi, x_lo)
+    ld = _lib.plane_ld(KH * KW * C_)
+    o_hi = torch.empty((N * OH * OW, ld), dtype=torch.float16, device=x_hi.device)
+    o_lo = torch.empty_like(o_hi) if x_lo is not None else None
+    _lib.call("dlc_im2col_planes", ptr(x_hi), ptr(x_lo), N, H, W, C_, x_hi.shape[1], KH, KW, stride, pad_t, pad_l, OH,
+              OW, ptr(o_hi), ptr(o_lo), ld, stream_ptr())
+    return o_hi, o_lo
+
+
+def maxpool_planes(x, N, H, W, C_, window, stride, need_lo=True):
+    _check_cuda(x)
+    OH, OW = (H - window) // stride + 1, (W - window) // stride + 1
+    ld = _lib.plane_ld(C_)
+    o_hi = torch.empty((N * OH * OW, ld), dtype=torch.float16, device=x.device)
+    o_lo = torch.empty_like(o_hi) if need_lo else None
+    _lib.call("dlc_maxpool_planes", ptr(x), N, H, W, C_, window, stride, OH, OW, ptr(o_hi), ptr(o_lo), ld,
+              stream_ptr())
+    return o_hi, o_lo, OH, OW
+
+
+def cnnvtl_quantise(segments, N, keep_cols):
+    """segments: list of float32 CUDA tensors [N, size_l]; keep_cols int64 CUDA [M] -> int8 [N, M]."""
+    _check_cuda(keep_cols, *segments)
+    n_seg = len(segments)
+    ptrs = (C.c_void_p * n_seg)(*[s.data_ptr() for s in segments])
+    sizes = (C.c_int64 * n_seg)(*[s.numel() // N for s in segments])
+    M = keep_cols.numel()
+    mm = torch.empty((N, 2), dtype=torch.float32, device=keep_cols.device)
+    out = torch.empty((N, M), dtype=torch.int8, device=keep_cols.device)
+    _lib.call("dlc_cnnvtl_quantise", ptrs, sizes, n_seg, N, ptr(keep_cols), M, ptr(mm), ptr(out), stream_ptr())
+    return out

@@ -53,6 +53,11 @@ extern "C" {
 
 const char* dlc_last_error(void);
 int dlc_version(void);
+/* Developer switch (key 0: K-block of the 3-product kernel, 32 or 64). Not part of the drop-in surface. */
+int dlc_debug_set(int key, int value);
+/* Developer switch: when on, dlc_sdav_similarity launches only its Gram/score kernel and reuses the workspace
+ * contents of the previous full call (used by bench.py to time that kernel alone). */
+int dlc_sdav_debug_gram_only(int on);
 /* 0 when the current CUDA device can run this library (compute capability 10.x), DLC_EUNSUPPORTED otherwise. */
 int dlc_device_check(void);
 int dlc_sm_count(void);
@@ -127,9 +132,15 @@ int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int r
  * full_asymmetric = 1 instead evaluates score(i, j) for every ordered pair i != j.
  * ------------------------------------------------------------------------------------------------------------ */
 size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D);
+/* w_dev: optional float64 [D] distinctive weights (from dlc_sdav_weights on another dataset); NULL = derive them
+ * from desc_dev itself, which is what the reference does for the dataset it was constructed with. */
 int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
-                        int precision, int full_asymmetric, float* S_dev, void* ws_dev, size_t ws_bytes,
-                        void* stream);
+                        const double* w_dev, int precision, int full_asymmetric, float* S_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
+/* w = exp(-(mean_rows(desc) - mu)^2 / (2 sigma^2)), float64 [D] (SimilarityCalculator.py:19-27).
+ * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 128*D*8). */
+int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, double sigma, double* w_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Row-wise candidate selection on a dense score matrix (loop candidates from S, or a k-way merge of partial

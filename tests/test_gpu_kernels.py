@@ -1,0 +1,314 @@
+"""Parity of the CUDA kernels (called through the C ABI via ctypes) against the float64 oracle. `-m gpu`."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hamming as o_ham
+from oracle import matcher as o_match
+from oracle import patches as o_patch
+from oracle import sda as o_sda
+from oracle import similarity as o_sim
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north star: descriptors and scores within 1e-3 relative:  |a-b| <= 1e-3 * max(1, |b|)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+def norm_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+# ------------------------------------------------------------------------------------------- tensor-core GEMM
+@pytest.mark.parametrize("m,k,n", [(3, 2, 2), (128, 64, 32), (130, 200, 96), (600, 1681, 2500), (257, 2500, 300)])
+@pytest.mark.parametrize("precision", ["fp16x2", "fp16"])
+def test_matmul_vs_oracle(cuda, m, k, n, precision):
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(m * 7 + k)
+    a = rng.uniform(0, 1, (m, k))
+    b = rng.standard_normal((k, n))
+    bias = rng.standard_normal(n)
+    ref = a @ b + bias
+    out = ops.matmul(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda(),
+                     act="none", precision=precision).cpu().numpy()
+    err = norm_err(out, ref)
+    print("matmul", (m, k, n), precision, "normwise", err, "max-abs", np.max(np.abs(out - ref)))
+    assert err < (2e-6 if precision == "fp16x2" else 2e-3)
+
+
+def test_matmul_known_answer(cuda, golden_dir):
+    """The reference's only test vector (test/TensorflowWrapperTest.py:11-21): exact."""
+    from deeploopcloser_b200 import ops
+    g = np.load(golden_dir + "/misc.npz")
+    x = torch.from_numpy(g["tw_x"]).cuda()
+    w = torch.from_numpy(g["tw_w"]).cuda()
+    y = ops.matmul(x.reshape(-1, 2), w).reshape(3, 2, 2).double().cpu().numpy()
+    assert np.array_equal(y, g["tw_expected"])
+
+
+@pytest.mark.parametrize("bk", [32, 64])
+def test_split_kernel_both_ring_shapes(cuda, bk):
+    from deeploopcloser_b200 import _lib, ops
+    _lib.call("dlc_debug_set", 0, bk)
+    try:
+        rng = np.random.default_rng(bk)
+        a = rng.uniform(0, 1, (300, 777))
+        b = rng.standard_normal((777, 520))
+        out = ops.matmul(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+        assert norm_err(out, a @ b) < 2e-6
+    finally:
+        _lib.call("dlc_debug_set", 0, 32)
+
+
+# ------------------------------------------------------------------------------------------- SDA encoder
+@pytest.mark.parametrize("scale,precision,tol", [("normal", "fp16x2", TOL), ("xavier", "fp16x2", TOL),
+                                                 ("xavier", "fp16", 5e-3)])
+def test_sda_encode_vs_oracle(cuda, scale, precision, tol):
+    from deeploopcloser_b200 import ops
+    dims = [1681, 2500, 2500, 2500, 2500, 2500]
+    ws, bs = o_sda.make_weights(dims, seed=1, scale=scale)
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 256, (4 * 30, 1681)).astype(np.float64) / 255.0  # patch-like inputs
+    ref = o_sda.sda_forward(x, ws, bs)
+    enc = ops.SdaEncoder(dims, precision)
+    for l, (w, b) in enumerate(zip(ws, bs)):
+        enc.set_layer(l, w, b)
+    out = enc.encode(torch.from_numpy(x).cuda()).cpu().numpy()
+    e_rel, e_norm = rel_err(out, ref), norm_err(out, ref)
+    print("sda", scale, precision, "max |a-b|/max(1,|b|)", e_rel, "normwise", e_norm)
+    assert out.shape == (120, 2500)
+    assert e_rel <= tol and e_norm <= tol
+
+
+def test_da_single_layer(cuda):
+    from deeploopcloser_b200 import ops
+    ws, bs = o_sda.make_weights([1681, 2500], seed=5)
+    x = np.random.default_rng(3).uniform(0, 1, (30, 1681))
+    enc = ops.SdaEncoder([1681, 2500], "fp16x2")
+    enc.set_layer(0, ws[0], bs[0])
+    out = enc.encode(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rel_err(out, o_sda.sda_forward(x, ws, bs)) <= TOL
+
+
+# ------------------------------------------------------------------------------------------- patch gather
+def test_patch_gather_golden(cuda, golden_dir):
+    from deeploopcloser_b200 import ops
+    g = np.load(golden_dir + "/patches.npz")
+    img = torch.from_numpy(g["img"]).cuda()
+    xy = torch.from_numpy(g["xy"]).cuda()
+    out = ops.patch_gather_f64(img, xy).cpu().numpy().reshape(g["out"].shape)
+    assert np.array_equal(out, g["out"])  # bit-exact vs the reference's own output
+    hi, lo = ops.patch_gather(img, xy)
+    v = (hi.double() + lo.double()).cpu().numpy()
+    assert v.shape == (60, 1728)
+    assert np.max(np.abs(v[:, :1681] - g["out"].reshape(60, 1681))) < 2e-7
+    assert np.all(v[:, 1681:] == 0)
+
+
+@pytest.mark.parametrize("quirk", [True, False])
+def test_patch_gather_random(cuda, quirk):
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(11)
+    B, H, W, P = 3, 480, 640, 30
+    img = rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+    xy = np.stack([rng.uniform(-3, W + 3, (B, P)), rng.uniform(-3, H + 3, (B, P))], axis=-1).astype(np.float32)
+    xy[0, 0] = [0.5, 1.5]
+    xy[0, 1] = [2.5, 3.5]
+    out = ops.patch_gather_f64(torch.from_numpy(img).cuda(), torch.from_numpy(xy).cuda(), swap_xy_quirk=quirk)
+    ref = np.concatenate([o_patch.extract_patches(img[b], xy[b], 41, quirk) for b in range(B)])
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------- Hamming
+def test_hamming_golden(cuda, golden_dir):
+    from deeploopcloser_b200 import ops
+    g = np.load(golden_dir + "/hamming.npz")
+    D = ops.hamming_matrix(torch.from_numpy(g["desc"]).cuda()).cpu().numpy()
+    assert np.array_equal(D, g["D"])
+
+
+@pytest.mark.parametrize("n,m,quirk", [(1, 1, True), (70, 2243, True), (130, 515, False)])
+def test_hamming_random(cuda, n, m, quirk):
+    from deeploopcloser_b200 import ops
+    desc = np.random.default_rng(n).integers(-128, 128, (n, m)).astype(np.int8)
+    D = ops.hamming_matrix(torch.from_numpy(desc).cuda(), quirk).cpu().numpy()
+    assert np.array_equal(D, o_ham.distance_matrix(desc, quirk))
+    assert np.all(np.diag(D) == 0)
+
+
+# ------------------------------------------------------------------------------------------- SDAV similarity
+def _check_similarity(S, desc, full):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, det = o_sim.similarity_matrix(desc.astype(np.float64), full_asymmetric=full, return_details=True)
+    n = len(desc)
+    bad = []
+    for i in range(n):
+        for j in range(n):
+            if i == j:
+                assert S[i, j] == -1.0
+                continue
+            if abs(S[i, j] - ref[i, j]) > TOL * max(1.0, abs(ref[i, j])):
+                bad.append((i, j, S[i, j], ref[i, j]))
+    # a mismatch is only acceptable when the oracle's nearest-neighbour choice was a tie within tolerance
+    ties = 0
+    for (i, j, got, want) in bad:
+        a, b = (i, j) if (full or i < j) else (j, i)
+        margin = o_sim.nn_margin(desc[a].astype(np.float64), desc[b].astype(np.float64))
+        assert margin.min() < 1e-3, "score mismatch at %s: got %r want %r (no NN tie, min margin %g)" % (
+            (i, j), got, want, margin.min())
+        ties += 1
+    print("similarity: %d pairs, %d tie-induced mismatches" % (n * (n - 1), ties))
+
+
+def test_similarity_golden(cuda, golden_dir):
+    from deeploopcloser_b200 import ops
+    g = np.load(golden_dir + "/similarity.npz")
+    for name in "abc":
+        desc = g["desc_" + name].astype(np.float32)
+        ref = g["S_" + name]  # produced by the reference's SimilarityCalculator
+        S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=True).cpu().numpy()
+        m = ~np.eye(len(ref), dtype=bool)
+        err = np.max(np.abs(S[m] - ref[m]) / np.maximum(1, np.abs(ref[m])))
+        print("similarity golden", name, err)
+        assert err <= TOL
+        assert np.all(np.diag(S) == -1)
+
+
+@pytest.mark.parametrize("n,p,d,full", [(9, 30, 2500, False), (21, 30, 300, True), (2, 5, 64, False), (1, 30, 64, False)])
+def test_similarity_random(cuda, n, p, d, full):
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(n)
+    desc = (1.0 / (1.0 + np.exp(-4.0 * rng.standard_normal((n, p, d))))).astype(np.float32)
+    S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=full).cpu().numpy()
+    _check_similarity(S, desc, full)
+    if not full:
+        assert np.array_equal(S, S.T)
+
+
+# ------------------------------------------------------------------------------------------- row top-k
+@pytest.mark.parametrize("largest", [True, False])
+def test_topk_rows(cuda, largest):
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal((37, 211)).astype(np.float32)
+    s[:, 5] = s[:, 9]  # ties -> lowest index
+    s[3, 7] = np.inf
+    s[4, 8] = -np.inf
+    s[5, 2] = np.nan
+    for band in (-1, 0, 3):
+        gs, gi = ops.topk_rows(torch.from_numpy(s).cuda(), 10, largest, band)
+        rs, ri = o_match.topk(s, 10, largest, band)
+        assert np.array_equal(gi.cpu().numpy(), ri)
+        assert np.array_equal(gs.cpu().numpy().astype(np.float64), rs)
+    # fewer candidates than k
+    gs, gi = ops.topk_rows(torch.from_numpy(s[:, :4].copy()).cuda(), 6, largest)
+    rs, ri = o_match.topk(s[:, :4], 6, largest)
+    assert np.array_equal(gi.cpu().numpy(), ri)
+
+
+# ------------------------------------------------------------------------------------------- global matcher
+def _stored(db_rows, metric, dtype):
+    x = torch.from_numpy(db_rows)
+    if metric == "cos":
+        x = x / x.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    td = torch.float16 if dtype == "fp16" else torch.bfloat16
+    return x.to(td).double().numpy()
+
+
+def _check_topk(scores, idx, ref_scores, k, smaller):
+    """indices identical except for ties within tolerance (reported); scores within TOL."""
+    ties = 0
+    for r in range(len(scores)):
+        rs, ri = o_match.topk(ref_scores[r:r + 1], k, largest=not smaller)
+        if not np.array_equal(idx[r], ri[0]):
+            for t in range(k):
+                if idx[r, t] != ri[0, t]:
+                    assert idx[r, t] >= 0
+                    got = ref_scores[r, idx[r, t]]
+                    assert abs(got - rs[0, t]) <= TOL * max(1, abs(rs[0, t])), (r, t, idx[r], ri[0])
+                    ties += 1
+        valid = idx[r] >= 0
+        want = ref_scores[r, idx[r][valid]]
+        assert np.all(np.abs(scores[r][valid] - want) <= TOL * np.maximum(1, np.abs(want)))
+    return ties
+
+
+@pytest.mark.parametrize("metric", ["cos", "dot", "l2"])
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,N,D,k", [(5, 1000, 128, 10), (130, 5000, 2500, 10), (300, 70000, 256, 32), (1, 37, 64, 5)])
+def test_match_topk(cuda, metric, dtype, B, N, D, k):
+    from deeploopcloser_b200.matcher import KeyframeDatabase
+    rng = np.random.default_rng(B + N)
+    db_rows = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    nplant = min(B, N) // 2
+    q[:nplant] = db_rows[rng.choice(N, nplant, replace=False)] + 0.05 * rng.standard_normal((nplant, D)).astype(np.float32)
+    if metric != "cos":  # keep dot/L2 magnitudes inside fp16 range and scores O(1..100)
+        db_rows *= 0.25
+        q *= 0.25
+    db = KeyframeDatabase(D, N + 7, metric, dtype)
+    half = N // 2
+    db.append(torch.from_numpy(db_rows[:half]).cuda())   # incremental insertion
+    db.append(torch.from_numpy(db_rows[half:]).cuda())
+    assert len(db) == N
+    scores, idx = db.topk(torch.from_numpy(q).cuda(), k)
+    scores, idx = scores.cpu().numpy().astype(np.float64), idx.cpu().numpy()
+    code = {"cos": o_match.COS, "dot": o_match.DOT, "l2": o_match.L2}[metric]
+    qr = torch.from_numpy(q)
+    if metric == "cos":
+        qr = qr / qr.norm(dim=1, keepdim=True)
+    # oracle on the values the kernel contracts: stored database rows, queries rounded to the storage type
+    td = torch.float16 if dtype == "fp16" else torch.bfloat16
+    q_used = qr.to(td).double().numpy() if metric != "cos" else qr.to(td).double().numpy()
+    ref = o_match.score_matrix(q_used, _stored(db_rows, metric, dtype), o_match.DOT if metric == "cos" else code)
+    ties = _check_topk(scores, idx, ref, min(k, N), metric == "l2")
+    print("match", metric, dtype, (B, N, D, k), "ties within tol:", ties)
+    # end-to-end accuracy vs the unrounded float64 definition
+    full = o_match.score_matrix(q.astype(np.float64), _stored(db_rows, metric, dtype), code)
+    top1 = full.argmin(1) if metric == "l2" else full.argmax(1)
+    agree = np.mean(idx[:, 0] == top1)
+    assert agree > 0.97
+
+
+def test_match_threshold(cuda):
+    from deeploopcloser_b200.matcher import KeyframeDatabase
+    rng = np.random.default_rng(9)
+    N, D, B = 3000, 96, 40
+    db_rows = rng.standard_normal((N, D)).astype(np.float32)
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    q[:10] = db_rows[:10] + 0.01
+    db = KeyframeDatabase(D, N, "cos", "fp16")
+    db.append(torch.from_numpy(db_rows).cuda())
+    thr = 0.25
+    counts, scores, idx = db.threshold(torch.from_numpy(q).cuda(), thr, 16)
+    qn = torch.from_numpy(q)
+    qn = (qn / qn.norm(dim=1, keepdim=True)).half().double().numpy()
+    ref = qn @ _stored(db_rows, "cos", "fp16").T
+    margin = np.abs(ref - thr).min()
+    rc, rs, ri = o_match.threshold(ref, thr, 16)
+    if margin > 1e-4:
+        assert np.array_equal(counts.cpu().numpy(), rc)
+        assert np.array_equal(idx.cpu().numpy(), ri)
+
+
+def test_match_empty_and_errors(cuda):
+    from deeploopcloser_b200 import _lib
+    from deeploopcloser_b200.matcher import KeyframeDatabase
+    db = KeyframeDatabase(64, 10, "cos", "fp16")
+    s, i = db.topk(torch.zeros((3, 64), device="cuda"), 4)
+    assert np.all(i.cpu().numpy() == -1)
+    db.append(torch.randn(10, 64, device="cuda"))
+    with pytest.raises(_lib.DlcError):
+        db.append(torch.randn(1, 64, device="cuda"))  # over capacity
+    with pytest.raises(_lib.DlcError):
+        db.topk(torch.zeros((3, 64), device="cuda"), 33)  # k > 32
