@@ -7,8 +7,8 @@
 // NPROD = 3 : error-compensated fp16 split, A ~= A_hi + A_lo, B ~= B_hi + B_lo,
 //             D = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (the dropped lo*lo term is ~2^-22 relative).
 //
-// Roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane),
-// warps 2..5 = epilogue (each owns the 32 TMEM lanes of its quarter: quarter = warp_idx % 4).
+// Roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane), warps 2.. = epilogue
+// (4 warps, or 8 with two-level accumulation; each reads the 32 TMEM lanes of its quarter = warp_idx % 4).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 // What happens to an accumulator tile is decided by the Policy's Epilogue (bias+sigmoid+re-split, argmin/score,
 // running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
@@ -50,20 +50,38 @@ struct GemmCfg {
 
 // Policy contract:
 //   using Cfg = GemmCfg<BK, NPROD>;
-//   struct Params { int n_tile; int k_blocks; int ab_fmt; ... };            (POD, passed by value)
+//   static constexpr bool kPromote;      two-level accumulation (see below)
+//   struct Params { int n_tile; int k_blocks; int ab_fmt; int kc; ... };            (POD, passed by value)
 //   static __device__ int  num_tiles(const Params&, int cta, int ncta);
 //   static __device__ TileCoord tile(const Params&, int cta, int ncta, int i);
 //   struct Epilogue { __device__ Epilogue(const Params&, int quarter, int lane, void* scratch);
-//                     __device__ void tile(TileCoord, uint32_t tmem_acc /*lane quarter already applied*/);
+//                     __device__ void begin_tile(TileCoord);
+//                     __device__ void chunk(TileCoord, int c, float (&v)[32]);   // columns [32c, 32c+32) of this
+//                     __device__ void end_tile(TileCoord);                       // thread's accumulator row
 //                     __device__ void finish(); };
+//
+// Two-level accumulation (kPromote). The tensor core adds into its fp32 accumulator with truncation, so a K = 2500
+// dot product accumulated in ~470 sequential steps carries a ~1e-5 relative bias (measured on B200) - too much for
+// the 1e-3 descriptor tolerance once five saturating layers amplify it. With kPromote the MMA warp accumulates only
+// `kc` K-blocks into a TMEM buffer, hands it to the epilogue warps and continues in the other buffer; the epilogue
+// warps (8 instead of 4: two per lane quarter, 128 columns each) add the partial sums in registers with
+// round-to-nearest fp32 adds and run the real epilogue on the register tile after the last K chunk.
+// Thread layout with two-level accumulation: warp group 0 = {TMA, MMA, 2 idle warps} shrinks to 56 registers per
+// thread (setmaxnreg), warp groups 1 and 2 = the 8 epilogue warps grow to 224 (128 of them hold the running sums).
+constexpr int kGemmThreadsPromote = 384;
+constexpr int kRegsLean = 56;
+constexpr int kRegsEpilogue = 224;
+
 template <class Policy>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(Policy::kPromote ? kGemmThreadsPromote : kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const typename Policy::Params p) {
   using Cfg = typename Policy::Cfg;
   constexpr int BK = Cfg::BK;
   constexpr int S = Cfg::kStages;
+  constexpr bool kPromote = Policy::kPromote;
+  constexpr int kEpiWarps = kPromote ? 8 : 4;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 4);  // one arrival per epilogue warp
+        mbar_init(&tempty[a], kEpiWarps);  // one arrival per epilogue warp
       }
       fence_mbar_init();
     }
@@ -109,10 +127,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  constexpr int kEpiWarp0 = kPromote ? 4 : 2;  // first epilogue warp
+
   const int my_tiles = Policy::num_tiles(p, cta, ncta);
   const int n_tile = p.n_tile;
   const int k_blocks = p.k_blocks;
+  // K chunks per tile: one (plain accumulation) or ceil(k_blocks / kc) (two-level accumulation)
+  const int kc = kPromote ? (p.kc > 0 ? p.kc : k_blocks) : k_blocks;
+  const int n_chunks = (k_blocks + kc - 1) / kc;
 
+  if (warp < kEpiWarp0) {
+  if (kPromote) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLean));
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -148,60 +173,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxTileN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full[stage], phase, 3);
+        int kb = 0;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1u, 2);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t a_lo = a_hi + Cfg::kABytes;
-          const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
-          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxTileN);
+          const int kb_end = kb + kc < k_blocks ? kb + kc : k_blocks;
+          for (int kk = 0; kb < kb_end; ++kb, ++kk) {
+            mbar_wait(&full[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t a_lo = a_hi + Cfg::kABytes;
+            const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint32_t koff = k * 32;  // 16 fp16 along K inside the swizzle span
-            const uint64_t dah = make_smem_desc(a_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-            const uint64_t dbh = make_smem_desc(b_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-            if (Cfg::NPROD == 3) {
-              // small cross terms first, dominant term last
-              const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-              const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-              umma_f16(d_tmem, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, dah, dbl, idesc, 1u);
-              umma_f16(d_tmem, dah, dbh, idesc, 1u);
-            } else {
-              umma_f16(d_tmem, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t koff = k * 32;  // 16 fp16 along K inside the swizzle span
+              const uint64_t dah = make_smem_desc(a_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+              const uint64_t dbh = make_smem_desc(b_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+              if (Cfg::NPROD == 3) {
+                // small cross terms first, dominant term last
+                const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+                const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+                umma_f16(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                umma_f16(d_tmem, dah, dbh, idesc, 1u);
+              } else {
+                umma_f16(d_tmem, dah, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty[stage]);  // smem slot is free once these MMAs have read it
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
-          umma_commit(&empty[stage]);  // smem slot is free once these MMAs have read it
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          umma_commit(&tfull[acc]);  // (partial) accumulator complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
+  }
   } else {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;
+    if (kPromote) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int half = kPromote ? (warp - kEpiWarp0) >> 2 : 0;
+    const int n_cchunks = n_tile >> 5;          // 32-column chunks in the accumulator
     typename Policy::Epilogue epi(p, quarter, lane, scratch);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const TileCoord tc = Policy::tile(p, cta, ncta, i);
-      mbar_wait(&tfull[acc], acc_phase, 4);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) + (static_cast<uint32_t>(quarter * 32) << 16);
-      epi.tile(tc, taddr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (kPromote) {
+        float sums[128];
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          mbar_wait(&tfull[acc], acc_phase, 4);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) +
+                                 (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 128);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (half * 4 + cc < n_cchunks) {
+              uint32_t v[32];
+              tmem_ld_x32(taddr + cc * 32, v);
+              tmem_ld_wait();
+              if (ch == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sums[cc * 32 + j] = __uint_as_float(v[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sums[cc * 32 + j] += __uint_as_float(v[j]);
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+        epi.begin_tile(tc);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          if (half * 4 + cc < n_cchunks) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sums[cc * 32 + j];
+            epi.chunk(tc, half * 4 + cc, v);
+          }
+        }
+        epi.end_tile(tc);
+      } else {
+        mbar_wait(&tfull[acc], acc_phase, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) + (static_cast<uint32_t>(quarter * 32) << 16);
+        epi.begin_tile(tc);
+        for (int c = 0; c < n_cchunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epi.chunk(tc, c, v);
+        }
+        epi.end_tile(tc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
     }
     epi.finish();
   }
@@ -264,7 +348,8 @@ inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<Policy><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  gemm_tc_kernel<Policy><<<grid, Policy::kPromote ? kGemmThreadsPromote : kGemmThreads, Cfg::kSmemBytes, stream>>>(
+      a0, a1, b0, b1, p);
   return cudaGetLastError();
 }
 

@@ -132,7 +132,7 @@ query_prep_kernel(const float* __restrict__ q, int B, int dim, int ld, int metri
 
 // ---------------- fused similarity + running top-K ----------------
 struct MatchParams {
-  int n_tile, k_blocks, ab_fmt;
+  int n_tile, k_blocks, ab_fmt, kc;
   int m_tiles;     // query tiles = CTA groups
   int slots;       // CTAs per group
   int n_tiles;     // database tiles
@@ -153,6 +153,7 @@ template <int BK, int KMAX>
 struct MatchPolicy {
   using Cfg = GemmCfg<BK, 1>;
   using Params = MatchParams;
+  static constexpr bool kPromote = false;  // operand rounding (fp16/bf16 storage) dominates the error here
   static constexpr uint64_t kHintA = kEvictLast;   // queries: tiny, re-read for every database tile
   static constexpr uint64_t kHintB = kEvictFirst;  // database: streamed once per pass
 
@@ -182,42 +183,43 @@ struct MatchPolicy {
       cnt = 0;
     }
 
-    __device__ __forceinline__ void tile(TileCoord tc, uint32_t taddr) {
-      const int row = tc.mt * kTileM + quarter * 32 + lane;
-      const bool l2 = p.metric == DLC_METRIC_L2;
+    int row;
+    bool l2;
+    float gscale, thr_key;
+    __device__ __forceinline__ void begin_tile(TileCoord tc) {
+      row = tc.mt * kTileM + quarter * 32 + lane;
+      l2 = p.metric == DLC_METRIC_L2;
       // selection key (larger = better): COS/DOT: G ; L2: 2 G - |d|^2   (|q|^2 is constant per row)
-      const float gscale = l2 ? 2.0f : 1.0f;
-      float thr_key = p.thr;
+      gscale = l2 ? 2.0f : 1.0f;
+      thr_key = p.thr;
       if (l2) thr_key = (row < p.B ? p.qaux[row] : 0.0f) - p.thr;  // dist <= thr  <=>  key >= |q|^2 - thr
-      const int chunks = p.n_tile >> 5;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int64_t col0 = static_cast<int64_t>(tc.nt) * p.n_tile + c * 32;
-        if (col0 >= p.db_rows) continue;  // warp-uniform
-        float my_dn = 0.0f;
-        if (l2) my_dn = (col0 + lane < p.db_rows) ? p.dn[col0 + lane] : 0.0f;
-        const int nvalid = p.db_rows - col0 < 32 ? static_cast<int>(p.db_rows - col0) : 32;
+    }
+    __device__ __forceinline__ void end_tile(TileCoord) {}
+
+    __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
+      const int64_t col0 = static_cast<int64_t>(tc.nt) * p.n_tile + c * 32;
+      if (col0 >= p.db_rows) return;  // warp-uniform
+      float my_dn = 0.0f;
+      if (l2) my_dn = (col0 + lane < p.db_rows) ? p.dn[col0 + lane] : 0.0f;
+      const int nvalid = p.db_rows - col0 < 32 ? static_cast<int>(p.db_rows - col0) : 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float key = __uint_as_float(v[j]) * gscale;
-          if (l2) key -= __shfl_sync(0xffffffffu, my_dn, j);
-          if (j < nvalid && row < p.B) {
-            if (p.use_thr && key >= thr_key) ++cnt;
-            if (key > ls[KMAX - 1]) {  // candidates arrive in increasing index: strict > keeps the lowest index on ties
-              float cs = key;
-              int ci = static_cast<int>(col0) + j;
+      for (int j = 0; j < 32; ++j) {
+        float key = v[j] * gscale;
+        if (l2) key -= __shfl_sync(0xffffffffu, my_dn, j);
+        if (j < nvalid && row < p.B) {
+          if (p.use_thr && key >= thr_key) ++cnt;
+          if (key > ls[KMAX - 1]) {  // candidates arrive in increasing index: strict > keeps the lowest index on ties
+            float cs = key;
+            int ci = static_cast<int>(col0) + j;
 #pragma unroll
-              for (int t = 0; t < KMAX; ++t) {
-                const bool up = cs > ls[t];
-                const float ts = ls[t];
-                const int ti = li[t];
-                ls[t] = up ? cs : ts;
-                li[t] = up ? ci : ti;
-                cs = up ? ts : cs;
-                ci = up ? ti : ci;
-              }
+            for (int t = 0; t < KMAX; ++t) {
+              const bool up = cs > ls[t];
+              const float ts = ls[t];
+              const int ti = li[t];
+              ls[t] = up ? cs : ts;
+              li[t] = up ? ci : ti;
+              cs = up ? ts : cs;
+              ci = up ? ti : ci;
             }
           }
         }
@@ -228,8 +230,9 @@ struct MatchPolicy {
       // Every CTA of a group writes its slot (CTAs without tiles write empty lists) so the merge reads defined data.
       const int cta = blockIdx.x;
       const int mt = cta % p.m_tiles, slot = cta / p.m_tiles;
-      const int row = mt * kTileM + quarter * 32 + lane;
-      if (row >= p.B) return;
+      const int frow = mt * kTileM + quarter * 32 + lane;
+      if (frow >= p.B) return;
+      const int row = frow;
       const int64_t o = (static_cast<int64_t>(row) * p.slots + slot) * KMAX;
 #pragma unroll
       for (int t = 0; t < KMAX; ++t) {

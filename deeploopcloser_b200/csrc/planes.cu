@@ -84,7 +84,7 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 // bias + activation epilogue
 // ------------------------------------------------------------------------------------------------
 struct BiasActParams {
-  int n_tile, k_blocks, ab_fmt;
+  int n_tile, k_blocks, ab_fmt, kc;
   int m_tiles, n_tiles;
   int M, N;
   const float* bias;
@@ -108,6 +108,7 @@ template <int BK, int NPROD>
 struct BiasActPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = BiasActParams;
+  static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
   static constexpr uint64_t kHintA = kEvictNormal;
   static constexpr uint64_t kHintB = kEvictLast;  // weights are re-read by every M tile: keep them in L2
 
@@ -129,66 +130,66 @@ struct BiasActPolicy {
     const int quarter, lane;
     __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
 
-    __device__ __forceinline__ void tile(TileCoord tc, uint32_t taddr) {
-      const int row = tc.mt * kTileM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int chunks = p.n_tile >> 5;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = tc.nt * p.n_tile + c * 32;
-        float h[32];
+    int row;
+    bool row_ok;
+    __device__ __forceinline__ void begin_tile(TileCoord tc) {
+      row = tc.mt * kTileM + quarter * 32 + lane;
+      row_ok = row < p.M;
+    }
+    __device__ __forceinline__ void end_tile(TileCoord) {}
+
+    __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
+      const int col0 = tc.nt * p.n_tile + c * 32;
+      float h[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float z = __uint_as_float(v[j]);
-          if (p.bias) z += __ldg(p.bias + col0 + j);
-          if (p.act == DLC_ACT_SIGMOID) z = 1.0f / (1.0f + expf(-z));
-          else if (p.act == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
-          h[j] = (col0 + j < p.N) ? z : 0.0f;
-        }
-        if (!row_ok) continue;
-        if (p.out_f32) {
-          float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
-          const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+      for (int j = 0; j < 32; ++j) {
+        float z = v[j];
+        if (p.bias) z += __ldg(p.bias + col0 + j);
+        if (p.act == DLC_ACT_SIGMOID) z = 1.0f / (1.0f + expf(-z));
+        else if (p.act == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
+        h[j] = (col0 + j < p.N) ? z : 0.0f;
+      }
+      if (!row_ok) return;
+      if (p.out_f32) {
+        float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
+        const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (vec_ok && col0 + j + 3 < p.N) {
-              *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
-            } else {
+        for (int j = 0; j < 32; j += 4) {
+          if (vec_ok && col0 + j + 3 < p.N) {
+            *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+          } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (col0 + j + q < p.N) o[j + q] = h[j + q];
-            }
+            for (int q = 0; q < 4; ++q)
+              if (col0 + j + q < p.N) o[j + q] = h[j + q];
           }
         }
-        if (p.out_hi && col0 < p.out_plane_ld) {
-          const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
-          if (p.ab_fmt == 1) {  // bf16 planes (single plane)
-            uint32_t w[16];
+      }
+      if (p.out_hi && col0 < p.out_plane_ld) {
+        const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
+        if (p.ab_fmt == 1) {  // bf16 planes (single plane)
+          uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack_bf2(h[2 * j], h[2 * j + 1]);
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + off);
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf2(h[2 * j], h[2 * j + 1]);
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + off);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-          } else {
-            uint32_t wh[16], wl[16];
+          for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        } else {
+          uint32_t wh[16], wl[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __half h0, l0, h1, l1;
-              split_f32(h[2 * j], h0, l0);
-              split_f32(h[2 * j + 1], h1, l1);
-              wh[j] = pack_h2(h0, h1);
-              wl[j] = pack_h2(l0, l1);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + off);
+          for (int j = 0; j < 16; ++j) {
+            __half h0, l0, h1, l1;
+            split_f32(h[2 * j], h0, l0);
+            split_f32(h[2 * j + 1], h1, l1);
+            wh[j] = pack_h2(h0, h1);
+            wl[j] = pack_h2(l0, l1);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + off);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
-            if (p.out_lo) {
-              uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_lo) + off);
+          for (int q = 0; q < 4; ++q) oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
+          if (p.out_lo) {
+            uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_lo) + off);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
-            }
+            for (int q = 0; q < 4; ++q) ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
           }
         }
       }
@@ -198,6 +199,7 @@ struct BiasActPolicy {
 };
 
 static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
+int g_promote_k = 256;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
 template <class Policy>
 static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int m, int n_pad,
@@ -216,6 +218,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
       return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (lo planes)");
   }
   p.k_blocks = ld / BK;
+  p.kc = std::max(1, g_promote_k / BK);
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
@@ -232,6 +235,10 @@ extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 
 extern "C" int dlc_debug_set(int key, int value) {
   if (key == 0 && (value == 32 || value == 64)) {
     g_split_bk = value;
+    return DLC_OK;
+  }
+  if (key == 2 && value >= 32) {
+    g_promote_k = value;
     return DLC_OK;
   }
   return fail(DLC_EINVAL, "dlc_debug_set: unknown key/value %d/%d", key, value);

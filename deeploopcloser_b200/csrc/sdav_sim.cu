@@ -78,8 +78,10 @@ rowstats_kernel(const float* __restrict__ H, int N, int P, int D, const double* 
 }
 
 // ---------------- Gram + argmin + score epilogue ----------------
+extern int g_promote_k;  // planes.cu
+
 struct GramParams {
-  int n_tile, k_blocks, ab_fmt;
+  int n_tile, k_blocks, ab_fmt, kc;
   const int2* tiles;  // (mt, nt) work list in L2-friendly order
   int num_tiles;
   int N, P;
@@ -94,6 +96,7 @@ template <int BK, int NPROD>
 struct GramPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = GramParams;
+  static constexpr bool kPromote = NPROD == 3;
   static constexpr uint64_t kHintA = kEvictNormal;
   static constexpr uint64_t kHintB = kEvictNormal;
 
@@ -113,45 +116,47 @@ struct GramPolicy {
     const int quarter, lane;
     __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
 
-    __device__ __forceinline__ void tile(TileCoord tc, uint32_t taddr) {
-      const int fa = tc.mt * kFramesPerMTile + quarter;  // this warp's frame i (lane = patch k)
-      const bool fa_ok = fa < p.N;
-      const double pa = fa_ok ? p.pw[fa * kFrameRows + lane] : 0.0;
-#pragma unroll 1
-      for (int c = 0; c < kFramesPerNTile; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int fb = tc.nt * kFramesPerNTile + c;  // frame j of this 32-column chunk
-        if (!fa_ok || fb >= p.N) continue;           // warp-uniform
-        if (fa == fb) {
-          if (lane == 0) p.S[static_cast<int64_t>(fa) * p.N + fa] = -1.0f;  // reference fill value (:31)
-          continue;
-        }
-        if (!p.full && fa > fb) continue;
-        const float my_nb = p.sqn[fb * kFrameRows + lane];
-        const double my_pb = p.pw[fb * kFrameRows + lane];
-        float best = INFINITY;
-        int bj = 0;
+    int fa;
+    bool fa_ok;
+    double pa;
+    __device__ __forceinline__ void begin_tile(TileCoord tc) {
+      fa = tc.mt * kFramesPerMTile + quarter;  // this warp's frame i (lane = patch k)
+      fa_ok = fa < p.N;
+      pa = fa_ok ? p.pw[fa * kFrameRows + lane] : 0.0;
+    }
+    __device__ __forceinline__ void end_tile(TileCoord) {}
+
+    // chunk c = the 32 accumulator columns of frame j = 8 nt + c
+    __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
+      const int fb = tc.nt * kFramesPerNTile + c;
+      if (!fa_ok || fb >= p.N) return;  // warp-uniform
+      if (fa == fb) {
+        if (lane == 0) p.S[static_cast<int64_t>(fa) * p.N + fa] = -1.0f;  // reference fill value (:31)
+        return;
+      }
+      if (!p.full && fa > fb) return;
+      const float my_nb = p.sqn[fb * kFrameRows + lane];
+      const double my_pb = p.pw[fb * kFrameRows + lane];
+      float best = INFINITY;
+      int bj = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float nb = __shfl_sync(0xffffffffu, my_nb, j);
-          // squared distance up to the per-row constant n_k; pad columns carry nb = +inf and never win
-          const float d = fmaf(-2.0f, __uint_as_float(v[j]), nb);
-          if (d < best) {  // strict: first minimum wins, like np.argmin
-            best = d;
-            bj = j;
-          }
+      for (int j = 0; j < 32; ++j) {
+        const float nb = __shfl_sync(0xffffffffu, my_nb, j);
+        // squared distance up to the per-row constant n_k; pad columns carry nb = +inf and never win
+        const float d = fmaf(-2.0f, v[j], nb);
+        if (d < best) {  // strict: first minimum wins, like np.argmin
+          best = d;
+          bj = j;
         }
-        const double pb = __shfl_sync(0xffffffffu, my_pb, bj);
-        const float s = static_cast<float>(fabs(pa - pb));
-        float val = lane < p.P ? p.a + p.b * logf(s) : 0.0f;
+      }
+      const double pb = __shfl_sync(0xffffffffu, my_pb, bj);
+      const float s = static_cast<float>(fabs(pa - pb));
+      float val = lane < p.P ? p.a + p.b * logf(s) : 0.0f;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
-        if (lane == 0) {
-          p.S[static_cast<int64_t>(fa) * p.N + fb] = val;
-          if (!p.full) p.S[static_cast<int64_t>(fb) * p.N + fa] = val;
-        }
+      for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+      if (lane == 0) {
+        p.S[static_cast<int64_t>(fa) * p.N + fb] = val;
+        if (!p.full) p.S[static_cast<int64_t>(fb) * p.N + fa] = val;
       }
     }
     __device__ __forceinline__ void finish() {}
@@ -215,6 +220,7 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
       !make_tmap_k_major(&tb1, lo, 0, L.ld, L.rows_pad, L.ld, BK, kMaxTileN))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = L.ld / BK;
+  p.kc = std::max(1, g_promote_k / BK);
   const int grid = std::min(p.num_tiles, sm_count());
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
   if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_sdav_similarity: launch failed: %s", cudaGetErrorString(e));
