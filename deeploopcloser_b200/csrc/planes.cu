@@ -85,6 +85,7 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 // ------------------------------------------------------------------------------------------------
 struct BiasActParams {
   int n_tile, k_blocks, ab_fmt, kc;
+  int dbg;  // developer switches for kernel experiments: 1 = skip stores, 2 = skip activation math
   int m_tiles, n_tiles;
   int M, N;
   const float* bias;
@@ -138,18 +139,57 @@ struct BiasActPolicy {
     }
     __device__ __forceinline__ void end_tile(TileCoord) {}
 
+    // bias + activation on one 32-column chunk. Branch-free per element: the activation switch and the
+    // "chunk fully inside N" test are hoisted out of the element loop; sigmoid uses the SFU approximations
+    // (ex2.approx / rcp.approx, ~1e-6 relative - three orders below the 1e-3 descriptor tolerance).
+    template <int ACT>
+    __device__ __forceinline__ void activate(float (&v)[32], float (&h)[32], int col0) {
+      float b[32];
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);  // bias has n_pad entries, 128-B aligned rows
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(b4 + q);
+          b[4 * q] = t.x;
+          b[4 * q + 1] = t.y;
+          b[4 * q + 2] = t.z;
+          b[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) b[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float z = v[j] + b[j];
+        if (ACT == DLC_ACT_SIGMOID) z = __fdividef(1.0f, 1.0f + __expf(-z));
+        else if (ACT == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
+        h[j] = z;
+      }
+      if (col0 + 32 > p.N) {  // chunk straddles / lies beyond the valid width: zero the padding columns
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j >= p.N) h[j] = 0.0f;
+      }
+    }
+
     __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
       const int col0 = tc.nt * p.n_tile + c * 32;
       float h[32];
+      if (p.dbg & 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float z = v[j];
-        if (p.bias) z += __ldg(p.bias + col0 + j);
-        if (p.act == DLC_ACT_SIGMOID) z = 1.0f / (1.0f + expf(-z));
-        else if (p.act == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
-        h[j] = (col0 + j < p.N) ? z : 0.0f;
-      }
+        for (int j = 0; j < 32; ++j) h[j] = v[j];
+      } else if (p.act == DLC_ACT_SIGMOID) activate<DLC_ACT_SIGMOID>(v, h, col0);
+      else if (p.act == DLC_ACT_RELU) activate<DLC_ACT_RELU>(v, h, col0);
+      else activate<DLC_ACT_NONE>(v, h, col0);
       if (!row_ok) return;
+      if (p.dbg & 1) {  // keep the values alive without the global stores
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += h[j];
+        if (acc == 123456.789f && p.out_f32) p.out_f32[0] = acc;
+        return;
+      }
       if (p.out_f32) {
         float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
         const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
@@ -199,7 +239,8 @@ struct BiasActPolicy {
 };
 
 static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
-int g_promote_k = 256;       // K elements accumulated inside the tensor core before promotion to fp32 registers
+int g_promote_k = 256;
+static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
 template <class Policy>
 static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int m, int n_pad,
@@ -219,6 +260,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   }
   p.k_blocks = ld / BK;
   p.kc = std::max(1, g_promote_k / BK);
+  p.dbg = g_dbg_flags;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
@@ -235,6 +277,10 @@ extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 
 extern "C" int dlc_debug_set(int key, int value) {
   if (key == 0 && (value == 32 || value == 64)) {
     g_split_bk = value;
+    return DLC_OK;
+  }
+  if (key == 3) {
+    g_dbg_flags = value;
     return DLC_OK;
   }
   if (key == 2 && value >= 32) {
@@ -303,6 +349,7 @@ extern "C" int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const
   DLC_CHECK_ARG(!out_f32_dev || out_ld >= n);
   DLC_CHECK_ARG(!out_hi_dev || (out_plane_ld >= 32 && out_plane_ld % 8 == 0));
   DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(a_hi_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_hi_dev) & 15) == 0);
+  DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(bias_dev) & 15) == 0);  // read as float4; must hold n_pad entries
 
   BiasActParams p{};
   // largest accumulator width (multiple of 32, <= 256) that divides the padded N

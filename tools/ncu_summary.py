@@ -1,0 +1,28 @@
+"""Print the handful of ncu metrics the roofline discussion needs from a `--page raw --csv` dump."""
+import csv
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__cycles_active.avg", "sm__inst_executed.sum", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.avg.per_second",
+        "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"]
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print("----", r[idx["Kernel Name"]][:70], "id", r[idx["ID"]])
+        for k in KEYS:
+            if k in idx:
+                print("   %-86s %s %s" % (k, r[idx[k]], units[idx[k]]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
