@@ -1,0 +1,191 @@
+"""Drop-in for `src.cnn_vtl.network.cnn_vtl.CnnVtl` (reference src/cnn_vtl/network/cnn_vtl.py).
+
+transform(x[N,H,W,3]) -> int8 [N, M]: AlexNet conv1..conv5 (ungrouped, no LRN, conv5 linear, cnn_vtl.py:33-93), all
+five conv outputs flattened + concatenated (:96-106), per-image min/max scaling to 0..255 and int8 cast (:109-116),
+random column sub-sampling fixed per instance (:119-128). On the B200 every convolution is im2col planes + one fused
+tcgen05 GEMM (bias + ReLU in the epilogue, NHWC output = the flattened descriptor segment); pooling, min/max and the
+quantise+gather tail are bytes-bound SIMT kernels. Only the kept columns are ever quantised.
+
+Differences from the reference, all explicit: weights are an argument (the AlexNet blob is a git-LFS pointer in the
+reference tree) - a dict {name: (W[kh,kw,cin,cout], b[cout])}, a path to a `bvlc_alexnet.npy`-style file, or
+`weights="synthetic"` for seeded He-scaled tensors; the column mask can be passed (`mask=` boolean [sum sizes] or
+`keep_cols=`) or seeded (`seed=`); frames are processed in chunks of `batch_size` images to bound memory."""
+import numpy as np
+
+# (name, kh, kw, cin, cout, stride, padding, relu)
+LAYERS = (
+    ("conv1", 11, 11, 3, 96, 4, "valid", True),
+    ("conv2", 5, 5, 96, 256, 1, "same", True),
+    ("conv3", 3, 3, 256, 384, 1, "same", True),
+    ("conv4", 3, 3, 384, 384, 1, "same", True),
+    ("conv5", 3, 3, 384, 256, 1, "same", False),
+)
+POOL_AFTER = ("conv1", "conv2")
+
+
+def compressed_size(value, compression):
+    """src/utils/MathUtils.py:1-4."""
+    return int(round(value * ((100 - compression) / 100)))
+
+
+def _out_hw(h, w, k, stride, padding):
+    if padding == "same":
+        return -(-h // stride), -(-w // stride)
+    return (h - k) // stride + 1, (w - k) // stride + 1
+
+
+def _same_pad_before(size, k, stride):
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return total // 2  # TF puts the extra pixel after
+
+
+def layer_geometry(height, width):
+    """Per conv layer: (H_in, W_in, OH, OW, pad_t, pad_l) for an input of height x width."""
+    geo = []
+    h, w = height, width
+    for name, kh, kw, cin, cout, stride, padding, relu in LAYERS:
+        oh, ow = _out_hw(h, w, kh, stride, padding)
+        pt = _same_pad_before(h, kh, stride) if padding == "same" else 0
+        pl = _same_pad_before(w, kw, stride) if padding == "same" else 0
+        geo.append((h, w, oh, ow, pt, pl))
+        h, w = oh, ow
+        if name in POOL_AFTER:
+            h, w = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+    return geo
+
+
+def synthetic_weights(seed):
+    rng = np.random.default_rng(seed)
+    params = {}
+    for name, kh, kw, cin, cout, *_ in LAYERS:
+        params[name] = (rng.standard_normal((kh, kw, cin, cout)) * np.sqrt(2.0 / (kh * kw * cin)),
+                        0.05 * rng.standard_normal(cout))
+    return params
+
+
+def _flat_fill(values, shape):
+    """tf.constant_initializer semantics for a value list shorter than the variable: fill the remainder with the
+    last value [TF1-doc] - this is what initialising UNGROUPED convs from grouped AlexNet tensors relies on
+    (cnn_vtl.py:140-148)."""
+    flat = np.asarray(values, dtype=np.float64).ravel()
+    n = int(np.prod(shape))
+    if flat.size > n:
+        raise ValueError("too many elements (%d) for shape %s" % (flat.size, shape))
+    if flat.size < n:
+        flat = np.concatenate([flat, np.full(n - flat.size, flat[-1])])
+    return flat.reshape(shape)
+
+
+def load_alexnet_npy(path):
+    raw = np.load(path, encoding="bytes", allow_pickle=True).item()
+    params = {}
+    for name, kh, kw, cin, cout, *_ in LAYERS:
+        key = name if name in raw else name.encode()
+        params[name] = (_flat_fill(raw[key][0], (kh, kw, cin, cout)), _flat_fill(raw[key][1], (cout,)))
+    return params
+
+
+class CnnVtl:
+    def __init__(self, input_shape=(1, 224, 224, 3), batch_size=10, compress_factor=99.59, weights=None, mask=None,
+                 keep_cols=None, seed=None, precision="fp16x2"):
+        self.input_shape = input_shape
+        self.batch_size = batch_size
+        self.compress_factor = compress_factor
+        self.precision = precision
+        _, self._H, self._W, c = input_shape
+        if c != 3:
+            raise ValueError("input_shape must be [N, H, W, 3]")
+        self._geo = layer_geometry(self._H, self._W)
+        self.layer_sizes = [g[2] * g[3] * L[4] for g, L in zip(self._geo, LAYERS)]
+        # ---- weights
+        if weights is None:
+            raise ValueError("CnnVtl needs weights=: a {name: (W, b)} dict, a path to bvlc_alexnet.npy, or "
+                             "'synthetic' (the reference's pretrained blob is not shipped with its repository)")
+        if isinstance(weights, str):
+            weights = synthetic_weights(0 if seed is None else seed) if weights == "synthetic" else load_alexnet_npy(weights)
+        self.params = {}
+        for name, kh, kw, cin, cout, *_ in LAYERS:
+            w, b = weights[name]
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            b = np.ascontiguousarray(b, dtype=np.float64)
+            if w.shape != (kh, kw, cin, cout) or b.shape != (cout,):
+                raise ValueError("%s: expected W %s and b %s" % (name, (kh, kw, cin, cout), (cout,)))
+            self.params[name] = (w, b)
+        # ---- column mask (cnn_vtl.py:119-126: per layer, compressed_size indices drawn WITH replacement)
+        total = int(np.sum(self.layer_sizes))
+        if keep_cols is not None:
+            self.keep_cols = np.unique(np.asarray(keep_cols, dtype=np.int64))
+        elif mask is not None:
+            mask = np.asarray(mask, dtype=bool)
+            if mask.shape != (total,):
+                raise ValueError("mask must have shape (%d,)" % total)
+            self.keep_cols = np.flatnonzero(mask).astype(np.int64)
+        else:
+            rng = np.random.default_rng(seed) if seed is not None else np.random.default_rng()
+            cols, start = [], 0
+            for s in self.layer_sizes:
+                cols.append(np.unique(rng.choice(np.arange(start, start + s), size=compressed_size(s, compress_factor))))
+                start += s
+            self.keep_cols = np.concatenate(cols).astype(np.int64)
+        if self.keep_cols.size and (self.keep_cols.min() < 0 or self.keep_cols.max() >= total):
+            raise ValueError("kept columns out of range")
+        self._dev = None
+
+    # ---- device state: packed weight planes, biases, kept columns
+    def _device_state(self):
+        if self._dev is None:
+            import torch
+
+            from . import _cuda, ops
+            _cuda.require_cuda()
+            split = self.precision == "fp16x2"
+            st = {"w": {}, "b": {}}
+            for name, kh, kw, cin, cout, *_ in LAYERS:
+                w, b = self.params[name]
+                wt = torch.from_numpy(w.reshape(kh * kw * cin, cout)).cuda()
+                st["w"][name] = ops.pack_weight_planes(wt, n_pad=cout, need_lo=split)
+                st["b"][name] = torch.from_numpy(b.astype(np.float32)).cuda()
+            st["keep"] = torch.from_numpy(self.keep_cols).cuda()
+            self._dev = st
+        return self._dev
+
+    def _forward_chunk(self, x):
+        """x: CUDA tensor [n, H, W, 3] (uint8 / float) -> int8 [n, M]."""
+        import torch
+
+        from . import ops
+        st = self._device_state()
+        split = self.precision == "fp16x2"
+        n = x.shape[0]
+        flat = x.reshape(n * self._H * self._W, 3).to(torch.float32).contiguous()
+        hi, lo = ops.split_planes(flat, need_lo=split)
+        cur_c = 3
+        segments = []
+        for (name, kh, kw, cin, cout, stride, padding, relu), (h, w, oh, ow, pt, pl) in zip(LAYERS, self._geo):
+            a_hi, a_lo = ops.im2col_planes(hi, lo, n, h, w, cur_c, kh, kw, stride, pt, pl, oh, ow)
+            w_hi, w_lo = st["w"][name]
+            pooled = name in POOL_AFTER
+            last = name == LAYERS[-1][0]
+            out, planes = ops.gemm_planes(a_hi, a_lo, w_hi, w_lo, n * oh * ow, cout, st["b"][name],
+                                          "relu" if relu else "none", self.precision, want_f32=True,
+                                          want_planes=not pooled and not last)
+            segments.append(out)
+            cur_c = cout
+            if pooled:
+                hi, lo, _, _ = ops.maxpool_planes(out, n, oh, ow, cout, 3, 2, need_lo=split)
+            elif not last:
+                hi, lo = planes
+        return ops.cnnvtl_quantise(segments, n, st["keep"])
+
+    def transform(self, x):
+        import torch
+        x = np.asarray(x)
+        if x.ndim != 4 or x.shape[1] != self._H or x.shape[2] != self._W or x.shape[3] != 3:
+            raise ValueError("expected input [N, %d, %d, 3], got %s" % (self._H, self._W, x.shape))
+        chunk = max(int(self.batch_size), 1)
+        outs = []
+        for s in range(0, x.shape[0], chunk):
+            xc = torch.from_numpy(np.ascontiguousarray(x[s:s + chunk])).cuda()
+            outs.append(self._forward_chunk(xc).cpu().numpy())
+        return np.concatenate(outs) if outs else np.zeros((0, self.keep_cols.size), dtype=np.int8)

@@ -1,0 +1,115 @@
+"""Drop-ins for `src.sdav.network.DenoisingAutoencoderVariant.DA` and
+`src.sdav.network.StackedDenoisingAutoencoderVariants.SDA` (reference files of the same names).
+`DA.transform(x[30, in]) -> [30, hidden]` = sigmoid(x w0 + b0) (DenoisingAutoencoderVariant.py:116-119, 254-259) runs
+as one fused tcgen05 kernel; `SDA` chains the layers (StackedDenoisingAutoencoderVariants.py:73-83). Constructor
+arguments are the reference's (the `graph` argument is accepted and ignored). Training raises NotImplementedError."""
+import logging
+
+import numpy as np
+
+
+def _check_common(sparse_level, sparse_penalty, consecutive_penalty, batch_size, learning_rate, epochs,
+                  corruption_level):
+    # the reference validates with py_v8n (DenoisingAutoencoderVariant.py:67-90); same constraints, plain Python
+    for name, v in (("learning_rate", learning_rate), ("sparse_level", sparse_level)):
+        if not isinstance(v, float) or v <= 0:
+            raise ValueError("%s must be a positive float" % name)
+    for name, v in (("sparse_penalty", sparse_penalty), ("consecutive_penalty", consecutive_penalty),
+                    ("corruption_level", corruption_level)):
+        if not isinstance(v, (float, int)) or not (0 <= v <= 1):
+            raise ValueError("%s must be in [0, 1]" % name)
+    for name, v in (("batch_size", batch_size), ("epochs", epochs)):
+        if not isinstance(v, int) or v <= 0:
+            raise ValueError("%s must be a positive int" % name)
+
+
+class DA:
+    def __init__(self, input_shape, hidden_units, sparse_level=0.05, sparse_penalty=1.0, consecutive_penalty=0.2,
+                 batch_size=10, learning_rate=0.1, epochs=100, layer_n=0, corruption_level=0.3, graph=None,
+                 seed=0, precision="fp16x2"):
+        _check_common(sparse_level, sparse_penalty, consecutive_penalty, batch_size, learning_rate, epochs,
+                      corruption_level)
+        if (not isinstance(input_shape, (list, tuple)) or len(input_shape) != 2 or
+                not all(isinstance(v, int) and v > 0 for v in input_shape)):
+            raise ValueError("input_shape must be a list of two positive ints")
+        if not isinstance(hidden_units, int) or hidden_units <= 0:
+            raise ValueError("hidden_units must be a positive int")
+        self.input_shape = list(input_shape)
+        self.hidden_units = hidden_units
+        self.sparse_level = sparse_level
+        self.sparse_penalty = sparse_penalty
+        self.consecutive_penalty = consecutive_penalty
+        self.batch_size = batch_size
+        self.learning_rate = learning_rate
+        self.epochs = epochs
+        self.corruption_level = corruption_level
+        self.layer_n = layer_n
+        self.precision = precision
+        self._encoder = None
+        rng = np.random.default_rng(seed + layer_n)
+        # encoder_weights ~ N(0,1), encoder_biases = 0 (DenoisingAutoencoderVariant.py:94-97)
+        self.set_weights(rng.standard_normal((self.input_shape[1], hidden_units)), np.zeros(hidden_units))
+
+    def set_weights(self, w0, b0):
+        w0 = np.ascontiguousarray(w0, dtype=np.float64)
+        b0 = np.ascontiguousarray(b0, dtype=np.float64)
+        if w0.shape != (self.input_shape[1], self.hidden_units) or b0.shape != (self.hidden_units,):
+            raise ValueError("expected w0 %s and b0 %s" % ((self.input_shape[1], self.hidden_units), (self.hidden_units,)))
+        self._w0, self._b0 = w0, b0
+        self._encoder = None
+
+    def transform(self, x, batch_n=-1):
+        import torch
+
+        from . import _cuda, ops
+        logging.info("  Layer %d: transform" % self.layer_n)
+        x = np.asarray(x, dtype=np.float64)
+        if list(x.shape) != self.input_shape:
+            raise ValueError("expected input of shape %s, got %s" % (self.input_shape, list(x.shape)))
+        if self._encoder is None:
+            _cuda.require_cuda()
+            self._encoder = ops.SdaEncoder([self.input_shape[1], self.hidden_units], self.precision)
+            self._encoder.set_layer(0, self._w0, self._b0)
+        out = self._encoder.encode(torch.from_numpy(np.ascontiguousarray(x)).cuda())
+        return out.to(torch.float64).cpu().numpy()
+
+    def fit(self, file_pattern):
+        raise NotImplementedError("DA.fit (training, DenoisingAutoencoderVariant.py:204-243) is outside the B200 hot path")
+
+    def fit_dataset(self, dataset):
+        raise NotImplementedError("DA.fit_dataset (training) is outside the B200 hot path")
+
+
+class SDA:
+    def __init__(self, input_shape, hidden_units, sparse_level=0.05, sparse_penalty=1, consecutive_penalty=0.2,
+                 batch_size=10, learning_rate=0.1, epochs=100, corruption_level=0.3, graph=None, seed=0,
+                 precision="fp16x2"):
+        if not isinstance(hidden_units, (list, tuple)) or len(hidden_units) < 2:
+            raise ValueError("hidden_units must list at least two layer widths")  # min_length(2), SDA :56
+        self.input_shape = list(input_shape)
+        self.hidden_units = list(hidden_units)
+        self.sparse_level = sparse_level
+        self.sparse_penalty = sparse_penalty
+        self.consecutive_penalty = consecutive_penalty
+        self.batch_size = batch_size
+        self.learning_rate = learning_rate
+        self.epochs = epochs
+        self.corruption_level = corruption_level
+        self._layers = []
+        for i, h in enumerate(self.hidden_units):  # StackedDenoisingAutoencoderVariants.py:73-83
+            shape = self.input_shape if i == 0 else [self.input_shape[0], self.hidden_units[i - 1]]
+            self._layers.append(DA(shape, h, sparse_level=float(sparse_level), sparse_penalty=float(sparse_penalty),
+                                   consecutive_penalty=float(consecutive_penalty), batch_size=batch_size,
+                                   learning_rate=float(learning_rate), epochs=epochs, layer_n=i,
+                                   corruption_level=float(corruption_level), seed=seed, precision=precision))
+
+    def transform(self, x):
+        """Chain the layers' transforms for one frame x [30, in] -> [30, hidden[-1]] (what SDA.fit feeds layer i+1
+        with, StackedDenoisingAutoencoderVariants.py:96-100)."""
+        for layer in self._layers:
+            x = layer.transform(x)
+        return x
+
+    def fit(self, file_pattern):
+        raise NotImplementedError("SDA.fit (layer-wise training, StackedDenoisingAutoencoderVariants.py:90-100) is "
+                                  "outside the B200 hot path")

@@ -82,6 +82,21 @@ def merge_partial_lists(scores, idx, k, smaller_is_better=False):
     return topk_rows(scores.contiguous(), k, largest=not smaller_is_better, cand_idx=idx.contiguous())
 
 
+def gather_partial_lists(scores, idx, group=None):
+    """All-gather per-rank partial top-k lists [B, k] -> candidate matrices [B, world * k] (rank-major columns),
+    identical on every rank. Pure torch.distributed plumbing: NCCL on the GPUs, gloo in the CPU tests."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    B, k = scores.shape
+    gs = torch.empty((world * B, k), dtype=scores.dtype, device=scores.device)  # rank-major concatenation
+    gi = torch.empty((world * B, k), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
+    cs = gs.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    ci = gi.view(world, B, k).permute(1, 0, 2).reshape(B, world * k).contiguous()
+    return cs, ci
+
+
 class ShardedKeyframeDatabase:
     """Row-sharded database: rank r owns the global rows it was given (contiguous block `row_offset + local`)."""
 
@@ -102,11 +117,5 @@ class ShardedKeyframeDatabase:
         s, i = self.local.topk(q, k, idx_offset=self.row_offset)
         if self.world == 1:
             return s, i
-        B = q.shape[0]
-        gs = torch.empty((self.world, B, k), dtype=torch.float32, device=q.device)
-        gi = torch.empty((self.world, B, k), dtype=torch.int64, device=q.device)
-        self.dist.all_gather_into_tensor(gs, s, group=self.group)
-        self.dist.all_gather_into_tensor(gi, i, group=self.group)
-        cs = gs.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
-        ci = gi.permute(1, 0, 2).reshape(B, self.world * k).contiguous()
+        cs, ci = gather_partial_lists(s, i, self.group)
         return merge_partial_lists(cs, ci, k, self.local.smaller_is_better)

@@ -1,0 +1,159 @@
+"""Drop-in for `src.sdav.network.SDAV.SDAV` (reference src/sdav/network/SDAV.py).
+
+Same attributes and method names as the reference class; `transform(x)` - the encoder forward, the hot path - runs on
+the B200 through libdlc (patches -> 5 fused GEMM+bias+sigmoid tcgen05 kernels) and returns the same flat float64
+[B*30, 2500] array (SDAV.py:163, 293-302). Weights are explicit and persistent here (the reference re-initialises
+or re-restores them inside every call, SDAV.py:232-240): seeded N(0,1) like `tf.random_normal` by default, or loaded
+from / saved to an .npz (`w{l}_e [in,out]`, `b{l}_e [out]`, float64).
+Training (`fit`, `fit_dataset`) is outside the accelerated path and raises NotImplementedError.
+"""
+import glob
+import logging
+import os
+
+import numpy as np
+
+from . import input_parser
+
+
+class SDAV:
+    def __init__(self, verbosity=logging.WARNING, weights_path=None, seed=0, precision="fp16x2", train_path=None):
+        self._configure_logging(verbosity)
+        self._set_train_path(train_path)
+        self._define_params()
+        self.losses = []
+        self.precision = precision
+        self._encoder = None
+        self._weights = None
+        self._biases = None
+        if weights_path is None and os.path.isdir(self.checkpoints_path):
+            cand = os.path.join(self.checkpoints_path, "sdav_weights.npz")
+            weights_path = cand if os.path.exists(cand) else None
+        if weights_path is not None:
+            self.load_weights(weights_path)
+        else:
+            self.init_weights(seed)
+        logging.info('Done initializing sdav')
+
+    # ---- parameters (SDAV.py:30-39)
+    def _define_params(self):
+        self.input_shape = [30, 1681]
+        self.hidden_units = [2500, 2500, 2500, 2500, 2500]
+        self.default_batch_size = 10
+        self.sparse_level = 0.05
+        self.sparse_penalty = 1.0
+        self.consecutive_penalty = 0.2
+        self.learning_rate = 0.1
+        self.epochs = 100
+        self.corruption_level = 0.3
+
+    def _set_train_path(self, train_path):
+        # the reference derives this from the location of a directory named 'deepLoopCloser' (PathUtils.py:1-11);
+        # here it is an explicit argument with a local default and nothing is created on disk until save_weights().
+        self.train_path = train_path or os.path.join(os.getcwd(), "training", "sdav")
+        self.checkpoints_path = self.train_path + '/checkpoints'
+        self.log_path = self.train_path + '/log'
+
+    def _configure_logging(self, verbosity):
+        self.logger = logging.getLogger()
+        self.logger.setLevel(verbosity)
+
+    @property
+    def dims(self):
+        return [self.input_shape[1]] + list(self.hidden_units)
+
+    # ---- weights
+    def init_weights(self, seed=0):
+        """tf.random_normal weights (sigma = 1), zero biases (SDAV.py:189-217), seeded."""
+        rng = np.random.default_rng(seed)
+        d = self.dims
+        self.set_weights([rng.standard_normal((k, n)) for k, n in zip(d[:-1], d[1:])], [np.zeros(n) for n in d[1:]])
+
+    def set_weights(self, weights, biases):
+        d = self.dims
+        if len(weights) != len(d) - 1 or len(biases) != len(d) - 1:
+            raise ValueError("expected %d weight matrices and biases" % (len(d) - 1))
+        self._weights = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
+        self._biases = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
+        for l, (w, b) in enumerate(zip(self._weights, self._biases)):
+            if w.shape != (d[l], d[l + 1]) or b.shape != (d[l + 1],):
+                raise ValueError("layer %d: expected W %s, b %s" % (l, (d[l], d[l + 1]), (d[l + 1],)))
+        self._encoder = None  # re-packed lazily on the device
+
+    def load_weights(self, path):
+        z = np.load(path)
+        n = len(self.hidden_units)
+        self.set_weights([z["w%d_e" % l] for l in range(n)], [z["b%d_e" % l] for l in range(n)])
+
+    def save_weights(self, path=None):
+        path = path or os.path.join(self.checkpoints_path, "sdav_weights.npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        arrays = {}
+        for l, (w, b) in enumerate(zip(self._weights, self._biases)):
+            arrays["w%d_e" % l] = w
+            arrays["b%d_e" % l] = b
+        np.savez(path, **arrays)
+        return path
+
+    def _get_encoder(self):
+        if self._encoder is None:
+            from . import _cuda, ops
+            _cuda.require_cuda()
+            enc = ops.SdaEncoder(self.dims, self.precision)
+            for l, (w, b) in enumerate(zip(self._weights, self._biases)):
+                enc.set_layer(l, w, b)
+            self._encoder = enc
+        return self._encoder
+
+    # ---- shapes (SDAV.py:165-169, 290-291)
+    def get_layer_input_shape(self, layer_n):
+        if layer_n == 0:
+            return self.input_shape
+        return [self.input_shape[0], self.hidden_units[layer_n - 1]]
+
+    def get_layers_input_shapes(self):
+        return list(map(self.get_layer_input_shape, range(1, 6)))
+
+    # ---- the hot path
+    def transform(self, x):
+        """x float64 [B, 30, 1681] -> float64 [B*30, 2500] (flat, like the reference's `_h4`)."""
+        import torch
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim != 3 or list(x.shape[1:]) != self.input_shape:
+            raise ValueError("expected input of shape [B, %d, %d], got %s" % (self.input_shape[0], self.input_shape[1], x.shape))
+        enc = self._get_encoder()
+        flat = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, x.shape[-1]))).cuda()
+        out = enc.encode(flat)
+        return out.to(torch.float64).cpu().numpy()
+
+    def transform_dataset(self, file_pattern, key_points=None):
+        """Encode every image matched by `file_pattern` (sorted) -> float64 [N, 30, 2500]. The reference's version
+        (SDAV.py:309-318) cannot run as written; this is its evident intent, and what
+        create_similarity_matrix.py:27 calls as `transform_all`. `key_points`: optional [N, 30, 2] (x, y) array or a
+        callable image -> [30, 2]; without it the SURF detector of CvInputParser is required."""
+        files = sorted(glob.glob(file_pattern))
+        if len(files) == 0:
+            logging.getLogger().error("Specified dataset is empty or could not find dataset")
+            return np.zeros((0, self.input_shape[0], self.hidden_units[-1]))
+        patch_size = int(round(np.sqrt(self.input_shape[1])))
+        parser = input_parser.CvInputParser(self.input_shape[0], patch_size)
+        frames = []
+        for i, f in enumerate(files):
+            kp = key_points(i, f) if callable(key_points) else (None if key_points is None else key_points[i])
+            frames.append(parser.parse_from_path(f, key_points=kp))
+        x = np.stack(frames)
+        return self.transform(x).reshape(len(files), self.input_shape[0], self.hidden_units[-1])
+
+    transform_all = transform_dataset  # name used by src/sdav/create_similarity_matrix.py:27
+
+    def get_dataset(self, file_pattern):
+        """Reference: a tf.data generator dataset of parsed frames (SDAV.py:219-221). Here: the sorted file list."""
+        return sorted(glob.glob(file_pattern))
+
+    # ---- training: not part of the accelerated path
+    def fit_dataset(self, dataset):
+        raise NotImplementedError("SDAV.fit_dataset (training, SDAV.py:242-275) is outside the B200 hot path; train "
+                                  "with the reference and load the weights with load_weights()/set_weights()")
+
+    def fit(self, x):
+        raise NotImplementedError("SDAV.fit (training, SDAV.py:277-288) is outside the B200 hot path")

@@ -1,0 +1,148 @@
+"""`-m gpu`: the reference-facing Python API (same import paths as the reference) running on the CUDA kernels,
+checked against the oracle and the reference-made golden vectors."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import cnnvtl as o_cnn
+from oracle import hamming as o_ham
+from oracle import sda as o_sda
+from oracle import similarity as o_sim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(np.asarray(a, float) - b) / np.maximum(1.0, np.abs(b))))
+
+
+def test_example(cuda):
+    """Port of the reference's only test (test/TensorflowWrapperTest.py:11-21), body kept line for line with
+    `tf.Session` -> `tw.Session`."""
+    import src.utils.TensorflowWrapper as tw
+    x = tw.constant([[[1, 2], [3, 4]], [[5, 6], [7, 8]], [[9, 10], [11, 12]]])
+    w = tw.constant([[2, 2], [2, 2]])
+    expected = np.array([[[6, 6], [14, 14]], [[22, 22], [30, 30]], [[38, 38], [46, 46]]]).astype(np.float64)
+
+    y = x.matmul(w.to_tf()).to_tf()
+
+    with tw.Session() as sess:
+        actual = sess.run(y)
+
+    assert np.array_equal(expected, actual)
+    assert actual.dtype == np.float64
+
+
+def test_tensorwrapper_encoder_layer(cuda):
+    """x.corrupt(0).matmul(W).add(b).sigmoid() - the exact expression of SDAV.py:129 - through placeholder + feed."""
+    import src.utils.TensorflowWrapper as tw
+    rng = np.random.default_rng(0)
+    W, b = rng.standard_normal((96, 40)), rng.standard_normal(40)
+    x0 = tw.placeholder(tw.float64, [None, 30, 96])
+    level = tw.placeholder(tw.float64, [])
+    h0 = x0.corrupt(level).matmul(tw.constant(W)).add(tw.constant(b)).sigmoid()
+    x = rng.uniform(0, 1, (3, 30, 96))
+    with tw.Session() as sess:
+        out = sess.run(h0.to_tf(), feed_dict={x0.to_tf(): x, level.to_tf(): 0})
+    assert out.shape == (3, 30, 40)
+    assert rel_err(out, o_sda.sigmoid(x @ W + b)) < 1e-5
+    with tw.Session(seed=1) as sess:  # corruption level 0.5 zeroes exactly half of each frame's mask
+        m = sess.run(tw.random_mask(tw.constant([30, 96], dtype=tw.int32), tw.constant(0.5)).to_tf())
+    assert m.shape == (30, 96) and m.sum() == 30 * 96 / 2
+
+
+def test_sdav_transform(cuda):
+    from src.sdav.network.SDAV import SDAV
+    model = SDAV(seed=1)
+    x = np.random.default_rng(0).integers(0, 256, (3, 30, 1681)).astype(np.float64) / 255.0
+    out = model.transform(x)
+    assert out.shape == (90, 2500) and out.dtype == np.float64          # flat, like SDAV.py:163
+    ref = o_sda.sda_forward(x, model._weights, model._biases)
+    err = rel_err(out, ref)
+    print("SDAV.transform N(0,1) weights: max |a-b|/max(1,|b|) =", err)
+    assert err <= TOL
+    with pytest.raises(ValueError):
+        model.transform(np.zeros((2, 30, 100)))
+
+
+def test_da_and_sda_transform(cuda):
+    from src.sdav.network.StackedDenoisingAutoencoderVariants import SDA
+    sda = SDA([30, 200], [64, 48], seed=3)
+    x = np.random.default_rng(1).uniform(0, 1, (30, 200))
+    out = sda.transform(x)
+    ref = o_sda.sda_forward(x, [l._w0 for l in sda._layers], [l._b0 for l in sda._layers])
+    assert out.shape == (30, 48) and rel_err(out, ref) <= TOL
+
+
+def test_cv_input_parser(cuda, golden_dir):
+    from src.sdav.input.CvInputParser import CvInputParser, get_vectorized_patches_from_key_points
+    g = np.load(golden_dir + "/patches.npz")
+    parser = CvInputParser(30, 41)
+    out = parser.parse(g["img"][0], key_points=g["xy"][0])
+    assert out.dtype == np.float64 and np.array_equal(out, g["out"][0])       # bit-exact vs the reference
+
+    class KP:
+        def __init__(self, x, y):
+            self.pt = (x, y)
+    ints = get_vectorized_patches_from_key_points(g["img"][1], [KP(*p) for p in g["xy"][1]], 41)
+    assert np.array_equal(ints, np.rint(g["out"][1] * 255).astype(int))
+
+
+def test_similarity_calculator(cuda, golden_dir):
+    from src.sdav.similarity.SimilarityCalculator import SimilarityCalculator
+    g = np.load(golden_dir + "/similarity.npz")
+    desc, ref = g["desc_a"], g["S_a"]
+    calc = SimilarityCalculator(desc)
+    assert abs(calc.similarity_score(desc[0], desc[1]) - ref[0, 1]) <= TOL * abs(ref[0, 1])
+    assert abs(calc.similarity_score(desc[3], desc[2]) - ref[3, 2]) <= TOL * abs(ref[3, 2])
+    S = calc.similarity_matrix()
+    iu = np.triu_indices(len(ref), 1)
+    assert np.max(np.abs(S[iu] - ref[iu]) / np.abs(ref[iu])) <= TOL and np.array_equal(S, S.T)
+    Si = calc.similarity_matrix(reference_int=True)
+    assert Si.dtype == np.int64 and Si[0, 1] == int(ref[0, 1])      # truncation toward zero (Appendix A.8)
+    s, i = calc.loop_candidates(k=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = o_sim.similarity_matrix(desc)
+    np.fill_diagonal(want, -np.inf)
+    assert np.array_equal(i[:, 0], want.argmax(1))
+
+
+def test_distance_calculator(cuda, golden_dir):
+    from src.cnn_vtl.similarity.DistanceCalculator import DistanceCalculator
+    g = np.load(golden_dir + "/hamming.npz")
+    assert DistanceCalculator.calculate_distance(g["ex_y1"], g["ex_y2"]) == int(g["ex_d"])   # basic_example.py recipe
+    assert DistanceCalculator.calculate_distance(list(g["desc"][0]), list(g["desc"][1])) == g["D"][0, 1]
+    assert np.array_equal(DistanceCalculator.distance_matrix(g["desc"]), g["D"])
+
+
+@pytest.mark.parametrize("hw", [(192, 240), (67, 83)])
+def test_cnnvtl_transform(cuda, hw):
+    from src.cnn_vtl.network.cnn_vtl import CnnVtl
+    H, W = hw
+    n = 3
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, (n, H, W, 3)).astype(np.float64)
+    params = o_cnn.make_weights(3)
+    sizes = o_cnn.layer_sizes(hw)
+    keep = o_cnn.make_keep_columns(sizes, compress_factor=99.0 if H < 100 else 99.59, seed=4)
+    net = CnnVtl(input_shape=[n, H, W, 3], batch_size=2, weights=params, keep_cols=keep)
+    assert net.layer_sizes == sizes
+    got = net.transform(x)
+    outs = o_cnn.conv_outputs(x, params)
+    want, scaled = o_cnn.descriptors_from_outputs(outs, keep)
+    assert got.shape == want.shape and got.dtype == np.int8
+    diff = (got.astype(np.int16) - want.astype(np.int16))
+    diff = (diff + 128) % 256 - 128                      # wrap-aware difference
+    mism = np.flatnonzero(diff.ravel())
+    # int8 truncation flips by one step where the float64 value sits within float32 rounding of an integer
+    frac = scaled.ravel()[mism] - np.floor(scaled.ravel()[mism])
+    print("cnn_vtl %s: %d of %d descriptor bytes differ (all +-1 at an integer boundary)" % (hw, mism.size, diff.size))
+    assert np.all(np.abs(diff) <= 1)
+    assert mism.size <= max(2, 0.002 * diff.size)
+    assert np.all(np.minimum(frac, 1 - frac) < 2e-3)
+    # and the Hamming matrix of the GPU descriptors is exact for those descriptors
+    from src.cnn_vtl.similarity.DistanceCalculator import DistanceCalculator
+    assert np.array_equal(DistanceCalculator.distance_matrix(got), o_ham.distance_matrix(got))

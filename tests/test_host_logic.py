@@ -1,0 +1,166 @@
+"""CPU: host-side mirror of the reference API (no kernel launches) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------- C ABI
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "dlc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dlc_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deeploopcloser_b200 import _lib
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "libdlc.so does not export %s" % n
+        assert n in _lib.PROTOTYPES, "no ctypes prototype for %s" % n
+    assert lib.dlc_version() >= 100
+    assert lib.dlc_plane_ld(1681) == 1728 and lib.dlc_plane_ld(2500) == 2560 and lib.dlc_plane_ld(64) == 64
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product raises instead of computing something on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from deeploopcloser_b200.da import DA
+    from deeploopcloser_b200.distance import DistanceCalculator
+    with pytest.raises(RuntimeError):
+        DA([30, 64], 32).transform(np.zeros((30, 64)))
+    with pytest.raises(RuntimeError):
+        DistanceCalculator.calculate_distance(np.zeros(8, np.int8), np.ones(8, np.int8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "deeploopcloser_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+# ------------------------------------------------------------------------------------------- TensorWrapper
+def test_tensorwrapper_reference_test_graph():
+    """Graph construction of the reference's only test (test/TensorflowWrapperTest.py:11-16): a 3-D x 2-D matmul is
+    flatten -> matmul -> re-batch (TensorflowWrapper.py:57-67)."""
+    import src.utils.TensorflowWrapper as tw
+    x = tw.constant([[[1, 2], [3, 4]], [[5, 6], [7, 8]], [[9, 10], [11, 12]]])
+    w = tw.constant([[2, 2], [2, 2]])
+    assert x.dimensions() == 3 and w.dimensions() == 2 and x.to_tf().dtype is np.float64
+    y = x.matmul(w.to_tf()).to_tf()
+    assert y.op == "reshape" and y.static_rank == 3
+    mm = y.inputs[0]
+    assert mm.op == "matmul" and mm.inputs[0].op == "reshape" and mm.inputs[0].static_rank == 2
+    assert tw.parameter_guard([x, 3]) == [x.to_tf(), 3]
+    assert x.batch_size().to_tf().op == "getitem" and w.batch_size() == 1
+
+
+def test_tensorwrapper_encoder_layer_pattern():
+    import src.utils.TensorflowWrapper as tw
+    x0 = tw.placeholder(tw.float64, [None, 30, 1681])
+    h0 = x0.corrupt(0).matmul(tw.constant(np.zeros((1681, 8)))).add(tw.constant(np.zeros(8))).sigmoid()
+    n = h0.to_tf()
+    assert n.op == "sigmoid" and n.inputs[0].op == "add"
+    assert h0.dimensions() == 3
+
+
+# ------------------------------------------------------------------------------------------- SDAV / DA / SDA
+def test_sdav_surface():
+    from src.sdav.network.SDAV import SDAV
+    m = SDAV.__new__(SDAV)
+    m._define_params()
+    assert m.input_shape == [30, 1681] and m.hidden_units == [2500] * 5 and m.default_batch_size == 10
+    assert (m.corruption_level, m.sparse_level, m.sparse_penalty, m.consecutive_penalty) == (0.3, 0.05, 1.0, 0.2)
+    assert m.learning_rate == 0.1 and m.epochs == 100
+    assert m.get_layer_input_shape(0) == [30, 1681] and m.get_layers_input_shapes() == [[30, 2500]] * 5
+    for name in ("transform", "transform_dataset", "transform_all", "fit", "fit_dataset", "get_dataset"):
+        assert callable(getattr(SDAV, name))
+
+
+def test_sdav_weight_roundtrip(tmp_path):
+    from deeploopcloser_b200.sdav import SDAV
+    m = SDAV.__new__(SDAV)
+    m._define_params()
+    m.hidden_units = [16, 8]
+    m.input_shape = [30, 25]
+    m._set_train_path(str(tmp_path))
+    m._encoder = None
+    m.init_weights(3)
+    p = m.save_weights()
+    w0 = m._weights[0].copy()
+    m.init_weights(4)
+    assert not np.array_equal(m._weights[0], w0)
+    m.load_weights(p)
+    assert np.array_equal(m._weights[0], w0) and m._weights[1].shape == (16, 8)
+    with pytest.raises(ValueError):
+        m.set_weights([w0], [np.zeros(16)])
+
+
+def test_da_sda_validation():
+    from src.sdav.network.DenoisingAutoencoderVariant import DA
+    from src.sdav.network.StackedDenoisingAutoencoderVariants import SDA
+    with pytest.raises(ValueError):
+        DA([30, 64], 32, learning_rate=-0.1)
+    with pytest.raises(ValueError):
+        DA([30], 32)
+    with pytest.raises(ValueError):
+        SDA([30, 64], [32])
+    s = SDA([30, 64], [32, 16], sparse_penalty=1)
+    assert [l.input_shape for l in s._layers] == [[30, 64], [30, 32]] and [l.layer_n for l in s._layers] == [0, 1]
+    with pytest.raises(NotImplementedError):
+        s.fit("x/*.ppm")
+
+
+# ------------------------------------------------------------------------------------------- input parser
+def test_boundaries_match_oracle():
+    from oracle import patches as o_patch
+    from src.sdav.input.CvInputParser import get_1d_boundaries, get_2d_boundaries
+    rng = np.random.default_rng(0)
+    pts = rng.integers(-5, 260, (200, 2))
+    for axis, L in ((0, 192), (1, 240)):
+        lo, hi = get_1d_boundaries([192, 240], pts, 41, axis)
+        olo, ohi = o_patch.window_bounds(L, pts[:, axis], 41)
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+    assert len(get_2d_boundaries([192, 240], pts, 41)) == 4
+    with pytest.raises(ValueError):
+        get_1d_boundaries([192, 240], pts, 40, 0)
+    with pytest.raises(ValueError):
+        get_1d_boundaries([192], pts, 41, 0)
+
+
+# ------------------------------------------------------------------------------------------- CnnVtl
+def test_cnnvtl_geometry_and_mask():
+    from deeploopcloser_b200 import cnn_vtl as c
+    from oracle import cnnvtl as o_cnn
+    net = c.CnnVtl(input_shape=[4, 192, 240, 3], weights="synthetic", seed=4)
+    assert net.layer_sizes == o_cnn.layer_sizes((192, 240))
+    assert net.keep_cols.size <= 2243 and np.all(np.diff(net.keep_cols) > 0)
+    assert c.layer_geometry(192, 240)[0][:4] == (192, 240, 46, 58) and c.layer_geometry(192, 240)[1][4:] == (2, 2)
+    # default 224x224 input: conv1 'valid' 11x11/4 -> 54x54 (TF floor rule), pools 3/2 -> 26 -> 12
+    assert c.CnnVtl((1, 224, 224, 3), weights="synthetic", seed=0).layer_sizes == [279936, 173056, 55296, 55296, 36864]
+    mask = np.zeros(546944, bool)
+    mask[[5, 300000, 546943]] = True
+    assert c.CnnVtl([1, 192, 240, 3], weights="synthetic", mask=mask).keep_cols.tolist() == [5, 300000, 546943]
+    with pytest.raises(ValueError):
+        c.CnnVtl([1, 192, 240, 3])  # weights are mandatory (the reference's blob is an LFS pointer)
+    assert np.array_equal(c._flat_fill([1, 2, 3], (2, 3)), [[1, 2, 3], [3, 3, 3]])
+    w = c.synthetic_weights(3)
+    ow = o_cnn.make_weights(3)
+    assert all(np.array_equal(w[k][0], ow[k][0]) for k in w)
+
+
+def test_mathutils_golden(golden_dir):
+    from src.utils.MathUtils import MathUtils
+    g = np.load(golden_dir + "/misc.npz")
+    assert [MathUtils.compressed_size(int(v), 99.59) for v in g["vals"]] == list(g["compressed"])

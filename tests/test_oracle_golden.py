@@ -1,0 +1,103 @@
+"""CPU: the oracle against the committed golden vectors (made by running the reference's own code, see
+tests/golden/make_golden.py) and against its own algebraic restatements."""
+import warnings
+
+import numpy as np
+
+from oracle import cnnvtl as o_cnn
+from oracle import hamming as o_ham
+from oracle import matcher as o_match
+from oracle import patches as o_patch
+from oracle import sda as o_sda
+from oracle import similarity as o_sim
+
+
+def test_patches_match_reference(golden_dir):
+    g = np.load(golden_dir + "/patches.npz")
+    for i in range(len(g["img"])):
+        assert np.array_equal(o_patch.extract_patches(g["img"][i], g["xy"][i], 41, True), g["out"][i])
+
+
+def test_patch_quirk_documented_case():
+    """keypoint (x=230.5, y=10.5) on a 192x240 image reads rows 151..191, cols 0..40."""
+    img = np.arange(192 * 240, dtype=np.int64).reshape(192, 240) % 251
+    out = o_patch.extract_patches(img.astype(np.uint8), np.array([[230.5, 10.5]]), 41, True)
+    want = img[151:192, 0:41].astype(np.uint8).reshape(-1) / 255.0
+    assert np.array_equal(out[0], want)
+    lo, hi = o_patch.window_bounds(192, [0, 20, 21, 100, 171, 172, 191, 230], 41)
+    assert list(lo) == [0, 0, 1, 80, 151, 151, 151, 151] and list(hi - lo) == [40] * 8
+
+
+def test_similarity_matches_reference(golden_dir):
+    g = np.load(golden_dir + "/similarity.npz")
+    for name in "abc":
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = o_sim.similarity_matrix(g["desc_" + name], full_asymmetric=True)
+        ref = g["S_" + name]
+        m = ~np.eye(len(ref), dtype=bool)
+        assert np.max(np.abs(S[m] - ref[m]) / np.maximum(1, np.abs(ref[m]))) < 1e-12
+
+
+def test_similarity_gram_restatement():
+    """The CUDA kernel's algebra: argmin_j (n_j - 2 G_kj) and s_k = |p_ik - p_jj*| reproduce similarity_score."""
+    rng = np.random.default_rng(3)
+    d = 1.0 / (1.0 + np.exp(-3 * rng.standard_normal((4, 30, 120))))
+    w = o_sim.distinctive_weights(d)
+    p = d @ w
+    for i in range(4):
+        for j in range(4):
+            if i == j:
+                continue
+            G = d[i] @ d[j].T
+            nj = (d[j] ** 2).sum(1)
+            jstar = np.argmin(nj[None, :] - 2 * G, axis=1)
+            s = np.abs(p[i] - p[j][jstar])
+            want, idx, _ = o_sim.similarity_score(d[i], d[j], w, return_details=True)
+            assert np.array_equal(jstar, idx)
+            assert abs(np.sum(10 - 10 * np.log(s)) - want) < 1e-9 * abs(want)
+
+
+def test_hamming_matches_reference(golden_dir):
+    g = np.load(golden_dir + "/hamming.npz")
+    assert np.array_equal(o_ham.distance_matrix(g["desc"]), g["D"])
+    assert o_ham.distance(g["ex_y1"], g["ex_y2"]) == int(g["ex_d"])
+    assert o_ham.SIGNED_LUT[0x80] == 1 and o_ham.SIGNED_LUT[0xFF] == 1 and o_ham.SIGNED_LUT[0x7F] == 7
+    d = g["desc"]
+    assert np.all(np.diag(o_ham.distance_matrix(d)) == 0)
+    assert not np.array_equal(o_ham.distance_matrix(d, True), o_ham.distance_matrix(d, False))
+
+
+def test_misc_golden(golden_dir):
+    g = np.load(golden_dir + "/misc.npz")
+    assert [o_cnn.compressed_size(int(v), 99.59) for v in g["vals"]] == list(g["compressed"])
+    x, w = g["tw_x"], g["tw_w"]
+    assert np.array_equal((x.reshape(-1, 2) @ w).reshape(3, 2, 2), g["tw_expected"])
+
+
+def test_sda_oracle_shapes_and_saturation():
+    dims = [1681, 64, 32]
+    ws, bs = o_sda.make_weights(dims, seed=0)
+    x = np.random.default_rng(0).uniform(0, 1, (3, 30, 1681))
+    out = o_sda.sda_forward(x, ws, bs)
+    assert out.shape == (90, 32) and out.min() >= 0 and out.max() <= 1
+    assert np.allclose(o_sda.sigmoid(np.array([-800.0, 0.0, 800.0])), [0.0, 0.5, 1.0])
+
+
+def test_cnnvtl_oracle_geometry():
+    sizes = o_cnn.layer_sizes((192, 240))
+    assert sizes == [256128, 157696, 49920, 49920, 33280] and sum(sizes) == 546944
+    assert o_cnn.layer_sizes((224, 224)) == [279936, 173056, 55296, 55296, 36864]
+    keep = o_cnn.make_keep_columns(sizes, seed=4)
+    assert len(keep) <= 2243 and np.all(np.diff(keep) > 0)
+    assert list(o_cnn.cast_int8_wrap(np.array([0.0, 127.9, 128.0, 255.0, 200.7]))) == [0, 127, -128, -1, -56]
+
+
+def test_matcher_oracle_ties_and_padding():
+    s = np.array([[1.0, 3.0, 3.0, 2.0], [np.nan, 0.5, 0.5, 0.5]])
+    ts, ti = o_match.topk(s, 3)
+    assert ti.tolist() == [[1, 2, 3], [1, 2, 3]]
+    ts, ti = o_match.topk(s, 3, largest=False, exclude_band=0)
+    assert ti.tolist() == [[3, 1, 2], [2, 3, -1]]
+    c, ts, ti = o_match.threshold(s, 2.5, 3)
+    assert c.tolist() == [2, 0] and ti.tolist() == [[1, 2, -1], [-1, -1, -1]]
