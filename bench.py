@@ -92,32 +92,52 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
-def cpu_step_sample(n_enc_frames=48, n_pairs=600, seed=0):
-    """Bounded sample of the reference CPU path (float64 oracle port): encode n_enc_frames frames and score n_pairs
-    frame pairs; returns frames/s for the full 1063-frame step extrapolated from the two per-unit costs."""
+_PAIR_STATE = {}
+
+
+def _score_pairs(args):
+    """Worker: score `n` random frame pairs with the literal per-pair algorithm (dataset mean hoisted)."""
+    from oracle import similarity as o_sim
+    seed, n = args
+    desc, w = _PAIR_STATE["desc"], _PAIR_STATE["w"]
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        for _ in range(n):
+            i, j = rng.choice(len(desc), 2, replace=False)
+            o_sim.similarity_score(desc[i], desc[j], w)
+    return time.perf_counter() - t0
+
+
+def cpu_step_sample(n_enc_frames=48, n_pairs=1200, seed=0):
+    """Bounded sample of the reference CPU path (float64 oracle port) on all host cores: encode n_enc_frames frames
+    (OpenBLAS threads) and score n_pairs frame pairs (one process per core); returns frames/s for the full 1063-frame
+    step extrapolated from the two per-unit costs. Must run in a process that has not initialised CUDA (it forks)."""
+    import multiprocessing as mp
+
     from oracle import patches as o_patch
     from oracle import sda as o_sda
     from oracle import similarity as o_sim
+    cores = os.cpu_count() or 1
     frames, xy = synthetic_inputs(seed)
     ws, bs = reference_weights()
     t0 = time.perf_counter()
     x = np.concatenate([o_patch.extract_patches(frames[i], xy[i], PATCH) for i in range(n_enc_frames)])
     desc = o_sda.sda_forward(x, ws, bs).reshape(n_enc_frames, P, -1)
     t_enc = (time.perf_counter() - t0) / n_enc_frames
-    w = o_sim.distinctive_weights(desc)          # dataset mean hoisted (the literal reference recomputes it per pair)
-    rng = np.random.default_rng(1)
+    _PAIR_STATE["desc"] = desc
+    _PAIR_STATE["w"] = o_sim.distinctive_weights(desc)  # dataset mean hoisted (the literal reference recomputes it per pair)
+    per = max(n_pairs // cores, 1)
     t0 = time.perf_counter()
-    with np.errstate(all="ignore"):
-        for _ in range(n_pairs):
-            i, j = rng.choice(n_enc_frames, 2, replace=False)
-            o_sim.similarity_score(desc[i], desc[j], w)
-    t_pair = (time.perf_counter() - t0) / n_pairs
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_score_pairs, [(100 + c, per) for c in range(cores)])
+    t_pair = (time.perf_counter() - t0) / (per * cores)   # wall time per pair with all cores busy
     pairs_per_frame = (N_FRAMES - 1) / 2.0
     fps = 1.0 / (t_enc + pairs_per_frame * t_pair)
-    sample = ("oracle port, float64: %d frames encoded (%.1f ms/frame, OpenBLAS threads) + %d frame pairs scored "
-              "(%.2f ms/pair, 1 thread), extrapolated to the 1063-frame step (%.0f pairs/frame)" %
-              (n_enc_frames, t_enc * 1e3, n_pairs, t_pair * 1e3, pairs_per_frame))
-    return fps, sample
+    sample = ("oracle port, float64, %d cores: %d frames encoded (%.1f ms/frame, OpenBLAS) + %d frame pairs scored "
+              "(%.3f ms/pair wall, one process per core), extrapolated to the 1063-frame step (%.0f pairs/frame)" %
+              (cores, n_enc_frames, t_enc * 1e3, per * cores, t_pair * 1e3, pairs_per_frame))
+    return fps, sample, cores
 
 
 def run_reference(args):
@@ -128,7 +148,7 @@ def run_reference(args):
     vals = []
     sample = ""
     for _ in range(args.warmup + args.steps):
-        fps, sample = cpu_step_sample(24, 150)
+        fps, sample, cores = cpu_step_sample(*args.cpu_sample)
         vals.append(fps)
     vals = vals[args.warmup:] or vals
     v = float(np.mean(vals))
@@ -177,14 +197,12 @@ def run_ours(args):
     def step_device():
         return pipe.run(frames_d, xy_d, k=K_CAND, exclude_band=0)
 
-    def step_e2e():
-        f = frames_pin.cuda(non_blocking=True)
-        x = xy_pin.cuda(non_blocking=True)
-        r = pipe.run(f, x, k=K_CAND, exclude_band=0)
-        out_s_pin.copy_(r["candidates"][0], non_blocking=True)
-        out_i_pin.copy_(r["candidates"][1], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return r
+    def e2e_steps(n):
+        """n sequences through the public streaming call: host (pinned) frames + keypoints in, candidate lists out;
+        every step's H2D and D2H copies are issued inside the timed region (upload of step i+1 overlaps step i)."""
+        outs = pipe.run_host_stream([(frames_pin, xy_pin)] * n, k=K_CAND, exclude_band=0)
+        out_s_pin.copy_(outs[-1][0])
+        out_i_pin.copy_(outs[-1][1])
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -211,7 +229,17 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * N_FRAMES / (ms_step * 1e-3)
 
-    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 1)) / args.steps
+    e2e_steps(max(args.warmup, 1))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_steps(args.steps)
+    e1.record()
+    barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_t.item()) / args.steps
     e2e_value = world * N_FRAMES / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel (Gram + argmin + score), timed alone with CUDA events on the launch stream
@@ -238,9 +266,16 @@ def run_ours(args):
         finally:
             _lib.call("dlc_sdav_debug_gram_only", 0)
         achieved = GRAM_FLOP / (gram_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_gram_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = {"kernel": "gemm_tc_kernel<GramPolicy> (SDAV Gram + argmin + score)", "bound": "tensor",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + ", sustained bf16",
                 "ms_per_launch": gram_ms, "algorithmic_flop_per_launch": GRAM_FLOP,
                 "note": "algorithmic FLOPs of the i<j pairs; precision mode %s issues %dx that on the tensor pipe" % (
                     args.precision, 3 if args.precision == "fp16x2" else 1)}
@@ -263,9 +298,15 @@ def run_ours(args):
         enc_only = max(stage_ms["encode_total"] - stage_ms["patch_gather"], 1e-6)
         stage_ms["encode_tflops_algorithmic"] = N_FRAMES * ENC_FLOP_PER_FRAME / (enc_only * 1e-3) / 1e12
         if world == 1 and not args.no_cpu_baseline:
-            fps, sample = cpu_step_sample()
-            cpu_base = {"value": fps, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": sample}
+            # timed in a fresh process (it forks one worker per core, which a CUDA-initialised process must not do)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                      "--warmup", "0", "--cpu-sample", "96,16000"], capture_output=True, text=True,
+                                     timeout=600).stdout
+                cpu_base = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])["cpu_baseline"]
+            except Exception as e:  # noqa: BLE001
+                cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                            "sample": "failed: %r" % (e,)}
 
     if rank == 0:
         launches_per_step = 1 + len(DIMS) - 1 + 5 + 1  # gather, 5 layers, (split, colsum, weights, rowstats, gram), top-k
@@ -297,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default="48,4800", type=lambda v: tuple(int(t) for t in v.split(",")),
+                    help="reference arm: frames encoded, frame pairs scored per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,7 +59,8 @@ PROTOTYPES = {
     "dlc_match_workspace_bytes": (_sz, [_p, _i, _i]),
     "dlc_match_topk": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _sz, _p]),
     "dlc_match_threshold": (_i, [_p, _p, _i, _f, _i, _i64, _p, _p, _p, _p, _sz, _p]),
-    "dlc_hamming_matrix": (_i, [_p, _i, _i, _i, _p, _p]),
+    "dlc_hamming_workspace_bytes": (_sz, [_i, _i]),
+    "dlc_hamming_matrix": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_im2col_planes": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_maxpool_planes": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_cnnvtl_quantise": (_i, [C.POINTER(_p), C.POINTER(_i64), _i, _i, _p, _i, _p, _p, _p]),

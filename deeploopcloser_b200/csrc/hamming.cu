@@ -77,23 +77,28 @@ __global__ void hamming_pack_kernel(const int8_t* __restrict__ d, int N, int M, 
 
 using namespace dlc;
 
+extern "C" size_t dlc_hamming_workspace_bytes(int N, int M) {
+  if (N <= 0 || M <= 0) return 0;
+  return sizeof(uint32_t) * static_cast<size_t>(N) * ((M + 3) / 4);
+}
+
 extern "C" int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quirk, int32_t* D_dev,
-                                  void* stream) {
+                                  void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(desc_dev && D_dev);
   DLC_CHECK_ARG(N >= 0 && M > 0);
   if (N == 0) return DLC_OK;
+  if (!ws_dev || ws_bytes < dlc_hamming_workspace_bytes(N, M) || (reinterpret_cast<uintptr_t>(ws_dev) & 3))
+    return fail(DLC_ENOMEM, "dlc_hamming_matrix: 4-byte aligned workspace of %zu bytes needed, %zu given",
+                dlc_hamming_workspace_bytes(N, M), ws_bytes);
   cudaStream_t s = as_stream(stream);
   const int Mw = (M + 3) / 4;
-  uint32_t* words = nullptr;
-  DLC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&words), sizeof(uint32_t) * static_cast<size_t>(N) * Mw, s));
+  uint32_t* words = static_cast<uint32_t*>(ws_dev);
   const int64_t total = static_cast<int64_t>(N) * Mw;
   hamming_pack_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 4096)), 256, 0, s>>>(desc_dev, N, M,
                                                                                                       Mw, words);
   dim3 grid(ceil_div(N, kHamTile), ceil_div(N, kHamTile));
   if (signed_bin_quirk) hamming_kernel<true><<<grid, 256, 0, s>>>(words, N, Mw, D_dev);
   else hamming_kernel<false><<<grid, 256, 0, s>>>(words, N, Mw, D_dev);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(words, s);
-  DLC_CUDA(e);
+  DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }

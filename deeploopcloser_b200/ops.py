@@ -203,7 +203,9 @@ def hamming_matrix(desc, signed_bin_quirk=True):
     assert desc.dtype == torch.int8
     N, M = desc.shape
     out = torch.empty((N, N), dtype=torch.int32, device=desc.device)
-    _lib.call("dlc_hamming_matrix", ptr(desc), N, M, int(bool(signed_bin_quirk)), ptr(out), stream_ptr())
+    ws, ws_bytes = _ws.get(_lib.call("dlc_hamming_workspace_bytes", N, M))
+    _lib.call("dlc_hamming_matrix", ptr(desc), N, M, int(bool(signed_bin_quirk)), ptr(out), ws, ws_bytes,
+              stream_ptr())
     return out
 
 

@@ -35,3 +35,51 @@ class LoopClosurePipeline:
         desc = self.encode(frames, xy)
         S, cand = self.match(desc, frames.shape[0], k, exclude_band)
         return {"descriptors": desc, "similarity": S, "candidates": cand}
+
+    def run_host_stream(self, batches, k=10, exclude_band=0):
+        """Process a stream of HOST batches [(frames uint8 [B,H,W], xy float32 [B,P,2]), ...] (pinned torch tensors)
+        end to end and return the candidate lists [(scores [B,k], idx [B,k]), ...] in pinned host memory.
+        The upload of batch i+1 runs on a copy stream while batch i computes (double-buffered device inputs), the
+        candidate lists come back with asynchronous D2H copies; one synchronisation at the end."""
+        batches = list(batches)
+        if not batches:
+            return []
+        compute = torch.cuda.current_stream()
+        copy = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream()
+        bufs, ready, consumed = [None, None], [None, None], [None, None]
+
+        def upload(i):
+            slot = i & 1
+            f_h, x_h = batches[i]
+            if consumed[slot] is not None:
+                copy.wait_event(consumed[slot])      # the compute stream is done reading this slot
+            with torch.cuda.stream(copy):
+                if bufs[slot] is None or bufs[slot][0].shape != f_h.shape or bufs[slot][1].shape != x_h.shape:
+                    bufs[slot] = (torch.empty(f_h.shape, dtype=f_h.dtype, device="cuda"),
+                                  torch.empty(x_h.shape, dtype=x_h.dtype, device="cuda"))
+                bufs[slot][0].copy_(f_h, non_blocking=True)
+                bufs[slot][1].copy_(x_h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            ready[slot] = ev
+
+        copy.wait_stream(compute)
+        upload(0)
+        outs = []
+        for i in range(len(batches)):
+            slot = i & 1
+            if i + 1 < len(batches):
+                upload(i + 1)
+            compute.wait_event(ready[slot])
+            f_d, x_d = bufs[slot]
+            r = self.run(f_d, x_d, k, exclude_band)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            consumed[slot] = ev
+            s_h = torch.empty(r["candidates"][0].shape, dtype=torch.float32).pin_memory()
+            i_h = torch.empty(r["candidates"][1].shape, dtype=torch.int64).pin_memory()
+            s_h.copy_(r["candidates"][0], non_blocking=True)
+            i_h.copy_(r["candidates"][1], non_blocking=True)
+            outs.append((s_h, i_h))
+        compute.synchronize()
+        return outs

@@ -180,7 +180,9 @@ int dlc_match_threshold(dlc_db* db, const float* q_dev, int B, float thr, int ma
  * desc_dev int8 [N, M]; D_dev int32 [N, N]. signed_bin_quirk = 1 reproduces the reference exactly
  * (bin() of the signed XOR: popcount of |int8(a ^ b)|); 0 = plain two's-complement popcount.
  * ------------------------------------------------------------------------------------------------------------ */
-int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quirk, int32_t* D_dev, void* stream);
+size_t dlc_hamming_workspace_bytes(int N, int M);
+int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quirk, int32_t* D_dev, void* ws_dev,
+                       size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a7  cnn_vtl conv head building blocks (src/cnn_vtl/network/cnn_vtl.py:28-128). The convolutions run as
