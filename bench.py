@@ -185,7 +185,7 @@ def run_ours(args):
 
     frames_h, xy_h = synthetic_inputs(100 + rank)
     ws, bs = reference_weights()
-    pipe = LoopClosurePipeline(DIMS, precision=args.precision)
+    pipe = LoopClosurePipeline(DIMS, precision=args.precision, sim_precision=args.sim_precision)
     pipe.set_weights(ws, bs)
     frames_pin = torch.from_numpy(frames_h).pin_memory()
     xy_pin = torch.from_numpy(xy_h).pin_memory()
@@ -250,16 +250,18 @@ def run_ours(args):
         pk = peaks()
         desc = pipe.encode(frames_d, xy_d)
         dview = desc.view(N_FRAMES, P, -1)
-        ops.sdav_similarity(dview, precision=args.precision)  # fills the workspace (planes, stats, tile list)
+        ops.sdav_similarity(dview, precision=args.sim_precision)  # fills the workspace (planes, stats, tile list)
         torch.cuda.synchronize()
+        sim_stats = ops.sdav_similarity_stats(N_FRAMES, P, DIMS[-1]) if args.sim_precision in ("auto", "fp16r") else None
+        products = 3 if (args.sim_precision == "fp16x2" or (sim_stats and not sim_stats["use_refine"])) else 1
         _lib.call("dlc_sdav_debug_gram_only", 1)
         try:
             reps = max(args.steps, 3)
-            ops.sdav_similarity(dview, precision=args.precision)
+            ops.sdav_similarity(dview, precision=args.sim_precision)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                ops.sdav_similarity(dview, precision=args.precision)
+                ops.sdav_similarity(dview, precision=args.sim_precision)
             e1.record()
             torch.cuda.synchronize()
             gram_ms = e0.elapsed_time(e1) / reps
@@ -272,13 +274,16 @@ def run_ours(args):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        roof = {"kernel": "gemm_tc_kernel<GramPolicy> (SDAV Gram + argmin + score)", "bound": "tensor",
+        roof = {"kernel": "gemm_tc_kernel<%s> (SDAV Gram + argmin + score)" % (
+                    "GramRefinePolicy" if products == 1 else "GramPolicy<32,3>"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
                 "peak_source": pk["source"] + ", sustained bf16",
                 "ms_per_launch": gram_ms, "algorithmic_flop_per_launch": GRAM_FLOP,
-                "note": "algorithmic FLOPs of the i<j pairs; precision mode %s issues %dx that on the tensor pipe" % (
-                    args.precision, 3 if args.precision == "fp16x2" else 1)}
+                "precision_probe": sim_stats,
+                "note": "algorithmic FLOPs of the i<j pairs (2*30*30*2500 each); similarity precision mode %s issues "
+                        "%dx that on the tensor pipe (in gram-only timing mode both gated kernels are launched, the "
+                        "unselected one returns immediately)" % (args.sim_precision, products)}
         # stage split (each stage timed alone; informational)
         def t_stage(fn, reps=3):
             fn()
@@ -293,7 +298,7 @@ def run_ours(args):
         split = args.precision == "fp16x2"
         stage_ms["patch_gather"] = t_stage(lambda: ops.patch_gather(frames_d, xy_d, PATCH, True, need_lo=split))
         stage_ms["encode_total"] = t_stage(lambda: pipe.encode(frames_d, xy_d))
-        stage_ms["similarity_total"] = t_stage(lambda: ops.sdav_similarity(dview, precision=args.precision))
+        stage_ms["similarity_total"] = t_stage(lambda: ops.sdav_similarity(dview, precision=args.sim_precision))
         stage_ms["gram_kernel"] = gram_ms
         enc_only = max(stage_ms["encode_total"] - stage_ms["patch_gather"], 1e-6)
         stage_ms["encode_tflops_algorithmic"] = N_FRAMES * ENC_FLOP_PER_FRAME / (enc_only * 1e-3) / 1e12
@@ -309,12 +314,13 @@ def run_ours(args):
                             "sample": "failed: %r" % (e,)}
 
     if rank == 0:
-        launches_per_step = 1 + len(DIMS) - 1 + 5 + 1  # gather, 5 layers, (split, colsum, weights, rowstats, gram), top-k
+        # gather, 5 layers, similarity (split, colsum, weights, rowstats, [probe, finalize, gated twin], gram), top-k
+        launches_per_step = 1 + len(DIMS) - 1 + (8 if args.sim_precision in ("auto", "fp16r") else 5) + 1
         line = {"metric": "loop-query frames/sec (encode+match)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo split operands, f32 accumulate" if
                 args.precision == "fp16x2" else "f16 operands, f32 accumulate", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "precision": args.precision,
+                "config": {"workload": WORKLOAD, "precision": args.precision, "sim_precision": args.sim_precision,
                            "weights": "N(0,1) init (reference default, no checkpoint shipped)",
                            "k": K_CAND, "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the 126 MB L2; no explicit flush",
                            "multi_gpu": "independent sequence per rank, no collective"},
@@ -333,10 +339,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"], help="encoder arithmetic")
+    ap.add_argument("--sim-precision", default="fp16x2", choices=["auto", "fp16r", "fp16x2", "fp16"],
+                    help="SDAV score-matrix arithmetic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="48,4800", type=lambda v: tuple(int(t) for t in v.split(",")),
                     help="reference arm: frames encoded, frame pairs scored per step")

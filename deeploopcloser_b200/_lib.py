@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdlc.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
-PREC_FP16, PREC_FP16X2, PREC_BF16 = 0, 1, 2
+PREC_FP16, PREC_FP16X2, PREC_BF16, PREC_AUTO, PREC_FP16_REFINED = 0, 1, 2, 3, 4
 F32, F64, F16, BF16, U8 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 METRIC_COS, METRIC_DOT, METRIC_L2 = 0, 1, 2
@@ -49,6 +49,7 @@ PROTOTYPES = {
     "dlc_sda_encode": (_i, [_p, _p, _p, _i, _p, _p, _sz, _p]),
     "dlc_sdav_similarity_workspace_bytes": (_sz, [_i, _i, _i]),
     "dlc_sdav_similarity": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _p, _p, _sz, _p]),
+    "dlc_sdav_similarity_stats": (_i, [_i, _i, _i, _p, _p, _p]),
     "dlc_sdav_weights": (_i, [_p, _i, _i, _i, _d, _d, _p, _p, _sz, _p]),
     "dlc_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "dlc_db_create": (_i, [C.POINTER(_p), _i, _i64, _i, _i]),

@@ -54,10 +54,15 @@ struct GemmCfg {
 //   struct Params { int n_tile; int k_blocks; int ab_fmt; int kc; ... };            (POD, passed by value)
 //   static __device__ int  num_tiles(const Params&, int cta, int ncta);
 //   static __device__ TileCoord tile(const Params&, int cta, int ncta, int i);
-//   struct Epilogue { __device__ Epilogue(const Params&, int quarter, int lane, void* scratch);
+//   static constexpr int kEpiWarps;      4 or 8 epilogue warps (forced to 8 by kPromote)
+//   static __device__ bool enabled(const Params&);                                  (device-side launch gate)
+//   struct Epilogue { __device__ Epilogue(const Params&, int quarter, int half, int lane, void* scratch);
 //                     __device__ void begin_tile(TileCoord);
-//                     __device__ void chunk(TileCoord, int c, float (&v)[32]);   // columns [32c, 32c+32) of this
-//                     __device__ void end_tile(TileCoord);                       // thread's accumulator row
+//                     template <int SLOT> __device__ void chunk(TileCoord, int c, float (&v)[32]);
+//                                       // columns [32c, 32c+32) of this thread's accumulator row; SLOT = compile-time
+//                                       // index of the chunk among this warp's chunks (for per-chunk register state)
+//                     __device__ void end_tile(TileCoord);    // last call that may rely on the accumulator
+//                     __device__ void post_tile(TileCoord);   // runs after the TMEM buffer went back to the MMA warp
 //                     __device__ void finish(); };
 //
 // Two-level accumulation (kPromote). The tensor core adds into its fp32 accumulator with truncation, so a K = 2500
@@ -72,8 +77,45 @@ constexpr int kGemmThreadsPromote = 384;
 constexpr int kRegsLean = 56;
 constexpr int kRegsEpilogue = 224;
 
+// Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, 128 accumulator columns each).
 template <class Policy>
-__global__ void __launch_bounds__(Policy::kPromote ? kGemmThreadsPromote : kGemmThreads, 1)
+__host__ __device__ constexpr int epi_warps() {
+  return Policy::kPromote ? 8 : Policy::kEpiWarps;
+}
+template <class Policy>
+__host__ __device__ constexpr int gemm_threads() {
+  return Policy::kPromote ? kGemmThreadsPromote : (Policy::kEpiWarps == 8 ? 320 : kGemmThreads);
+}
+
+// One 32-column chunk of this thread's accumulator row; SLOT is a compile-time constant so that per-chunk epilogue
+// state indexed by it stays in registers.
+template <class Epi, int SLOT>
+__device__ __forceinline__ void epi_slot_from_tmem(Epi& epi, TileCoord tc, uint32_t taddr, int half, int n_cchunks) {
+  const int c = half * 4 + SLOT;
+  if (c < n_cchunks) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr + c * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    epi.template chunk<SLOT>(tc, c, v);
+  }
+}
+template <class Epi, int SLOT>
+__device__ __forceinline__ void epi_slot_from_regs(Epi& epi, TileCoord tc, const float (&sums)[128], int half,
+                                                   int n_cchunks) {
+  const int c = half * 4 + SLOT;
+  if (c < n_cchunks) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = sums[SLOT * 32 + j];
+    epi.template chunk<SLOT>(tc, c, v);
+  }
+}
+
+template <class Policy>
+__global__ void __launch_bounds__(gemm_threads<Policy>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                const typename Policy::Params p) {
@@ -81,7 +123,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int BK = Cfg::BK;
   constexpr int S = Cfg::kStages;
   constexpr bool kPromote = Policy::kPromote;
-  constexpr int kEpiWarps = kPromote ? 8 : 4;
+  constexpr int kEpiWarps = epi_warps<Policy>();
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,7 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   constexpr int kEpiWarp0 = kPromote ? 4 : 2;  // first epilogue warp
 
-  const int my_tiles = Policy::num_tiles(p, cta, ncta);
+  // a launch can be gated off by device-side state (e.g. the Gram precision probe picks one of two kernels)
+  const int my_tiles = Policy::enabled(p) ? Policy::num_tiles(p, cta, ncta) : 0;
   const int n_tile = p.n_tile;
   const int k_blocks = p.k_blocks;
   // K chunks per tile: one (plain accumulation) or ceil(k_blocks / kc) (two-level accumulation)
@@ -219,9 +263,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ===================== epilogue warps =====================
     if (kPromote) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
-    const int half = kPromote ? (warp - kEpiWarp0) >> 2 : 0;
+    const int half = kEpiWarps == 8 ? (warp - kEpiWarp0) >> 2 : 0;  // which 128-column half this warp owns
     const int n_cchunks = n_tile >> 5;          // 32-column chunks in the accumulator
-    typename Policy::Epilogue epi(p, quarter, lane, scratch);
+    typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int i = 0; i < my_tiles; ++i) {
@@ -255,34 +299,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (acc == 0) acc_phase ^= 1u;
         }
         epi.begin_tile(tc);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (half * 4 + cc < n_cchunks) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = sums[cc * 32 + j];
-            epi.chunk(tc, half * 4 + cc, v);
-          }
-        }
+        using Epi = typename Policy::Epilogue;
+        epi_slot_from_regs<Epi, 0>(epi, tc, sums, half, n_cchunks);
+        epi_slot_from_regs<Epi, 1>(epi, tc, sums, half, n_cchunks);
+        epi_slot_from_regs<Epi, 2>(epi, tc, sums, half, n_cchunks);
+        epi_slot_from_regs<Epi, 3>(epi, tc, sums, half, n_cchunks);
         epi.end_tile(tc);
+        epi.post_tile(tc);
       } else {
         mbar_wait(&tfull[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) + (static_cast<uint32_t>(quarter * 32) << 16);
         epi.begin_tile(tc);
-        for (int c = 0; c < n_cchunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epi.chunk(tc, c, v);
+        using Epi = typename Policy::Epilogue;
+        epi_slot_from_tmem<Epi, 0>(epi, tc, taddr, half, n_cchunks);
+        epi_slot_from_tmem<Epi, 1>(epi, tc, taddr, half, n_cchunks);
+        epi_slot_from_tmem<Epi, 2>(epi, tc, taddr, half, n_cchunks);
+        epi_slot_from_tmem<Epi, 3>(epi, tc, taddr, half, n_cchunks);
+        if (kEpiWarps == 4) {  // one warp per lane quarter walks all 8 chunks
+          epi_slot_from_tmem<Epi, 4>(epi, tc, taddr, half, n_cchunks);
+          epi_slot_from_tmem<Epi, 5>(epi, tc, taddr, half, n_cchunks);
+          epi_slot_from_tmem<Epi, 6>(epi, tc, taddr, half, n_cchunks);
+          epi_slot_from_tmem<Epi, 7>(epi, tc, taddr, half, n_cchunks);
         }
         epi.end_tile(tc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        epi.post_tile(tc);  // work that no longer needs the accumulator (TMEM buffer already handed back)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -348,8 +392,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<Policy><<<grid, Policy::kPromote ? kGemmThreadsPromote : kGemmThreads, Cfg::kSmemBytes, stream>>>(
-      a0, a1, b0, b1, p);
+  gemm_tc_kernel<Policy><<<grid, gemm_threads<Policy>(), Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
   return cudaGetLastError();
 }
 

@@ -154,6 +154,8 @@ struct MatchPolicy {
   using Cfg = GemmCfg<BK, 1>;
   using Params = MatchParams;
   static constexpr bool kPromote = false;  // operand rounding (fp16/bf16 storage) dominates the error here
+  static constexpr int kEpiWarps = 4;
+  static __device__ __forceinline__ bool enabled(const Params&) { return true; }
   static constexpr uint64_t kHintA = kEvictLast;   // queries: tiny, re-read for every database tile
   static constexpr uint64_t kHintB = kEvictFirst;  // database: streamed once per pass
 
@@ -174,7 +176,7 @@ struct MatchPolicy {
     float ls[KMAX];
     int li[KMAX];  // database row (local to this database); INT_MAX = empty
     int cnt;
-    __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {
+    __device__ Epilogue(const Params& p_, int quarter_, int, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {
 #pragma unroll
       for (int t = 0; t < KMAX; ++t) {
         ls[t] = -INFINITY;
@@ -195,7 +197,9 @@ struct MatchPolicy {
       if (l2) thr_key = (row < p.B ? p.qaux[row] : 0.0f) - p.thr;  // dist <= thr  <=>  key >= |q|^2 - thr
     }
     __device__ __forceinline__ void end_tile(TileCoord) {}
+    __device__ __forceinline__ void post_tile(TileCoord) {}
 
+    template <int SLOT>
     __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
       const int64_t col0 = static_cast<int64_t>(tc.nt) * p.n_tile + c * 32;
       if (col0 >= p.db_rows) return;  // warp-uniform

@@ -110,6 +110,8 @@ struct BiasActPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = BiasActParams;
   static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
+  static constexpr int kEpiWarps = 4;
+  static __device__ __forceinline__ bool enabled(const Params&) { return true; }
   static constexpr uint64_t kHintA = kEvictNormal;
   static constexpr uint64_t kHintB = kEvictLast;  // weights are re-read by every M tile: keep them in L2
 
@@ -129,7 +131,7 @@ struct BiasActPolicy {
   struct Epilogue {
     const Params& p;
     const int quarter, lane;
-    __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
+    __device__ Epilogue(const Params& p_, int quarter_, int, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
 
     int row;
     bool row_ok;
@@ -138,6 +140,7 @@ struct BiasActPolicy {
       row_ok = row < p.M;
     }
     __device__ __forceinline__ void end_tile(TileCoord) {}
+    __device__ __forceinline__ void post_tile(TileCoord) {}
 
     // bias + activation on one 32-column chunk. Branch-free per element: the activation switch and the
     // "chunk fully inside N" test are hoisted out of the element loop; sigmoid uses the SFU approximations
@@ -173,6 +176,7 @@ struct BiasActPolicy {
       }
     }
 
+    template <int SLOT>
     __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
       const int col0 = tc.nt * p.n_tile + c * 32;
       float h[32];

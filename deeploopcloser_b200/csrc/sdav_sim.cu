@@ -80,26 +80,88 @@ rowstats_kernel(const float* __restrict__ H, int N, int P, int D, const double* 
 // ---------------- Gram + argmin + score epilogue ----------------
 extern int g_promote_k;  // planes.cu
 
+// Device-side precision decision written by the probe (see below); both Gram kernels are always launched and the
+// one that is not selected returns immediately, so the choice needs no host round trip.
+struct GramControl {
+  int use_refine;       // 1: one-product kernel + exact refinement, 0: three-product kernel
+  float margin;         // candidates within `margin` of the approximate minimum are re-evaluated exactly
+  float sigma;          // estimated std of the approximate squared-distance error (diagnostic)
+  float flagged_frac;   // estimated fraction of rows needing refinement (diagnostic)
+  unsigned long long flagged_rows;   // counted by the refine kernel (diagnostic)
+  unsigned long long refined_cands;  // "
+};
+
 struct GramParams {
   int n_tile, k_blocks, ab_fmt, kc;
   const int2* tiles;  // (mt, nt) work list in L2-friendly order
   int num_tiles;
-  int N, P;
+  int N, P, D;
+  const float* desc;  // [N, P, D] float32 descriptors (exact refinement reads them)
   const float* sqn;   // [N*32]
   const double* pw;   // [N*32]
   float a, b;
   int full;           // 1: every ordered pair i != j; 0: i < j, mirrored
   float* S;           // [N, N]
+  GramControl* ctl;   // NULL: always enabled
+  int want_refine;    // this launch runs only when ctl->use_refine == want_refine
 };
 
+// score of one frame pair from the per-row matches: sum_k (a + b ln |p_ik - p_j,bj(k)|), warp-wide
+__device__ __forceinline__ void pair_score(const GramParams& p, int fa, int fb, int lane, double pa, int bj) {
+  const double my_pb = p.pw[fb * kFrameRows + lane];
+  const double pb = __shfl_sync(0xffffffffu, my_pb, bj);
+  const float s = static_cast<float>(fabs(pa - pb));
+  float val = lane < p.P ? p.a + p.b * logf(s) : 0.0f;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+  if (lane == 0) {
+    p.S[static_cast<int64_t>(fa) * p.N + fb] = val;
+    if (!p.full) p.S[static_cast<int64_t>(fb) * p.N + fa] = val;
+  }
+}
+
+// exact squared distance between two float32 rows, accumulated in float64, whole warp cooperates
+__device__ __forceinline__ double exact_d2(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
+  double acc0 = 0.0, acc1 = 0.0;
+  if ((D & 3) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    const int n4 = D >> 2;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+      const double d0 = static_cast<double>(x.x - y.x), d1 = static_cast<double>(x.y - y.y);
+      const double d2 = static_cast<double>(x.z - y.z), d3 = static_cast<double>(x.w - y.w);
+      acc0 = fma(d0, d0, acc0);
+      acc1 = fma(d1, d1, acc1);
+      acc0 = fma(d2, d2, acc0);
+      acc1 = fma(d3, d3, acc1);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const double d = static_cast<double>(a[i] - b[i]);
+      acc0 = fma(d, d, acc0);
+    }
+  }
+  acc0 += acc1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+  return acc0;
+}
+
+// ---- (A) three fp16 products + two-level accumulation: every Gram entry good to ~1e-7 relative
 template <int BK, int NPROD>
 struct GramPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = GramParams;
   static constexpr bool kPromote = NPROD == 3;
+  static constexpr int kEpiWarps = 4;
   static constexpr uint64_t kHintA = kEvictNormal;
   static constexpr uint64_t kHintB = kEvictNormal;
 
+  static __device__ __forceinline__ bool enabled(const Params& p) {
+    return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
+  }
   static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
     return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
   }
@@ -114,7 +176,7 @@ struct GramPolicy {
   struct Epilogue {
     const Params& p;
     const int quarter, lane;
-    __device__ Epilogue(const Params& p_, int quarter_, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
+    __device__ Epilogue(const Params& p_, int quarter_, int, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
 
     int fa;
     bool fa_ok;
@@ -125,8 +187,10 @@ struct GramPolicy {
       pa = fa_ok ? p.pw[fa * kFrameRows + lane] : 0.0;
     }
     __device__ __forceinline__ void end_tile(TileCoord) {}
+    __device__ __forceinline__ void post_tile(TileCoord) {}
 
     // chunk c = the 32 accumulator columns of frame j = 8 nt + c
+    template <int SLOT>
     __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
       const int fb = tc.nt * kFramesPerNTile + c;
       if (!fa_ok || fb >= p.N) return;  // warp-uniform
@@ -136,7 +200,6 @@ struct GramPolicy {
       }
       if (!p.full && fa > fb) return;
       const float my_nb = p.sqn[fb * kFrameRows + lane];
-      const double my_pb = p.pw[fb * kFrameRows + lane];
       float best = INFINITY;
       int bj = 0;
 #pragma unroll
@@ -149,19 +212,234 @@ struct GramPolicy {
           bj = j;
         }
       }
-      const double pb = __shfl_sync(0xffffffffu, my_pb, bj);
-      const float s = static_cast<float>(fabs(pa - pb));
-      float val = lane < p.P ? p.a + p.b * logf(s) : 0.0f;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
-      if (lane == 0) {
-        p.S[static_cast<int64_t>(fa) * p.N + fb] = val;
-        if (!p.full) p.S[static_cast<int64_t>(fb) * p.N + fa] = val;
-      }
+      pair_score(p, fa, fb, lane, pa, bj);
     }
     __device__ __forceinline__ void finish() {}
   };
 };
+
+// ---- (B) one fp16 product + exact refinement. The single-product Gram entry carries the fp16 rounding of the
+// operands (std `sigma` on the squared distance, estimated by the probe). A row whose runner-up lies within
+// `margin` (>= 8 sigma) of the approximate minimum is re-evaluated: the candidates inside the margin get their exact
+// float64-accumulated squared distance straight from the float32 descriptors and the first exact minimum wins.
+// Rows outside the margin already have the reference's argmin. 3x fewer tensor-core FLOPs than (A).
+struct GramRefinePolicy {
+  using Cfg = GemmCfg<64, 1>;
+  using Params = GramParams;
+  static constexpr bool kPromote = false;
+  static constexpr int kEpiWarps = 8;
+  static constexpr uint64_t kHintA = kEvictNormal;
+  static constexpr uint64_t kHintB = kEvictNormal;
+
+  static __device__ __forceinline__ bool enabled(const Params& p) {
+    return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
+  }
+  static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
+    return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
+  }
+  static __device__ __forceinline__ TileCoord tile(const Params& p, int cta, int ncta, int i) {
+    const int2 t = __ldg(p.tiles + cta + i * ncta);
+    TileCoord tc;
+    tc.mt = t.x;
+    tc.nt = t.y;
+    return tc;
+  }
+
+  struct Epilogue {
+    const Params& p;
+    const int quarter, half, lane;
+    float margin;
+    __device__ Epilogue(const Params& p_, int quarter_, int half_, int lane_, void*)
+        : p(p_), quarter(quarter_), half(half_), lane(lane_) {
+      margin = p.ctl ? p.ctl->margin : 0.0f;
+    }
+
+    int fa;
+    bool fa_ok;
+    double pa;
+    int bj[4];          // approximate argmin of my row for each of this warp's 4 chunks
+    uint32_t mk[4];     // candidate mask when the row needs refinement, else 0
+    __device__ __forceinline__ void begin_tile(TileCoord tc) {
+      fa = tc.mt * kFramesPerMTile + quarter;
+      fa_ok = fa < p.N;
+      pa = fa_ok ? p.pw[fa * kFrameRows + lane] : 0.0;
+    }
+
+    __device__ __forceinline__ bool chunk_active(int fb) const {
+      return fa_ok && fb < p.N && fa != fb && (p.full || fa < fb);
+    }
+
+    template <int SLOT>
+    __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
+      const int fb = tc.nt * kFramesPerNTile + c;
+      bj[SLOT] = 0;
+      mk[SLOT] = 0;
+      if (!chunk_active(fb)) return;  // warp-uniform
+      const float my_nb = p.sqn[fb * kFrameRows + lane];
+      float d[32];
+      float best = INFINITY;
+      int b = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float nb = __shfl_sync(0xffffffffu, my_nb, j);
+        d[j] = fmaf(-2.0f, v[j], nb);
+        if (d[j] < best) {
+          best = d[j];
+          b = j;
+        }
+      }
+      uint32_t m = 0;
+      const float lim = best + margin;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (d[j] <= lim) m |= 1u << j;
+      bj[SLOT] = b;
+      mk[SLOT] = (lane < p.P && (m & (m - 1)) != 0) ? m : 0u;  // more than one candidate inside the margin
+    }
+    __device__ __forceinline__ void end_tile(TileCoord) {}
+
+    template <int SLOT>
+    __device__ __forceinline__ void finish_chunk(TileCoord tc) {
+      const int fb = tc.nt * kFramesPerNTile + half * 4 + SLOT;
+      if (fa_ok && fb < p.N && fa == fb) {
+        if (lane == 0) p.S[static_cast<int64_t>(fa) * p.N + fa] = -1.0f;
+        return;
+      }
+      if (!chunk_active(fb)) return;
+      uint32_t fl = __ballot_sync(0xffffffffu, mk[SLOT] != 0);
+      if (fl) {
+        if (lane == 0 && p.ctl) atomicAdd(&p.ctl->flagged_rows, static_cast<unsigned long long>(__popc(fl)));
+        const float* abase = p.desc + static_cast<int64_t>(fa) * p.P * p.D;
+        const float* bbase = p.desc + static_cast<int64_t>(fb) * p.P * p.D;
+        while (fl) {
+          const int L = __ffs(fl) - 1;
+          fl &= fl - 1;
+          uint32_t m = __shfl_sync(0xffffffffu, mk[SLOT], L);
+          if (lane == 0 && p.ctl) atomicAdd(&p.ctl->refined_cands, static_cast<unsigned long long>(__popc(m)));
+          const float* arow = abase + static_cast<int64_t>(L) * p.D;
+          double best = INFINITY;
+          int bx = 0;
+          while (m) {  // ascending j + strict '<'  ->  first exact minimum, like np.argmin
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const double dd = exact_d2(arow, bbase + static_cast<int64_t>(j) * p.D, p.D, lane);
+            if (dd < best) {
+              best = dd;
+              bx = j;
+            }
+          }
+          if (lane == L) bj[SLOT] = bx;
+        }
+      }
+      pair_score(p, fa, fb, lane, pa, bj[SLOT]);
+    }
+
+    // runs after the accumulator went back to the MMA warp: refinement + scores never stall the tensor pipe
+    __device__ __forceinline__ void post_tile(TileCoord tc) {
+      finish_chunk<0>(tc);
+      finish_chunk<1>(tc);
+      finish_chunk<2>(tc);
+      finish_chunk<3>(tc);
+    }
+    __device__ __forceinline__ void finish() {}
+  };
+};
+
+// ---- probe: estimate the single-product error and the share of rows it would leave ambiguous
+constexpr int kProbeSamples = 2048;
+struct ProbeAccum {
+  double sum_err2;        // sum over sampled (row, candidate) of (approximate - exact squared distance)^2
+  unsigned long long n_err;
+  unsigned long long max_row_bits;
+};
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+// one warp per sample: a random row k of frame fa against all P rows of a random other frame fb
+__global__ void __launch_bounds__(256)
+gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, ProbeAccum* acc, float* gaps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= kProbeSamples) return;
+  const uint32_t h = hash_u32(0x9e3779b9u * (warp + 1));
+  const int fa = h % N;
+  int fb = hash_u32(h) % N;
+  if (fb == fa) fb = (fb + 1) % N;
+  const int k = hash_u32(h ^ 0x5bd1e995u) % P;
+  const float* a = desc + (static_cast<int64_t>(fa) * P + k) * D;
+  double row_err2 = 0.0;
+  double d1 = INFINITY, d2 = INFINITY;
+  for (int j = 0; j < P; ++j) {
+    const float* b = desc + (static_cast<int64_t>(fb) * P + j) * D;
+    double g = 0.0, gr = 0.0, nb = 0.0;
+    for (int c = lane; c < D; c += 32) {
+      const float x = a[c], y = b[c];
+      g = fma(static_cast<double>(x), static_cast<double>(y), g);
+      gr = fma(static_cast<double>(__half2float(__float2half_rn(x))), static_cast<double>(__half2float(__float2half_rn(y))), gr);
+      nb = fma(static_cast<double>(y), static_cast<double>(y), nb);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, off);
+      gr += __shfl_xor_sync(0xffffffffu, gr, off);
+      nb += __shfl_xor_sync(0xffffffffu, nb, off);
+    }
+    const double e = 2.0 * (g - gr);  // error of the approximate squared distance n_j - 2 G
+    row_err2 += e * e;
+    const double dist = nb - 2.0 * g;
+    if (dist < d1) {
+      d2 = d1;
+      d1 = dist;
+    } else if (dist < d2) {
+      d2 = dist;
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&acc->sum_err2, row_err2);
+    atomicAdd(&acc->n_err, static_cast<unsigned long long>(P));
+    const double mean_row = row_err2 / P;
+    atomicMax(&acc->max_row_bits, static_cast<unsigned long long>(__double_as_longlong(mean_row)));  // >= 0: bit order = value order
+    gaps[warp] = static_cast<float>(d2 - d1);
+  }
+}
+__global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* gaps, const float* sqn, int rows_pad,
+                                           int P, float max_flag_frac, int force, GramControl* ctl) {
+  __shared__ int s_cnt;
+  __shared__ float s_nmax;
+  if (threadIdx.x == 0) {
+    s_cnt = 0;
+    s_nmax = 0.0f;
+  }
+  __syncthreads();
+  const double rms = sqrt(acc->sum_err2 / static_cast<double>(acc->n_err > 0 ? acc->n_err : 1));
+  const double rms_max = sqrt(__longlong_as_double(static_cast<long long>(acc->max_row_bits)));
+  float nmax = 0.0f;
+  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x)
+    if ((r % kFrameRows) < P) nmax = fmaxf(nmax, sqn[r]);
+  atomicMax(reinterpret_cast<int*>(&s_nmax), __float_as_int(nmax));  // non-negative floats order like ints
+  __syncthreads();
+  // >= 8 sigma of the operand-rounding error (global and worst sampled row) plus an allowance for the tensor core's
+  // truncating fp32 accumulation (differential part ~1e-6 of the largest Gram entry)
+  const float margin = static_cast<float>(fmax(8.0 * rms, 4.0 * rms_max)) + 4e-6f * s_nmax;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < kProbeSamples; i += blockDim.x) cnt += gaps[i] < margin ? 1 : 0;
+  atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float frac = static_cast<float>(s_cnt) / kProbeSamples;
+    ctl->margin = margin;
+    ctl->sigma = static_cast<float>(rms);
+    ctl->flagged_frac = frac;
+    ctl->use_refine = force >= 0 ? force : (frac <= max_flag_frac ? 1 : 0);
+    ctl->flagged_rows = 0;
+    ctl->refined_cands = 0;
+  }
+}
 
 // Work list: super-blocks of kMGroup M tiles; inside a super-block N tile outermost so the ~148 concurrently
 // running tiles touch kMGroup A row-blocks and ~148/kMGroup B row-blocks (fits L2) instead of streaming all of H.
@@ -181,7 +459,7 @@ static void build_tile_list(int N, int full, std::vector<int2>& out) {
 }
 
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_part, off_w, off_sqn, off_pw, off_tiles, total;
+  size_t off_hi, off_lo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ctl, off_probe, off_gaps, total;
   int ld, rows_pad, max_tiles;
 };
 static SimWorkspace sim_layout(int N, int P, int D) {
@@ -203,6 +481,9 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_sqn = take(sizeof(float) * w.rows_pad);
   w.off_pw = take(sizeof(double) * w.rows_pad);
   w.off_tiles = take(sizeof(int2) * w.max_tiles);
+  w.off_ctl = take(sizeof(GramControl));
+  w.off_probe = take(sizeof(ProbeAccum));
+  w.off_gaps = take(sizeof(float) * kProbeSamples);
   w.total = o;
   (void)P;
   return w;
@@ -234,6 +515,11 @@ using namespace dlc;
 // Developer switch (dlc_debug_set key 1): launch only the Gram/score kernel, reusing the operand planes, statistics
 // and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
 static int g_gram_only = 0;
+// AUTO uses the one-product + refinement kernel only when the probe expects at most this share of rows to need the
+// exact re-evaluation. Measured on B200 (1063 frames): refinement costs ~10 us per 1000 flagged rows per SM because
+// each candidate streams two 10 KB float32 rows; at 2.8 % flagged rows it is slower (6.6 ms) than three products
+// (5.4 ms), at <= 0.4 % it wins (< 2.5 ms).
+static float g_max_flag_frac = 0.004f;
 extern "C" int dlc_sdav_debug_gram_only(int on) {
   g_gram_only = on ? 1 : 0;
   return DLC_OK;
@@ -267,7 +553,8 @@ extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, d
   DLC_CHECK_ARG(P >= 1 && P <= kFrameRows);
   DLC_CHECK_ARG(D >= 1);
   DLC_CHECK_ARG(sigma != 0.0);
-  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2);
+  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2 || precision == DLC_PREC_AUTO ||
+                precision == DLC_PREC_FP16_REFINED);
   DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0);
   const SimWorkspace L = sim_layout(N, P, D);
   if (ws_bytes < L.total)
@@ -309,12 +596,56 @@ extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, d
   p.num_tiles = static_cast<int>(tiles.size());
   p.N = N;
   p.P = P;
+  p.D = D;
+  p.desc = desc_dev;
   p.sqn = sqn;
   p.pw = pw;
   p.a = static_cast<float>(a);
   p.b = static_cast<float>(b);
   p.full = full_asymmetric ? 1 : 0;
   p.S = S_dev;
+  p.ctl = nullptr;
+  p.want_refine = 0;
   if (precision == DLC_PREC_FP16X2) return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
-  return run_gram<GramPolicy<64, 1>>(L, ws, p, s);
+  if (precision == DLC_PREC_FP16) return run_gram<GramPolicy<64, 1>>(L, ws, p, s);
+
+  // DLC_PREC_AUTO / DLC_PREC_FP16_REFINED: probe the single-product error on the data, then launch both kernels; the
+  // device-side control block lets exactly one of them run (no host round trip).
+  GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
+  p.ctl = ctl;
+  if (!g_gram_only) {
+    ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
+    float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
+    DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
+    if (N >= 2) {
+      gram_probe_kernel<<<ceil_div(kProbeSamples, 8), 256, 0, s>>>(desc_dev, N, P, D, acc, gaps);
+    } else {
+      DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
+    }
+    gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, sqn, L.rows_pad, P, g_max_flag_frac,
+                                                 precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
+    DLC_CUDA(cudaGetLastError());
+  }
+  p.want_refine = 1;
+  if (int rc = run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
+  p.want_refine = 0;
+  return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+}
+
+// Diagnostics of the last AUTO / FP16_REFINED call that used this workspace: out_host[0..5] = use_refine, margin,
+// sigma, estimated flagged fraction, flagged rows, refined candidates. Synchronises the stream.
+extern "C" int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream) {
+  DLC_CHECK_ARG(ws_dev && out_host && N >= 1 && P >= 1 && D >= 1);
+  const SimWorkspace L = sim_layout(N, P, D);
+  GramControl c;
+  DLC_CUDA(cudaMemcpyAsync(&c, static_cast<const char*>(ws_dev) + L.off_ctl, sizeof(c), cudaMemcpyDeviceToHost,
+                           as_stream(stream)));
+  DLC_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  out_host[0] = c.use_refine;
+  out_host[1] = c.margin;
+  out_host[2] = c.sigma;
+  out_host[3] = c.flagged_frac;
+  out_host[4] = static_cast<double>(c.flagged_rows);
+  out_host[5] = static_cast<double>(c.refined_cands);
+  return DLC_OK;
 }

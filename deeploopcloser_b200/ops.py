@@ -9,7 +9,8 @@ import torch
 from . import _lib
 from ._cuda import Workspace, ptr, stream_ptr
 
-PRECISIONS = {"fp16": _lib.PREC_FP16, "fp16x2": _lib.PREC_FP16X2, "bf16": _lib.PREC_BF16}
+PRECISIONS = {"fp16": _lib.PREC_FP16, "fp16x2": _lib.PREC_FP16X2, "bf16": _lib.PREC_BF16, "auto": _lib.PREC_AUTO,
+              "fp16r": _lib.PREC_FP16_REFINED}
 METRICS = {"cos": _lib.METRIC_COS, "cosine": _lib.METRIC_COS, "dot": _lib.METRIC_DOT, "l2": _lib.METRIC_L2}
 _DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
@@ -183,6 +184,16 @@ def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, prec
     _lib.call("dlc_sdav_similarity", ptr(desc), N, P, D, float(mu), float(sigma), float(a), float(b), ptr(weights),
               precision_code(precision), int(bool(full_asymmetric)), ptr(out), ws, ws_bytes, stream_ptr())
     return out
+
+
+def sdav_similarity_stats(N, P, D):
+    """Diagnostics of the last auto / fp16r similarity call (synchronises): dict with the probe's decision."""
+    import ctypes
+    out = (ctypes.c_double * 6)()
+    ws, _ = _ws.get(_lib.call("dlc_sdav_similarity_workspace_bytes", N, P, D))
+    _lib.call("dlc_sdav_similarity_stats", N, P, D, ws, ctypes.cast(out, ctypes.c_void_p), stream_ptr())
+    keys = ("use_refine", "margin", "sigma", "flagged_frac_estimate", "flagged_rows", "refined_candidates")
+    return dict(zip(keys, list(out)))
 
 
 def topk_rows(scores, k, largest=True, exclude_band=-1, cand_idx=None):

@@ -7,9 +7,13 @@ from . import ops
 
 class LoopClosurePipeline:
     def __init__(self, dims=(1681, 2500, 2500, 2500, 2500, 2500), precision="fp16x2", patch=41, swap_xy_quirk=True,
-                 mu=0.5, sigma=0.2, a=10.0, b=-10.0):
+                 mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="fp16x2"):
         self.dims = list(dims)
         self.precision = precision
+        # "fp16x2": three-product Gram (default). "auto": a device-side probe picks one fp16 product + exact
+        # refinement of ambiguous rows when very few rows need it (well separated patches), else the three-product
+        # kernel. "fp16r": always refine (most exact, slower when many rows are near-ties).
+        self.sim_precision = sim_precision
         self.patch = patch
         self.swap_xy_quirk = swap_xy_quirk
         self.sim_args = dict(mu=mu, sigma=sigma, a=a, b=b)
@@ -27,7 +31,7 @@ class LoopClosurePipeline:
 
     def match(self, desc, n_frames, k=10, exclude_band=0):
         P = desc.shape[0] // n_frames
-        S = ops.sdav_similarity(desc.view(n_frames, P, -1), precision=self.precision, **self.sim_args)
+        S = ops.sdav_similarity(desc.view(n_frames, P, -1), precision=self.sim_precision, **self.sim_args)
         cand = ops.topk_rows(S, min(k, max(n_frames - 1, 1)), largest=True, exclude_band=exclude_band)
         return S, cand
 

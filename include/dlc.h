@@ -33,6 +33,11 @@ extern "C" {
 #define DLC_PREC_FP16 0   /* one fp16 product                           (~1e-3 on well-scaled weights)          */
 #define DLC_PREC_FP16X2 1 /* fp16 hi/lo split, 3 products, ~22-bit operands (meets 1e-3 on N(0,1) weights too) */
 #define DLC_PREC_BF16 2   /* one bf16 product (matcher databases stored as bf16)                                */
+/* dlc_sdav_similarity only: */
+#define DLC_PREC_AUTO 3         /* probe the data on the device, then FP16_REFINED if few rows need refinement,  */
+                                /* else FP16X2                                                                    */
+#define DLC_PREC_FP16_REFINED 4 /* one fp16 product; rows whose nearest-neighbour choice is ambiguous under the   */
+                                /* fp16 rounding error are re-evaluated exactly (float64-accumulated distances)   */
 
 /* dtypes for untyped buffers */
 #define DLC_F32 0
@@ -137,6 +142,9 @@ size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D);
 int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
                         const double* w_dev, int precision, int full_asymmetric, float* S_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
+/* Diagnostics of the last AUTO / FP16_REFINED call on this workspace: out_host[6] = {use_refine, margin, sigma,
+ * estimated flagged fraction, flagged rows, refined candidates}. Synchronises the stream. */
+int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream);
 /* w = exp(-(mean_rows(desc) - mu)^2 / (2 sigma^2)), float64 [D] (SimilarityCalculator.py:19-27).
  * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 128*D*8). */
 int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, double sigma, double* w_dev,

@@ -176,7 +176,10 @@ def test_similarity_golden(cuda, golden_dir):
     for name in "abc":
         desc = g["desc_" + name].astype(np.float32)
         ref = g["S_" + name]  # produced by the reference's SimilarityCalculator
-        S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=True).cpu().numpy()
+        for precision in ("fp16x2", "fp16r", "auto"):
+            S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=True, precision=precision).cpu().numpy()
+            m = ~np.eye(len(ref), dtype=bool)
+            assert np.max(np.abs(S[m] - ref[m]) / np.maximum(1, np.abs(ref[m]))) <= TOL, precision
         m = ~np.eye(len(ref), dtype=bool)
         err = np.max(np.abs(S[m] - ref[m]) / np.maximum(1, np.abs(ref[m])))
         print("similarity golden", name, err)
@@ -184,15 +187,40 @@ def test_similarity_golden(cuda, golden_dir):
         assert np.all(np.diag(S) == -1)
 
 
+@pytest.mark.parametrize("precision", ["fp16x2", "fp16r", "auto"])
 @pytest.mark.parametrize("n,p,d,full", [(9, 30, 2500, False), (21, 30, 300, True), (2, 5, 64, False), (1, 30, 64, False)])
-def test_similarity_random(cuda, n, p, d, full):
+def test_similarity_random(cuda, n, p, d, full, precision):
     from deeploopcloser_b200 import ops
     rng = np.random.default_rng(n)
     desc = (1.0 / (1.0 + np.exp(-4.0 * rng.standard_normal((n, p, d))))).astype(np.float32)
-    S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=full).cpu().numpy()
+    S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), full_asymmetric=full, precision=precision).cpu().numpy()
+    if precision != "fp16x2":
+        print(precision, ops.sdav_similarity_stats(n, p, d))
     _check_similarity(S, desc, full)
     if not full:
         assert np.array_equal(S, S.T)
+
+
+@pytest.mark.parametrize("precision", ["fp16r", "auto"])
+def test_similarity_refinement_handles_near_ties(cuda, precision):
+    """Frames built so that many rows have two almost equidistant candidates (gap far below the fp16 rounding error of
+    a single-product Gram entry): the refinement must still pick the reference's argmin."""
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(42)
+    n, p, d = 12, 30, 1024
+    desc = rng.uniform(0.05, 0.95, (n, p, d)).astype(np.float32)
+    for f in range(1, n):           # frame f holds near-copies of patches of frame 0, in pairs 1e-4 apart
+        for k in range(0, p, 2):
+            base = desc[0, (k + f) % p]
+            desc[f, k] = base + 3e-3 * rng.standard_normal(d).astype(np.float32)
+            desc[f, k + 1] = desc[f, k] + 2e-5 * rng.standard_normal(d).astype(np.float32)
+    desc = np.clip(desc, 0, 1)
+    S = ops.sdav_similarity(torch.from_numpy(desc).cuda(), precision=precision).cpu().numpy()
+    st = ops.sdav_similarity_stats(n, p, d)
+    print(precision, st)
+    _check_similarity(S, desc, False)
+    if precision == "fp16r":
+        assert st["use_refine"] == 1 and st["flagged_rows"] > 0
 
 
 # ------------------------------------------------------------------------------------------- row top-k
