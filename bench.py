@@ -60,6 +60,9 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML in-process, ~every 5 ms;
+    falls back to polling nvidia-smi when pynvml is unavailable)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
@@ -67,11 +70,38 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.stop_flag = threading.Event()
         self.max_mhz = None
+        self.how = None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-free way: NVML index = visible list entry
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                idx = int(ids[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        self.how = "nvml"
+        while not self.stop_flag.is_set():
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self.stop_flag.wait(0.005)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.how = "nvidia-smi"
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
@@ -84,11 +114,18 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:  # noqa: BLE001
+            self._run_smi()
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_mhz_min": float(np.min(self.samples)) if self.samples else None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": self.how}
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
@@ -204,28 +241,28 @@ def run_ours(args):
         out_s_pin.copy_(outs[-1][0])
         out_i_pin.copy_(outs[-1][1])
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if sampler:
+            sampler.start()          # clocks are sampled during the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if sampler:
+            sampler.stop_flag.set()
+            sampler.join()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_total = timed(step_device, args.steps, args.warmup)
-    if sampler:
-        sampler.stop_flag.set()
-        sampler.join()
+    ms_total = timed(step_device, args.steps, args.warmup, sampler)
     ms_step = ms_total / args.steps
     value = world * N_FRAMES / (ms_step * 1e-3)
 

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "dlc_sdav_similarity_stats": (_i, [_i, _i, _i, _p, _p, _p]),
     "dlc_sdav_weights": (_i, [_p, _i, _i, _i, _d, _d, _p, _p, _sz, _p]),
     "dlc_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "dlc_mean_pool_rows": (_i, [_p, _i, _i, _i, _p, _p]),
     "dlc_db_create": (_i, [C.POINTER(_p), _i, _i64, _i, _i]),
     "dlc_db_destroy": (_i, [_p]),
     "dlc_db_size": (_i64, [_p]),

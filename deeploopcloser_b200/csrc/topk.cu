@@ -6,6 +6,8 @@
 // HBM/L2-bound integer/compare work: one warp per row, k selection passes with warp-shuffle arg-reduction.
 #include <math.h>
 
+#include <algorithm>
+
 #include "topk.h"
 #include "util.h"
 
@@ -122,4 +124,34 @@ extern "C" int dlc_topk_rows(const float* scores_dev, const int64_t* cand_idx_de
   DLC_CHECK_ARG(k >= 1);
   return topk_rows_impl(scores_dev, cand_idx_dev, rows, cols, ld, k, largest, exclude_band, nullptr, 1.0f,
                         out_scores_dev, out_idx_dev, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame-level descriptor for the global matcher: mean over the `group_rows` patch descriptors of a frame
+// ([groups*group_rows, cols] -> [groups, cols]). New definition (north star config 5), flagged in DESIGN.md: the
+// reference never forms a single descriptor per frame. Bytes-bound, coalesced over columns.
+namespace dlc {
+__global__ void __launch_bounds__(256)
+mean_pool_rows_kernel(const float* __restrict__ x, int groups, int group_rows, int cols, float* __restrict__ out) {
+  const int g = blockIdx.y;
+  const float inv = 1.0f / static_cast<float>(group_rows);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
+    const float* p = x + static_cast<int64_t>(g) * group_rows * cols + c;
+    float acc = 0.0f;
+    for (int r = 0; r < group_rows; ++r) acc += p[static_cast<int64_t>(r) * cols];
+    out[static_cast<int64_t>(g) * cols + c] = acc * inv;
+  }
+  (void)groups;
+}
+}  // namespace dlc
+
+extern "C" int dlc_mean_pool_rows(const float* x_dev, int groups, int group_rows, int cols, float* out_dev,
+                                  void* stream) {
+  DLC_CHECK_ARG(x_dev && out_dev);
+  DLC_CHECK_ARG(groups >= 0 && groups <= 65535 && group_rows >= 1 && cols >= 1);
+  if (groups == 0) return DLC_OK;
+  dim3 grid(std::min(ceil_div(cols, 256), 16), groups);
+  mean_pool_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(x_dev, groups, group_rows, cols, out_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
 }

@@ -207,6 +207,16 @@ def topk_rows(scores, k, largest=True, exclude_band=-1, cand_idx=None):
     return o_s, o_i
 
 
+def mean_pool_rows(x, group_rows):
+    """[groups*group_rows, cols] float32 -> [groups, cols] (frame-level descriptor = mean of its patch descriptors)."""
+    _check_cuda(x)
+    rows, cols = x.shape
+    groups = rows // group_rows
+    out = torch.empty((groups, cols), dtype=torch.float32, device=x.device)
+    _lib.call("dlc_mean_pool_rows", ptr(x), groups, group_rows, cols, ptr(out), stream_ptr())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ Hamming
 def hamming_matrix(desc, signed_bin_quirk=True):
     """desc int8 [N,M] -> int32 [N,N]."""

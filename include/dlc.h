@@ -161,6 +161,11 @@ int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, doub
 int dlc_topk_rows(const float* scores_dev, const int64_t* cand_idx_dev, int rows, int cols, int ld, int k,
                   int largest, int exclude_band, float* out_scores_dev, int64_t* out_idx_dev, void* stream);
 
+/* Frame-level descriptor for the global matcher: mean over the `group_rows` patch descriptors of each frame,
+ * x_dev float32 [groups*group_rows, cols] -> out_dev float32 [groups, cols]. New definition (the reference never
+ * forms one descriptor per frame); the database L2-normalises it on append when the metric is cosine. */
+int dlc_mean_pool_rows(const float* x_dev, int groups, int group_rows, int cols, float* out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Keyframe database + global matcher (cosine / dot / L2 similarity matrix with fused per-row top-k). New capability.
  * ------------------------------------------------------------------------------------------------------------ */

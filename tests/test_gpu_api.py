@@ -146,3 +146,29 @@ def test_cnnvtl_transform(cuda, hw):
     # and the Hamming matrix of the GPU descriptors is exact for those descriptors
     from src.cnn_vtl.similarity.DistanceCalculator import DistanceCalculator
     assert np.array_equal(DistanceCalculator.distance_matrix(got), o_ham.distance_matrix(got))
+
+
+def test_streaming_loop_closer(cuda):
+    """Config-5 style streaming on one GPU: frames inserted by one step are found again (top-1, cosine ~ 1) when the
+    same frames come back; the frame descriptor equals the oracle's mean of patch descriptors."""
+    import torch
+    from deeploopcloser_b200.streaming import StreamingLoopCloser
+    from oracle import patches as o_patch
+    dims = [1681, 96, 64]
+    ws, bs = o_sda.make_weights(dims, seed=2, scale="normal")   # N(0,1): saturating, frame descriptors well separated
+    sl = StreamingLoopCloser(capacity_per_rank=64, dims=dims, k=3)
+    sl.set_weights(ws, bs)
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (8, 120, 160), dtype=np.uint8)
+    xy = np.stack([rng.uniform(0, 160, (8, 30)), rng.uniform(0, 120, (8, 30))], -1).astype(np.float32)
+    f_d, x_d = torch.from_numpy(frames).cuda(), torch.from_numpy(xy).cuda()
+    q = sl.frame_descriptors(f_d, x_d).cpu().numpy()
+    x = np.concatenate([o_patch.extract_patches(frames[i], xy[i]) for i in range(8)])
+    want = o_sda.sda_forward(x, ws, bs).reshape(8, 30, -1).mean(1)
+    assert rel_err(q, want) <= TOL
+    s0, i0 = sl.step(f_d, x_d)                       # empty database: all padding
+    assert np.all(i0.cpu().numpy() == -1)
+    s1, i1 = sl.step(f_d, x_d)                       # same frames again: each finds its own earlier copy
+    assert np.array_equal(i1[:, 0].cpu().numpy(), np.arange(8))
+    assert np.all(np.abs(s1[:, 0].cpu().numpy() - 1.0) < 2e-3)
+    assert len(sl.db.local) == 16
