@@ -84,9 +84,9 @@ extern "C" size_t dlc_hamming_workspace_bytes(int N, int M) {
 
 extern "C" int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quirk, int32_t* D_dev,
                                   void* ws_dev, size_t ws_bytes, void* stream) {
-  DLC_CHECK_ARG(desc_dev && D_dev);
   DLC_CHECK_ARG(N >= 0 && M > 0);
   if (N == 0) return DLC_OK;
+  DLC_CHECK_ARG(desc_dev && D_dev);
   if (!ws_dev || ws_bytes < dlc_hamming_workspace_bytes(N, M) || (reinterpret_cast<uintptr_t>(ws_dev) & 3))
     return fail(DLC_ENOMEM, "dlc_hamming_matrix: 4-byte aligned workspace of %zu bytes needed, %zu given",
                 dlc_hamming_workspace_bytes(N, M), ws_bytes);

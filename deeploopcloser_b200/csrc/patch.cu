@@ -99,8 +99,8 @@ patch_gather_f64_kernel(const uint8_t* __restrict__ img, int H, int W, const flo
 using namespace dlc;
 
 static int check_patch_args(const void* img, int B, int H, int W, const void* xy, int P, int patch) {
-  DLC_CHECK_ARG(img && xy);
   DLC_CHECK_ARG(B >= 0 && P > 0);
+  DLC_CHECK_ARG((img && xy) || B == 0);
   DLC_CHECK_ARG(patch > 0 && (patch & 1) == 1);  // CvInputParser.py:64-65: patch size must be odd
   DLC_CHECK_ARG(H >= patch && W >= patch);
   return DLC_OK;
@@ -109,7 +109,7 @@ static int check_patch_args(const void* img, int B, int H, int W, const void* xy
 extern "C" int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
                                 int swap_xy_quirk, void* out_hi_dev, void* out_lo_dev, int ld, void* stream) {
   if (int rc = check_patch_args(img_dev, B, H, W, xy_dev, P, patch)) return rc;
-  DLC_CHECK_ARG(out_hi_dev);
+  DLC_CHECK_ARG(out_hi_dev || B == 0);
   DLC_CHECK_ARG(ld >= patch * patch && ld % 8 == 0);
   if (B == 0) return DLC_OK;
   patch_gather_planes_kernel<<<B * P, 128, 0, as_stream(stream)>>>(img_dev, H, W, xy_dev, P, patch, swap_xy_quirk,
@@ -122,7 +122,7 @@ extern "C" int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, con
 extern "C" int dlc_patch_gather_f64(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P,
                                     int patch, int swap_xy_quirk, double* out_dev, void* stream) {
   if (int rc = check_patch_args(img_dev, B, H, W, xy_dev, P, patch)) return rc;
-  DLC_CHECK_ARG(out_dev);
+  DLC_CHECK_ARG(out_dev || B == 0);
   if (B == 0) return DLC_OK;
   patch_gather_f64_kernel<<<B * P, 128, 0, as_stream(stream)>>>(img_dev, H, W, xy_dev, P, patch, swap_xy_quirk,
                                                                out_dev);

@@ -296,7 +296,7 @@ extern "C" int dlc_debug_set(int key, int value) {
 
 extern "C" int dlc_split_planes(const void* src_dev, int src_dtype, int rows, int cols, int src_ld, int group_in,
                                 int group_out, void* hi_dev, void* lo_dev, int ld, void* stream) {
-  DLC_CHECK_ARG(src_dev && hi_dev);
+  DLC_CHECK_ARG((src_dev && hi_dev) || rows == 0);
   DLC_CHECK_ARG(src_dtype == DLC_F32 || src_dtype == DLC_F64);
   DLC_CHECK_ARG(rows >= 0 && cols > 0 && src_ld >= cols);
   DLC_CHECK_ARG(group_in >= 1 && group_out >= group_in);

@@ -353,3 +353,85 @@ def test_match_empty_and_errors(cuda):
         db.append(torch.randn(1, 64, device="cuda"))  # over capacity
     with pytest.raises(_lib.DlcError):
         db.topk(torch.zeros((3, 64), device="cuda"), 33)  # k > 32
+
+
+# ------------------------------------------------------------------------------------------- edge cases
+def test_gemm_bf16_planes_and_odd_tiles(cuda):
+    """bf16 operand planes (DLC_PREC_BF16) and accumulator widths other than 256 (96 / 192 / 160 columns)."""
+    from deeploopcloser_b200 import _lib, ops
+    from deeploopcloser_b200._cuda import ptr, stream_ptr
+    rng = np.random.default_rng(1)
+    for m, k, n, n_pad in ((200, 130, 96, 96), (77, 300, 384, 384), (129, 64, 150, 160)):
+        a = rng.standard_normal((m, k)).astype(np.float32)
+        b = rng.standard_normal((k, n)).astype(np.float32)
+        ld = _lib.plane_ld(k)
+        A = torch.zeros((m, ld), dtype=torch.bfloat16, device="cuda")
+        A[:, :k] = torch.from_numpy(a).cuda().to(torch.bfloat16)
+        Bt = torch.zeros((n_pad, ld), dtype=torch.bfloat16, device="cuda")
+        Bt[:n, :k] = torch.from_numpy(b.T.copy()).cuda().to(torch.bfloat16)
+        out = torch.empty((m, n), dtype=torch.float32, device="cuda")
+        _lib.call("dlc_gemm_planes", ptr(A), None, ptr(Bt), None, m, n, n_pad, ld, None, _lib.ACT_RELU, _lib.PREC_BF16,
+                  ptr(out), n, None, None, 0, stream_ptr())
+        ref = np.maximum(A[:, :k].double().cpu().numpy() @ Bt[:n, :k].double().cpu().numpy().T, 0)
+        assert norm_err(out.cpu().numpy(), ref) < 1e-5, (m, k, n)
+        # fp16x2 on the same shapes through the generic wrapper
+        got = ops.matmul(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), act="relu").cpu().numpy()
+        assert norm_err(got, np.maximum(a.astype(np.float64) @ b.astype(np.float64), 0)) < 3e-6
+
+
+def test_empty_and_degenerate_inputs(cuda):
+    from deeploopcloser_b200 import _lib, ops
+    # zero patches / zero rows are accepted and produce empty outputs
+    img = torch.zeros((0, 64, 64), dtype=torch.uint8, device="cuda")
+    xy = torch.zeros((0, 30, 2), dtype=torch.float32, device="cuda")
+    hi, lo = ops.patch_gather(img, xy)
+    assert hi.shape == (0, 1728)
+    hi, lo = ops.split_planes(torch.zeros((0, 10), dtype=torch.float64, device="cuda"))
+    assert hi.shape == (0, 64)
+    assert ops.hamming_matrix(torch.zeros((0, 8), dtype=torch.int8, device="cuda")).shape == (0, 0)
+    # image smaller than the patch, even patch size, k = 0: loud errors, not silent garbage
+    with pytest.raises(_lib.DlcError):
+        ops.patch_gather(torch.zeros((1, 40, 64), dtype=torch.uint8, device="cuda"),
+                         torch.zeros((1, 3, 2), dtype=torch.float32, device="cuda"))
+    with pytest.raises(_lib.DlcError):
+        ops.patch_gather(torch.zeros((1, 64, 64), dtype=torch.uint8, device="cuda"),
+                         torch.zeros((1, 3, 2), dtype=torch.float32, device="cuda"), patch=40)
+    with pytest.raises(_lib.DlcError):
+        ops.topk_rows(torch.zeros((2, 4), device="cuda"), 0)
+    with pytest.raises(_lib.DlcError):
+        ops.sdav_similarity(torch.zeros((2, 33, 8), device="cuda"))      # more than 32 patch rows per frame
+    enc = ops.SdaEncoder([64, 32], "fp16x2")
+    with pytest.raises(_lib.DlcError):
+        enc.encode(torch.zeros((4, 64), device="cuda"))                   # weights never set
+
+
+def test_similarity_identical_patches_give_inf(cuda):
+    """log(0): a matched pair of identical patches makes the reference score +inf (SimilarityCalculator.py:48 with
+    b < 0); the kernel must reproduce that, not a NaN or a large finite number."""
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(3)
+    desc = rng.uniform(0.1, 0.9, (3, 30, 128)).astype(np.float32)
+    desc[1, 4] = desc[0, 7]                      # frame 0 patch 7 has an exact twin in frame 1
+    S = ops.sdav_similarity(torch.from_numpy(desc).cuda()).cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = o_sim.similarity_matrix(desc.astype(np.float64))
+    assert np.isposinf(ref[0, 1]) and np.isposinf(S[0, 1]) and np.isposinf(S[1, 0])
+    assert np.isfinite(S[0, 2]) and abs(S[0, 2] - ref[0, 2]) <= TOL * abs(ref[0, 2])
+
+
+def test_match_threshold_l2(cuda):
+    from deeploopcloser_b200.matcher import KeyframeDatabase
+    rng = np.random.default_rng(2)
+    N, D, B = 800, 64, 9
+    rows = (rng.standard_normal((N, D)) * 0.25).astype(np.float32)
+    q = rows[:B] + 0.01
+    db = KeyframeDatabase(D, N, "l2", "fp16")
+    db.append(torch.from_numpy(rows).cuda())
+    counts, scores, idx = db.threshold(torch.from_numpy(q).cuda(), 0.5, 8)
+    st = torch.from_numpy(rows).half().double().numpy()
+    ref = o_match.score_matrix(torch.from_numpy(q).half().double().numpy(), st, o_match.L2)
+    rc, rs, ri = o_match.threshold(ref, 0.5, 8, smaller_is_better=True)
+    if np.abs(ref - 0.5).min() > 1e-3:
+        assert np.array_equal(counts.cpu().numpy(), rc) and np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(idx[:, 0].cpu().numpy(), np.arange(B))
