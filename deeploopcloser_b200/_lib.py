@@ -63,6 +63,13 @@ PROTOTYPES = {
     "dlc_match_threshold": (_i, [_p, _p, _i, _f, _i, _i64, _p, _p, _p, _p, _sz, _p]),
     "dlc_hamming_workspace_bytes": (_sz, [_i, _i]),
     "dlc_hamming_matrix": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
+    "dlc_cnnvtl_create": (_i, [C.POINTER(_p), _i, _i, _i]),
+    "dlc_cnnvtl_destroy": (_i, [_p]),
+    "dlc_cnnvtl_set_conv": (_i, [_p, _i, _p, _p]),
+    "dlc_cnnvtl_descriptor_len": (_i64, [_p]),
+    "dlc_cnnvtl_set_keep_cols": (_i, [_p, _p, _i]),
+    "dlc_cnnvtl_workspace_bytes": (_sz, [_p, _i]),
+    "dlc_cnnvtl_forward": (_i, [_p, _p, _i, _i, _p, C.POINTER(_p), _p, _sz, _p]),
     "dlc_im2col_planes": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_maxpool_planes": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_cnnvtl_quantise": (_i, [C.POINTER(_p), C.POINTER(_i64), _i, _i, _p, _i, _p, _p, _p]),

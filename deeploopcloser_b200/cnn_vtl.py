@@ -2,9 +2,11 @@
 
 transform(x[N,H,W,3]) -> int8 [N, M]: AlexNet conv1..conv5 (ungrouped, no LRN, conv5 linear, cnn_vtl.py:33-93), all
 five conv outputs flattened + concatenated (:96-106), per-image min/max scaling to 0..255 and int8 cast (:109-116),
-random column sub-sampling fixed per instance (:119-128). On the B200 every convolution is im2col planes + one fused
-tcgen05 GEMM (bias + ReLU in the epilogue, NHWC output = the flattened descriptor segment); pooling, min/max and the
-quantise+gather tail are bytes-bound SIMT kernels. Only the kept columns are ever quantised.
+random column sub-sampling fixed per instance (:119-128). On the B200 every convolution is ONE tcgen05 kernel behind
+a `dlc_cnnvtl` handle: conv2..conv5 are implicit GEMMs (im2col-mode TMA reads the NHWC activation tap by tap), and
+bias + ReLU, the per-image min/max and the gather of the kept columns are fused into the epilogue, so neither an
+im2col matrix nor the 546,944-wide float descriptor is ever written. `_forward_chunk_explicit` is the
+explicit-im2col formulation built from the library's building blocks, kept as a cross-check.
 
 Differences from the reference, all explicit: weights are an argument (the AlexNet blob is a git-LFS pointer in the
 reference tree) - a dict {name: (W[kh,kw,cin,cout], b[cout])}, a path to a `bvlc_alexnet.npy`-style file, or
@@ -131,8 +133,42 @@ class CnnVtl:
         if self.keep_cols.size and (self.keep_cols.min() < 0 or self.keep_cols.max() >= total):
             raise ValueError("kept columns out of range")
         self._dev = None
+        self._head = None
 
-    # ---- device state: packed weight planes, biases, kept columns
+    # ---- fused path: one dlc_cnnvtl handle per instance
+    def _fused_head(self):
+        if self._head is None:
+            from . import _cuda, ops
+            _cuda.require_cuda()
+            head = ops.CnnVtlHead(self._H, self._W, self.precision)
+            for l, (name, *_r) in enumerate(LAYERS):
+                head.set_conv(l, *self.params[name])
+            if self.keep_cols.size:
+                head.set_keep_cols(self.keep_cols)
+            self._head = head
+        return self._head
+
+    def _forward_chunk(self, x):
+        """x: CUDA tensor [n, H, W, 3] (uint8 / float32 / float64) -> int8 [n, M]."""
+        import torch
+        if x.dtype not in (torch.uint8, torch.float32, torch.float64):
+            x = x.to(torch.float64)
+        head = self._fused_head()
+        if not self.keep_cols.size:
+            return torch.empty((x.shape[0], 0), dtype=torch.int8, device=x.device)
+        return head.forward(x.contiguous())
+
+    def conv_outputs(self, x):
+        """Diagnostics: float32 NHWC outputs of conv1..conv5 for a CUDA batch x (fused path)."""
+        import torch
+        head = self._fused_head()
+        n = x.shape[0]
+        outs = [torch.empty((n, g[2], g[3], L[4]), dtype=torch.float32, device=x.device)
+                for g, L in zip(self._geo, LAYERS)]
+        head.forward(x.contiguous(), layer_outputs=outs, quantise=False)
+        return outs
+
+    # ---- explicit-im2col path (cross-check): packed weight planes, biases, kept columns
     def _device_state(self):
         if self._dev is None:
             import torch
@@ -150,7 +186,7 @@ class CnnVtl:
             self._dev = st
         return self._dev
 
-    def _forward_chunk(self, x):
+    def _forward_chunk_explicit(self, x):
         """x: CUDA tensor [n, H, W, 3] (uint8 / float) -> int8 [n, M]."""
         import torch
 

@@ -1,0 +1,244 @@
+// Bias + activation epilogue policy of the tcgen05 contraction (shared by the SDA encoder layers, the generic
+// dlc_gemm_planes entry point and - with CONV = true - the cnn_vtl convolutions, which add an im2col-mode A operand
+// and the descriptor tail: per-image min/max and the raw values of the kept descriptor columns).
+#pragma once
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "gemm_sm100.cuh"
+#include "util.h"
+
+namespace dlc {
+
+// ------------------------------------------------------------------------------------------------
+// bias + activation epilogue
+// ------------------------------------------------------------------------------------------------
+struct BiasActParams {
+  int n_tile, k_blocks, ab_fmt, kc;
+  int dbg;  // developer switches for kernel experiments: 1 = skip stores, 2 = skip activation math
+  int m_tiles, n_tiles;
+  int M, N;
+  const float* bias;
+  int act;
+  float* out_f32;
+  int out_ld;
+  void* out_hi;
+  void* out_lo;
+  int out_plane_ld;
+  // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
+  int cv_implicit, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
+  // ---- CONV only: descriptor tail. Row m = output pixel (image m / cv_ohw); the layer's flattened NHWC output
+  // occupies columns [seg_word0*32, ...) of the concatenated descriptor (cnn_vtl.py:96-106).
+  int* mm;                    // [images, 2] per-image running min / max as order-preserving ints
+  const uint32_t* keep_bits;  // bit c of word w set = descriptor column 32*w + c is kept (cnn_vtl.py:119-128)
+  const int* keep_rank;       // number of kept columns before word w
+  float* raw;                 // [images, raw_ld] unquantised values of the kept columns
+  int raw_ld;
+  int seg_word0;
+};
+
+// float <-> int whose signed order equals the float order (for atomicMin / atomicMax on floats)
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat16 x = __float2bfloat16_rn(a), y = __float2bfloat16_rn(b);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(x)) | (static_cast<uint32_t>(__bfloat16_as_ushort(y)) << 16);
+}
+
+template <int BK, int NPROD, bool CONV = false>
+struct BiasActPolicy {
+  using Cfg = GemmCfg<BK, NPROD>;
+  using Params = BiasActParams;
+  static constexpr bool kIm2colA = CONV;
+  static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
+  static constexpr int kEpiWarps = 4;
+  static __device__ __forceinline__ bool enabled(const Params&) { return true; }
+  static constexpr uint64_t kHintA = kEvictNormal;
+  static constexpr uint64_t kHintB = kEvictLast;  // weights are re-read by every M tile: keep them in L2
+
+  static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
+    const int total = p.m_tiles * p.n_tiles;
+    return cta < total ? (total - cta + ncta - 1) / ncta : 0;
+  }
+  // N fastest: the CTAs running concurrently share one A row-block (read from HBM once, then L2).
+  static __device__ __forceinline__ TileCoord tile(const Params& p, int cta, int ncta, int i) {
+    const int t = cta + i * ncta;
+    TileCoord tc;
+    tc.mt = t / p.n_tiles;
+    tc.nt = t - tc.mt * p.n_tiles;
+    return tc;
+  }
+
+  struct Epilogue {
+    const Params& p;
+    const int quarter, lane;
+    __device__ Epilogue(const Params& p_, int quarter_, int, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
+
+    int row;
+    bool row_ok;
+    // CONV: image / pixel of this thread's row and the running min / max of the values it produced in this tile
+    int img, pix;
+    float t_lo, t_hi;
+    __device__ __forceinline__ void begin_tile(TileCoord tc) {
+      row = tc.mt * kTileM + quarter * 32 + lane;
+      row_ok = row < p.M;
+      if (CONV) {
+        img = row / p.cv_ohw;
+        pix = row - img * p.cv_ohw;
+        t_lo = INFINITY;
+        t_hi = -INFINITY;
+      }
+    }
+    __device__ __forceinline__ void end_tile(TileCoord) {
+      if (CONV) {
+        if (!p.mm) return;
+        // rows of a warp are consecutive pixels: usually one image -> one atomic pair per warp
+        const int img0 = __shfl_sync(0xffffffffu, img, 0);
+        const bool same = __all_sync(0xffffffffu, !row_ok || img == img0);
+        if (same) {
+          float lo = t_lo, hi = t_hi;  // rows beyond M still hold +inf / -inf
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+          }
+          if (lane == 0 && lo <= hi) {
+            atomicMin(p.mm + 2 * img0, float_to_ordered(lo));
+            atomicMax(p.mm + 2 * img0 + 1, float_to_ordered(hi));
+          }
+        } else if (row_ok && t_lo <= t_hi) {
+          atomicMin(p.mm + 2 * img, float_to_ordered(t_lo));
+          atomicMax(p.mm + 2 * img + 1, float_to_ordered(t_hi));
+        }
+      }
+    }
+    __device__ __forceinline__ void post_tile(TileCoord) {}
+
+    // bias + activation on one 32-column chunk. Branch-free per element: the activation switch and the
+    // "chunk fully inside N" test are hoisted out of the element loop; sigmoid uses the SFU approximations
+    // (ex2.approx / rcp.approx, ~1e-6 relative - three orders below the 1e-3 descriptor tolerance).
+    template <int ACT>
+    __device__ __forceinline__ void activate(float (&v)[32], float (&h)[32], int col0) {
+      float b[32];
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);  // bias has n_pad entries, 128-B aligned rows
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(b4 + q);
+          b[4 * q] = t.x;
+          b[4 * q + 1] = t.y;
+          b[4 * q + 2] = t.z;
+          b[4 * q + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) b[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float z = v[j] + b[j];
+        if (ACT == DLC_ACT_SIGMOID) z = __fdividef(1.0f, 1.0f + __expf(-z));
+        else if (ACT == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
+        h[j] = z;
+      }
+      if (col0 + 32 > p.N) {  // chunk straddles / lies beyond the valid width: zero the padding columns
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j >= p.N) h[j] = 0.0f;
+      }
+    }
+
+    template <int SLOT>
+    __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
+      const int col0 = tc.nt * p.n_tile + c * 32;
+      float h[32];
+      if (p.dbg & 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = v[j];
+      } else if (p.act == DLC_ACT_SIGMOID) activate<DLC_ACT_SIGMOID>(v, h, col0);
+      else if (p.act == DLC_ACT_RELU) activate<DLC_ACT_RELU>(v, h, col0);
+      else activate<DLC_ACT_NONE>(v, h, col0);
+      if (!row_ok) return;
+      if (CONV) {
+        if (p.mm) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            t_lo = fminf(t_lo, h[j]);
+            t_hi = fmaxf(t_hi, h[j]);
+          }
+        }
+        if (p.keep_bits) {  // N is a multiple of 32 for every conv layer: this chunk is one word of the column mask
+          const int word = p.seg_word0 + pix * (p.N >> 5) + (col0 >> 5);
+          const uint32_t bits = __ldg(p.keep_bits + word);
+          if (bits) {
+            float* dst = p.raw + static_cast<int64_t>(img) * p.raw_ld + __ldg(p.keep_rank + word);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((bits >> j) & 1u) dst[__popc(bits & ((1u << j) - 1u))] = h[j];
+          }
+        }
+      }
+      if (p.dbg & 1) {  // keep the values alive without the global stores
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += h[j];
+        if (acc == 123456.789f && p.out_f32) p.out_f32[0] = acc;
+        return;
+      }
+      if (p.out_f32) {
+        float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
+        const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (vec_ok && col0 + j + 3 < p.N) {
+            *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col0 + j + q < p.N) o[j + q] = h[j + q];
+          }
+        }
+      }
+      if (p.out_hi && col0 < p.out_plane_ld) {
+        const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
+        if (p.ab_fmt == 1) {  // bf16 planes (single plane)
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf2(h[2 * j], h[2 * j + 1]);
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        } else {
+          uint32_t wh[16], wl[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __half h0, l0, h1, l1;
+            split_f32(h[2 * j], h0, l0);
+            split_f32(h[2 * j + 1], h1, l1);
+            wh[j] = pack_h2(h0, h1);
+            wl[j] = pack_h2(l0, l1);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
+          if (p.out_lo) {
+            uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_lo) + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+          }
+        }
+      }
+    }
+    __device__ __forceinline__ void finish() {}
+  };
+};
+
+
+}  // namespace dlc

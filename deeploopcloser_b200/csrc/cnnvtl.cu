@@ -1,17 +1,26 @@
-// a7: building blocks of the cnn_vtl AlexNet conv head (src/cnn_vtl/network/cnn_vtl.py:28-128).
-// Convolutions run as im2col operand planes + the tcgen05 contraction of planes.cu (bias + ReLU fused, NHWC in and
-// out, so the GEMM output [N*OH*OW, Cout] IS the NHWC activation and also the flattened per-image descriptor
-// segment of cnn_vtl.py:96-106). Max-pooling and the min/max -> int8 -> column-gather tail (cnn_vtl.py:109-128) are
-// bytes-bound SIMT kernels; the tail touches the full 546,944-wide descriptor once (for min/max) and then only the
-// ~2,243 kept columns.
+// a7: the cnn_vtl AlexNet conv head (src/cnn_vtl/network/cnn_vtl.py:28-128).
+//
+// Fused path (dlc_cnnvtl_* handle): every convolution is ONE tcgen05 kernel. conv2..conv5 (stride 1) are implicit
+// GEMMs - the A operand is the NHWC activation itself, read tap by tap with im2col-mode TMA, so no im2col matrix
+// ever exists in memory; conv1 (11x11 / 4 on 3 channels, 6-byte pixels: below TMA's 16-byte granule) reads a patch
+// matrix written straight from the uint8 image. Bias + ReLU, the re-split of the activation into the next layer's
+// fp16 planes, the per-image min/max of cnn_vtl.py:109-111 and the gather of the ~2,243 kept descriptor columns
+// (:119-128) all happen in the GEMM epilogue: the 546,944-wide float descriptor of :96-106 is never materialised.
+//
+// Building blocks (dlc_im2col_planes / dlc_maxpool_planes / dlc_cnnvtl_quantise) are the explicit-im2col
+// formulation of the same head; the GPU tests use them to cross-check the implicit path.
 #include <math.h>
 
 #include <algorithm>
 
-#include "ptx.cuh"
+#include <vector>
+
+#include "bias_act.cuh"
 #include "util.h"
 
 namespace dlc {
+
+extern int g_promote_k;  // planes.cu: K elements accumulated in TMEM before promotion to fp32 registers
 
 // x planes [N*H*W, ld_in] -> im2col planes [N*OH*OW, ld]; column = (kh*KW + kw)*C + c; 8 columns per thread.
 __global__ void __launch_bounds__(256)
@@ -114,12 +123,6 @@ struct SegTable {
   int n_seg;
 };
 
-__device__ __forceinline__ int float_to_ordered(float f) {
-  const int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
-
 __global__ void minmax_init_kernel(int N, int* mm) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < N) {
@@ -167,6 +170,128 @@ __global__ void quantise_gather_kernel(SegTable st, int N, const int64_t* __rest
   int q = 0;
   if (scaled == scaled && fabs(scaled) < 2147483648.0) q = static_cast<int>(scaled);  // trunc toward zero
   else q = static_cast<int>(0x80000000u);                                              // cvttsd2si "indefinite"
+  out[t] = static_cast<int8_t>(q & 0xff);
+}
+
+// ---------------- fused path kernels ----------------
+template <typename T>
+__device__ __forceinline__ void split_any(T x, __half& hi, __half& lo) {
+  if (sizeof(T) == 8) split_f64(static_cast<double>(x), hi, lo);
+  else split_f32(static_cast<float>(x), hi, lo);
+}
+
+// conv1 patch matrix straight from the NHWC image (C = 3): row = output pixel, column = kh*(KW*3) + kw*3 + c, i.e.
+// each filter row kh is a run of KW*3 contiguous source elements. 8 columns (one 16-byte store) per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv1_patch_kernel(const T* __restrict__ x, int N, int H, int W, int KH, int KW, int stride, int OH, int OW,
+                   __half* __restrict__ o_hi, __half* __restrict__ o_lo, int ld) {
+  const int chunks = ld >> 3;
+  const int run = KW * 3;
+  const int K = KH * run;
+  const int64_t total = static_cast<int64_t>(N) * OH * OW * chunks;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(t % chunks);
+    const int64_t orow = t / chunks;
+    const int ow = static_cast<int>(orow % OW);
+    const int oh = static_cast<int>((orow / OW) % OH);
+    const int n = static_cast<int>(orow / (static_cast<int64_t>(OW) * OH));
+    const T* src0 = x + ((static_cast<int64_t>(n) * H + oh * stride) * W + ow * stride) * 3;
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+    int col = ch << 3;
+    int kh = col / run;
+    int r = col - kh * run;
+#pragma unroll
+    for (int q = 0; q < 8; ++q, ++col) {
+      h[q] = __float2half_rn(0.f);
+      l[q] = __float2half_rn(0.f);
+      if (col < K) split_any(src0[static_cast<int64_t>(kh) * W * 3 + r], h[q], l[q]);
+      if (++r == run) {
+        r = 0;
+        ++kh;
+      }
+    }
+    const int64_t o = orow * ld + (ch << 3);
+    *reinterpret_cast<uint4*>(o_hi + o) = *reinterpret_cast<const uint4*>(h);
+    if (o_lo) *reinterpret_cast<uint4*>(o_lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// VALID max-pool on NHWC planes (value = hi + lo) -> planes; 8 channels per thread, only the C valid channels.
+__global__ void __launch_bounds__(256)
+maxpool_planes_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int N, int H, int W, int C,
+                      int ld, int window, int stride, int OH, int OW, __half* __restrict__ o_hi,
+                      __half* __restrict__ o_lo) {
+  const int chunks = C >> 3;
+  const int64_t total = static_cast<int64_t>(N) * OH * OW * chunks;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(t % chunks);
+    const int64_t orow = t / chunks;
+    const int ow = static_cast<int>(orow % OW);
+    const int oh = static_cast<int>((orow / OW) % OH);
+    const int n = static_cast<int>(orow / (static_cast<int64_t>(OW) * OH));
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int dy = 0; dy < window; ++dy)
+      for (int dx = 0; dx < window; ++dx) {
+        const int64_t src = ((static_cast<int64_t>(n) * H + oh * stride + dy) * W + ow * stride + dx) * ld + (ch << 3);
+        const uint4 vh = *reinterpret_cast<const uint4*>(x_hi + src);
+        const __half* ph = reinterpret_cast<const __half*>(&vh);
+        if (x_lo) {
+          const uint4 vl = *reinterpret_cast<const uint4*>(x_lo + src);
+          const __half* pl = reinterpret_cast<const __half*>(&vl);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], __half2float(ph[q]) + __half2float(pl[q]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], __half2float(ph[q]));
+        }
+      }
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) split_f32(m[q], h[q], l[q]);
+    const int64_t o = orow * ld + (ch << 3);
+    *reinterpret_cast<uint4*>(o_hi + o) = *reinterpret_cast<const uint4*>(h);
+    if (o_lo) *reinterpret_cast<uint4*>(o_lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// HWIO float64 filter [KH*KW, Cin, Cout] -> K-major planes [Cout, ld]: column = tap * c_pad + c (c_pad = Cin rounded
+// up to the K block so that a K block never straddles two taps), zeros elsewhere.
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(const double* __restrict__ w, int taps, int cin, int cout, int c_pad, __half* __restrict__ hi,
+                        __half* __restrict__ lo, int ld) {
+  const int64_t total = static_cast<int64_t>(cout) * ld;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(t % cout);  // fastest across threads -> coalesced reads of w
+    const int k = static_cast<int>(t / cout);
+    const int tap = k / c_pad, c = k - tap * c_pad;
+    __half h = __float2half_rn(0.f), l = __float2half_rn(0.f);
+    if (tap < taps && c < cin) split_f64(w[(static_cast<int64_t>(tap) * cin + c) * cout + j], h, l);
+    hi[static_cast<int64_t>(j) * ld + k] = h;
+    if (lo) lo[static_cast<int64_t>(j) * ld + k] = l;
+  }
+}
+
+// int8 quantisation of the gathered kept columns (same arithmetic as quantise_gather_kernel)
+__global__ void quantise_raw_kernel(const float* __restrict__ raw, int N, int M, int raw_ld, const int* __restrict__ mm,
+                                    int8_t* __restrict__ out) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(N) * M) return;
+  const int n = static_cast<int>(t / M), m = static_cast<int>(t % M);
+  const double d = static_cast<double>(raw[static_cast<int64_t>(n) * raw_ld + m]);
+  const double lo = static_cast<double>(ordered_to_float(mm[2 * n]));
+  const double hi = static_cast<double>(ordered_to_float(mm[2 * n + 1]));
+  const double scaled = (d - lo) * (255.0 / (hi - lo));
+  int q = 0;
+  if (scaled == scaled && fabs(scaled) < 2147483648.0) q = static_cast<int>(scaled);
+  else q = static_cast<int>(0x80000000u);
   out[t] = static_cast<int8_t>(q & 0xff);
 }
 
@@ -230,5 +355,377 @@ extern "C" int dlc_cnnvtl_quantise(const float* const* seg_ptrs_host, const int6
   const int64_t total = static_cast<int64_t>(N) * M;
   quantise_gather_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(st, N, keep_cols_dev, M, mm, out_dev);
   DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused conv head behind a handle
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kConvLayers = 5;
+struct ConvSpec {
+  int kh, kw, cin, cout, stride;
+  bool same, relu, pool_after;
+};
+// cnn_vtl.py:33-93: ungrouped AlexNet convs, no LRN, conv5 linear, 3x3/2 max-pool after conv1 and conv2
+constexpr ConvSpec kSpec[kConvLayers] = {
+    {11, 11, 3, 96, 4, false, true, true},   {5, 5, 96, 256, 1, true, true, true}, {3, 3, 256, 384, 1, true, true, false},
+    {3, 3, 384, 384, 1, true, true, false}, {3, 3, 384, 256, 1, true, false, false},
+};
+
+struct ConvGeo {
+  int H, W, OH, OW;            // input / output spatial size
+  int pad_t, pad_l, pad_b, pad_r;
+  int in_ld;                   // pixel pitch (elements) of the input activation planes (implicit layers)
+  int bk;                      // K block of this layer's kernel
+  int c_pad, k_ld;             // channels per tap padded to bk; total K of the weight planes
+  int out_ld;                  // pixel pitch of the output activation planes
+  int PH, PW;                  // pooled size (pool_after)
+};
+
+void same_pad(int size, int k, int stride, int* out, int* before, int* after) {
+  *out = (size + stride - 1) / stride;
+  int total = (*out - 1) * stride + k - size;
+  if (total < 0) total = 0;
+  *before = total / 2;  // TF puts the extra pixel after
+  *after = total - total / 2;
+}
+
+}  // namespace
+
+struct dlc_cnnvtl {
+  int H = 0, W = 0, precision = DLC_PREC_FP16X2;
+  ConvGeo geo[kConvLayers];
+  void* w_hi[kConvLayers] = {nullptr};
+  void* w_lo[kConvLayers] = {nullptr};
+  float* bias[kConvLayers] = {nullptr};
+  bool is_set[kConvLayers] = {false};
+  int64_t seg_size[kConvLayers];   // descriptor columns contributed by each layer (OH*OW*Cout)
+  int64_t seg_start[kConvLayers];
+  int64_t total_cols = 0;
+  uint32_t* keep_bits = nullptr;   // device
+  int* keep_rank = nullptr;        // device
+  int M = 0;
+};
+
+extern "C" int dlc_cnnvtl_create(dlc_cnnvtl** h, int H, int W, int precision) {
+  DLC_CHECK_ARG(h);
+  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2);
+  DLC_CHECK_ARG(H >= 11 && W >= 11 && H <= 8192 && W <= 8192);
+  if (int rc = dlc_device_check()) return rc;
+  dlc_cnnvtl* c = new dlc_cnnvtl();
+  c->H = H;
+  c->W = W;
+  c->precision = precision;
+  int hh = H, ww = W, in_ld = 0;
+  int64_t start = 0;
+  for (int l = 0; l < kConvLayers; ++l) {
+    const ConvSpec& s = kSpec[l];
+    ConvGeo& g = c->geo[l];
+    g.H = hh;
+    g.W = ww;
+    g.in_ld = in_ld;
+    if (s.same) {
+      same_pad(hh, s.kh, s.stride, &g.OH, &g.pad_t, &g.pad_b);
+      same_pad(ww, s.kw, s.stride, &g.OW, &g.pad_l, &g.pad_r);
+    } else {
+      g.OH = (hh - s.kh) / s.stride + 1;
+      g.OW = (ww - s.kw) / s.stride + 1;
+      g.pad_t = g.pad_l = g.pad_b = g.pad_r = 0;
+    }
+    if (l == 0) {  // explicit patch matrix, K = KH*KW*3 padded to a multiple of 64
+      g.bk = precision == DLC_PREC_FP16X2 ? 32 : 64;
+      g.c_pad = s.cin;
+      g.k_ld = dlc_plane_ld(s.kh * s.kw * s.cin);
+    } else {       // implicit GEMM: a K block is bk channels of one tap
+      g.bk = (precision == DLC_PREC_FP16X2 || s.cin % 64 != 0) ? 32 : 64;
+      g.c_pad = (s.cin + g.bk - 1) / g.bk * g.bk;
+      g.k_ld = s.kh * s.kw * g.c_pad;
+    }
+    g.out_ld = dlc_plane_ld(s.cout);
+    c->seg_size[l] = static_cast<int64_t>(g.OH) * g.OW * s.cout;
+    c->seg_start[l] = start;
+    start += c->seg_size[l];
+    hh = g.OH;
+    ww = g.OW;
+    g.PH = g.PW = 0;
+    if (s.pool_after) {
+      if (hh < 3 || ww < 3) {
+        delete c;
+        return fail(DLC_EINVAL, "dlc_cnnvtl_create: %dx%d input is too small for the conv head", H, W);
+      }
+      g.PH = hh = (hh - 3) / 2 + 1;
+      g.PW = ww = (ww - 3) / 2 + 1;
+    }
+    in_ld = g.out_ld;
+  }
+  c->total_cols = start;
+  for (int l = 0; l < kConvLayers; ++l) {
+    const size_t plane = static_cast<size_t>(kSpec[l].cout) * c->geo[l].k_ld * 2;
+    cudaError_t e = cudaMalloc(&c->w_hi[l], plane);
+    if (e == cudaSuccess && precision == DLC_PREC_FP16X2) e = cudaMalloc(&c->w_lo[l], plane);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->bias[l]), sizeof(float) * kSpec[l].cout);
+    if (e != cudaSuccess) {
+      dlc_cnnvtl_destroy(c);
+      return fail(DLC_ENOMEM, "dlc_cnnvtl_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+  }
+  *h = c;
+  return DLC_OK;
+}
+
+extern "C" int dlc_cnnvtl_destroy(dlc_cnnvtl* h) {
+  if (!h) return DLC_OK;
+  for (int l = 0; l < kConvLayers; ++l) {
+    if (h->w_hi[l]) cudaFree(h->w_hi[l]);
+    if (h->w_lo[l]) cudaFree(h->w_lo[l]);
+    if (h->bias[l]) cudaFree(h->bias[l]);
+  }
+  if (h->keep_bits) cudaFree(h->keep_bits);
+  if (h->keep_rank) cudaFree(h->keep_rank);
+  delete h;
+  return DLC_OK;
+}
+
+extern "C" int64_t dlc_cnnvtl_descriptor_len(const dlc_cnnvtl* h) { return h ? h->total_cols : 0; }
+
+extern "C" int dlc_cnnvtl_set_conv(dlc_cnnvtl* h, int layer, const double* w_host, const double* b_host) {
+  DLC_CHECK_ARG(h && w_host && b_host);
+  DLC_CHECK_ARG(layer >= 0 && layer < kConvLayers);
+  const ConvSpec& s = kSpec[layer];
+  const ConvGeo& g = h->geo[layer];
+  const size_t wbytes = sizeof(double) * s.kh * s.kw * s.cin * s.cout;
+  double* w_dev = nullptr;
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&w_dev), wbytes));
+  int rc = DLC_OK;
+  cudaError_t e = cudaMemcpy(w_dev, w_host, wbytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_cnnvtl_set_conv: H2D copy failed: %s", cudaGetErrorString(e));
+  if (rc == DLC_OK) {
+    const int64_t total = static_cast<int64_t>(s.cout) * g.k_ld;
+    pack_conv_weight_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16)), 256>>>(
+        w_dev, s.kh * s.kw, s.cin, s.cout, g.c_pad, static_cast<__half*>(h->w_hi[layer]),
+        static_cast<__half*>(h->w_lo[layer]), g.k_ld);
+    std::vector<float> b(s.cout);
+    for (int i = 0; i < s.cout; ++i) b[i] = static_cast<float>(b_host[i]);
+    e = cudaMemcpy(h->bias[layer], b.data(), sizeof(float) * b.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_cnnvtl_set_conv: %s", cudaGetErrorString(e));
+  }
+  cudaFree(w_dev);
+  if (rc == DLC_OK) h->is_set[layer] = true;
+  return rc;
+}
+
+extern "C" int dlc_cnnvtl_set_keep_cols(dlc_cnnvtl* h, const int64_t* keep_cols_host, int M) {
+  DLC_CHECK_ARG(h && keep_cols_host && M > 0);
+  const int64_t words = (h->total_cols + 31) / 32;
+  std::vector<uint32_t> bits(words, 0u);
+  std::vector<int> rank(words, 0);
+  for (int i = 0; i < M; ++i) {
+    const int64_t c = keep_cols_host[i];
+    if (c < 0 || c >= h->total_cols) return fail(DLC_EINVAL, "dlc_cnnvtl_set_keep_cols: column %lld out of range", (long long)c);
+    if (i > 0 && c <= keep_cols_host[i - 1])
+      return fail(DLC_EINVAL, "dlc_cnnvtl_set_keep_cols: columns must be strictly increasing");
+    bits[c >> 5] |= 1u << (c & 31);
+  }
+  int run = 0;
+  for (int64_t w = 0; w < words; ++w) {
+    rank[w] = run;
+    run += __builtin_popcount(bits[w]);
+  }
+  if (h->keep_bits) cudaFree(h->keep_bits);
+  if (h->keep_rank) cudaFree(h->keep_rank);
+  h->keep_bits = nullptr;
+  h->keep_rank = nullptr;
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->keep_bits), words * 4));
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->keep_rank), words * 4));
+  DLC_CUDA(cudaMemcpy(h->keep_bits, bits.data(), words * 4, cudaMemcpyHostToDevice));
+  DLC_CUDA(cudaMemcpy(h->keep_rank, rank.data(), words * 4, cudaMemcpyHostToDevice));
+  h->M = M;
+  return DLC_OK;
+}
+
+namespace {
+
+// Workspace carve-up for n images (every buffer 256-byte aligned).
+struct ConvWs {
+  size_t a1[2];                 // conv1 patch matrix planes
+  size_t act[kConvLayers][2];   // conv output planes (conv5 has none)
+  size_t pool[kConvLayers][2];  // pooled planes (after conv1, conv2)
+  size_t raw, mm, total;
+};
+
+ConvWs carve(const dlc_cnnvtl* h, int n) {
+  ConvWs w{};
+  size_t off = 0;
+  const int planes = h->precision == DLC_PREC_FP16X2 ? 2 : 1;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += align_up(bytes, 256);
+    return at;
+  };
+  // TMA boxes of the last M tile may start inside the buffer and run past its logical end only in the zero-filled
+  // out-of-bounds sense (the tensor maps carry the true extents), so no slack rows are needed.
+  for (int p = 0; p < 2; ++p)
+    w.a1[p] = p < planes ? take(static_cast<size_t>(n) * h->geo[0].OH * h->geo[0].OW * h->geo[0].k_ld * 2) : 0;
+  for (int l = 0; l < kConvLayers; ++l) {
+    const ConvGeo& g = h->geo[l];
+    for (int p = 0; p < 2; ++p) {
+      w.act[l][p] = (p < planes && l + 1 < kConvLayers) ? take(static_cast<size_t>(n) * g.OH * g.OW * g.out_ld * 2) : 0;
+      w.pool[l][p] = (p < planes && kSpec[l].pool_after) ? take(static_cast<size_t>(n) * g.PH * g.PW * g.out_ld * 2) : 0;
+    }
+  }
+  w.raw = take(static_cast<size_t>(n) * std::max(h->M, 1) * 4);
+  w.mm = take(static_cast<size_t>(n) * 8);
+  w.total = off;
+  return w;
+}
+
+template <class Policy>
+int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_lo, BiasActParams p,
+             cudaStream_t stream) {
+  constexpr int BK = Policy::Cfg::BK;
+  constexpr bool split = Policy::Cfg::NPROD == 3;
+  const ConvSpec& s = kSpec[l];
+  const ConvGeo& g = h->geo[l];
+  CUtensorMap ta0, ta1, tb0, tb1;
+  bool ok;
+  if (l == 0) {
+    ok = make_tmap_k_major(&ta0, a_hi, 0, g.k_ld, p.M, g.k_ld, BK, kTileM);
+    if (ok && split) ok = make_tmap_k_major(&ta1, a_lo, 0, g.k_ld, p.M, g.k_ld, BK, kTileM);
+  } else {
+    ok = make_tmap_im2col_nhwc(&ta0, a_hi, 0, n, g.H, g.W, s.cin, g.in_ld, s.kh, s.kw, g.pad_t, g.pad_l, g.pad_b,
+                               g.pad_r, BK);
+    if (ok && split)
+      ok = make_tmap_im2col_nhwc(&ta1, a_lo, 0, n, g.H, g.W, s.cin, g.in_ld, s.kh, s.kw, g.pad_t, g.pad_l, g.pad_b,
+                                 g.pad_r, BK);
+  }
+  if (!split) ta1 = ta0;
+  if (ok) ok = make_tmap_k_major(&tb0, h->w_hi[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
+  tb1 = tb0;
+  if (ok && split) ok = make_tmap_k_major(&tb1, h->w_lo[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
+  if (!ok) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed for conv%d", l + 1);
+  p.k_blocks = g.k_ld / BK;
+  p.kc = std::max(1, g_promote_k / BK);
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  if (e != cudaSuccess)
+    return fail(DLC_ECUDA, "dlc_cnnvtl_forward: conv%d launch failed: %s", l + 1, cudaGetErrorString(e));
+  return DLC_OK;
+}
+
+}  // namespace
+
+extern "C" size_t dlc_cnnvtl_workspace_bytes(const dlc_cnnvtl* h, int n) {
+  if (!h || n <= 0) return 0;
+  return carve(h, n).total + 256;
+}
+
+extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype, int n, int8_t* out_dev,
+                                  float* const* seg_f32_dev_host, void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(h && x_dev && ws_dev);
+  DLC_CHECK_ARG(n > 0);
+  DLC_CHECK_ARG(x_dtype == DLC_U8 || x_dtype == DLC_F32 || x_dtype == DLC_F64);
+  DLC_CHECK_ARG(out_dev || seg_f32_dev_host);
+  for (int l = 0; l < kConvLayers; ++l)
+    if (!h->is_set[l]) return fail(DLC_EINVAL, "dlc_cnnvtl_forward: conv%d has no weights (dlc_cnnvtl_set_conv)", l + 1);
+  if (out_dev && !h->keep_bits) return fail(DLC_EINVAL, "dlc_cnnvtl_forward: no kept columns (dlc_cnnvtl_set_keep_cols)");
+  if (static_cast<int64_t>(n) * h->geo[0].OH * h->geo[0].OW > 0x7fffffff / 2)
+    return fail(DLC_EINVAL, "dlc_cnnvtl_forward: too many images in one call (%d); split the batch", n);
+  const ConvWs w = carve(h, n);
+  if (ws_bytes < w.total)
+    return fail(DLC_ENOMEM, "dlc_cnnvtl_forward: workspace of %zu bytes needed, %zu given", w.total + 256, ws_bytes);
+  DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0);
+  cudaStream_t s = as_stream(stream);
+  const bool split = h->precision == DLC_PREC_FP16X2;
+  char* base = static_cast<char*>(ws_dev);
+  auto at = [&](size_t off) { return static_cast<void*>(base + off); };
+  int* mm = reinterpret_cast<int*>(at(w.mm));
+  float* raw = reinterpret_cast<float*>(at(w.raw));
+
+  minmax_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, mm);
+  // conv1 patch matrix from the image
+  {
+    const ConvGeo& g = h->geo[0];
+    const int64_t total = static_cast<int64_t>(n) * g.OH * g.OW * (g.k_ld / 8);
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 32));
+    __half* o_hi = static_cast<__half*>(at(w.a1[0]));
+    __half* o_lo = split ? static_cast<__half*>(at(w.a1[1])) : nullptr;
+    if (x_dtype == DLC_U8)
+      conv1_patch_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x_dev), n, g.H, g.W, kSpec[0].kh,
+                                                       kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+    else if (x_dtype == DLC_F32)
+      conv1_patch_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x_dev), n, g.H, g.W, kSpec[0].kh,
+                                                     kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+    else
+      conv1_patch_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x_dev), n, g.H, g.W, kSpec[0].kh,
+                                                      kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+    DLC_CUDA(cudaGetLastError());
+  }
+  const void* in_hi = at(w.a1[0]);
+  const void* in_lo = split ? at(w.a1[1]) : nullptr;
+  for (int l = 0; l < kConvLayers; ++l) {
+    const ConvSpec& sp = kSpec[l];
+    const ConvGeo& g = h->geo[l];
+    const bool last = l + 1 == kConvLayers;
+    BiasActParams p{};
+    int n_tile = 0;
+    for (int cand = 256; cand >= 32; cand -= 32)
+      if (sp.cout % cand == 0) {
+        n_tile = cand;
+        break;
+      }
+    p.n_tile = n_tile;
+    p.ab_fmt = 0;
+    p.M = n * g.OH * g.OW;
+    p.N = sp.cout;
+    p.m_tiles = ceil_div(p.M, kTileM);
+    p.n_tiles = sp.cout / n_tile;
+    p.bias = h->bias[l];
+    p.act = sp.relu ? DLC_ACT_RELU : DLC_ACT_NONE;
+    p.out_f32 = seg_f32_dev_host ? seg_f32_dev_host[l] : nullptr;
+    p.out_ld = sp.cout;
+    p.out_hi = last ? nullptr : at(w.act[l][0]);
+    p.out_lo = (last || !split) ? nullptr : at(w.act[l][1]);
+    p.out_plane_ld = g.out_ld;
+    p.cv_implicit = l > 0;
+    p.cv_ohw = g.OH * g.OW;
+    p.cv_ow = g.OW;
+    p.cv_pad_t = g.pad_t;
+    p.cv_pad_l = g.pad_l;
+    p.cv_kw = sp.kw;
+    p.cv_cblocks = g.c_pad / g.bk;
+    p.mm = out_dev ? mm : nullptr;
+    p.keep_bits = out_dev ? h->keep_bits : nullptr;
+    p.keep_rank = h->keep_rank;
+    p.raw = raw;
+    p.raw_ld = h->M;
+    p.seg_word0 = static_cast<int>(h->seg_start[l] / 32);
+    int rc;
+    if (split) rc = run_conv<BiasActPolicy<32, 3, true>>(h, l, n, in_hi, in_lo, p, s);
+    else if (g.bk == 32) rc = run_conv<BiasActPolicy<32, 1, true>>(h, l, n, in_hi, in_lo, p, s);
+    else rc = run_conv<BiasActPolicy<64, 1, true>>(h, l, n, in_hi, in_lo, p, s);
+    if (rc != DLC_OK) return rc;
+    in_hi = p.out_hi;
+    in_lo = p.out_lo;
+    if (sp.pool_after) {
+      __half* o_hi = static_cast<__half*>(at(w.pool[l][0]));
+      __half* o_lo = split ? static_cast<__half*>(at(w.pool[l][1])) : nullptr;
+      const int64_t total = static_cast<int64_t>(n) * g.PH * g.PW * (sp.cout / 8);
+      const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 32));
+      maxpool_planes_kernel<<<grid, 256, 0, s>>>(static_cast<const __half*>(in_hi), static_cast<const __half*>(in_lo),
+                                                 n, g.OH, g.OW, sp.cout, g.out_ld, 3, 2, g.PH, g.PW, o_hi, o_lo);
+      DLC_CUDA(cudaGetLastError());
+      in_hi = o_hi;
+      in_lo = o_lo;
+    }
+  }
+  if (out_dev) {
+    const int64_t total = static_cast<int64_t>(n) * h->M;
+    quantise_raw_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(raw, n, h->M, h->M, mm, out_dev);
+    DLC_CUDA(cudaGetLastError());
+  }
   return DLC_OK;
 }

@@ -13,6 +13,8 @@
 // What happens to an accumulator tile is decided by the Policy's Epilogue (bias+sigmoid+re-split, argmin/score,
 // running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace dlc {
@@ -76,6 +78,15 @@ struct GemmCfg {
 constexpr int kGemmThreadsPromote = 384;
 constexpr int kRegsLean = 56;
 constexpr int kRegsEpilogue = 224;
+
+// Optional policy member `static constexpr bool kIm2colA = true`: the A operand may be an NHWC activation tensor
+// read with im2col-mode TMA (implicit-GEMM convolution) instead of a materialised K-major matrix. Params then
+// carries: cv_implicit (runtime switch), cv_ohw (output pixels per image), cv_ow, cv_pad_t, cv_pad_l, cv_kw,
+// cv_cblocks (K blocks per filter tap); K block kb = (tap kh*KW+kw, channel block), B's K order is (kh, kw, c).
+template <class P, class = void>
+struct policy_im2col_a : std::false_type {};
+template <class P>
+struct policy_im2col_a<P, std::enable_if_t<P::kIm2colA>> : std::true_type {};
 
 // Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, 128 accumulator columns each).
 template <class Policy>
@@ -192,12 +203,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const TileCoord tc = Policy::tile(p, cta, ncta, i);
         const int m0 = tc.mt * kTileM;
         const int n0 = tc.nt * n_tile;
+        // implicit-GEMM A operand: first output pixel of the tile -> base input pixel (w, h, image)
+        int cv_w = 0, cv_h = 0, cv_n = 0, cv_tap = 0, cv_cb = 0;
+        bool implicit_a = false;
+        if constexpr (policy_im2col_a<Policy>::value) {
+          implicit_a = p.cv_implicit != 0;
+          if (implicit_a) {
+            cv_n = m0 / p.cv_ohw;
+            const int rem = m0 - cv_n * p.cv_ohw;
+            const int oh = rem / p.cv_ow;
+            cv_h = oh - p.cv_pad_t;
+            cv_w = rem - oh * p.cv_ow - p.cv_pad_l;
+          }
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 1);
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
-          if (Cfg::NPROD == 3) tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
+          if constexpr (policy_im2col_a<Policy>::value) {
+            if (implicit_a) {
+              const int kh = cv_tap / p.cv_kw;
+              const uint16_t off_h = static_cast<uint16_t>(kh), off_w = static_cast<uint16_t>(cv_tap - kh * p.cv_kw);
+              tma_load_im2col_4d(st, &tmA0, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
+              if (Cfg::NPROD == 3)
+                tma_load_im2col_4d(st + Cfg::kABytes, &tmA1, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
+              if (++cv_cb == p.cv_cblocks) {
+                cv_cb = 0;
+                ++cv_tap;
+              }
+            }
+          }
+          if (!implicit_a) {
+            tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
+            if (Cfg::NPROD == 3) tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
+          }
           uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
           tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
           if (Cfg::NPROD == 3) tma_load_2d(sb + Cfg::kBBytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
@@ -376,6 +415,46 @@ inline bool make_tmap_k_major(CUtensorMap* m, const void* base, int ab_fmt, uint
   CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMapDataType dt = ab_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// NHWC activation planes [N, H, W, C] (pixel pitch `ld_elems`) read in im2col mode for a stride-1 convolution with
+// a KH x KW filter and pad_t / pad_l zero pixels before (pad_b / pad_r after): one load = 128 consecutive output
+// pixels x bk channels of one filter tap. Bounding box of the base pixel: [-pad, size + pad_after - (K - 1)).
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeIm2col get_encode_im2col() {
+  static PFN_encodeIm2col fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeIm2col>(sym);
+  }
+  return fn;
+}
+
+inline bool make_tmap_im2col_nhwc(CUtensorMap* m, const void* base, int ab_fmt, int N, int H, int W, int C,
+                                  uint64_t ld_elems, int KH, int KW, int pad_t, int pad_l, int pad_b, int pad_r,
+                                  int bk) {
+  PFN_encodeIm2col enc = get_encode_im2col();
+  if (!enc) return false;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t gstride[3] = {ld_elems * 2, ld_elems * 2 * W, ld_elems * 2 * W * H};
+  int lower[2] = {-pad_l, -pad_t};                          // {W, H}
+  int upper[2] = {pad_r - (KW - 1), pad_b - (KH - 1)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapDataType dt = ab_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(m, dt, 4, const_cast<void*>(base), gdim, gstride, lower, upper, static_cast<cuuint32_t>(bk),
+                   static_cast<cuuint32_t>(kTileM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }

@@ -88,6 +88,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 4-D im2col-mode load from an NHWC tensor (dims C, W, H, N): `pixelsPerColumn` consecutive output pixels starting
+// at base pixel (w, h, n) - walking W, then H, then N inside the map's bounding box - each contributing
+// `channelsPerPixel` channels from c0 of the input pixel base + (off_w, off_h). Pixels outside the tensor read as
+// zero, which is the convolution's zero padding. The smem image is the same [pixels][channels] swizzled tile a
+// tiled 2-D load of a materialised im2col matrix would produce.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                   int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM load
 // ----------------------------------------------------------------------------------------------

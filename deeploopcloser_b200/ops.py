@@ -230,6 +230,55 @@ def hamming_matrix(desc, signed_bin_quirk=True):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ fused conv head
+class CnnVtlHead:
+    """Owner of a dlc_cnnvtl handle: packed conv filters and the kept-column tables live on the device."""
+
+    def __init__(self, height, width, precision="fp16x2"):
+        self.precision = precision
+        self._h = C.c_void_p()
+        _lib.call("dlc_cnnvtl_create", C.byref(self._h), int(height), int(width), precision_code(precision))
+        self.descriptor_len = int(_lib.call("dlc_cnnvtl_descriptor_len", self._h))
+        self.n_keep = 0
+        self._ws = Workspace()
+
+    def set_conv(self, layer, w, b):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        _lib.call("dlc_cnnvtl_set_conv", self._h, layer, w.ctypes.data, b.ctypes.data)
+
+    def set_keep_cols(self, keep_cols):
+        keep = np.ascontiguousarray(keep_cols, dtype=np.int64)
+        _lib.call("dlc_cnnvtl_set_keep_cols", self._h, keep.ctypes.data, int(keep.size))
+        self.n_keep = int(keep.size)
+
+    def forward(self, x, layer_outputs=None, quantise=True):
+        """x CUDA [n, H, W, 3] uint8 / float32 / float64 -> int8 [n, M]. layer_outputs: optional list of 5 float32
+        CUDA tensors (or None entries) receiving the conv outputs."""
+        _check_cuda(x)
+        n = x.shape[0]
+        out = torch.empty((n, self.n_keep), dtype=torch.int8, device=x.device) if quantise else None
+        segs = None
+        if layer_outputs is not None:
+            _check_cuda(*layer_outputs)
+            segs = (C.c_void_p * 5)(*[ptr(t) for t in layer_outputs])
+        dt = {torch.uint8: _lib.U8, torch.float32: _lib.F32, torch.float64: _lib.F64}[x.dtype]
+        ws, ws_bytes = self._ws.get(_lib.call("dlc_cnnvtl_workspace_bytes", self._h, n))
+        _lib.call("dlc_cnnvtl_forward", self._h, ptr(x), dt, n, ptr(out), segs, ws, ws_bytes, stream_ptr())
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.call("dlc_cnnvtl_destroy", self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------ conv blocks
 def im2col_planes(x_hi, x_lo, N, H, W, C_, KH, KW, stride, pad_t, pad_l, OH, OW):
     _check_cuda(x_hi, x_lo)

@@ -198,8 +198,35 @@ int dlc_hamming_matrix(const int8_t* desc_dev, int N, int M, int signed_bin_quir
                        size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * a7  cnn_vtl conv head building blocks (src/cnn_vtl/network/cnn_vtl.py:28-128). The convolutions run as
- *     im2col planes + dlc_gemm_planes (bias + ReLU fused), NHWC throughout.
+ * a7/a8  cnn_vtl conv head, fused.  Replaces CnnVtl._define_model + CnnVtl.transform
+ *        (src/cnn_vtl/network/cnn_vtl.py:28-128, 130-133): conv1 11x11/4 VALID 96 ReLU -> maxpool 3/2 -> conv2 5x5
+ *        SAME 256 ReLU -> maxpool 3/2 -> conv3/conv4 3x3 SAME 384 ReLU -> conv5 3x3 SAME 256 linear; the five conv
+ *        outputs flattened (NHWC) and concatenated; per-image (d - min) * 255 / (max - min); int8 cast; column
+ *        sub-sampling. One tcgen05 kernel per convolution (conv2..5 are implicit GEMMs over im2col-mode TMA; bias,
+ *        ReLU, the min/max and the gather of the kept columns live in the epilogue), so neither an im2col matrix
+ *        nor the 546,944-wide float descriptor is ever written to memory.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct dlc_cnnvtl dlc_cnnvtl;
+/* H x W = spatial size of the input images (cnn_vtl.py:29 input_shape[1:3]); precision DLC_PREC_FP16X2 or _FP16. */
+int dlc_cnnvtl_create(dlc_cnnvtl** h, int H, int W, int precision);
+int dlc_cnnvtl_destroy(dlc_cnnvtl* h);
+/* layer 0..4 = conv1..conv5. w_host float64 HWIO [kh, kw, cin, cout] (tf.layers.conv2d kernel layout), b_host [cout]. */
+int dlc_cnnvtl_set_conv(dlc_cnnvtl* h, int layer, const double* w_host, const double* b_host);
+/* Length of the concatenated descriptor before sub-sampling (546,944 for 192x240 inputs). */
+int64_t dlc_cnnvtl_descriptor_len(const dlc_cnnvtl* h);
+/* The kept columns of cnn_vtl.py:119-128 as strictly increasing indices into the concatenated descriptor. */
+int dlc_cnnvtl_set_keep_cols(dlc_cnnvtl* h, const int64_t* keep_cols_host, int M);
+size_t dlc_cnnvtl_workspace_bytes(const dlc_cnnvtl* h, int n);
+/* x_dev [n, H, W, 3] NHWC (DLC_U8, DLC_F32 or DLC_F64; BGR 0..255 like cv2.imread, no mean subtraction) ->
+ * out_dev int8 [n, M]. seg_f32_dev_host: optional host array of 5 device pointers (entries may be NULL); entry l
+ * receives conv(l+1)'s float32 NHWC output [n, OH, OW, cout] (diagnostics / parity tests). out_dev may be NULL when
+ * only the layer outputs are wanted. ws_dev must be 256-byte aligned. */
+int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype, int n, int8_t* out_dev,
+                       float* const* seg_f32_dev_host, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a7  cnn_vtl conv head building blocks: the explicit-im2col formulation of the same head (im2col planes +
+ *     dlc_gemm_planes, NHWC throughout), kept as an independent cross-check of the fused path.
  * ------------------------------------------------------------------------------------------------------------ */
 /* x planes NHWC [N,H,W,C] (row = pixel, ld_in >= C) -> im2col planes [N*OH*OW, ld] with column (kh*KW + kw)*C + c,
  * zero padding of pad_t/pad_l pixels (TF 'SAME' puts the extra pixel at the bottom/right). */
