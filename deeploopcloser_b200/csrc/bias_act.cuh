@@ -26,7 +26,7 @@ struct BiasActParams {
   void* out_lo;
   int out_plane_ld;
   // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
-  int cv_implicit, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
+  int cv_implicit, cv_a_lo_zero, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
   // ---- CONV only: descriptor tail. Row m = output pixel (image m / cv_ohw); the layer's flattened NHWC output
   // occupies columns [seg_word0*32, ...) of the concatenated descriptor (cnn_vtl.py:96-106).
   int* mm;                    // [images, 2] per-image running min / max as order-preserving ints

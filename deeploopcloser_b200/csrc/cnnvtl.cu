@@ -180,42 +180,44 @@ __device__ __forceinline__ void split_any(T x, __half& hi, __half& lo) {
   else split_f32(static_cast<float>(x), hi, lo);
 }
 
-// conv1 patch matrix straight from the NHWC image (C = 3): row = output pixel, column = kh*(KW*3) + kw*3 + c, i.e.
-// each filter row kh is a run of KW*3 contiguous source elements. 8 columns (one 16-byte store) per thread.
+// conv1 (11x11 / 4 VALID on 3 channels: 6-byte pixels, below TMA's 16-byte granule) is run as a 3x3 / 1 VALID
+// convolution over the space-to-depth(4) image: s2d pixel (sh, sw) holds the 4 x 4 x 3 = 48 values of image rows
+// 4sh..4sh+3, columns 4sw..4sw+3 in (dy, dx, c) order (96 bytes of a 128-byte pixel pitch), and filter tap (th, tw)
+// channel (dy, dx, c) is W1[4th+dy, 4tw+dx, c] (zero where an index reaches 11). One thread = one (pixel, dy):
+// 12 contiguous source elements -> 24 contiguous bytes per plane.
 template <typename T>
 __global__ void __launch_bounds__(256)
-conv1_patch_kernel(const T* __restrict__ x, int N, int H, int W, int KH, int KW, int stride, int OH, int OW,
-                   __half* __restrict__ o_hi, __half* __restrict__ o_lo, int ld) {
-  const int chunks = ld >> 3;
-  const int run = KW * 3;
-  const int K = KH * run;
-  const int64_t total = static_cast<int64_t>(N) * OH * OW * chunks;
+s2d4_planes_kernel(const T* __restrict__ x, int N, int H, int W, int SH, int SW, __half* __restrict__ o_hi,
+                   __half* __restrict__ o_lo, int ld) {
+  const int64_t total = static_cast<int64_t>(N) * SH * SW * 4;
   for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
        t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(t % chunks);
-    const int64_t orow = t / chunks;
-    const int ow = static_cast<int>(orow % OW);
-    const int oh = static_cast<int>((orow / OW) % OH);
-    const int n = static_cast<int>(orow / (static_cast<int64_t>(OW) * OH));
-    const T* src0 = x + ((static_cast<int64_t>(n) * H + oh * stride) * W + ow * stride) * 3;
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
-    int col = ch << 3;
-    int kh = col / run;
-    int r = col - kh * run;
+    const int dy = static_cast<int>(t & 3);
+    const int64_t spix = t >> 2;
+    const int sw = static_cast<int>(spix % SW);
+    const int sh = static_cast<int>((spix / SW) % SH);
+    const int n = static_cast<int>(spix / (static_cast<int64_t>(SW) * SH));
+    const int r = 4 * sh + dy;
+    __align__(8) __half h[12];
+    __align__(8) __half l[12];
 #pragma unroll
-    for (int q = 0; q < 8; ++q, ++col) {
+    for (int q = 0; q < 12; ++q) {
       h[q] = __float2half_rn(0.f);
       l[q] = __float2half_rn(0.f);
-      if (col < K) split_any(src0[static_cast<int64_t>(kh) * W * 3 + r], h[q], l[q]);
-      if (++r == run) {
-        r = 0;
-        ++kh;
-      }
     }
-    const int64_t o = orow * ld + (ch << 3);
-    *reinterpret_cast<uint4*>(o_hi + o) = *reinterpret_cast<const uint4*>(h);
-    if (o_lo) *reinterpret_cast<uint4*>(o_lo + o) = *reinterpret_cast<const uint4*>(l);
+    if (r < H) {
+      const T* src = x + ((static_cast<int64_t>(n) * H + r) * W + 4 * sw) * 3;
+      const int valid = min(4, W - 4 * sw) * 3;
+#pragma unroll
+      for (int q = 0; q < 12; ++q)
+        if (q < valid) split_any(src[q], h[q], l[q]);
+    }
+    const int64_t o = spix * ld + dy * 12;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      reinterpret_cast<uint2*>(o_hi + o)[q] = reinterpret_cast<const uint2*>(h)[q];
+      if (o_lo) reinterpret_cast<uint2*>(o_lo + o)[q] = reinterpret_cast<const uint2*>(l)[q];
+    }
   }
 }
 
@@ -382,6 +384,7 @@ struct ConvGeo {
   int c_pad, k_ld;             // channels per tap padded to bk; total K of the weight planes
   int out_ld;                  // pixel pitch of the output activation planes
   int PH, PW;                  // pooled size (pool_after)
+  int vkh, vkw, vcin;          // the filter the kernel sees: the spec's, or 3 x 3 x 48 for the space-to-depth conv1
 };
 
 void same_pad(int size, int k, int stride, int* out, int* before, int* after) {
@@ -434,15 +437,25 @@ extern "C" int dlc_cnnvtl_create(dlc_cnnvtl** h, int H, int W, int precision) {
       g.OW = (ww - s.kw) / s.stride + 1;
       g.pad_t = g.pad_l = g.pad_b = g.pad_r = 0;
     }
-    if (l == 0) {  // explicit patch matrix, K = KH*KW*3 padded to a multiple of 64
-      g.bk = precision == DLC_PREC_FP16X2 ? 32 : 64;
-      g.c_pad = s.cin;
-      g.k_ld = dlc_plane_ld(s.kh * s.kw * s.cin);
-    } else {       // implicit GEMM: a K block is bk channels of one tap
-      g.bk = (precision == DLC_PREC_FP16X2 || s.cin % 64 != 0) ? 32 : 64;
-      g.c_pad = (s.cin + g.bk - 1) / g.bk * g.bk;
-      g.k_ld = s.kh * s.kw * g.c_pad;
+    g.vkh = s.kh;
+    g.vkw = s.kw;
+    g.vcin = s.cin;
+    if (l == 0) {  // space-to-depth(4): 3x3 VALID over [OH + 2, OW + 2] pixels of 48 channels
+      if (s.stride != 4 || s.kh > 12 || s.kw > 12 || s.cin != 3) {
+        delete c;
+        return fail(DLC_EUNSUPPORTED, "dlc_cnnvtl_create: conv1 must be <=12x12 / 4 on 3 channels");
+      }
+      g.H = g.OH + 2;
+      g.W = g.OW + 2;
+      g.in_ld = 64;
+      g.vkh = g.vkw = 3;
+      g.vcin = 48;
     }
+    // implicit GEMM: a K block is bk channels of one tap
+    g.bk = (precision == DLC_PREC_FP16X2 || g.vcin % 64 != 0) ? 32 : 64;
+    if (l == 0 && precision != DLC_PREC_FP16X2) g.bk = 64;  // 48 channels + 16 zero-filled = one 64-wide block
+    g.c_pad = (g.vcin + g.bk - 1) / g.bk * g.bk;
+    g.k_ld = g.vkh * g.vkw * g.c_pad;
     g.out_ld = dlc_plane_ld(s.cout);
     c->seg_size[l] = static_cast<int64_t>(g.OH) * g.OW * s.cout;
     c->seg_start[l] = start;
@@ -495,16 +508,31 @@ extern "C" int dlc_cnnvtl_set_conv(dlc_cnnvtl* h, int layer, const double* w_hos
   DLC_CHECK_ARG(layer >= 0 && layer < kConvLayers);
   const ConvSpec& s = kSpec[layer];
   const ConvGeo& g = h->geo[layer];
-  const size_t wbytes = sizeof(double) * s.kh * s.kw * s.cin * s.cout;
+  const int taps = g.vkh * g.vkw;
+  const size_t wcount = static_cast<size_t>(taps) * g.vcin * s.cout;
+  const size_t wbytes = sizeof(double) * wcount;
+  std::vector<double> w_s2d;
+  const double* w_src = w_host;
+  if (layer == 0) {  // W1[kh, kw, c, :] -> tap (kh / 4, kw / 4), channel ((kh % 4) * 4 + kw % 4) * 3 + c
+    w_s2d.assign(wcount, 0.0);
+    for (int kh = 0; kh < s.kh; ++kh)
+      for (int kw = 0; kw < s.kw; ++kw)
+        for (int c = 0; c < s.cin; ++c) {
+          const size_t dst = ((static_cast<size_t>(kh / 4) * 3 + kw / 4) * 48 + ((kh % 4) * 4 + kw % 4) * 3 + c) * s.cout;
+          const size_t src = ((static_cast<size_t>(kh) * s.kw + kw) * s.cin + c) * s.cout;
+          for (int j = 0; j < s.cout; ++j) w_s2d[dst + j] = w_host[src + j];
+        }
+    w_src = w_s2d.data();
+  }
   double* w_dev = nullptr;
   DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&w_dev), wbytes));
   int rc = DLC_OK;
-  cudaError_t e = cudaMemcpy(w_dev, w_host, wbytes, cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMemcpy(w_dev, w_src, wbytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_cnnvtl_set_conv: H2D copy failed: %s", cudaGetErrorString(e));
   if (rc == DLC_OK) {
     const int64_t total = static_cast<int64_t>(s.cout) * g.k_ld;
     pack_conv_weight_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16)), 256>>>(
-        w_dev, s.kh * s.kw, s.cin, s.cout, g.c_pad, static_cast<__half*>(h->w_hi[layer]),
+        w_dev, taps, g.vcin, s.cout, g.c_pad, static_cast<__half*>(h->w_hi[layer]),
         static_cast<__half*>(h->w_lo[layer]), g.k_ld);
     std::vector<float> b(s.cout);
     for (int i = 0; i < s.cout; ++i) b[i] = static_cast<float>(b_host[i]);
@@ -550,7 +578,7 @@ namespace {
 
 // Workspace carve-up for n images (every buffer 256-byte aligned).
 struct ConvWs {
-  size_t a1[2];                 // conv1 patch matrix planes
+  size_t a1[2];                 // space-to-depth image planes (conv1's input)
   size_t act[kConvLayers][2];   // conv output planes (conv5 has none)
   size_t pool[kConvLayers][2];  // pooled planes (after conv1, conv2)
   size_t raw, mm, total;
@@ -568,7 +596,7 @@ ConvWs carve(const dlc_cnnvtl* h, int n) {
   // TMA boxes of the last M tile may start inside the buffer and run past its logical end only in the zero-filled
   // out-of-bounds sense (the tensor maps carry the true extents), so no slack rows are needed.
   for (int p = 0; p < 2; ++p)
-    w.a1[p] = p < planes ? take(static_cast<size_t>(n) * h->geo[0].OH * h->geo[0].OW * h->geo[0].k_ld * 2) : 0;
+    w.a1[p] = p < planes ? take(static_cast<size_t>(n) * h->geo[0].H * h->geo[0].W * h->geo[0].in_ld * 2) : 0;
   for (int l = 0; l < kConvLayers; ++l) {
     const ConvGeo& g = h->geo[l];
     for (int p = 0; p < 2; ++p) {
@@ -590,18 +618,12 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   const ConvSpec& s = kSpec[l];
   const ConvGeo& g = h->geo[l];
   CUtensorMap ta0, ta1, tb0, tb1;
-  bool ok;
-  if (l == 0) {
-    ok = make_tmap_k_major(&ta0, a_hi, 0, g.k_ld, p.M, g.k_ld, BK, kTileM);
-    if (ok && split) ok = make_tmap_k_major(&ta1, a_lo, 0, g.k_ld, p.M, g.k_ld, BK, kTileM);
-  } else {
-    ok = make_tmap_im2col_nhwc(&ta0, a_hi, 0, n, g.H, g.W, s.cin, g.in_ld, s.kh, s.kw, g.pad_t, g.pad_l, g.pad_b,
+  bool ok = make_tmap_im2col_nhwc(&ta0, a_hi, 0, n, g.H, g.W, g.vcin, g.in_ld, g.vkh, g.vkw, g.pad_t, g.pad_l, g.pad_b,
+                             g.pad_r, BK);
+  ta1 = ta0;
+  if (ok && split && a_lo)
+    ok = make_tmap_im2col_nhwc(&ta1, a_lo, 0, n, g.H, g.W, g.vcin, g.in_ld, g.vkh, g.vkw, g.pad_t, g.pad_l, g.pad_b,
                                g.pad_r, BK);
-    if (ok && split)
-      ok = make_tmap_im2col_nhwc(&ta1, a_lo, 0, n, g.H, g.W, s.cin, g.in_ld, s.kh, s.kw, g.pad_t, g.pad_l, g.pad_b,
-                                 g.pad_r, BK);
-  }
-  if (!split) ta1 = ta0;
   if (ok) ok = make_tmap_k_major(&tb0, h->w_hi[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
   tb1 = tb0;
   if (ok && split) ok = make_tmap_k_major(&tb1, h->w_lo[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
@@ -646,26 +668,27 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
   float* raw = reinterpret_cast<float*>(at(w.raw));
 
   minmax_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, mm);
-  // conv1 patch matrix from the image
+  // space-to-depth image planes for conv1; 8-bit pixels are exact in fp16, so their residual plane is skipped
+  const bool a_lo_zero = x_dtype == DLC_U8;
   {
     const ConvGeo& g = h->geo[0];
-    const int64_t total = static_cast<int64_t>(n) * g.OH * g.OW * (g.k_ld / 8);
+    const int64_t total = static_cast<int64_t>(n) * g.H * g.W * 4;
     const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 32));
     __half* o_hi = static_cast<__half*>(at(w.a1[0]));
-    __half* o_lo = split ? static_cast<__half*>(at(w.a1[1])) : nullptr;
+    __half* o_lo = (split && !a_lo_zero) ? static_cast<__half*>(at(w.a1[1])) : nullptr;
     if (x_dtype == DLC_U8)
-      conv1_patch_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x_dev), n, g.H, g.W, kSpec[0].kh,
-                                                       kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+      s2d4_planes_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(x_dev), n, h->H, h->W, g.H, g.W,
+                                                       o_hi, o_lo, g.in_ld);
     else if (x_dtype == DLC_F32)
-      conv1_patch_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x_dev), n, g.H, g.W, kSpec[0].kh,
-                                                     kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+      s2d4_planes_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x_dev), n, h->H, h->W, g.H, g.W, o_hi,
+                                                     o_lo, g.in_ld);
     else
-      conv1_patch_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x_dev), n, g.H, g.W, kSpec[0].kh,
-                                                      kSpec[0].kw, kSpec[0].stride, g.OH, g.OW, o_hi, o_lo, g.k_ld);
+      s2d4_planes_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double*>(x_dev), n, h->H, h->W, g.H, g.W, o_hi,
+                                                      o_lo, g.in_ld);
     DLC_CUDA(cudaGetLastError());
   }
   const void* in_hi = at(w.a1[0]);
-  const void* in_lo = split ? at(w.a1[1]) : nullptr;
+  const void* in_lo = (split && !a_lo_zero) ? at(w.a1[1]) : nullptr;
   for (int l = 0; l < kConvLayers; ++l) {
     const ConvSpec& sp = kSpec[l];
     const ConvGeo& g = h->geo[l];
@@ -690,12 +713,13 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     p.out_hi = last ? nullptr : at(w.act[l][0]);
     p.out_lo = (last || !split) ? nullptr : at(w.act[l][1]);
     p.out_plane_ld = g.out_ld;
-    p.cv_implicit = l > 0;
+    p.cv_implicit = 1;
+    p.cv_a_lo_zero = (l == 0 && a_lo_zero) ? 1 : 0;
     p.cv_ohw = g.OH * g.OW;
     p.cv_ow = g.OW;
     p.cv_pad_t = g.pad_t;
     p.cv_pad_l = g.pad_l;
-    p.cv_kw = sp.kw;
+    p.cv_kw = g.vkw;
     p.cv_cblocks = g.c_pad / g.bk;
     p.mm = out_dev ? mm : nullptr;
     p.keep_bits = out_dev ? h->keep_bits : nullptr;

@@ -81,7 +81,7 @@ constexpr int kRegsEpilogue = 224;
 
 // Optional policy member `static constexpr bool kIm2colA = true`: the A operand may be an NHWC activation tensor
 // read with im2col-mode TMA (implicit-GEMM convolution) instead of a materialised K-major matrix. Params then
-// carries: cv_implicit (runtime switch), cv_ohw (output pixels per image), cv_ow, cv_pad_t, cv_pad_l, cv_kw,
+// carries: cv_implicit (runtime switch), cv_a_lo_zero (A has no residual plane), cv_ohw (output pixels per image), cv_ow, cv_pad_t, cv_pad_l, cv_kw,
 // cv_cblocks (K blocks per filter tap); K block kb = (tap kh*KW+kw, channel block), B's K order is (kh, kw, c).
 template <class P, class = void>
 struct policy_im2col_a : std::false_type {};
@@ -196,7 +196,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kABytes + n_tile * BK * 2);
+      // cv_a_lo_zero: the A operand is exactly representable in fp16 (8-bit pixels), so its residual plane is
+      // neither loaded nor multiplied
+      bool a_lo_zero = false;
+      if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
+      const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kABytes + n_tile * BK * 2) - (a_lo_zero ? Cfg::kABytes : 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -225,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const int kh = cv_tap / p.cv_kw;
               const uint16_t off_h = static_cast<uint16_t>(kh), off_w = static_cast<uint16_t>(cv_tap - kh * p.cv_kw);
               tma_load_im2col_4d(st, &tmA0, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
-              if (Cfg::NPROD == 3)
+              if (Cfg::NPROD == 3 && !a_lo_zero)
                 tma_load_im2col_4d(st + Cfg::kABytes, &tmA1, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
               if (++cv_cb == p.cv_cblocks) {
                 cv_cb = 0;
@@ -235,7 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           if (!implicit_a) {
             tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
-            if (Cfg::NPROD == 3) tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
+            if (Cfg::NPROD == 3 && !a_lo_zero)
+              tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
           }
           uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
           tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
@@ -251,6 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_idesc_f16(kTileM, n_tile, p.ab_fmt);
+      bool a_lo_zero = false;
+      if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -278,8 +285,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 // small cross terms first, dominant term last
                 const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
                 const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-                umma_f16(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
-                umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                if (!a_lo_zero) {
+                  umma_f16(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+                  umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, dah, dbl, idesc, (kk | k) != 0 ? 1u : 0u);
+                }
                 umma_f16(d_tmem, dah, dbh, idesc, 1u);
               } else {
                 umma_f16(d_tmem, dah, dbh, idesc, (kk | k) != 0 ? 1u : 0u);

@@ -435,3 +435,69 @@ def test_match_threshold_l2(cuda):
     if np.abs(ref - 0.5).min() > 1e-3:
         assert np.array_equal(counts.cpu().numpy(), rc) and np.array_equal(idx.cpu().numpy(), ri)
     assert np.array_equal(idx[:, 0].cpu().numpy(), np.arange(B))
+
+
+# ------------------------------------------------------------------------------------------- fused cnn_vtl head
+@pytest.mark.parametrize("hw,n", [((67, 83), 3), ((192, 240), 2), ((224, 224), 1), ((35, 43), 5)])
+@pytest.mark.parametrize("dtype", ["uint8", "float64"])
+def test_cnnvtl_fused_layers_vs_oracle(cuda, hw, n, dtype):
+    """Every convolution of the fused head (conv1 from the image, conv2..5 as implicit GEMMs over im2col-mode TMA)
+    against the float64 oracle, layer by layer; M tiles cross image boundaries (130 / 12 pixels per image)."""
+    from deeploopcloser_b200.cnn_vtl import CnnVtl
+    from oracle import cnnvtl as o_cnn
+    H, W = hw
+    rng = np.random.default_rng(H + n)
+    x = rng.integers(0, 256, (n, H, W, 3)).astype(np.uint8)
+    if dtype == "float64":
+        x = x.astype(np.float64) + rng.uniform(0, 0.5, x.shape)     # non-integer pixels exercise the lo plane
+    params = o_cnn.make_weights(3)
+    net = CnnVtl(input_shape=[n, H, W, 3], batch_size=n, weights=params, keep_cols=[0])
+    want = o_cnn.conv_outputs(x.astype(np.float64), params)
+    got = net.conv_outputs(torch.from_numpy(x).cuda())
+    for l, (g, w) in enumerate(zip(got, want)):
+        g = g.cpu().numpy()
+        assert g.shape == w.shape
+        # activations reach several hundred (0..255 inputs, He-scaled filters): tolerance relative to the layer scale
+        scale = max(1.0, float(np.abs(w).max()))
+        err = float(np.max(np.abs(g - w))) / scale
+        print("conv%d %s n=%d %s: max|err|/max|act| = %.2e, normwise %.2e" % (l + 1, hw, n, dtype, err, norm_err(g, w)))
+        assert err <= 1e-4 and norm_err(g, w) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "fp16"])
+def test_cnnvtl_fused_equals_explicit(cuda, precision):
+    """The fused head (implicit GEMM, min/max + kept-column gather in the epilogue) produces the same int8
+    descriptors as the explicit-im2col formulation built from the library's building blocks."""
+    from deeploopcloser_b200.cnn_vtl import CnnVtl
+    from oracle import cnnvtl as o_cnn
+    n, H, W = 4, 96, 128
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.integers(0, 256, (n, H, W, 3)).astype(np.uint8)).cuda()
+    params = o_cnn.make_weights(7)
+    keep = o_cnn.make_keep_columns(o_cnn.layer_sizes((H, W)), compress_factor=98.0, seed=1)
+    net = CnnVtl(input_shape=[n, H, W, 3], batch_size=n, weights=params, keep_cols=keep, precision=precision)
+    fused = net._forward_chunk(x).cpu().numpy()
+    explicit = net._forward_chunk_explicit(x).cpu().numpy()
+    ndiff = int((fused != explicit).sum())
+    print("fused vs explicit (%s): %d of %d bytes differ" % (precision, ndiff, fused.size))
+    assert fused.shape == explicit.shape == (n, keep.size)
+    d = (fused.astype(np.int16) - explicit.astype(np.int16) + 128) % 256 - 128      # wrap-aware
+    assert np.all(np.abs(d) <= 1)
+    # fp16x2: identical up to the last bit of a float32 (pooling on hi+lo vs on float32). fp16: the two formulations
+    # order K differently (conv1 runs on the space-to-depth image), so single-product rounding noise flips a few
+    # values that sit on an integer boundary of the 0..255 scale.
+    assert ndiff <= (0.001 if precision == "fp16x2" else 0.01) * fused.size
+
+
+def test_cnnvtl_handle_errors(cuda):
+    from deeploopcloser_b200 import _lib, ops
+    head = ops.CnnVtlHead(64, 64)
+    x = torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(_lib.DlcError):          # no weights yet
+        head.forward(x)
+    with pytest.raises(_lib.DlcError):          # columns must be strictly increasing and in range
+        head.set_keep_cols([5, 5])
+    with pytest.raises(_lib.DlcError):
+        head.set_keep_cols([head.descriptor_len])
+    with pytest.raises(_lib.DlcError):          # too small for conv1 + two pools
+        ops.CnnVtlHead(8, 8)
