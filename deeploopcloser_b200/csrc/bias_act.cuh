@@ -1,6 +1,6 @@
 // Bias + activation epilogue policy of the tcgen05 contraction (shared by the SDA encoder layers, the generic
 // dlc_gemm_planes entry point and - with CONV = true - the cnn_vtl convolutions, which add an im2col-mode A operand
-// and the descriptor tail: per-image min/max and the raw values of the kept descriptor columns).
+// and the per-image min/max of the descriptor tail).
 #pragma once
 #include <cuda_bf16.h>
 #include <math.h>
@@ -27,14 +27,9 @@ struct BiasActParams {
   int out_plane_ld;
   // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
   int cv_implicit, cv_a_lo_zero, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
-  // ---- CONV only: descriptor tail. Row m = output pixel (image m / cv_ohw); the layer's flattened NHWC output
-  // occupies columns [seg_word0*32, ...) of the concatenated descriptor (cnn_vtl.py:96-106).
-  int* mm;                    // [images, 2] per-image running min / max as order-preserving ints
-  const uint32_t* keep_bits;  // bit c of word w set = descriptor column 32*w + c is kept (cnn_vtl.py:119-128)
-  const int* keep_rank;       // number of kept columns before word w
-  float* raw;                 // [images, raw_ld] unquantised values of the kept columns
-  int raw_ld;
-  int seg_word0;
+  // ---- CONV only: descriptor tail. Row m = output pixel of image m / cv_ohw; the per-image min / max of every conv
+  // output (cnn_vtl.py:109-111) is reduced here, as order-preserving ints.
+  int* mm;  // [images, 2]
 };
 
 // float <-> int whose signed order equals the float order (for atomicMin / atomicMax on floats)
@@ -57,6 +52,7 @@ struct BiasActPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = BiasActParams;
   static constexpr bool kIm2colA = CONV;
+  static constexpr bool kAltTiles = CONV;
   static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
   static constexpr int kEpiWarps = 4;
   static __device__ __forceinline__ bool enabled(const Params&) { return true; }
@@ -172,16 +168,6 @@ struct BiasActPolicy {
           for (int j = 0; j < 32; ++j) {
             t_lo = fminf(t_lo, h[j]);
             t_hi = fmaxf(t_hi, h[j]);
-          }
-        }
-        if (p.keep_bits) {  // N is a multiple of 32 for every conv layer: this chunk is one word of the column mask
-          const int word = p.seg_word0 + pix * (p.N >> 5) + (col0 >> 5);
-          const uint32_t bits = __ldg(p.keep_bits + word);
-          if (bits) {
-            float* dst = p.raw + static_cast<int64_t>(img) * p.raw_ld + __ldg(p.keep_rank + word);
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if ((bits >> j) & 1u) dst[__popc(bits & ((1u << j) - 1u))] = h[j];
           }
         }
       }

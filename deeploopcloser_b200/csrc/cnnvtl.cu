@@ -281,13 +281,30 @@ pack_conv_weight_kernel(const double* __restrict__ w, int taps, int cin, int cou
   }
 }
 
-// int8 quantisation of the gathered kept columns (same arithmetic as quantise_gather_kernel)
-__global__ void quantise_raw_kernel(const float* __restrict__ raw, int N, int M, int raw_ld, const int* __restrict__ mm,
-                                    int8_t* __restrict__ out) {
+// Descriptor tail of the fused head: gather the kept columns from the conv outputs' hi/lo planes (value = hi + lo,
+// float32-exact to ~22 bits), scale with the per-image min/max the epilogues reduced, cast to int8 with the same
+// arithmetic as quantise_gather_kernel (cnn_vtl.py:109-128).
+struct PlaneSegTable {
+  const __half* hi[kMaxSeg];
+  const __half* lo[kMaxSeg];
+  int64_t start[kMaxSeg];  // first column of the layer in the concatenated descriptor
+  int cout[kMaxSeg];
+  int ld[kMaxSeg];
+  int pix[kMaxSeg];        // output pixels per image
+  int n_seg;
+};
+__global__ void quantise_gather_planes_kernel(PlaneSegTable st, int N, const int64_t* __restrict__ keep, int M,
+                                              const int* __restrict__ mm, int8_t* __restrict__ out) {
   const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= static_cast<int64_t>(N) * M) return;
   const int n = static_cast<int>(t / M), m = static_cast<int>(t % M);
-  const double d = static_cast<double>(raw[static_cast<int64_t>(n) * raw_ld + m]);
+  const int64_t col = keep[m];
+  int seg = 0;
+  while (seg + 1 < st.n_seg && col >= st.start[seg + 1]) ++seg;
+  const int64_t rel = col - st.start[seg];
+  const int pixel = static_cast<int>(rel / st.cout[seg]), ch = static_cast<int>(rel % st.cout[seg]);
+  const int64_t off = (static_cast<int64_t>(n) * st.pix[seg] + pixel) * st.ld[seg] + ch;
+  const double d = static_cast<double>(__half2float(st.hi[seg][off]) + __half2float(st.lo[seg][off]));
   const double lo = static_cast<double>(ordered_to_float(mm[2 * n]));
   const double hi = static_cast<double>(ordered_to_float(mm[2 * n + 1]));
   const double scaled = (d - lo) * (255.0 / (hi - lo));
@@ -407,8 +424,7 @@ struct dlc_cnnvtl {
   int64_t seg_size[kConvLayers];   // descriptor columns contributed by each layer (OH*OW*Cout)
   int64_t seg_start[kConvLayers];
   int64_t total_cols = 0;
-  uint32_t* keep_bits = nullptr;   // device
-  int* keep_rank = nullptr;        // device
+  int64_t* keep_cols = nullptr;    // device, strictly increasing
   int M = 0;
 };
 
@@ -495,8 +511,7 @@ extern "C" int dlc_cnnvtl_destroy(dlc_cnnvtl* h) {
     if (h->w_lo[l]) cudaFree(h->w_lo[l]);
     if (h->bias[l]) cudaFree(h->bias[l]);
   }
-  if (h->keep_bits) cudaFree(h->keep_bits);
-  if (h->keep_rank) cudaFree(h->keep_rank);
+  if (h->keep_cols) cudaFree(h->keep_cols);
   delete h;
   return DLC_OK;
 }
@@ -547,29 +562,17 @@ extern "C" int dlc_cnnvtl_set_conv(dlc_cnnvtl* h, int layer, const double* w_hos
 
 extern "C" int dlc_cnnvtl_set_keep_cols(dlc_cnnvtl* h, const int64_t* keep_cols_host, int M) {
   DLC_CHECK_ARG(h && keep_cols_host && M > 0);
-  const int64_t words = (h->total_cols + 31) / 32;
-  std::vector<uint32_t> bits(words, 0u);
-  std::vector<int> rank(words, 0);
   for (int i = 0; i < M; ++i) {
     const int64_t c = keep_cols_host[i];
-    if (c < 0 || c >= h->total_cols) return fail(DLC_EINVAL, "dlc_cnnvtl_set_keep_cols: column %lld out of range", (long long)c);
+    if (c < 0 || c >= h->total_cols)
+      return fail(DLC_EINVAL, "dlc_cnnvtl_set_keep_cols: column %lld out of range", static_cast<long long>(c));
     if (i > 0 && c <= keep_cols_host[i - 1])
       return fail(DLC_EINVAL, "dlc_cnnvtl_set_keep_cols: columns must be strictly increasing");
-    bits[c >> 5] |= 1u << (c & 31);
   }
-  int run = 0;
-  for (int64_t w = 0; w < words; ++w) {
-    rank[w] = run;
-    run += __builtin_popcount(bits[w]);
-  }
-  if (h->keep_bits) cudaFree(h->keep_bits);
-  if (h->keep_rank) cudaFree(h->keep_rank);
-  h->keep_bits = nullptr;
-  h->keep_rank = nullptr;
-  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->keep_bits), words * 4));
-  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->keep_rank), words * 4));
-  DLC_CUDA(cudaMemcpy(h->keep_bits, bits.data(), words * 4, cudaMemcpyHostToDevice));
-  DLC_CUDA(cudaMemcpy(h->keep_rank, rank.data(), words * 4, cudaMemcpyHostToDevice));
+  if (h->keep_cols) cudaFree(h->keep_cols);
+  h->keep_cols = nullptr;
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->keep_cols), sizeof(int64_t) * M));
+  DLC_CUDA(cudaMemcpy(h->keep_cols, keep_cols_host, sizeof(int64_t) * M, cudaMemcpyHostToDevice));
   h->M = M;
   return DLC_OK;
 }
@@ -579,9 +582,9 @@ namespace {
 // Workspace carve-up for n images (every buffer 256-byte aligned).
 struct ConvWs {
   size_t a1[2];                 // space-to-depth image planes (conv1's input)
-  size_t act[kConvLayers][2];   // conv output planes (conv5 has none)
+  size_t act[kConvLayers][2];   // conv output planes, hi and lo (the descriptor tail gathers from them)
   size_t pool[kConvLayers][2];  // pooled planes (after conv1, conv2)
-  size_t raw, mm, total;
+  size_t mm, total;
 };
 
 ConvWs carve(const dlc_cnnvtl* h, int n) {
@@ -600,11 +603,10 @@ ConvWs carve(const dlc_cnnvtl* h, int n) {
   for (int l = 0; l < kConvLayers; ++l) {
     const ConvGeo& g = h->geo[l];
     for (int p = 0; p < 2; ++p) {
-      w.act[l][p] = (p < planes && l + 1 < kConvLayers) ? take(static_cast<size_t>(n) * g.OH * g.OW * g.out_ld * 2) : 0;
+      w.act[l][p] = take(static_cast<size_t>(n) * g.OH * g.OW * g.out_ld * 2);
       w.pool[l][p] = (p < planes && kSpec[l].pool_after) ? take(static_cast<size_t>(n) * g.PH * g.PW * g.out_ld * 2) : 0;
     }
   }
-  w.raw = take(static_cast<size_t>(n) * std::max(h->M, 1) * 4);
   w.mm = take(static_cast<size_t>(n) * 8);
   w.total = off;
   return w;
@@ -629,7 +631,8 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   if (ok && split) ok = make_tmap_k_major(&tb1, h->w_lo[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
   if (!ok) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed for conv%d", l + 1);
   p.k_blocks = g.k_ld / BK;
-  p.kc = std::max(1, g_promote_k / BK);
+  // a short K range (conv1: 576) is accumulated in one TMEM pass, which also enables the alternate-tile epilogue
+  p.kc = g.k_ld <= 1024 ? p.k_blocks : std::max(1, g_promote_k / BK);
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
@@ -653,7 +656,7 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
   DLC_CHECK_ARG(out_dev || seg_f32_dev_host);
   for (int l = 0; l < kConvLayers; ++l)
     if (!h->is_set[l]) return fail(DLC_EINVAL, "dlc_cnnvtl_forward: conv%d has no weights (dlc_cnnvtl_set_conv)", l + 1);
-  if (out_dev && !h->keep_bits) return fail(DLC_EINVAL, "dlc_cnnvtl_forward: no kept columns (dlc_cnnvtl_set_keep_cols)");
+  if (out_dev && !h->keep_cols) return fail(DLC_EINVAL, "dlc_cnnvtl_forward: no kept columns (dlc_cnnvtl_set_keep_cols)");
   if (static_cast<int64_t>(n) * h->geo[0].OH * h->geo[0].OW > 0x7fffffff / 2)
     return fail(DLC_EINVAL, "dlc_cnnvtl_forward: too many images in one call (%d); split the batch", n);
   const ConvWs w = carve(h, n);
@@ -665,7 +668,6 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
   char* base = static_cast<char*>(ws_dev);
   auto at = [&](size_t off) { return static_cast<void*>(base + off); };
   int* mm = reinterpret_cast<int*>(at(w.mm));
-  float* raw = reinterpret_cast<float*>(at(w.raw));
 
   minmax_init_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, mm);
   // space-to-depth image planes for conv1; 8-bit pixels are exact in fp16, so their residual plane is skipped
@@ -710,8 +712,8 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     p.act = sp.relu ? DLC_ACT_RELU : DLC_ACT_NONE;
     p.out_f32 = seg_f32_dev_host ? seg_f32_dev_host[l] : nullptr;
     p.out_ld = sp.cout;
-    p.out_hi = last ? nullptr : at(w.act[l][0]);
-    p.out_lo = (last || !split) ? nullptr : at(w.act[l][1]);
+    p.out_hi = at(w.act[l][0]);
+    p.out_lo = at(w.act[l][1]);  // written in both precision modes: the descriptor tail reads hi + lo
     p.out_plane_ld = g.out_ld;
     p.cv_implicit = 1;
     p.cv_a_lo_zero = (l == 0 && a_lo_zero) ? 1 : 0;
@@ -722,18 +724,13 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     p.cv_kw = g.vkw;
     p.cv_cblocks = g.c_pad / g.bk;
     p.mm = out_dev ? mm : nullptr;
-    p.keep_bits = out_dev ? h->keep_bits : nullptr;
-    p.keep_rank = h->keep_rank;
-    p.raw = raw;
-    p.raw_ld = h->M;
-    p.seg_word0 = static_cast<int>(h->seg_start[l] / 32);
     int rc;
     if (split) rc = run_conv<BiasActPolicy<32, 3, true>>(h, l, n, in_hi, in_lo, p, s);
     else if (g.bk == 32) rc = run_conv<BiasActPolicy<32, 1, true>>(h, l, n, in_hi, in_lo, p, s);
     else rc = run_conv<BiasActPolicy<64, 1, true>>(h, l, n, in_hi, in_lo, p, s);
     if (rc != DLC_OK) return rc;
     in_hi = p.out_hi;
-    in_lo = p.out_lo;
+    in_lo = split ? p.out_lo : nullptr;
     if (sp.pool_after) {
       __half* o_hi = static_cast<__half*>(at(w.pool[l][0]));
       __half* o_lo = split ? static_cast<__half*>(at(w.pool[l][1])) : nullptr;
@@ -747,8 +744,19 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     }
   }
   if (out_dev) {
+    PlaneSegTable st{};
+    st.n_seg = kConvLayers;
+    for (int l = 0; l < kConvLayers; ++l) {
+      st.hi[l] = static_cast<const __half*>(at(w.act[l][0]));
+      st.lo[l] = static_cast<const __half*>(at(w.act[l][1]));
+      st.start[l] = h->seg_start[l];
+      st.cout[l] = kSpec[l].cout;
+      st.ld[l] = h->geo[l].out_ld;
+      st.pix[l] = h->geo[l].OH * h->geo[l].OW;
+    }
     const int64_t total = static_cast<int64_t>(n) * h->M;
-    quantise_raw_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(raw, n, h->M, h->M, mm, out_dev);
+    quantise_gather_planes_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, s>>>(st, n, h->keep_cols, h->M, mm,
+                                                                                        out_dev);
     DLC_CUDA(cudaGetLastError());
   }
   return DLC_OK;

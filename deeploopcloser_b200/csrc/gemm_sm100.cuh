@@ -9,7 +9,7 @@
 //
 // Roles: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane), warps 2.. = epilogue
 // (4 warps, or 8 with two-level accumulation; each reads the 32 TMEM lanes of its quarter = warp_idx % 4).
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
+// Pipelines: smem ring full/empty (TMA <-> MMA; depth chosen at launch from n_tile, up to 12 stages), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 // What happens to an accumulator tile is decided by the Policy's Epilogue (bias+sigmoid+re-split, argmin/score,
 // running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
 #pragma once
@@ -38,16 +38,27 @@ struct GemmCfg {
   static_assert(NPROD == 1 || NPROD == 3, "1 product or the 3-product fp16 split");
   static constexpr int kPlanes = NPROD == 3 ? 2 : 1;
   static constexpr int kABytes = kTileM * BK * 2;     // one A plane tile
-  static constexpr int kBBytes = kMaxTileN * BK * 2;  // one B plane tile, sized for n_tile = 256
-  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kBBytes = kMaxTileN * BK * 2;  // one B plane tile at n_tile = 256
+  // The smem ring is carved at run time: a stage holds the A plane tile(s) and B plane tile(s) of the launch's
+  // actual n_tile, so narrow accumulators (n_tile = 96 of cnn_vtl's conv1) get a deeper ring - with little MMA
+  // work per stage, the bytes in flight are what hides the TMA latency.
+  static constexpr int kMaxStages = 12;
+  static constexpr int kRingBytes = 208 * 1024;
   static constexpr uint32_t kSwizzleMode = BK == 64 ? 2u : 4u;  // UMMA layout code: 2 = 128B, 4 = 64B
   static constexpr uint32_t kSBO = 8 * BK * 2;                  // bytes between 8-row groups
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBarrierBytes + kEpiScratchBytes;
-  static_assert(kStages >= 2, "need at least a double buffer");
-  static_assert((2 * kStages + 4) * 8 + 8 <= kBarrierBytes, "barrier block too small");
+  static constexpr int kSmemBytes = 1024 + 16 /*alignment slack*/ + kBarrierBytes + kEpiScratchBytes + kRingBytes;
+  static_assert((2 * kMaxStages + 4) * 8 + 8 <= kBarrierBytes, "barrier block too small");
   static_assert(kSmemBytes <= 227 * 1024, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(kRingBytes / (kPlanes * (kABytes + kBBytes)) >= 2, "need at least a double buffer");
+  // bytes of one stage / number of stages for a launch (a_planes = 1 when the A residual plane is skipped)
+  __host__ __device__ static constexpr int stage_bytes(int n_tile, int a_planes) {
+    return a_planes * kABytes + kPlanes * n_tile * BK * 2;
+  }
+  __host__ __device__ static constexpr int stages(int n_tile, int a_planes) {
+    const int s = kRingBytes / stage_bytes(n_tile, a_planes);
+    return s < kMaxStages ? s : kMaxStages;
+  }
 };
 
 // Policy contract:
@@ -87,6 +98,15 @@ template <class P, class = void>
 struct policy_im2col_a : std::false_type {};
 template <class P>
 struct policy_im2col_a<P, std::enable_if_t<P::kIm2colA>> : std::true_type {};
+
+// Optional policy member `static constexpr bool kAltTiles = true` (two-level-accumulation policies): when the
+// accumulator is at most 128 columns wide and the whole K range is one chunk, the two groups of four epilogue warps
+// take alternate tiles (group g owns TMEM buffer g) instead of splitting the columns of every tile, so a narrow,
+// short-K contraction - whose epilogue costs more than its MMAs - has two tile times to drain each tile.
+template <class P, class = void>
+struct policy_alt_tiles : std::false_type {};
+template <class P>
+struct policy_alt_tiles<P, std::enable_if_t<P::kAltTiles>> : std::true_type {};
 
 // Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, 128 accumulator columns each).
 template <class Policy>
@@ -132,20 +152,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                const typename Policy::Params p) {
   using Cfg = typename Policy::Cfg;
   constexpr int BK = Cfg::BK;
-  constexpr int S = Cfg::kStages;
+  constexpr int SMAX = Cfg::kMaxStages;
   constexpr bool kPromote = Policy::kPromote;
   constexpr int kEpiWarps = epi_warps<Policy>();
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
 
+  // smem: [barriers | epilogue scratch | pad to 1024 | ring of S stages]
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
   uint64_t* full = bars;
-  uint64_t* empty = bars + S;
-  uint64_t* tfull = bars + 2 * S;
-  uint64_t* tempty = bars + 2 * S + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-  void* scratch = smem + S * Cfg::kStageBytes + Cfg::kBarrierBytes;
+  uint64_t* empty = bars + SMAX;
+  uint64_t* tfull = bars + 2 * SMAX;
+  uint64_t* tempty = bars + 2 * SMAX + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SMAX + 4);
+  void* scratch = reinterpret_cast<uint8_t*>(bars) + Cfg::kBarrierBytes;
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(scratch) + kEpiScratchBytes + 1023) & ~uintptr_t(1023));
+
+  // cv_a_lo_zero (im2col policies): the A operand is exactly representable in fp16 (8-bit pixels), so its residual
+  // plane is neither staged nor multiplied
+  bool a_lo_zero = false;
+  if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
+  const int a_planes = a_lo_zero ? 1 : Cfg::kPlanes;
+  const int stage_bytes = Cfg::stage_bytes(p.n_tile, a_planes);
+  const int S = Cfg::stages(p.n_tile, a_planes);
+  const int b_plane_bytes = p.n_tile * BK * 2;
+  bool alt_tiles = false;
+  if constexpr (kPromote && policy_alt_tiles<Policy>::value)
+    alt_tiles = p.n_tile <= 128 && (p.kc <= 0 || p.kc >= p.k_blocks);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], kEpiWarps);  // one arrival per epilogue warp
+        mbar_init(&tempty[a], alt_tiles ? kEpiWarps / 2 : kEpiWarps);  // one arrival per epilogue warp that reads it
       }
       fence_mbar_init();
     }
@@ -196,11 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      // cv_a_lo_zero: the A operand is exactly representable in fp16 (8-bit pixels), so its residual plane is
-      // neither loaded nor multiplied
-      bool a_lo_zero = false;
-      if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
-      const uint32_t tx_bytes = Cfg::kPlanes * (Cfg::kABytes + n_tile * BK * 2) - (a_lo_zero ? Cfg::kABytes : 0);
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
@@ -223,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 1);
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          uint8_t* st = smem + stage * stage_bytes;
           if constexpr (policy_im2col_a<Policy>::value) {
             if (implicit_a) {
               const int kh = cv_tap / p.cv_kw;
@@ -242,9 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (Cfg::NPROD == 3 && !a_lo_zero)
               tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
           }
-          uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+          uint8_t* sb = st + a_planes * Cfg::kABytes;
           tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
-          if (Cfg::NPROD == 3) tma_load_2d(sb + Cfg::kBBytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
+          if (Cfg::NPROD == 3) tma_load_2d(sb + b_plane_bytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -256,8 +286,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_idesc_f16(kTileM, n_tile, p.ab_fmt);
-      bool a_lo_zero = false;
-      if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -272,10 +300,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int kk = 0; kb < kb_end; ++kb, ++kk) {
             mbar_wait(&full[stage], phase, 3);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
             const uint32_t a_lo = a_hi + Cfg::kABytes;
-            const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
-            const uint32_t b_lo = b_hi + Cfg::kBBytes;
+            const uint32_t b_hi = a_hi + a_planes * Cfg::kABytes;
+            const uint32_t b_lo = b_hi + b_plane_bytes;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint32_t koff = k * 32;  // 16 fp16 along K inside the swizzle span
@@ -318,7 +346,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int col_half = alt_tiles ? 0 : half;  // alternate-tile mode: this group reads all (<= 4) column chunks
     for (int i = 0; i < my_tiles; ++i) {
+      if (kPromote && alt_tiles) {
+        if ((i & 1) != half) continue;            // the other group's tile
+        acc = half;                               // one chunk per tile: tile i accumulates in buffer i & 1
+        acc_phase = static_cast<uint32_t>(i >> 1) & 1u;
+      }
       const TileCoord tc = Policy::tile(p, cta, ncta, i);
       if (kPromote) {
         float sums[128];
@@ -326,10 +360,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(&tfull[acc], acc_phase, 4);
           tc_fence_after();
           const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) +
-                                 (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 128);
+                                 (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col_half * 128);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
-            if (half * 4 + cc < n_cchunks) {
+            if (col_half * 4 + cc < n_cchunks) {
               uint32_t v[32];
               tmem_ld_x32(taddr + cc * 32, v);
               tmem_ld_wait();
@@ -350,10 +384,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         epi.begin_tile(tc);
         using Epi = typename Policy::Epilogue;
-        epi_slot_from_regs<Epi, 0>(epi, tc, sums, half, n_cchunks);
-        epi_slot_from_regs<Epi, 1>(epi, tc, sums, half, n_cchunks);
-        epi_slot_from_regs<Epi, 2>(epi, tc, sums, half, n_cchunks);
-        epi_slot_from_regs<Epi, 3>(epi, tc, sums, half, n_cchunks);
+        epi_slot_from_regs<Epi, 0>(epi, tc, sums, col_half, n_cchunks);
+        epi_slot_from_regs<Epi, 1>(epi, tc, sums, col_half, n_cchunks);
+        epi_slot_from_regs<Epi, 2>(epi, tc, sums, col_half, n_cchunks);
+        epi_slot_from_regs<Epi, 3>(epi, tc, sums, col_half, n_cchunks);
         epi.end_tile(tc);
         epi.post_tile(tc);
       } else {

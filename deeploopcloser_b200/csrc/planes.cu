@@ -82,6 +82,7 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 
 static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
 int g_promote_k = 256;
+extern int g_sim_mgroup;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
 template <class Policy>
@@ -123,6 +124,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 3) {
     g_dbg_flags = value;
+    return DLC_OK;
+  }
+  if (key == 4 && value >= 1) {
+    g_sim_mgroup = value;
     return DLC_OK;
   }
   if (key == 2 && value >= 32) {

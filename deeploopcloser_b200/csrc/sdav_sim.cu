@@ -25,7 +25,7 @@ namespace dlc {
 constexpr int kFrameRows = 32;                          // padded patch rows per frame
 constexpr int kFramesPerMTile = kTileM / kFrameRows;    // 4
 constexpr int kFramesPerNTile = kMaxTileN / kFrameRows; // 8
-constexpr int kMGroup = 8;                              // M tiles per L2 super-block of the tile order
+int g_sim_mgroup = 8;                                   // M tiles per L2 super-block of the tile order (dlc_debug_set key 4)
 
 // ---------------- column mean -> distinctive weights (deterministic two-stage reduction) ----------------
 constexpr int kColSumSlabs = 128;
@@ -441,13 +441,13 @@ __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* g
   }
 }
 
-// Work list: super-blocks of kMGroup M tiles; inside a super-block N tile outermost so the ~148 concurrently
-// running tiles touch kMGroup A row-blocks and ~148/kMGroup B row-blocks (fits L2) instead of streaming all of H.
+// Work list: super-blocks of g_sim_mgroup M tiles; inside a super-block N tile outermost so the ~148 concurrently
+// running tiles touch g_sim_mgroup A row-blocks and ~148/g_sim_mgroup B row-blocks (fits L2) instead of streaming all of H.
 static void build_tile_list(int N, int full, std::vector<int2>& out) {
   const int m_tiles = ceil_div(N, kFramesPerMTile), n_tiles = ceil_div(N, kFramesPerNTile);
   out.clear();
-  for (int g0 = 0; g0 < m_tiles; g0 += kMGroup) {
-    const int g1 = std::min(g0 + kMGroup, m_tiles);
+  for (int g0 = 0; g0 < m_tiles; g0 += g_sim_mgroup) {
+    const int g1 = std::min(g0 + g_sim_mgroup, m_tiles);
     for (int nt = 0; nt < n_tiles; ++nt)
       for (int mt = g0; mt < g1; ++mt) {
         const int fa_min = mt * kFramesPerMTile;
