@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlc.so")
+LIB_PATH = os.environ.get("DLC_LIB_PATH") or os.path.join(_HERE, "libdlc.so")  # env override: developer A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP16, PREC_FP16X2, PREC_BF16, PREC_AUTO, PREC_FP16_REFINED = 0, 1, 2, 3, 4
@@ -90,6 +90,8 @@ def load():
             "`make -C deeploopcloser_b200/csrc` (sm_100a, nvcc). deeploopcloser_b200 has no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in PROTOTYPES.items():
+        if os.environ.get("DLC_LIB_PATH") and not hasattr(lib, name):
+            continue  # developer A/B build of an older revision
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args

@@ -228,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp < kEpiWarp0) {
   if (kPromote) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLean));
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ===================== TMA producer =====================
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
       int stage = 0;
@@ -238,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m0 = tc.mt * kTileM;
         const int n0 = tc.nt * n_tile;
         // implicit-GEMM A operand: first output pixel of the tile -> base input pixel (w, h, image)
-        int cv_w = 0, cv_h = 0, cv_n = 0, cv_tap = 0, cv_cb = 0;
+        int cv_w = 0, cv_h = 0, cv_n = 0, cv_kh = 0, cv_kwi = 0, cv_cb = 0;
         bool implicit_a = false;
         if constexpr (policy_im2col_a<Policy>::value) {
           implicit_a = p.cv_implicit != 0;
@@ -256,14 +256,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           uint8_t* st = smem + stage * stage_bytes;
           if constexpr (policy_im2col_a<Policy>::value) {
             if (implicit_a) {
-              const int kh = cv_tap / p.cv_kw;
-              const uint16_t off_h = static_cast<uint16_t>(kh), off_w = static_cast<uint16_t>(cv_tap - kh * p.cv_kw);
+              const uint16_t off_h = static_cast<uint16_t>(cv_kh), off_w = static_cast<uint16_t>(cv_kwi);
               tma_load_im2col_4d(st, &tmA0, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
               if (Cfg::NPROD == 3 && !a_lo_zero)
                 tma_load_im2col_4d(st + Cfg::kABytes, &tmA1, &full[stage], cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
               if (++cv_cb == p.cv_cblocks) {
                 cv_cb = 0;
-                ++cv_tap;
+                if (++cv_kwi == p.cv_kw) {
+                  cv_kwi = 0;
+                  ++cv_kh;
+                }
               }
             }
           }
@@ -283,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_idesc_f16(kTileM, n_tile, p.ab_fmt);
       int stage = 0;

@@ -18,6 +18,23 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One lane of the (converged) warp. A branch on this predicate is known to the compiler to run a single thread, so
+// TMA / tcgen05 operands go straight to uniform registers (a `lane == 0` test makes it emit a per-lane loop instead).
+__device__ __forceinline__ bool elect_one_sync() {
+#ifdef DLC_NO_ELECT  // developer A/B switch: the older `lane == 0` role test
+  return (threadIdx.x & 31) == 0;
+#endif
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

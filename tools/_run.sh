@@ -1,5 +1,11 @@
-timeout 300 python tools/diag_cnnvtl.py > gpurun_out/diag_cnn.log 2>&1
-grep "descriptors\|FAILED\|Error" gpurun_out/diag_cnn.log | tail; grep "conv1 " gpurun_out/diag_cnn.log
-timeout 900 python -m pytest tests -x -q -m gpu -k "cnnvtl" > gpurun_out/pytest_cnn.log 2>&1; tail -5 gpurun_out/pytest_cnn.log
-timeout 300 python tools/bench_cnnvtl.py 128 > gpurun_out/cnn_fused_128.log 2>&1; tail -1 gpurun_out/cnn_fused_128.log
-timeout 300 python tools/bench_cnnvtl.py 1063 > gpurun_out/cnn_fused_1063.log 2>&1; tail -1 gpurun_out/cnn_fused_1063.log
+for lib in libdlc_old.so libdlc_noelect.so libdlc.so libdlc_old.so; do
+  echo "== $lib"
+  DLC_LIB_PATH=$PWD/deeploopcloser_b200/$lib timeout 300 python tools/bench_matcher.py --batches 32,1024 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['B'], round(d['ms'],3), round(d['tflops'],1), round(d['db_gbs'],1))
+    elif 'rror' in l: print(l.strip()[:200])
+"
+done
+nvidia-smi --query-gpu=clocks.sm,clocks.mem,power.draw,clocks_event_reasons.active --format=csv
