@@ -11,7 +11,7 @@ explicit-im2col formulation built from the library's building blocks, kept as a 
 Differences from the reference, all explicit: weights are an argument (the AlexNet blob is a git-LFS pointer in the
 reference tree) - a dict {name: (W[kh,kw,cin,cout], b[cout])}, a path to a `bvlc_alexnet.npy`-style file, or
 `weights="synthetic"` for seeded He-scaled tensors; the column mask can be passed (`mask=` boolean [sum sizes] or
-`keep_cols=`) or seeded (`seed=`); frames are processed in chunks of `batch_size` images to bound memory."""
+`keep_cols=`) or seeded (`seed=`); frames are processed in device chunks of `DEVICE_CHUNK` images to bound memory."""
 import numpy as np
 
 # (name, kh, kw, cin, cout, stride, padding, relu)
@@ -214,14 +214,19 @@ class CnnVtl:
                 hi, lo = planes
         return ops.cnnvtl_quantise(segments, n, st["keep"])
 
+    # images per device pass of transform(): bounds the workspace (~7 MB per 192x240 image); the reference feeds
+    # all N images to one session.run and never uses `batch_size` in transform (cnn_vtl.py:130-133)
+    DEVICE_CHUNK = 256
+
     def transform(self, x):
         import torch
         x = np.asarray(x)
         if x.ndim != 4 or x.shape[1] != self._H or x.shape[2] != self._W or x.shape[3] != 3:
             raise ValueError("expected input [N, %d, %d, 3], got %s" % (self._H, self._W, x.shape))
-        chunk = max(int(self.batch_size), 1)
+        if x.dtype not in (np.uint8, np.float32, np.float64):
+            x = x.astype(np.float64)
         outs = []
-        for s in range(0, x.shape[0], chunk):
-            xc = torch.from_numpy(np.ascontiguousarray(x[s:s + chunk])).cuda()
+        for s in range(0, x.shape[0], self.DEVICE_CHUNK):
+            xc = torch.from_numpy(np.ascontiguousarray(x[s:s + self.DEVICE_CHUNK])).cuda()
             outs.append(self._forward_chunk(xc).cpu().numpy())
         return np.concatenate(outs) if outs else np.zeros((0, self.keep_cols.size), dtype=np.int8)

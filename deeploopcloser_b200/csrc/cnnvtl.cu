@@ -469,7 +469,9 @@ extern "C" int dlc_cnnvtl_create(dlc_cnnvtl** h, int H, int W, int precision) {
     }
     // implicit GEMM: a K block is bk channels of one tap
     g.bk = (precision == DLC_PREC_FP16X2 || g.vcin % 64 != 0) ? 32 : 64;
-    if (l == 0 && precision != DLC_PREC_FP16X2) g.bk = 64;  // 48 channels + 16 zero-filled = one 64-wide block
+    // conv1: 48 channels + 16 zero-filled = one 64-wide block per tap. Its K loop is short and its accumulator
+    // narrow, so the per-K-block issue overhead of the producer / MMA threads matters: use the wide block.
+    if (l == 0) g.bk = 64;
     g.c_pad = (g.vcin + g.bk - 1) / g.bk * g.bk;
     g.k_ld = g.vkh * g.vkw * g.c_pad;
     g.out_ld = dlc_plane_ld(s.cout);
@@ -725,7 +727,8 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     p.cv_cblocks = g.c_pad / g.bk;
     p.mm = out_dev ? mm : nullptr;
     int rc;
-    if (split) rc = run_conv<BiasActPolicy<32, 3, true>>(h, l, n, in_hi, in_lo, p, s);
+    if (split && g.bk == 64) rc = run_conv<BiasActPolicy<64, 3, true>>(h, l, n, in_hi, in_lo, p, s);
+    else if (split) rc = run_conv<BiasActPolicy<32, 3, true>>(h, l, n, in_hi, in_lo, p, s);
     else if (g.bk == 32) rc = run_conv<BiasActPolicy<32, 1, true>>(h, l, n, in_hi, in_lo, p, s);
     else rc = run_conv<BiasActPolicy<64, 1, true>>(h, l, n, in_hi, in_lo, p, s);
     if (rc != DLC_OK) return rc;

@@ -129,6 +129,7 @@ def test_cnnvtl_transform(cuda, hw):
     sizes = o_cnn.layer_sizes(hw)
     keep = o_cnn.make_keep_columns(sizes, compress_factor=99.0 if H < 100 else 99.59, seed=4)
     net = CnnVtl(input_shape=[n, H, W, 3], batch_size=2, weights=params, keep_cols=keep)
+    net.DEVICE_CHUNK = 2                                  # two device passes (2 + 1 images)
     assert net.layer_sizes == sizes
     got = net.transform(x)
     outs = o_cnn.conv_outputs(x, params)
