@@ -50,13 +50,40 @@ class DA:
         # encoder_weights ~ N(0,1), encoder_biases = 0 (DenoisingAutoencoderVariant.py:94-97)
         self.set_weights(rng.standard_normal((self.input_shape[1], hidden_units)), np.zeros(hidden_units))
 
-    def set_weights(self, w0, b0):
+    def set_weights(self, w0, b0, b1=None):
         w0 = np.ascontiguousarray(w0, dtype=np.float64)
         b0 = np.ascontiguousarray(b0, dtype=np.float64)
-        if w0.shape != (self.input_shape[1], self.hidden_units) or b0.shape != (self.hidden_units,):
-            raise ValueError("expected w0 %s and b0 %s" % ((self.input_shape[1], self.hidden_units), (self.hidden_units,)))
-        self._w0, self._b0 = w0, b0
+        b1 = np.zeros(self.input_shape[1]) if b1 is None else np.ascontiguousarray(b1, dtype=np.float64)
+        if (w0.shape != (self.input_shape[1], self.hidden_units) or b0.shape != (self.hidden_units,) or
+                b1.shape != (self.input_shape[1],)):
+            raise ValueError("expected w0 %s, b0 %s and b1 %s" % ((self.input_shape[1], self.hidden_units),
+                                                                 (self.hidden_units,), (self.input_shape[1],)))
+        self._w0, self._b0, self._b1 = w0, b0, b1
         self._encoder = None
+
+    # ---- the reference's checkpoints (DenoisingAutoencoderVariant.py:160-174): <train>/checkpoints/layer_<n>_/
+    def load_checkpoint(self, path):
+        """Restore encoder_variables/encoder_weights, encoder_biases and decoder_variables/decoder_biases from a
+        TensorFlow checkpoint prefix or a directory holding the `checkpoint` state file."""
+        import os
+
+        from . import tf_checkpoint
+        prefix = tf_checkpoint.latest_checkpoint(path) if os.path.isdir(path) else path
+        if prefix is None:
+            raise FileNotFoundError("no TensorFlow checkpoint state file in %s" % path)
+        t = tf_checkpoint.load_checkpoint(prefix)
+        wn, bn, dn = tf_checkpoint.DA_VARIABLE_NAMES
+        self.set_weights(t[wn], t[bn], t[dn])
+        self.global_step = int(t["global_step"]) if "global_step" in t else 0
+
+    def save_checkpoint(self, prefix):
+        import numpy as _np
+
+        from . import tf_checkpoint
+        wn, bn, dn = tf_checkpoint.DA_VARIABLE_NAMES
+        return tf_checkpoint.save_checkpoint(prefix, {wn: self._w0, bn: self._b0, dn: self._b1,
+                                                      "global_step": _np.array(int(getattr(self, "global_step", 0)),
+                                                                               dtype=_np.int32)})
 
     def transform(self, x, batch_n=-1):
         import torch

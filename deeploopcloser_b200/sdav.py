@@ -4,7 +4,8 @@ Same attributes and method names as the reference class; `transform(x)` - the en
 the B200 through libdlc (patches -> 5 fused GEMM+bias+sigmoid tcgen05 kernels) and returns the same flat float64
 [B*30, 2500] array (SDAV.py:163, 293-302). Weights are explicit and persistent here (the reference re-initialises
 or re-restores them inside every call, SDAV.py:232-240): seeded N(0,1) like `tf.random_normal` by default, or loaded
-from / saved to an .npz (`w{l}_e [in,out]`, `b{l}_e [out]`, float64).
+from / saved to an .npz (`w{l}_e [in,out]`, `b{l}_e [out]`, `b{l}_d [in]`, float64) or the reference's own TensorFlow
+checkpoints (`tf_checkpoint.py`: variables `Variable` ... `Variable_14`, SDAV.py:188-217, 228-240).
 Training (`fit`, `fit_dataset`) is outside the accelerated path and raises NotImplementedError.
 """
 import glob
@@ -13,7 +14,7 @@ import os
 
 import numpy as np
 
-from . import input_parser
+from . import input_parser, tf_checkpoint
 
 
 class SDAV:
@@ -26,9 +27,15 @@ class SDAV:
         self._encoder = None
         self._weights = None
         self._biases = None
+        self._dec_biases = None
+        self.global_step = 0
         if weights_path is None and os.path.isdir(self.checkpoints_path):
+            # SDAV._load_or_init_session (SDAV.py:232-240): restore the latest checkpoint if the directory has one
             cand = os.path.join(self.checkpoints_path, "sdav_weights.npz")
-            weights_path = cand if os.path.exists(cand) else None
+            if os.path.exists(cand):
+                weights_path = cand
+            elif tf_checkpoint.latest_checkpoint(self.checkpoints_path):
+                weights_path = self.checkpoints_path
         if weights_path is not None:
             self.load_weights(weights_path)
         else:
@@ -69,29 +76,65 @@ class SDAV:
         d = self.dims
         self.set_weights([rng.standard_normal((k, n)) for k, n in zip(d[:-1], d[1:])], [np.zeros(n) for n in d[1:]])
 
-    def set_weights(self, weights, biases):
+    def set_weights(self, weights, biases, decoder_biases=None):
         d = self.dims
         if len(weights) != len(d) - 1 or len(biases) != len(d) - 1:
             raise ValueError("expected %d weight matrices and biases" % (len(d) - 1))
         self._weights = [np.ascontiguousarray(w, dtype=np.float64) for w in weights]
         self._biases = [np.ascontiguousarray(b, dtype=np.float64) for b in biases]
-        for l, (w, b) in enumerate(zip(self._weights, self._biases)):
-            if w.shape != (d[l], d[l + 1]) or b.shape != (d[l + 1],):
-                raise ValueError("layer %d: expected W %s, b %s" % (l, (d[l], d[l + 1]), (d[l + 1],)))
+        if decoder_biases is None:
+            decoder_biases = [np.zeros(k) for k in d[:-1]]           # tf.zeros (SDAV.py:193, 199, ...)
+        self._dec_biases = [np.ascontiguousarray(b, dtype=np.float64) for b in decoder_biases]
+        for l, (w, b, bd) in enumerate(zip(self._weights, self._biases, self._dec_biases)):
+            if w.shape != (d[l], d[l + 1]) or b.shape != (d[l + 1],) or bd.shape != (d[l],):
+                raise ValueError("layer %d: expected W %s, b %s, decoder b %s" % (l, (d[l], d[l + 1]), (d[l + 1],), (d[l],)))
         self._encoder = None  # re-packed lazily on the device
 
     def load_weights(self, path):
-        z = np.load(path)
+        """`path`: an .npz written by save_weights, a TensorFlow checkpoint prefix, or a directory holding the
+        reference's `checkpoint` state file (the latest checkpoint is restored, like SDAV.py:232-236)."""
         n = len(self.hidden_units)
-        self.set_weights([z["w%d_e" % l] for l in range(n)], [z["b%d_e" % l] for l in range(n)])
+        if path.endswith(".npz"):
+            z = np.load(path)
+            dec = [z["b%d_d" % l] for l in range(n)] if "b0_d" in z else None
+            self.set_weights([z["w%d_e" % l] for l in range(n)], [z["b%d_e" % l] for l in range(n)], dec)
+            self.global_step = int(z["global_step"]) if "global_step" in z else 0
+            return
+        prefix = path
+        if os.path.isdir(path):
+            prefix = tf_checkpoint.latest_checkpoint(path)
+            if prefix is None:
+                raise FileNotFoundError("no TensorFlow checkpoint state file in %s" % path)
+        logging.info('Restoring session from %s' % prefix)
+        tensors = tf_checkpoint.load_checkpoint(prefix)
+        names = tf_checkpoint.sdav_variable_names(n)
+        missing = [nm for trio in names for nm in trio if nm not in tensors]
+        if missing:
+            raise KeyError("checkpoint %s lacks the SDAV variables %s (has %s)" % (prefix, missing, sorted(tensors)))
+        self.set_weights([tensors[w] for w, _, _ in names], [tensors[b] for _, b, _ in names],
+                         [tensors[bd] for _, _, bd in names])
+        self.global_step = int(tensors["global_step"]) if "global_step" in tensors else 0
 
-    def save_weights(self, path=None):
+    def save_weights(self, path=None, fmt=None):
+        """fmt "npz" (default for *.npz paths) or "tf": a TensorFlow V2 checkpoint the reference can restore
+        (`<checkpoints>/checkpoint_file-<global_step>` + the `checkpoint` state file, SDAV.py:228-230, 273-275)."""
+        if fmt is None:
+            fmt = "tf" if (path is not None and not path.endswith(".npz")) else "npz"
+        step = int(getattr(self, "global_step", 0))
+        if fmt == "tf":
+            prefix = path or "%s-%d" % (os.path.join(self.checkpoints_path, "checkpoint_file"), step)
+            tensors = {"global_step": np.array(step, dtype=np.int32)}
+            for (wn, bn, dn), w, b, bd in zip(tf_checkpoint.sdav_variable_names(len(self.hidden_units)),
+                                              self._weights, self._biases, self._dec_biases):
+                tensors[wn], tensors[bn], tensors[dn] = w, b, bd
+            return tf_checkpoint.save_checkpoint(prefix, tensors)
         path = path or os.path.join(self.checkpoints_path, "sdav_weights.npz")
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        arrays = {}
-        for l, (w, b) in enumerate(zip(self._weights, self._biases)):
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        arrays = {"global_step": np.array(step, dtype=np.int32)}
+        for l, (w, b, bd) in enumerate(zip(self._weights, self._biases, self._dec_biases)):
             arrays["w%d_e" % l] = w
             arrays["b%d_e" % l] = b
+            arrays["b%d_d" % l] = bd
         np.savez(path, **arrays)
         return path
 
