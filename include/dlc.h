@@ -242,6 +242,43 @@ int dlc_maxpool_planes(const float* x_dev, int N, int H, int W, int C, int windo
 int dlc_cnnvtl_quantise(const float* const* seg_ptrs_host, const int64_t* seg_sizes_host, int n_seg, int N,
                         const int64_t* keep_cols_dev, int M, float* minmax_dev, int8_t* out_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step of the denoising autoencoders (callers: train.py -> SDAV.fit_dataset,
+ * train-sdav.py -> SDA.fit -> DA.fit_dataset). Replaces the TensorFlow graph pieces of SDAV._define_model /
+ * _define_loss_for_layer / _define_optimizer (src/sdav/network/SDAV.py:120-186, 223-226) and DA._define_fitting_model /
+ * _define_loss / _define_optimizer / _corrupt_tensor (src/sdav/network/DenoisingAutoencoderVariant.py:103-158,
+ * 182-202). These are the elementwise / reduction kernels; the contractions between them are dlc_gemm_planes calls
+ * (forward, tied-weight decoder, gradient into the hidden layer, gradient into the input, and ONE GEMM for the
+ * weight gradient x~^T dzh + dzy^T h with the two contractions concatenated along K). All activations float32
+ * [R, C] row-major (R = batch * patches), master weights float64.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* out = x * keep[r % mask_rows] + add[r % mask_rows] (keep / add optional, [mask_rows, C] float32 0/1 masks:
+ * SDAV's shared [P, C] masking noise, TensorflowWrapper.py:34-38, or DA's [R, C] zeros/ones masks) -> float32
+ * and/or operand planes [R, ld]. */
+int dlc_train_corrupt(const float* x_dev, const float* keep_dev, const float* add_dev, int R, int C, int mask_rows,
+                      float* out_f32_dev, void* out_hi_dev, void* out_lo_dev, int ld, void* stream);
+/* softmax_cross_entropy_with_logits_v2(labels, logits = y) averaged over the R rows (SDAV.py:172): adds the loss to
+ * loss_dev[0]; dzy = d loss / d (decoder pre-activation) = dy * y * (1 - y) as float32 and/or planes; dlabel
+ * (optional) = d loss / d labels. */
+int dlc_train_xent_grad(const float* y_dev, const float* labels_dev, int R, int C, float* dzy_f32_dev,
+                        void* dzy_hi_dev, void* dzy_lo_dev, int ld, float* dlabel_dev, double* loss_dev, void* stream);
+/* dzh = (dh_rec + dh_up + cs_coef * sign(h - sparse_level) + cc_coef * d(sum_b ||h[b] - h[b+1]||_F)/dh) * h * (1 - h)
+ * for h [B*P, C]; dh_rec / dh_up optional. cs_coef = sparse_penalty / count, cc_coef = consecutive_penalty / (B - 1)
+ * (SDAV.py:174-183); the two loss terms are added to loss_dev[0]. norms_dev: B - 1 doubles of scratch. */
+int dlc_train_hidden_grad(const float* h_dev, const float* dh_rec_dev, const float* dh_up_dev, int B, int P, int C,
+                          float sparse_level, double cs_coef, double cc_coef, double* norms_dev, float* dzh_f32_dev,
+                          void* dzh_hi_dev, void* dzh_lo_dev, int ld, double* loss_dev, void* stream);
+/* out[c] = sum_r a[r, c] (bias gradients), float64. */
+int dlc_train_colsum(const float* a_dev, int R, int C, double* out_dev, void* stream);
+/* a [R, C] -> transposed planes [C, ld]: plane[c][col_off + r] = a[r][c], zero for R <= r < r_pad. */
+int dlc_train_transpose_planes(const float* a_dev, int R, int C, void* hi_dev, void* lo_dev, int ld, int col_off,
+                               int r_pad, void* stream);
+/* w -= lr * grad (GradientDescentOptimizer, SDAV.py:225); grad float32 or float64. */
+int dlc_train_sgd(double* w_dev, const void* grad_dev, int grad_dtype, int64_t n, double lr, void* stream);
+/* out = (dx + extra) * keep[r % mask_rows]: gradient through x_l = h_{l-1} * mask_l (+ the label gradient). */
+int dlc_train_mask_grad(const float* dx_dev, const float* extra_dev, const float* keep_dev, int R, int C,
+                        int mask_rows, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

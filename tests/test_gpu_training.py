@@ -1,0 +1,85 @@
+"""One SGD step of the denoising-autoencoder training graphs on the B200 (dlc_train_* kernels + tcgen05 GEMMs through
+the C ABI) against the float64 oracle (oracle/train.py, itself pinned by finite differences). `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import train as o_train
+
+pytestmark = pytest.mark.gpu
+
+
+def _nerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _setup(dims, B, P, seed, scale):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (B, P, dims[0]))
+    Ws = [scale * rng.standard_normal((k, n)) for k, n in zip(dims[:-1], dims[1:])]
+    bs = [0.1 * rng.standard_normal(n) for n in dims[1:]]
+    bds = [0.1 * rng.standard_normal(k) for k in dims[:-1]]
+    return rng, x, Ws, bs, bds
+
+
+@pytest.mark.parametrize("dims,B,P,top", [((70, 96, 40), 4, 5, 0), ((70, 96, 40), 4, 5, 1), ((300, 130, 64, 33), 3, 30, 2),
+                                          ((1681, 2500), 10, 30, 0)])
+def test_sdav_train_step_vs_oracle(cuda, dims, B, P, top):
+    from deeploopcloser_b200.training import DaeStackTrainer
+    rng, x, Ws, bs, bds = _setup(dims, B, P, 7 + top, 0.3 if dims[0] < 1000 else 0.05)
+    masks = [o_train.sdav_mask(P, d, 0.3, rng) for d in dims[:top + 1]]
+    tr = DaeStackTrainer(dims, patches=P)
+    tr.set_weights(Ws, bs, bds)
+    xd = torch.from_numpy(x).float().cuda()
+    md = [torch.from_numpy(m).float().cuda() for m in masks]
+    loss = float(tr.step(xd, top, md).item())
+    want_loss, dW, db, dbd = o_train.sdav_loss_and_grads(x, Ws, bs, bds, top, masks)
+    g = tr.last_grads
+    print("loss %.9f vs %.9f" % (loss, want_loss))
+    assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
+    for l in range(top + 1):
+        e_w, e_b = _nerr(g["dW"][l].cpu().numpy(), dW[l]), _nerr(g["db"][l].cpu().numpy(), db[l])
+        print("layer %d: dW normwise err %.2e, db %.2e" % (l, e_w, e_b))
+        assert e_w <= 1e-4 and e_b <= 1e-4
+    assert _nerr(g["dbd"].cpu().numpy(), dbd) <= 1e-4
+    # the update itself: every layer <= top moved by lr * grad, the decoder bias only at `top`
+    _, W2, b2, bd2 = o_train.sdav_train_step(x, Ws, bs, bds, top, masks, lr=0.1)
+    gW, gb, gbd = tr.get_weights()
+    for l in range(len(dims) - 1):
+        assert _nerr(gW[l], W2[l]) <= 1e-6 and _nerr(gb[l], b2[l]) <= 1e-5
+        assert np.allclose(gbd[l], bd2[l], rtol=0, atol=1e-6)
+    assert tr.global_step == 1
+
+
+def test_da_train_step_vs_oracle(cuda):
+    from deeploopcloser_b200.training import DaeStackTrainer
+    dims, B, P = (120, 200), 5, 6
+    rng, x, Ws, bs, bds = _setup(dims, B, P, 3, 0.3)
+    zm, om = o_train.da_masks(B * P, dims[0], 0.3, rng)
+    tr = DaeStackTrainer(dims, patches=P)
+    tr.set_weights(Ws, bs, bds)
+    loss = float(tr.step(torch.from_numpy(x).float().cuda(), 0, [torch.from_numpy(zm).float().cuda()],
+                         [torch.from_numpy(om).float().cuda()], mask_rows=B * P, da_mode=True).item())
+    want_loss, dW, db0, db1 = o_train.da_loss_and_grads(x, Ws[0], bs[0], bds[0], zm, om)
+    g = tr.last_grads
+    assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
+    assert _nerr(g["dW"][0].cpu().numpy(), dW) <= 1e-4
+    assert _nerr(g["db"][0].cpu().numpy(), db0) <= 1e-4 and _nerr(g["dbd"].cpu().numpy(), db1) <= 1e-4
+
+
+def test_training_reduces_the_loss(cuda):
+    """A few SGD steps on a fixed batch and fixed masks lower loss_0 monotonically (sanity of the whole chain)."""
+    from deeploopcloser_b200.training import DaeStackTrainer
+    dims, B, P = (64, 48), 6, 4
+    rng, x, Ws, bs, bds = _setup(dims, B, P, 11, 0.2)
+    tr = DaeStackTrainer(dims, patches=P, learning_rate=0.05)
+    tr.set_weights(Ws, bs, bds)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    masks = tr.sdav_masks(0, 0.3, gen)
+    assert int((masks[0] == 0).sum().item()) == int(round(P * dims[0] * 0.3))
+    xd = torch.from_numpy(x).float().cuda()
+    losses = [float(tr.step(xd, 0, masks).item()) for _ in range(8)]
+    print("losses", losses)
+    assert all(b < a for a, b in zip(losses, losses[1:]))
