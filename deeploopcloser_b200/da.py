@@ -2,7 +2,8 @@
 `src.sdav.network.StackedDenoisingAutoencoderVariants.SDA` (reference files of the same names).
 `DA.transform(x[30, in]) -> [30, hidden]` = sigmoid(x w0 + b0) (DenoisingAutoencoderVariant.py:116-119, 254-259) runs
 as one fused tcgen05 kernel; `SDA` chains the layers (StackedDenoisingAutoencoderVariants.py:73-83). Constructor
-arguments are the reference's (the `graph` argument is accepted and ignored). Training raises NotImplementedError."""
+arguments are the reference's (the `graph` argument is accepted and ignored). `fit` / `fit_dataset` run the reference's
+training schedule with every SGD step on the B200 (`training.DaeStackTrainer`)."""
 import logging
 
 import numpy as np
@@ -100,11 +101,59 @@ class DA:
         out = self._encoder.encode(torch.from_numpy(np.ascontiguousarray(x)).cuda())
         return out.to(torch.float64).cpu().numpy()
 
-    def fit(self, file_pattern):
-        raise NotImplementedError("DA.fit (training, DenoisingAutoencoderVariant.py:204-243) is outside the B200 hot path")
+    # ---- training (DenoisingAutoencoderVariant.py:103-158, 182-243): every SGD step on the B200
+    def fit(self, file_pattern, key_points=None):
+        """DA.fit (:204-208): parse the images matched by `file_pattern` into frames and fit on them."""
+        import glob
 
-    def fit_dataset(self, dataset):
-        raise NotImplementedError("DA.fit_dataset (training) is outside the B200 hot path")
+        from . import input_parser
+        logging.info("  Layer:%d fit" % self.layer_n)
+        patch_size = int(round(np.sqrt(self.input_shape[1])))
+        parser = input_parser.CvInputParser(self.input_shape[0], patch_size)
+        frames = []
+        for i, f in enumerate(sorted(glob.glob(file_pattern))):
+            kp = key_points(i, f) if callable(key_points) else (None if key_points is None else key_points[i])
+            frames.append(parser.parse_from_path(f, key_points=kp))
+        return self.fit_dataset(frames)
+
+    def fit_dataset(self, dataset, seed=None):
+        """DA.fit_dataset (:210-243): batches of `batch_size` frames [30, in]; `epochs` steps of the train_step on each;
+        a trailing batch smaller than batch_size is ignored with the reference's warning. The corruption masks are
+        drawn once per instance, like the graph constants of _corrupt_tensor (:182-202). Returns the last loss."""
+        import torch
+
+        from .training import DaeStackTrainer
+        frames = [np.asarray(f, dtype=np.float64) for f in dataset]
+        trainer = DaeStackTrainer([self.input_shape[1], self.hidden_units], patches=self.input_shape[0],
+                                  sparse_level=self.sparse_level, sparse_penalty=self.sparse_penalty,
+                                  consecutive_penalty=self.consecutive_penalty, learning_rate=self.learning_rate)
+        trainer.set_weights([self._w0], [self._b0], [self._b1])
+        trainer.global_step = int(getattr(self, "global_step", 0))
+        rows = self.batch_size * self.input_shape[0]
+        if getattr(self, "_masks", None) is None:
+            gen = None
+            if seed is not None:
+                gen = torch.Generator(device="cuda")
+                gen.manual_seed(seed)
+            self._masks = trainer.da_masks(rows, self.corruption_level, gen)
+        zm, om = self._masks
+        loss = None
+        for batch_n, s in enumerate(range(0, len(frames), self.batch_size)):
+            batch = frames[s:s + self.batch_size]
+            if len(batch) != self.batch_size:
+                logging.warning("Ignored last batch because it was smaller than the specified batch size. To avoid this "
+                                "choose a batch size that is a factor of the dataset size.")
+                break
+            xd = torch.from_numpy(np.ascontiguousarray(np.stack(batch), dtype=np.float32)).cuda()
+            for step in range(self.epochs):
+                loss = trainer.step(xd, 0, [zm], [om], mask_rows=rows, da_mode=True)
+                if logging.getLogger().isEnabledFor(logging.INFO):
+                    logging.info('    Layer:%d Batch:%d fit, Epoch:%d/%d, Loss:%s' % (self.layer_n, batch_n, step + 1,
+                                                                                    self.epochs, float(loss.item())))
+        ws, bs, bds = trainer.get_weights()
+        self.set_weights(ws[0], bs[0], bds[0])
+        self.global_step = int(trainer.global_step)
+        return None if loss is None else float(loss.item())
 
 
 class SDA:
@@ -137,6 +186,25 @@ class SDA:
             x = layer.transform(x)
         return x
 
-    def fit(self, file_pattern):
-        raise NotImplementedError("SDA.fit (layer-wise training, StackedDenoisingAutoencoderVariants.py:90-100) is "
-                                  "outside the B200 hot path")
+    def fit(self, file_pattern, key_points=None):
+        """SDA.fit (StackedDenoisingAutoencoderVariants.py:90-100): fit layer 0 on the parsed frames, then each next
+        layer on the frames mapped through the previous layers' transform."""
+        import glob
+
+        from . import input_parser
+        logging.info("Fit SDAV")
+        patch_size = int(round(np.sqrt(self.input_shape[1])))
+        parser = input_parser.CvInputParser(self.input_shape[0], patch_size)
+        frames = []
+        for i, f in enumerate(sorted(glob.glob(file_pattern))):
+            kp = key_points(i, f) if callable(key_points) else (None if key_points is None else key_points[i])
+            frames.append(parser.parse_from_path(f, key_points=kp))
+        return self.fit_dataset(frames)
+
+    def fit_dataset(self, frames):
+        losses = []
+        for i, layer in enumerate(self._layers):
+            losses.append(layer.fit_dataset(frames))
+            if i + 1 < len(self._layers):
+                frames = [layer.transform(f) for f in frames]
+        return losses

@@ -6,7 +6,8 @@ the B200 through libdlc (patches -> 5 fused GEMM+bias+sigmoid tcgen05 kernels) a
 or re-restores them inside every call, SDAV.py:232-240): seeded N(0,1) like `tf.random_normal` by default, or loaded
 from / saved to an .npz (`w{l}_e [in,out]`, `b{l}_e [out]`, `b{l}_d [in]`, float64) or the reference's own TensorFlow
 checkpoints (`tf_checkpoint.py`: variables `Variable` ... `Variable_14`, SDAV.py:188-217, 228-240).
-Training (`fit`, `fit_dataset`) is outside the accelerated path and raises NotImplementedError.
+Training (`fit`, `fit_dataset`: the reference's greedy layer schedule, SDAV.py:242-288) runs every SGD step on the
+B200 through `training.DaeStackTrainer` (tcgen05 GEMMs + the dlc_train_* kernels).
 """
 import glob
 import logging
@@ -18,10 +19,15 @@ from . import input_parser, tf_checkpoint
 
 
 class SDAV:
-    def __init__(self, verbosity=logging.WARNING, weights_path=None, seed=0, precision="fp16x2", train_path=None):
+    def __init__(self, verbosity=logging.WARNING, weights_path=None, seed=0, precision="fp16x2", train_path=None,
+                 input_shape=None, hidden_units=None):
         self._configure_logging(verbosity)
         self._set_train_path(train_path)
         self._define_params()
+        if input_shape is not None:          # extension: other geometries than the reference's fixed 30 x 1681 -> 5 x 2500
+            self.input_shape = list(input_shape)
+        if hidden_units is not None:
+            self.hidden_units = list(hidden_units)
         self.losses = []
         self.precision = precision
         self._encoder = None
@@ -193,10 +199,82 @@ class SDAV:
         """Reference: a tf.data generator dataset of parsed frames (SDAV.py:219-221). Here: the sorted file list."""
         return sorted(glob.glob(file_pattern))
 
-    # ---- training: not part of the accelerated path
-    def fit_dataset(self, dataset):
-        raise NotImplementedError("SDAV.fit_dataset (training, SDAV.py:242-275) is outside the B200 hot path; train "
-                                  "with the reference and load the weights with load_weights()/set_weights()")
+    # ---- training (SURVEY 8f rank 2): the reference's greedy schedule, each step on the B200
+    def _get_trainer(self):
+        from .training import DaeStackTrainer
+        tr = DaeStackTrainer(self.dims, patches=self.input_shape[0], sparse_level=self.sparse_level,
+                             sparse_penalty=self.sparse_penalty, consecutive_penalty=self.consecutive_penalty,
+                             learning_rate=self.learning_rate)
+        tr.set_weights(self._weights, self._biases, self._dec_biases)
+        tr.global_step = int(self.global_step)
+        return tr
 
-    def fit(self, x):
-        raise NotImplementedError("SDAV.fit (training, SDAV.py:277-288) is outside the B200 hot path")
+    def _adopt(self, trainer):
+        ws, bs, bds = trainer.get_weights()
+        self.set_weights(ws, bs, bds)
+        self.global_step = int(trainer.global_step)
+
+    def _fit_batch(self, trainer, layer, batch, generator=None, log_batch=None):
+        import torch
+        xd = torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)).cuda()
+        loss = None
+        for step in range(self.epochs):
+            masks = trainer.sdav_masks(layer, self.corruption_level, generator)      # redrawn on every run (:34-38)
+            loss = trainer.step(xd, layer, masks)
+            if log_batch is not None and self.logger.isEnabledFor(logging.INFO):
+                logging.info('    Layer:%d Batch:%d fit, Epoch:%d/%d, Loss:%s' % (layer, log_batch, step + 1,
+                                                                                self.epochs, float(loss.item())))
+        return None if loss is None else float(loss.item())
+
+    def fit(self, x, seed=None):
+        """SDAV.fit (SDAV.py:277-288): for each of the five layers, `epochs` SGD steps of train_steps[i] on the batch
+        x [B, 30, 1681]. Returns the last loss of every layer."""
+        import torch
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim != 3 or list(x.shape[1:]) != self.input_shape:
+            raise ValueError("expected input of shape [B, %d, %d], got %s" % (self.input_shape[0], self.input_shape[1], x.shape))
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(seed)
+        trainer = self._get_trainer()
+        losses = [self._fit_batch(trainer, i, x, gen) for i in range(len(self.hidden_units))]
+        self._adopt(trainer)
+        return losses
+
+    def fit_dataset(self, dataset, key_points=None, seed=None, save=True):
+        """SDAV.fit_dataset (SDAV.py:242-275): for each layer, walk the dataset in batches of `default_batch_size`
+        frames and run `epochs` steps of train_steps[i] on every batch; a checkpoint is written after each layer
+        (TensorFlow format, `<checkpoints>/checkpoint_file-<global_step>`). `dataset`: the file list returned by
+        get_dataset(), or an iterable of parsed frames [30, 1681]; `key_points` as in transform_dataset."""
+        import torch
+        frames = self._materialise(dataset, key_points)
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(seed)
+        trainer = self._get_trainer()
+        bs = self.default_batch_size
+        for i in range(len(self.hidden_units)):
+            logging.info('Fitting layer %d' % i)
+            for batch_n, s in enumerate(range(0, len(frames), bs)):
+                batch = frames[s:s + bs]
+                if len(batch) < 2:       # the consecutive-frame term of a single frame is a mean over nothing (NaN)
+                    logging.warning("Ignored a trailing batch of one frame")
+                    continue
+                self._fit_batch(trainer, i, batch, gen, log_batch=batch_n)
+            self._adopt(trainer)
+            if save:
+                logging.info('Saving trained params to %s with global_step %s' % (self.checkpoints_path, self.global_step))
+                self.save_weights(fmt="tf")
+
+    def _materialise(self, dataset, key_points):
+        if len(dataset) and isinstance(dataset[0], str):
+            patch_size = int(round(np.sqrt(self.input_shape[1])))
+            parser = input_parser.CvInputParser(self.input_shape[0], patch_size)
+            out = []
+            for i, f in enumerate(dataset):
+                kp = key_points(i, f) if callable(key_points) else (None if key_points is None else key_points[i])
+                out.append(parser.parse_from_path(f, key_points=kp))
+            return np.stack(out)
+        return np.asarray(dataset, dtype=np.float64)

@@ -83,3 +83,38 @@ def test_training_reduces_the_loss(cuda):
     losses = [float(tr.step(xd, 0, masks).item()) for _ in range(8)]
     print("losses", losses)
     assert all(b < a for a, b in zip(losses, losses[1:]))
+
+
+def test_sdav_and_da_fit_api(cuda, tmp_path):
+    """The reference's training entry points (train.py -> SDAV.fit_dataset, train-sdav.py -> SDA.fit -> DA.fit_dataset)
+    run on the B200: the loss falls, weights move for every layer, and the TensorFlow-format checkpoint written after
+    each layer restores into a fresh instance that encodes identically."""
+    import logging
+    from src.sdav.network.SDAV import SDAV
+    from src.sdav.network.StackedDenoisingAutoencoderVariants import SDA
+    rng = np.random.default_rng(0)
+    net = SDAV(verbosity=logging.ERROR, train_path=str(tmp_path / "sdav"), seed=1, input_shape=[6, 49],
+               hidden_units=[40, 32])
+    net.epochs, net.default_batch_size, net.learning_rate = 3, 4, 0.05
+    net.set_weights([0.2 * w for w in net._weights], net._biases)
+    w_before = [w.copy() for w in net._weights]
+    frames = rng.uniform(0, 1, (9, 6, 49))                 # 2 batches of 4 + a single trailing frame (ignored)
+    first = net.fit(frames[:4], seed=3)
+    assert len(first) == 2 and all(np.isfinite(first))
+    net.fit_dataset(frames, seed=4)
+    assert all(not np.array_equal(a, b) for a, b in zip(w_before, net._weights))
+    assert net.global_step == 2 * 3 + 2 * 2 * 3            # fit: 2 layers x 3 epochs; fit_dataset: 2 layers x 2 batches x 3
+    # a fresh instance restores the latest checkpoint of the directory by itself (SDAV._load_or_init_session)
+    again = SDAV(verbosity=logging.ERROR, train_path=str(tmp_path / "sdav"), input_shape=[6, 49], hidden_units=[40, 32])
+    assert again.global_step == net.global_step
+    assert all(np.array_equal(a, b) for a, b in zip(again._weights, net._weights))
+    assert np.array_equal(again.transform(frames[:2]), net.transform(frames[:2]))
+
+    sda = SDA([6, 49], [40, 32], batch_size=4, epochs=4, learning_rate=0.05, seed=2)
+    for layer in sda._layers:
+        layer.set_weights(0.2 * layer._w0, layer._b0)
+    losses = sda.fit_dataset(list(frames))
+    assert len(losses) == 2 and all(np.isfinite(losses))
+    l0 = sda._layers[0]
+    first_loss = l0.fit_dataset(list(frames[:4]))           # continues from the trained weights, same fixed masks
+    assert first_loss < 1e9 and l0.global_step == 2 * 4 + 4

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_training.py -x -q -s > gpurun_out/pytest_train.log 2>&1; tail -30 gpurun_out/pytest_train.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; tail -15 gpurun_out/pytest.log
