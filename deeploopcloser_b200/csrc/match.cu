@@ -199,33 +199,57 @@ struct MatchPolicy {
     __device__ __forceinline__ void end_tile(TileCoord) {}
     __device__ __forceinline__ void post_tile(TileCoord) {}
 
+    // One sorted insertion (larger key first; candidates arrive in increasing index, so the strict > keeps the
+    // lowest index on ties).
+    __device__ __forceinline__ void insert(float cs, int ci) {
+#pragma unroll
+      for (int t = 0; t < KMAX; ++t) {
+        const bool up = cs > ls[t];
+        const float ts = ls[t];
+        const int ti = li[t];
+        ls[t] = up ? cs : ts;
+        li[t] = up ? ci : ti;
+        cs = up ? ts : cs;
+        ci = up ? ti : ci;
+      }
+    }
+
+    // 32 scores of this thread's query against 32 consecutive database rows. Fast path (almost every chunk once the
+    // list is warm: a new row beats the current K-th best with probability ~K / rows seen): one max over the 32 keys
+    // and one compare. Slow path: the keys go through a small local array and ONE rolled insertion loop - the
+    // unrolled form (32 x K-step insertions per chunk, 8 chunks) was 29k instructions and ran out of the
+    // instruction cache (ncu: `no_inst` was the top stall of the epilogue warps and the tensor pipe sat at 30 %).
     template <int SLOT>
     __device__ __forceinline__ void chunk(TileCoord tc, int c, float (&v)[32]) {
       const int64_t col0 = static_cast<int64_t>(tc.nt) * p.n_tile + c * 32;
       if (col0 >= p.db_rows) return;  // warp-uniform
-      float my_dn = 0.0f;
-      if (l2) my_dn = (col0 + lane < p.db_rows) ? p.dn[col0 + lane] : 0.0f;
       const int nvalid = p.db_rows - col0 < 32 ? static_cast<int>(p.db_rows - col0) : 32;
+      if (l2) {
+        const float my_dn = (col0 + lane < p.db_rows) ? p.dn[col0 + lane] : 0.0f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float key = v[j] * gscale;
-        if (l2) key -= __shfl_sync(0xffffffffu, my_dn, j);
-        if (j < nvalid && row < p.B) {
-          if (p.use_thr && key >= thr_key) ++cnt;
-          if (key > ls[KMAX - 1]) {  // candidates arrive in increasing index: strict > keeps the lowest index on ties
-            float cs = key;
-            int ci = static_cast<int>(col0) + j;
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * 2.0f - __shfl_sync(0xffffffffu, my_dn, j);
+      }
+      if (nvalid < 32) {  // last database tile only
 #pragma unroll
-            for (int t = 0; t < KMAX; ++t) {
-              const bool up = cs > ls[t];
-              const float ts = ls[t];
-              const int ti = li[t];
-              ls[t] = up ? cs : ts;
-              li[t] = up ? ci : ti;
-              cs = up ? ts : cs;
-              ci = up ? ti : ci;
-            }
-          }
+        for (int j = 0; j < 32; ++j)
+          if (j >= nvalid) v[j] = -INFINITY;
+      }
+      if (row >= p.B) return;
+      if (p.use_thr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cnt += (v[j] >= thr_key && j < nvalid) ? 1 : 0;
+      }
+      float cmax = v[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+      if (cmax > ls[KMAX - 1]) {
+        float kl[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) kl[j] = v[j];
+#pragma unroll 1
+        for (int j = 0; j < nvalid; ++j) {
+          const float key = kl[j];
+          if (key > ls[KMAX - 1]) insert(key, static_cast<int>(col0) + j);
         }
       }
     }
