@@ -1,0 +1,154 @@
+"""BASELINE.json's full sizes through size-independent properties (the oracle cannot run whole at these sizes):
+symmetry / fill values, sortedness, idempotence, planted answers, a merge-of-halves identity, and spot checks of
+random entries against the float64 oracle. `-m gpu`."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cnnvtl as o_cnn
+from oracle import hamming as o_ham
+from oracle import patches as o_patch
+from oracle import sda as o_sda
+from oracle import similarity as o_sim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def config2(cuda):
+    """Config 2: 1063 frames 240x192, 30 keypoints, reference-default N(0,1) weights -> descriptors, S, candidates."""
+    import bench
+    from deeploopcloser_b200.pipeline import LoopClosurePipeline
+    frames, xy = bench.synthetic_inputs(100)
+    ws, bs = bench.reference_weights()
+    pipe = LoopClosurePipeline(bench.DIMS, precision="fp16x2", sim_precision="fp16x2")
+    pipe.set_weights(ws, bs)
+    f_d, x_d = torch.from_numpy(frames).cuda(), torch.from_numpy(xy).cuda()
+    res = pipe.run(f_d, x_d, k=bench.K_CAND, exclude_band=0)
+    torch.cuda.synchronize()
+    return {"frames": frames, "xy": xy, "ws": ws, "bs": bs, "pipe": pipe, "f_d": f_d, "x_d": x_d, "res": res}
+
+
+def test_config2_descriptors_spot_check_and_idempotence(config2):
+    c = config2
+    desc = c["res"]["descriptors"]
+    assert tuple(desc.shape) == (1063 * 30, 2500)
+    again = c["pipe"].encode(c["f_d"], c["x_d"])
+    assert torch.equal(desc, again)                                   # same inputs -> same bits
+    rng = np.random.default_rng(0)
+    picks = np.sort(rng.choice(1063, 6, replace=False))
+    x = np.concatenate([o_patch.extract_patches(c["frames"][i], c["xy"][i]) for i in picks])
+    want = o_sda.sda_forward(x, c["ws"], c["bs"])
+    got = torch.cat([desc[i * 30:(i + 1) * 30] for i in picks]).cpu().numpy()
+    err = float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))))
+    print("config 2 descriptors, 6 frames vs oracle: max rel err %.2e" % err)
+    assert err <= TOL
+    assert float(desc.min()) >= 0.0 and float(desc.max()) <= 1.0      # sigmoid range
+
+
+def test_config2_similarity_matrix_properties(config2):
+    c = config2
+    S = c["res"]["similarity"].cpu().numpy()
+    assert S.shape == (1063, 1063)
+    assert np.array_equal(S, S.T)                                     # the reference mirrors i<j (create_similarity_matrix.py:36-38)
+    assert np.all(np.diag(S) == -1.0)                                 # np.full(..., -1) fill (:31)
+    desc = c["res"]["descriptors"].cpu().numpy().astype(np.float64).reshape(1063, 30, 2500)
+    w = o_sim.distinctive_weights(desc)
+    rng = np.random.default_rng(1)
+    worst = 0.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for _ in range(150):
+            i, j = sorted(rng.choice(1063, 2, replace=False))
+            want = o_sim.similarity_score(desc[i], desc[j], w)
+            worst = max(worst, abs(S[i, j] - want) / max(1.0, abs(want)))
+    print("config 2 scores, 150 random pairs vs oracle: max rel err %.2e" % worst)
+    assert worst <= TOL
+
+
+def test_config2_candidates_are_the_sorted_row_maxima(config2):
+    c = config2
+    S = c["res"]["similarity"].cpu().numpy().astype(np.float64)
+    scores, idx = [t.cpu().numpy() for t in c["res"]["candidates"]]
+    assert scores.shape == (1063, 10) and idx.shape == (1063, 10)
+    assert np.all(np.diff(scores, axis=1) <= 0)                       # best first
+    masked = S.copy()
+    np.fill_diagonal(masked, -np.inf)                                  # exclude_band = 0 drops the frame itself
+    order = np.argsort(-masked, axis=1, kind="stable")[:, :10]         # ties -> lowest index
+    assert np.array_equal(idx, order)
+    assert np.array_equal(scores, np.take_along_axis(S, idx, 1).astype(np.float32))
+
+
+def test_config3_cnnvtl_descriptors_and_hamming_matrix(cuda):
+    """Config 3: 1063 frames 192x240x3 -> int8 descriptors -> exact Hamming matrix."""
+    from deeploopcloser_b200 import ops
+    from deeploopcloser_b200.cnn_vtl import CnnVtl
+    N, H, W = 1063, 192, 240
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    params = o_cnn.make_weights(3)
+    keep = o_cnn.make_keep_columns(o_cnn.layer_sizes((H, W)), seed=4)
+    net = CnnVtl(input_shape=[N, H, W, 3], weights=params, keep_cols=keep)
+    d = net.transform(x)
+    assert d.shape == (N, keep.size) and d.dtype == np.int8
+    assert np.array_equal(d[:300], net.transform(x[:300]))            # chunking does not change a frame's descriptor
+    picks = np.sort(rng.choice(N, 3, replace=False))
+    want = o_cnn.transform(x[picks].astype(np.float64), params, keep)
+    diff = (d[picks].astype(np.int16) - want.astype(np.int16) + 128) % 256 - 128
+    print("config 3 descriptors, 3 frames vs oracle: %d of %d bytes differ" % (int((diff != 0).sum()), diff.size))
+    assert np.all(np.abs(diff) <= 1) and (diff != 0).sum() <= 0.002 * diff.size
+    D = ops.hamming_matrix(torch.from_numpy(d).cuda()).cpu().numpy()
+    assert D.shape == (N, N) and np.array_equal(D, D.T) and np.all(np.diag(D) == 0)
+    for _ in range(40):
+        i, j = rng.choice(N, 2, replace=False)
+        assert D[i, j] == o_ham.distance(d[i], d[j])
+
+
+def test_config4_matcher_full_size_properties(cuda):
+    """Config 4 on one GPU: 1 M x 4096 database, 1024 queries, top-10. Planted near-duplicates come back first,
+    lists are sorted, and the list over the whole database equals the merge of the lists over its two halves."""
+    from deeploopcloser_b200.matcher import KeyframeDatabase, merge_partial_lists
+    rows, dim, B, k = 1_000_000, 4096, 1024, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    whole = KeyframeDatabase(dim, rows, "cos", "fp16")
+    halves = [KeyframeDatabase(dim, rows // 2, "cos", "fp16") for _ in range(2)]
+    planted = None
+    for s in range(0, rows, 62500):
+        chunk = torch.randn((62500, dim), device="cuda", generator=g)
+        if s == 0:
+            planted = chunk[:100].clone()
+        whole.append(chunk)
+        halves[s // (rows // 2)].append(chunk)
+    q = torch.randn((B, dim), device="cuda", generator=g)
+    q[:100] = planted + 0.05 * torch.randn((100, dim), device="cuda", generator=g)
+    s_w, i_w = whole.topk(q, k)
+    assert torch.equal(i_w[:100, 0].cpu(), torch.arange(100))
+    assert bool((s_w[:, :-1] >= s_w[:, 1:]).all()) and int(i_w.min()) >= 0 and int(i_w.max()) < rows
+    assert float(s_w.max()) <= 1.0 + 1e-3                               # cosine
+    parts = [halves[h].topk(q, k, idx_offset=h * (rows // 2)) for h in range(2)]
+    s_m, i_m = merge_partial_lists(torch.cat([p[0] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k)
+    assert torch.equal(i_m, i_w) and torch.equal(s_m, s_w)
+    again_s, again_i = whole.topk(q, k)
+    assert torch.equal(again_i, i_w) and torch.equal(again_s, s_w)      # deterministic
+
+
+def test_config5_streaming_batch_256(cuda):
+    """Config 5 shape on one GPU: 640x480 frames, batch 256: a batch that comes back finds its own earlier copy."""
+    from deeploopcloser_b200.streaming import StreamingLoopCloser
+    import bench
+    ws, bs = bench.reference_weights()
+    sl = StreamingLoopCloser(capacity_per_rank=4096, dims=bench.DIMS, k=10)
+    sl.set_weights(ws, bs)
+    rng = np.random.default_rng(3)
+    frames = torch.from_numpy(rng.integers(0, 256, (256, 480, 640), dtype=np.uint8)).cuda()
+    xy = torch.from_numpy(np.stack([rng.uniform(0, 640, (256, 30)), rng.uniform(0, 480, (256, 30))], -1)
+                          .astype(np.float32)).cuda()
+    s0, i0 = sl.step(frames, xy)
+    assert bool((i0 == -1).all())                                       # empty database
+    s1, i1 = sl.step(frames, xy)
+    assert torch.equal(i1[:, 0].cpu(), torch.arange(256))
+    assert bool((s1[:, 0] > 0.999).all()) and len(sl.db.local) == 512
