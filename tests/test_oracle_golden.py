@@ -101,3 +101,43 @@ def test_matcher_oracle_ties_and_padding():
     assert ti.tolist() == [[3, 1, 2], [2, 3, -1]]
     c, ts, ti = o_match.threshold(s, 2.5, 3)
     assert c.tolist() == [2, 0] and ti.tolist() == [[1, 2, -1], [-1, -1, -1]]
+
+
+# ------------------------------------------------------------------------------------------- independent cross-checks
+def test_cnnvtl_oracle_matches_torch_conv2d():
+    """The conv-head oracle (NumPy sliding windows, TF 'SAME' = extra pixel after) against an independent float64
+    implementation: torch.nn.functional.conv2d / max_pool2d on CPU with the same explicit padding."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 255, (2, 43, 51, 3))
+    params = o_cnn.make_weights(5)
+    outs = o_cnn.conv_outputs(x, params)
+    h = torch.from_numpy(x).permute(0, 3, 1, 2)
+    for (name, kh, kw, cin, cout, stride, padding, relu), want in zip(o_cnn.LAYERS, outs):
+        w = torch.from_numpy(params[name][0]).permute(3, 2, 0, 1)            # HWIO -> OIHW
+        b = torch.from_numpy(params[name][1])
+        if padding == "same":
+            ph = max((-(-h.shape[2] // stride) - 1) * stride + kh - h.shape[2], 0)
+            pw = max((-(-h.shape[3] // stride) - 1) * stride + kw - h.shape[3], 0)
+            h = F.pad(h, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+        h = F.conv2d(h, w, b, stride=stride)
+        if relu:
+            h = torch.relu(h)
+        got = h.permute(0, 2, 3, 1).numpy()
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= 1e-9 * max(1.0, np.abs(want).max()), name
+        if name in ("conv1", "conv2"):
+            h = F.max_pool2d(h, 3, 2)
+
+
+def test_sda_oracle_matches_torch():
+    import torch
+    from oracle import sda as o_sda
+    dims = [37, 29, 23]
+    ws, bs = o_sda.make_weights(dims, seed=4, scale="normal")
+    x = np.random.default_rng(1).uniform(0, 1, (11, dims[0]))
+    h = torch.from_numpy(x)
+    for w, b in zip(ws, bs):
+        h = torch.sigmoid(h @ torch.from_numpy(w) + torch.from_numpy(b))
+    assert np.max(np.abs(h.numpy() - o_sda.sda_forward(x, ws, bs))) <= 1e-14

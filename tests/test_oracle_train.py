@@ -82,3 +82,35 @@ def test_da_gradients_match_finite_differences():
         assert abs(g - db0[idx]) <= 1e-6 * max(1.0, abs(g))
     for idx, g in _fd(f, b1, 4, rng):
         assert abs(g - db1[idx]) <= 1e-6 * max(1.0, abs(g))
+
+
+@pytest.mark.parametrize("layer_i", [0, 2])
+def test_sdav_gradients_match_torch_autograd(layer_i):
+    """Independent pin of the training oracle: the SDAV loss written with torch ops (float64, CPU) and differentiated
+    by autograd - including the gradient that softmax_cross_entropy_with_logits_v2 sends into its labels - gives the
+    oracle's analytic gradients."""
+    import torch
+    rng, x, Ws, bs, bds, masks = _setup(5, B=4, P=3, dims=(7, 6, 5, 4))
+    loss, dW, db, dbd = o_train.sdav_loss_and_grads(x, Ws, bs, bds, layer_i, masks)
+    B, P, _ = x.shape
+    tW = [torch.tensor(w, requires_grad=True) for w in Ws]
+    tb = [torch.tensor(b, requires_grad=True) for b in bs]
+    tbd = [torch.tensor(b, requires_grad=True) for b in bds]
+    cur = torch.tensor(x)
+    for l in range(layer_i + 1):
+        xc = (cur.reshape(B, P, -1) * torch.tensor(masks[l])[None]).reshape(B * P, -1)
+        h = torch.sigmoid(xc @ tW[l] + tb[l])
+        cur = h
+    y = torch.sigmoid(h @ tW[layer_i].T + tbd[layer_i])
+    labels = torch.tensor(x).reshape(B * P, -1) if layer_i == 0 else xc
+    cd = torch.mean(-(labels * torch.log_softmax(y, dim=1)).sum(dim=1))
+    h3 = h.reshape(B, P, -1)
+    cs = torch.mean(torch.abs((h3 if layer_i == 0 else h) - 0.05).sum(dim=1))       # 3-D: patch axis; 2-D: hidden axis
+    cc = torch.mean(torch.sqrt(((h3[:-1] - h3[1:]) ** 2).sum(dim=(1, 2))))
+    t_loss = cd + 1.0 * cs + 0.2 * cc
+    t_loss.backward()
+    assert abs(float(t_loss) - loss) <= 1e-12 * abs(loss)
+    for l in range(layer_i + 1):
+        assert np.allclose(tW[l].grad.numpy(), dW[l], rtol=1e-10, atol=1e-13)
+        assert np.allclose(tb[l].grad.numpy(), db[l], rtol=1e-10, atol=1e-13)
+    assert np.allclose(tbd[layer_i].grad.numpy(), dbd, rtol=1e-10, atol=1e-13)
