@@ -25,12 +25,33 @@ struct BiasActParams {
   void* out_hi;
   void* out_lo;
   int out_plane_ld;
+  // Plane outputs leave through TMA stores: each epilogue warp stages its 32 x 32 tile (64-byte rows, SWIZZLE_64B
+  // layout) in shared memory and one lane issues cp.async.bulk.tensor stores - full 64-byte row segments instead of
+  // 32 row-strided 16-byte stores per instruction (the LSU wavefronts of those were what the epilogue waited on).
+  // Rows beyond M are clipped by the tensor map.
+  int use_tma_store;
+  alignas(64) CUtensorMap tm_out_hi;
+  alignas(64) CUtensorMap tm_out_lo;
   // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
   int cv_implicit, cv_a_lo_zero, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
   // ---- CONV only: descriptor tail. Row m = output pixel of image m / cv_ohw; the per-image min / max of every conv
   // output (cnn_vtl.py:109-111) is reduced here, as order-preserving ints.
   int* mm;  // [images, 2]
 };
+
+// Tensor maps of the plane outputs for the epilogue's staged TMA stores: box = 32 columns x 32 rows, SWIZZLE_64B.
+extern int g_tma_store;  // planes.cu
+inline bool attach_plane_store_maps(BiasActParams& p) {
+  p.use_tma_store = 0;
+  if (!p.out_hi || !g_tma_store) return true;
+  if (!make_tmap_k_major(&p.tm_out_hi, p.out_hi, p.ab_fmt, p.out_plane_ld, p.M, p.out_plane_ld, 32, 32)) return false;
+  p.tm_out_lo = p.tm_out_hi;
+  if (p.out_lo && p.ab_fmt != 1 &&
+      !make_tmap_k_major(&p.tm_out_lo, p.out_lo, p.ab_fmt, p.out_plane_ld, p.M, p.out_plane_ld, 32, 32))
+    return false;
+  p.use_tma_store = 1;
+  return true;
+}
 
 // float <-> int whose signed order equals the float order (for atomicMin / atomicMax on floats)
 __device__ __forceinline__ int float_to_ordered(float f) {
@@ -53,6 +74,7 @@ struct BiasActPolicy {
   using Params = BiasActParams;
   static constexpr bool kIm2colA = CONV;
   static constexpr bool kAltTiles = CONV;
+  static constexpr int kScratchBytes = 8 * 4096;  // per epilogue warp: a hi and a lo staging tile of 32 x 64 bytes
   static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
   static constexpr int kEpiWarps = 4;
   static __device__ __forceinline__ bool enabled(const Params&) { return true; }
@@ -75,7 +97,10 @@ struct BiasActPolicy {
   struct Epilogue {
     const Params& p;
     const int quarter, lane;
-    __device__ Epilogue(const Params& p_, int quarter_, int, int lane_, void*) : p(p_), quarter(quarter_), lane(lane_) {}
+    uint8_t* stage;  // this warp's staging tiles: hi at +0, lo at +2048
+    __device__ Epilogue(const Params& p_, int quarter_, int half_, int lane_, void* scratch)
+        : p(p_), quarter(quarter_), lane(lane_),
+          stage(static_cast<uint8_t*>(scratch) + (half_ * 4 + quarter_) * 4096) {}
 
     int row;
     bool row_ok;
@@ -161,16 +186,6 @@ struct BiasActPolicy {
       } else if (p.act == DLC_ACT_SIGMOID) activate<DLC_ACT_SIGMOID>(v, h, col0);
       else if (p.act == DLC_ACT_RELU) activate<DLC_ACT_RELU>(v, h, col0);
       else activate<DLC_ACT_NONE>(v, h, col0);
-      if (!row_ok) return;
-      if (CONV) {
-        if (p.mm) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            t_lo = fminf(t_lo, h[j]);
-            t_hi = fmaxf(t_hi, h[j]);
-          }
-        }
-      }
       if (p.dbg & 1) {  // keep the values alive without the global stores
         float acc = 0.f;
 #pragma unroll
@@ -178,51 +193,98 @@ struct BiasActPolicy {
         if (acc == 123456.789f && p.out_f32) p.out_f32[0] = acc;
         return;
       }
-      if (p.out_f32) {
-        float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
-        const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+      if (row_ok) {
+        if (CONV) {
+          if (p.mm) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (vec_ok && col0 + j + 3 < p.N) {
-            *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
-          } else {
+            for (int j = 0; j < 32; ++j) {
+              t_lo = fminf(t_lo, h[j]);
+              t_hi = fmaxf(t_hi, h[j]);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* o = p.out_f32 + static_cast<int64_t>(row) * p.out_ld + col0;
+          const bool vec_ok = ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (col0 + j + q < p.N) o[j + q] = h[j + q];
+          for (int j = 0; j < 32; j += 4) {
+            if (vec_ok && col0 + j + 3 < p.N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col0 + j + q < p.N) o[j + q] = h[j + q];
+            }
           }
         }
       }
+      // plane outputs: every lane of the warp takes part in the staged store (rows beyond M are clipped by TMA)
       if (p.out_hi && col0 < p.out_plane_ld) {
-        const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
-        if (p.ab_fmt == 1) {  // bf16 planes (single plane)
-          uint32_t w[16];
+        const bool bf16 = p.ab_fmt == 1;  // bf16 planes have no residual plane
+        const bool want_lo = !bf16 && p.out_lo;
+        // 8 values -> one 16-byte piece of the hi plane and one of the lo plane (packed just before they are stored,
+        // so only 8 words are live at a time next to the 128 running sums of the two-level accumulation)
+        auto pack8 = [&](int q, uint4& vh, uint4& vl) {
+          uint32_t wh[4], wl[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) w[j] = pack_bf2(h[2 * j], h[2 * j + 1]);
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_hi) + off);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        } else {
-          uint32_t wh[16], wl[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __half h0, l0, h1, l1;
-            split_f32(h[2 * j], h0, l0);
-            split_f32(h[2 * j + 1], h1, l1);
-            wh[j] = pack_h2(h0, h1);
-            wl[j] = pack_h2(l0, l1);
+          for (int j = 0; j < 4; ++j) {
+            const float a = h[8 * q + 2 * j], b = h[8 * q + 2 * j + 1];
+            if (bf16) {
+              wh[j] = pack_bf2(a, b);
+              wl[j] = 0u;
+            } else {
+              __half h0, l0, h1, l1;
+              split_f32(a, h0, l0);
+              split_f32(b, h1, l1);
+              wh[j] = pack_h2(h0, h1);
+              wl[j] = pack_h2(l0, l1);
+            }
           }
-          uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + off);
+          vh = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          vl = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        };
+        if (!p.use_tma_store) {  // direct 16-byte stores (developer A/B switch)
+          if (row_ok) {
+            const int64_t off = static_cast<int64_t>(row) * p.out_plane_ld + col0;
+            uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_hi) + off);
+            uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + off);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) oh[q] = make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3]);
-          if (p.out_lo) {
-            uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_lo) + off);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ol[q] = make_uint4(wl[4 * q], wl[4 * q + 1], wl[4 * q + 2], wl[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) {
+              uint4 vh, vl;
+              pack8(q, vh, vl);
+              oh[q] = vh;
+              if (want_lo) ol[q] = vl;
+            }
           }
+          return;
+        }
+        // ---- staged TMA store (all 32 lanes take part; rows beyond M are clipped by the tensor map)
+        store_pending = true;
+        if (lane == 0) tma_store_wait_read();  // the previous tile of this warp has left the staging buffer
+        __syncwarp();
+        const int sw = (lane >> 1) & 3;         // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 vh, vl;
+          pack8(q, vh, vl);
+          const int pos = (q ^ sw) * 16;
+          *reinterpret_cast<uint4*>(stage + lane * 64 + pos) = vh;
+          if (want_lo) *reinterpret_cast<uint4*>(stage + 2048 + lane * 64 + pos) = vl;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int row0 = row - lane;
+          tma_store_2d(&p.tm_out_hi, stage, col0, row0);
+          if (want_lo) tma_store_2d(&p.tm_out_lo, stage + 2048, col0, row0);
+          tma_store_commit();
         }
       }
     }
-    __device__ __forceinline__ void finish() {}
+    bool store_pending = false;
+    __device__ __forceinline__ void finish() {
+      if (lane == 0 && store_pending) tma_store_wait_all();
+    }
   };
 };
 

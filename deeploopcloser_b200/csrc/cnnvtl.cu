@@ -635,6 +635,7 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   p.k_blocks = g.k_ld / BK;
   // a short K range (conv1: 576) is accumulated in one TMEM pass, which also enables the alternate-tile epilogue
   p.kc = g.k_ld <= 1024 ? p.k_blocks : std::max(1, g_promote_k / BK);
+  if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);

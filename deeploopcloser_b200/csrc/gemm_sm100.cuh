@@ -23,7 +23,6 @@ constexpr int kTileM = 128;
 constexpr int kMaxTileN = 256;
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;  // two 256-column fp32 accumulators
-constexpr int kEpiScratchBytes = 4096;
 
 struct TileCoord {
   int mt;
@@ -47,16 +46,14 @@ struct GemmCfg {
   static constexpr uint32_t kSwizzleMode = BK == 64 ? 2u : 4u;  // UMMA layout code: 2 = 128B, 4 = 64B
   static constexpr uint32_t kSBO = 8 * BK * 2;                  // bytes between 8-row groups
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = 1024 + 16 /*alignment slack*/ + kBarrierBytes + kEpiScratchBytes + kRingBytes;
   static_assert((2 * kMaxStages + 4) * 8 + 8 <= kBarrierBytes, "barrier block too small");
-  static_assert(kSmemBytes <= 227 * 1024, "exceeds the 227 KB per-CTA shared memory limit");
   static_assert(kRingBytes / (kPlanes * (kABytes + kBBytes)) >= 2, "need at least a double buffer");
   // bytes of one stage / number of stages for a launch (a_planes = 1 when the A residual plane is skipped)
   __host__ __device__ static constexpr int stage_bytes(int n_tile, int a_planes) {
     return a_planes * kABytes + kPlanes * n_tile * BK * 2;
   }
-  __host__ __device__ static constexpr int stages(int n_tile, int a_planes) {
-    const int s = kRingBytes / stage_bytes(n_tile, a_planes);
+  __host__ __device__ static constexpr int stages(int n_tile, int a_planes, int ring = kRingBytes) {
+    const int s = ring / stage_bytes(n_tile, a_planes);
     return s < kMaxStages ? s : kMaxStages;
   }
 };
@@ -108,6 +105,28 @@ struct policy_alt_tiles : std::false_type {};
 template <class P>
 struct policy_alt_tiles<P, std::enable_if_t<P::kAltTiles>> : std::true_type {};
 
+// Optional policy member `static constexpr int kScratchBytes`: 1024-byte-aligned shared memory handed to the
+// epilogue (e.g. per-warp staging tiles for TMA stores); it is taken out of the operand ring.
+template <class P, class = void>
+struct policy_scratch {
+  static constexpr int value = 0;
+};
+template <class P>
+struct policy_scratch<P, std::enable_if_t<(P::kScratchBytes > 0)>> {
+  static constexpr int value = P::kScratchBytes;
+};
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kSmemFixed = 1024 + 16 /*alignment slack*/ + 1024 /*barrier block, padded*/;
+template <class Policy>
+__host__ __device__ constexpr int ring_bytes() {
+  const int avail = (kSmemLimit - kSmemFixed - policy_scratch<Policy>::value) / 1024 * 1024;
+  return avail < Policy::Cfg::kRingBytes ? avail : Policy::Cfg::kRingBytes;
+}
+template <class Policy>
+__host__ __device__ constexpr int smem_bytes() {
+  return kSmemFixed + policy_scratch<Policy>::value + ring_bytes<Policy>();
+}
+
 // Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, 128 accumulator columns each).
 template <class Policy>
 __host__ __device__ constexpr int epi_warps() {
@@ -149,7 +168,7 @@ template <class Policy>
 __global__ void __launch_bounds__(gemm_threads<Policy>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               const typename Policy::Params p) {
+               const __grid_constant__ typename Policy::Params p) {
   using Cfg = typename Policy::Cfg;
   constexpr int BK = Cfg::BK;
   constexpr int SMAX = Cfg::kMaxStages;
@@ -157,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int kEpiWarps = epi_warps<Policy>();
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
 
-  // smem: [barriers | epilogue scratch | pad to 1024 | ring of S stages]
+  // smem: [barriers | pad to 1024 | epilogue scratch (policy) | ring of S stages]
   extern __shared__ uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
   uint64_t* full = bars;
@@ -165,9 +184,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tfull = bars + 2 * SMAX;
   uint64_t* tempty = bars + 2 * SMAX + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SMAX + 4);
-  void* scratch = reinterpret_cast<uint8_t*>(bars) + Cfg::kBarrierBytes;
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(scratch) + kEpiScratchBytes + 1023) & ~uintptr_t(1023));
+  uint8_t* scratch_b = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(bars) + Cfg::kBarrierBytes + 1023) & ~uintptr_t(1023));
+  void* scratch = scratch_b;
+  uint8_t* smem = scratch_b + policy_scratch<Policy>::value;  // scratch sizes are multiples of 1024
 
   // cv_a_lo_zero (im2col policies): the A operand is exactly representable in fp16 (8-bit pixels), so its residual
   // plane is neither staged nor multiplied
@@ -175,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
   const int a_planes = a_lo_zero ? 1 : Cfg::kPlanes;
   const int stage_bytes = Cfg::stage_bytes(p.n_tile, a_planes);
-  const int S = Cfg::stages(p.n_tile, a_planes);
+  const int S = Cfg::stages(p.n_tile, a_planes, ring_bytes<Policy>());
   const int b_plane_bytes = p.n_tile * BK * 2;
   bool alt_tiles = false;
   if constexpr (kPromote && policy_alt_tiles<Policy>::value)
@@ -513,12 +533,14 @@ inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
   using Cfg = typename Policy::Cfg;
   static bool attr_set = false;
   if (!attr_set) {
+    static_assert(smem_bytes<Policy>() <= kSmemLimit, "exceeds the 227 KB per-CTA shared memory limit");
+    static_assert(policy_scratch<Policy>::value % 1024 == 0, "epilogue scratch must be a multiple of 1024 bytes");
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+                                         smem_bytes<Policy>());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_tc_kernel<Policy><<<grid, gemm_threads<Policy>(), Cfg::kSmemBytes, stream>>>(a0, a1, b0, b1, p);
+  gemm_tc_kernel<Policy><<<grid, gemm_threads<Policy>(), smem_bytes<Policy>(), stream>>>(a0, a1, b0, b1, p);
   return cudaGetLastError();
 }
 

@@ -82,6 +82,7 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 
 static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
 int g_promote_k = 256;
+int g_tma_store = 1;  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern int g_sim_mgroup;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
@@ -104,6 +105,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   p.k_blocks = ld / BK;
   p.kc = std::max(1, g_promote_k / BK);
   p.dbg = g_dbg_flags;
+  if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
@@ -124,6 +126,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 3) {
     g_dbg_flags = value;
+    return DLC_OK;
+  }
+  if (key == 5) {
+    g_tma_store = value ? 1 : 0;
     return DLC_OK;
   }
   if (key == 4 && value >= 1) {

@@ -1,4 +1,8 @@
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -o gpurun_out/prof_gram_v2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_gram.log 2>&1
-tail -2 gpurun_out/ncu_gram.log
-python tools/bench_matcher.py --rows 500000 --batches 1024 --reps 3 > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 2 -c 1 -o gpurun_out/prof_match_v2 python tools/bench_matcher.py --rows 500000 --batches 1024 --reps 3 > gpurun_out/ncu_match2.log 2>&1
-tail -1 gpurun_out/ncu_match2.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
+timeout 300 python tools/bench_cnnvtl.py 1063 > gpurun_out/cnn_fused_1063.log 2>&1; tail -1 gpurun_out/cnn_fused_1063.log | cut -c1-200
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks']['sm_mhz'], d['roofline']['ms_per_launch'], d['stages_ms'])"
+python - <<'PY'
+import sys; sys.path.insert(0,'.')
+from deeploopcloser_b200 import _lib
+import subprocess
+PY
