@@ -37,41 +37,52 @@ __device__ __forceinline__ PatchOrigin patch_origin(const float* xy, int H, int 
   return o;
 }
 
-__global__ void __launch_bounds__(128)
+// (hi, lo) fp16 pair of v / 255 for the 256 pixel values, computed once per process on the device.
+__device__ uint32_t g_pixel_lut[256];
+__global__ void pixel_lut_kernel() {
+  const int i = threadIdx.x;
+  __half h, l;
+  split_f64(static_cast<double>(i) / 255.0, h, l);
+  g_pixel_lut[i] = static_cast<uint32_t>(__half_as_ushort(h)) | (static_cast<uint32_t>(__half_as_ushort(l)) << 16);
+}
+
+// kPatchesPerCta patches per CTA (one warp-pair each); a thread produces 8 consecutive K entries = one 16-byte store
+// per plane, walking (patch row, patch column) incrementally instead of dividing per element.
+constexpr int kPatchesPerCta = 4;
+constexpr int kThreadsPerPatch = 64;
+__global__ void __launch_bounds__(kPatchesPerCta* kThreadsPerPatch)
 patch_gather_planes_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ xy, int P,
-                           int patch, int swap_xy_quirk, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                           int ld) {
-  __shared__ uint32_t lut[256];  // (hi, lo) fp16 pair of v/255
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    __half h, l;
-    split_f64(static_cast<double>(i) / 255.0, h, l);
-    lut[i] = static_cast<uint32_t>(__half_as_ushort(h)) | (static_cast<uint32_t>(__half_as_ushort(l)) << 16);
-  }
+                           int64_t n_patches, int patch, int swap_xy_quirk, __half* __restrict__ out_hi,
+                           __half* __restrict__ out_lo, int ld) {
+  __shared__ uint32_t lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_pixel_lut[i];
   __syncthreads();
-  const int64_t pidx = blockIdx.x;  // b * P + p
+  const int64_t pidx = static_cast<int64_t>(blockIdx.x) * kPatchesPerCta + threadIdx.x / kThreadsPerPatch;  // b * P + p
+  if (pidx >= n_patches) return;
+  const int t = threadIdx.x % kThreadsPerPatch;
   const int b = static_cast<int>(pidx / P);
   const PatchOrigin o = patch_origin(xy + pidx * 2, H, W, patch, swap_xy_quirk);
-  const uint8_t* src = img + static_cast<int64_t>(b) * H * W;
+  const uint8_t* src = img + static_cast<int64_t>(b) * H * W + static_cast<int64_t>(o.r0) * W + o.c0;
   const int n = patch * patch;
   const int chunks = ld >> 3;
-  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+  for (int c = t; c < chunks; c += kThreadsPerPatch) {
+    int e = c * 8;
+    int pr = e / patch;
+    int pc = e - pr * patch;
+    uint32_t v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q, ++e) {
+      v[q] = e < n ? lut[src[pr * W + pc]] : 0u;  // (0, 0) for the K padding
+      if (++pc == patch) {
+        pc = 0;
+        ++pr;
+      }
+    }
     uint32_t hh[4], ll[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      uint32_t e2[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int e = c * 8 + q * 2 + t;
-        uint32_t v = 0;  // (0, 0) for the K padding
-        if (e < n) {
-          const int pr = e / patch;
-          const int pc = e - pr * patch;
-          v = lut[src[static_cast<int64_t>(o.r0 + pr) * W + (o.c0 + pc)]];
-        }
-        e2[t] = v;
-      }
-      hh[q] = (e2[0] & 0xFFFFu) | (e2[1] << 16);
-      ll[q] = (e2[0] >> 16) | (e2[1] & 0xFFFF0000u);
+      hh[q] = (v[2 * q] & 0xFFFFu) | (v[2 * q + 1] << 16);
+      ll[q] = (v[2 * q] >> 16) | (v[2 * q + 1] & 0xFFFF0000u);
     }
     const int64_t off = pidx * ld + c * 8;
     *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
@@ -112,9 +123,20 @@ extern "C" int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, con
   DLC_CHECK_ARG(out_hi_dev || B == 0);
   DLC_CHECK_ARG(ld >= patch * patch && ld % 8 == 0);
   if (B == 0) return DLC_OK;
-  patch_gather_planes_kernel<<<B * P, 128, 0, as_stream(stream)>>>(img_dev, H, W, xy_dev, P, patch, swap_xy_quirk,
-                                                                  static_cast<__half*>(out_hi_dev),
-                                                                  static_cast<__half*>(out_lo_dev), ld);
+  static bool lut_ready[64] = {false};  // per device; built (and waited for) once, so later calls on any stream see it
+  int dev = 0;
+  DLC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !lut_ready[dev]) {
+    pixel_lut_kernel<<<1, 256, 0, as_stream(stream)>>>();
+    DLC_CUDA(cudaGetLastError());
+    DLC_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    if (dev >= 0 && dev < 64) lut_ready[dev] = true;
+  }
+  const int64_t n_patches = static_cast<int64_t>(B) * P;
+  const int grid = static_cast<int>((n_patches + kPatchesPerCta - 1) / kPatchesPerCta);
+  patch_gather_planes_kernel<<<grid, kPatchesPerCta * kThreadsPerPatch, 0, as_stream(stream)>>>(
+      img_dev, H, W, xy_dev, P, n_patches, patch, swap_xy_quirk, static_cast<__half*>(out_hi_dev),
+      static_cast<__half*>(out_lo_dev), ld);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
