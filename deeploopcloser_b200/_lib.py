@@ -49,6 +49,7 @@ PROTOTYPES = {
     "dlc_sda_encode": (_i, [_p, _p, _p, _i, _p, _p, _sz, _p]),
     "dlc_sdav_similarity_workspace_bytes": (_sz, [_i, _i, _i]),
     "dlc_sdav_similarity": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _p, _p, _sz, _p]),
+    "dlc_sdav_similarity_part": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_sdav_similarity_stats": (_i, [_i, _i, _i, _p, _p, _p]),
     "dlc_sdav_weights": (_i, [_p, _i, _i, _i, _d, _d, _p, _p, _sz, _p]),
     "dlc_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

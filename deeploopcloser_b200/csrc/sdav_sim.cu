@@ -443,13 +443,18 @@ __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* g
 
 // Work list: super-blocks of g_sim_mgroup M tiles; inside a super-block N tile outermost so the ~148 concurrently
 // running tiles touch g_sim_mgroup A row-blocks and ~148/g_sim_mgroup B row-blocks (fits L2) instead of streaming all of H.
-static void build_tile_list(int N, int full, std::vector<int2>& out) {
+static void build_tile_list(int N, int full, int part, int n_parts, std::vector<int2>& out) {
   const int m_tiles = ceil_div(N, kFramesPerMTile), n_tiles = ceil_div(N, kFramesPerNTile);
   out.clear();
-  for (int g0 = 0; g0 < m_tiles; g0 += g_sim_mgroup) {
-    const int g1 = std::min(g0 + g_sim_mgroup, m_tiles);
+  // M tiles owned by this part: every n_parts-th one (interleaved, so the triangle's long and short rows are
+  // dealt evenly), grouped into super-blocks of g_sim_mgroup owned tiles.
+  std::vector<int> owned;
+  for (int mt = part; mt < m_tiles; mt += n_parts) owned.push_back(mt);
+  for (size_t g0 = 0; g0 < owned.size(); g0 += g_sim_mgroup) {
+    const size_t g1 = std::min(g0 + static_cast<size_t>(g_sim_mgroup), owned.size());
     for (int nt = 0; nt < n_tiles; ++nt)
-      for (int mt = g0; mt < g1; ++mt) {
+      for (size_t g = g0; g < g1; ++g) {
+        const int mt = owned[g];
         const int fa_min = mt * kFramesPerMTile;
         const int fb_max = std::min(nt * kFramesPerNTile + kFramesPerNTile - 1, N - 1);
         // upper-triangle mode needs a pair fa < fb, or the diagonal block (to write the -1 fill)
@@ -502,6 +507,7 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = L.ld / BK;
   p.kc = std::max(1, g_promote_k / BK);
+  if (p.num_tiles == 0) return DLC_OK;  // a part that owns no tile (more parts than M tiles)
   const int grid = std::min(p.num_tiles, sm_count());
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
   if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_sdav_similarity: launch failed: %s", cudaGetErrorString(e));
@@ -545,9 +551,28 @@ extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, doub
   return DLC_OK;
 }
 
+static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
+                                double b, const double* w_dev, int precision, int full_asymmetric, int part,
+                                int n_parts, float* S_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
 extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
                                    double b, const double* w_dev, int precision, int full_asymmetric,
                                    float* S_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  return sdav_similarity_impl(desc_dev, N, P, D, mu, sigma, a, b, w_dev, precision, full_asymmetric, 0, 1, S_dev,
+                              ws_dev, ws_bytes, stream);
+}
+
+extern "C" int dlc_sdav_similarity_part(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
+                                        double b, const double* w_dev, int precision, int full_asymmetric, int part,
+                                        int n_parts, float* S_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(n_parts >= 1 && part >= 0 && part < n_parts);
+  return sdav_similarity_impl(desc_dev, N, P, D, mu, sigma, a, b, w_dev, precision, full_asymmetric, part, n_parts,
+                              S_dev, ws_dev, ws_bytes, stream);
+}
+
+static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
+                                double b, const double* w_dev, int precision, int full_asymmetric, int part,
+                                int n_parts, float* S_dev, void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(desc_dev && S_dev && ws_dev);
   DLC_CHECK_ARG(N >= 1 && N <= (1 << 20));
   DLC_CHECK_ARG(P >= 1 && P <= kFrameRows);
@@ -563,7 +588,7 @@ extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, d
   char* ws = static_cast<char*>(ws_dev);
   const int64_t rows = static_cast<int64_t>(N) * P;
 
-  double* part = reinterpret_cast<double*>(ws + L.off_part);
+  double* colsum_part = reinterpret_cast<double*>(ws + L.off_part);
   double* w = reinterpret_cast<double*>(ws + L.off_w);
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
@@ -577,14 +602,16 @@ extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, d
   if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
     w = const_cast<double*>(w_dev);
   } else {
-    colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
-    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w);
+    colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
+    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w);
   }
   rowstats_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(desc_dev, N, P, D, w, sqn, pw);
   DLC_CUDA(cudaGetLastError());
 
   // 4. tile work list (host-built, tiny) -> device
-  build_tile_list(N, full_asymmetric, tiles);
+  build_tile_list(N, full_asymmetric, part, n_parts, tiles);
+  // a part of the matrix: entries other parts own stay zero, so the parts combine with a sum (all-reduce)
+  if (n_parts > 1) DLC_CUDA(cudaMemsetAsync(S_dev, 0, sizeof(float) * static_cast<size_t>(N) * N, s));
   DLC_CUDA(cudaMemcpyAsync(ws + L.off_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
   }  // !g_gram_only
 

@@ -186,6 +186,20 @@ def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, prec
     return out
 
 
+def sdav_similarity_part(desc, part, n_parts, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="fp16x2",
+                         out=None):
+    """The entries of the [N,N] score matrix owned by `part` of `n_parts` (other entries zero): sum over parts = the
+    full matrix of sdav_similarity."""
+    _check_cuda(desc, weights)
+    N, P, D = desc.shape
+    if out is None:
+        out = torch.empty((N, N), dtype=torch.float32, device=desc.device)
+    ws, ws_bytes = _ws.get(_lib.call("dlc_sdav_similarity_workspace_bytes", N, P, D))
+    _lib.call("dlc_sdav_similarity_part", ptr(desc), N, P, D, float(mu), float(sigma), float(a), float(b), ptr(weights),
+              precision_code(precision), 0, int(part), int(n_parts), ptr(out), ws, ws_bytes, stream_ptr())
+    return out
+
+
 def sdav_similarity_stats(N, P, D):
     """Diagnostics of the last auto / fp16r similarity call (synchronises): dict with the probe's decision."""
     import ctypes

@@ -87,3 +87,48 @@ class LoopClosurePipeline:
             outs.append((s_h, i_h))
         compute.synchronize()
         return outs
+
+
+class ShardedSequencePipeline(LoopClosurePipeline):
+    """ONE sequence over the GPUs of a box (strong scaling of BASELINE config 2): one process per GPU
+    (torch.distributed, NCCL). Frames are dealt in contiguous blocks: every rank gathers + encodes its block, the
+    descriptors are all-gathered (every rank needs all of them for the score matrix), every rank evaluates its
+    interleaved tile rows of the SDAV score matrix (`dlc_sdav_similarity_part`), the parts are summed with an
+    all-reduce, and the candidate lists are selected on every rank (identical everywhere). Two exchange steps:
+    N*30*D*4 bytes of descriptors and N*N*4 bytes of scores; everything else is rank-local."""
+
+    def __init__(self, *args, group=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    @staticmethod
+    def frame_block(n_frames, rank, world):
+        """(start, end, per): frames [start, end) belong to `rank`; `per` = block length used for the gather."""
+        per = -(-n_frames // world)
+        start = min(rank * per, n_frames)
+        return start, min(start + per, n_frames), per
+
+    def run(self, frames, xy, k=10, exclude_band=0):
+        """frames uint8 [N,H,W] and xy float32 [N,P,2]: the WHOLE sequence, resident on every rank."""
+        n, P = frames.shape[0], xy.shape[1]
+        D = self.dims[-1]
+        start, end, per = self.frame_block(n, self.rank, self.world)
+        local = torch.zeros((per * P, D), dtype=torch.float32, device=frames.device)
+        if end > start:
+            local[:(end - start) * P] = self.encode(frames[start:end], xy[start:end])
+        if self.world > 1:
+            gathered = torch.empty((self.world * per * P, D), dtype=torch.float32, device=frames.device)
+            self.dist.all_gather_into_tensor(gathered, local, group=self.group)
+            desc = gathered[:n * P]
+        else:
+            desc = local[:n * P]
+        S = ops.sdav_similarity_part(desc.view(n, P, D), self.rank, self.world, precision=self.sim_precision,
+                                     **self.sim_args)
+        if self.world > 1:
+            self.dist.all_reduce(S, group=self.group)
+        cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
+        return {"descriptors": desc, "similarity": S, "candidates": cand}

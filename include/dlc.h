@@ -142,6 +142,13 @@ size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D);
 int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
                         const double* w_dev, int precision, int full_asymmetric, float* S_dev, void* ws_dev,
                         size_t ws_bytes, void* stream);
+/* One part of the same matrix, for a sequence whose score matrix is split over `n_parts` GPUs: part
+ * `part` evaluates the 128-row tile rows part, part + n_parts, ... (interleaved, which balances the triangle) against
+ * all columns and leaves every entry it does not own at zero, so the parts combine with a sum (NCCL all-reduce);
+ * each pair (i, j) and the diagonal fill are produced by exactly one part. */
+int dlc_sdav_similarity_part(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
+                             const double* w_dev, int precision, int full_asymmetric, int part, int n_parts,
+                             float* S_dev, void* ws_dev, size_t ws_bytes, void* stream);
 /* Diagnostics of the last AUTO / FP16_REFINED call on this workspace: out_host[6] = {use_refine, margin, sigma,
  * estimated flagged fraction, flagged rows, refined candidates}. Synchronises the stream. */
 int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream);

@@ -58,3 +58,65 @@ def test_sharded_exchange_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def _seq_worker(rank, world, port, q):
+    """ShardedSequencePipeline.run with the three GPU stages replaced by oracle stand-ins: the host logic under test
+    is the frame blocks, the descriptor all-gather (with the padded last block), the parts-sum all-reduce and that
+    every rank ends with the same matrix."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deeploopcloser_b200 import ops
+        from deeploopcloser_b200.pipeline import ShardedSequencePipeline
+        from oracle import similarity as o_sim
+        n, P, D = 7, 3, 5                                  # 7 frames over 2 ranks: blocks of 4 and 3 (+1 pad)
+        rng = np.random.default_rng(3)
+        table = rng.uniform(0, 1, (n, P, D)).astype(np.float32)   # "descriptor" of frame f = table[f]
+        pipe = ShardedSequencePipeline.__new__(ShardedSequencePipeline)
+        pipe.dims, pipe.dist, pipe.group, pipe.rank, pipe.world = [1, D], dist, None, rank, world
+        pipe.sim_precision, pipe.sim_args = "fp16x2", {}
+        pipe.encode = lambda frames, xy: torch.from_numpy(table[frames.numpy()[:, 0, 0]].reshape(-1, D))
+
+        def fake_part(desc, part, n_parts, **kw):          # rows part, part + n_parts, ... of the oracle matrix
+            S = o_sim.similarity_matrix(desc.numpy().astype(np.float64))
+            own = np.zeros_like(S)
+            iu = np.triu_indices(n, 1)
+            for i, j in zip(*iu):
+                if i % n_parts == part:
+                    own[i, j] = own[j, i] = S[i, j]
+            if part == 0:
+                np.fill_diagonal(own, -1.0)
+            return torch.from_numpy(own.astype(np.float32))
+
+        def fake_topk(S, k, largest=True, exclude_band=-1):
+            return torch.topk(S, k, dim=1)
+
+        ops.sdav_similarity_part, ops.topk_rows = fake_part, fake_topk
+        frames = torch.arange(n).reshape(n, 1, 1).repeat(1, 2, 2)          # frame id stored in its pixels
+        xy = torch.zeros((n, P, 2))
+        res = pipe.run(frames, xy, k=2)
+        want = o_sim.similarity_matrix(table.astype(np.float64))
+        assert np.allclose(res["similarity"].numpy(), want, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(res["descriptors"].numpy(), table.reshape(-1, D))
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()[-600:] or repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sequence_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seq_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

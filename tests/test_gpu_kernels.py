@@ -501,3 +501,35 @@ def test_cnnvtl_handle_errors(cuda):
         head.set_keep_cols([head.descriptor_len])
     with pytest.raises(_lib.DlcError):          # too small for conv1 + two pools
         ops.CnnVtlHead(8, 8)
+
+
+@pytest.mark.parametrize("n,n_parts", [(21, 2), (21, 3), (70, 8), (5, 4)])
+def test_similarity_parts_sum_to_the_whole(cuda, n, n_parts):
+    """dlc_sdav_similarity_part: the parts of the score matrix (interleaved tile rows; what each GPU of a box
+    evaluates when ONE sequence is split over the GPUs) are disjoint and sum to the full matrix bit for bit."""
+    from deeploopcloser_b200 import ops
+    rng = np.random.default_rng(n)
+    desc = torch.from_numpy(rng.uniform(0, 1, (n, 30, 300)).astype(np.float32)).cuda()
+    whole = ops.sdav_similarity(desc)
+    parts = [ops.sdav_similarity_part(desc, p, n_parts).clone() for p in range(n_parts)]
+    nz = torch.stack([(p != 0) for p in parts]).sum(0)
+    assert int(nz.max()) <= 1                                   # every entry is owned by at most one part
+    assert torch.equal(torch.stack(parts).sum(0), whole)
+
+
+def test_sharded_sequence_pipeline_single_rank(cuda):
+    """ShardedSequencePipeline with one rank is the plain pipeline (the multi-rank exchange is covered by
+    tools/check_sharded_sequence.py under torchrun and by the gloo test of the host logic)."""
+    from deeploopcloser_b200.pipeline import LoopClosurePipeline, ShardedSequencePipeline
+    rng = np.random.default_rng(2)
+    dims = [1681, 128, 64]
+    ws, bs = o_sda.make_weights(dims, seed=1, scale="xavier")
+    frames = torch.from_numpy(rng.integers(0, 256, (9, 120, 160), dtype=np.uint8)).cuda()
+    xy = torch.from_numpy(np.stack([rng.uniform(0, 160, (9, 30)), rng.uniform(0, 120, (9, 30))], -1).astype(np.float32)).cuda()
+    a, b = LoopClosurePipeline(dims), ShardedSequencePipeline(dims)
+    a.set_weights(ws, bs)
+    b.set_weights(ws, bs)
+    ra, rb = a.run(frames, xy, k=3), b.run(frames, xy, k=3)
+    assert torch.equal(ra["similarity"], rb["similarity"]) and torch.equal(ra["candidates"][1], rb["candidates"][1])
+    assert ShardedSequencePipeline.frame_block(1063, 7, 8) == (931, 1063, 133)
+    assert ShardedSequencePipeline.frame_block(5, 3, 4) == (5, 5, 2)        # more ranks than needed: empty block

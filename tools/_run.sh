@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "patch or smoke or config2 or sda or stream" > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks']['sm_mhz'], d['roofline']['ms_per_launch'], d['stages_ms'])"
-python -c "import __graft_entry__ as g; g.smoke()"
+timeout 600 python -m pytest tests -x -q -m gpu -k "parts_sum or sharded_sequence or similarity" > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512"
+timeout 300 $TR tools/check_sharded_sequence.py > gpurun_out/sharded_seq2.log 2>&1; grep '^{' gpurun_out/sharded_seq2.log || tail -5 gpurun_out/sharded_seq2.log

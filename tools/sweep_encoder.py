@@ -1,0 +1,38 @@
+"""Encoder timing on the bench workload under the developer switches of the 3-product kernel: K block (32 / 64),
+two-level accumulation chunk (promote_k), plane-output path (TMA store vs direct stores)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from deeploopcloser_b200 import _lib  # noqa: E402
+from deeploopcloser_b200.pipeline import LoopClosurePipeline  # noqa: E402
+
+frames, xy = bench.synthetic_inputs(100)
+ws, bs = bench.reference_weights()
+pipe = LoopClosurePipeline(bench.DIMS, precision="fp16x2")
+pipe.set_weights(ws, bs)
+f_d, x_d = torch.from_numpy(frames).cuda(), torch.from_numpy(xy).cuda()
+
+
+def timed(reps=20):
+    for _ in range(3):
+        pipe.encode(f_d, x_d)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        pipe.encode(f_d, x_d)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for bk, pk, tma in [(32, 256, 1), (32, 256, 0), (64, 256, 1), (32, 512, 1), (32, 128, 1), (32, 256, 1)]:
+    _lib.call("dlc_debug_set", 0, bk)
+    _lib.call("dlc_debug_set", 2, pk)
+    _lib.call("dlc_debug_set", 5, tma)
+    print(json.dumps({"split_bk": bk, "promote_k": pk, "tma_store": tma, "encode_ms": timed()}))
