@@ -14,6 +14,7 @@
 // running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
 #pragma once
 #include <type_traits>
+#include <utility>
 
 #include "ptx.cuh"
 
@@ -127,6 +128,18 @@ __host__ __device__ constexpr int smem_bytes() {
   return kSmemFixed + policy_scratch<Policy>::value + ring_bytes<Policy>();
 }
 
+// Optional policy member `static int chunk_stride(const Params&)`: distance in accumulator columns between the
+// 32-column chunks handed to the epilogue (default 32). The SDAV Gram kernel packs its N side at 30 rows per frame,
+// so chunk c (= frame c of the tile) starts at column 30 c and n_tile is 240: no MMA work on the 2 pad rows.
+template <class P, class = void>
+struct policy_chunk_stride {
+  static __device__ __forceinline__ int get(const typename P::Params&) { return 32; }
+};
+template <class P>
+struct policy_chunk_stride<P, std::void_t<decltype(P::chunk_stride(std::declval<const typename P::Params&>()))>> {
+  static __device__ __forceinline__ int get(const typename P::Params& p) { return P::chunk_stride(p); }
+};
+
 // Epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, 128 accumulator columns each).
 template <class Policy>
 __host__ __device__ constexpr int epi_warps() {
@@ -140,11 +153,12 @@ __host__ __device__ constexpr int gemm_threads() {
 // One 32-column chunk of this thread's accumulator row; SLOT is a compile-time constant so that per-chunk epilogue
 // state indexed by it stays in registers.
 template <class Epi, int SLOT>
-__device__ __forceinline__ void epi_slot_from_tmem(Epi& epi, TileCoord tc, uint32_t taddr, int half, int n_cchunks) {
+__device__ __forceinline__ void epi_slot_from_tmem(Epi& epi, TileCoord tc, uint32_t taddr, int half, int n_cchunks,
+                                                   int cstride) {
   const int c = half * 4 + SLOT;
   if (c < n_cchunks) {
     uint32_t r[32];
-    tmem_ld_x32(taddr + c * 32, r);
+    tmem_ld_x32(taddr + c * cstride, r);
     tmem_ld_wait();
     float v[32];
 #pragma unroll
@@ -364,7 +378,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (kPromote) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
     const int half = kEpiWarps == 8 ? (warp - kEpiWarp0) >> 2 : 0;  // which 128-column half this warp owns
-    const int n_cchunks = n_tile >> 5;          // 32-column chunks in the accumulator
+    const int cstride = policy_chunk_stride<Policy>::get(p);  // columns between chunks (32 unless the policy packs tighter)
+    const int n_cchunks = n_tile / cstride;     // chunks in the accumulator
     typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -382,12 +397,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(&tfull[acc], acc_phase, 4);
           tc_fence_after();
           const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) +
-                                 (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(col_half * 128);
+                                 (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(col_half * 4 * cstride);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             if (col_half * 4 + cc < n_cchunks) {
               uint32_t v[32];
-              tmem_ld_x32(taddr + cc * 32, v);
+              tmem_ld_x32(taddr + cc * cstride, v);
               tmem_ld_wait();
               if (ch == 0) {
 #pragma unroll
@@ -418,15 +434,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) + (static_cast<uint32_t>(quarter * 32) << 16);
         epi.begin_tile(tc);
         using Epi = typename Policy::Epilogue;
-        epi_slot_from_tmem<Epi, 0>(epi, tc, taddr, half, n_cchunks);
-        epi_slot_from_tmem<Epi, 1>(epi, tc, taddr, half, n_cchunks);
-        epi_slot_from_tmem<Epi, 2>(epi, tc, taddr, half, n_cchunks);
-        epi_slot_from_tmem<Epi, 3>(epi, tc, taddr, half, n_cchunks);
+        epi_slot_from_tmem<Epi, 0>(epi, tc, taddr, half, n_cchunks, cstride);
+        epi_slot_from_tmem<Epi, 1>(epi, tc, taddr, half, n_cchunks, cstride);
+        epi_slot_from_tmem<Epi, 2>(epi, tc, taddr, half, n_cchunks, cstride);
+        epi_slot_from_tmem<Epi, 3>(epi, tc, taddr, half, n_cchunks, cstride);
         if (kEpiWarps == 4) {  // one warp per lane quarter walks all 8 chunks
-          epi_slot_from_tmem<Epi, 4>(epi, tc, taddr, half, n_cchunks);
-          epi_slot_from_tmem<Epi, 5>(epi, tc, taddr, half, n_cchunks);
-          epi_slot_from_tmem<Epi, 6>(epi, tc, taddr, half, n_cchunks);
-          epi_slot_from_tmem<Epi, 7>(epi, tc, taddr, half, n_cchunks);
+          epi_slot_from_tmem<Epi, 4>(epi, tc, taddr, half, n_cchunks, cstride);
+          epi_slot_from_tmem<Epi, 5>(epi, tc, taddr, half, n_cchunks, cstride);
+          epi_slot_from_tmem<Epi, 6>(epi, tc, taddr, half, n_cchunks, cstride);
+          epi_slot_from_tmem<Epi, 7>(epi, tc, taddr, half, n_cchunks, cstride);
         }
         epi.end_tile(tc);
         tc_fence_before();

@@ -82,6 +82,9 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 
 static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
 int g_promote_k = 256;
+// Valid K of the next dlc_gemm_planes call on this thread (0 = the whole ld). Callers that know their operands are zero
+// beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
+thread_local int g_gemm_k_valid = 0;
 int g_tma_store = 1;  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern int g_sim_mgroup;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
@@ -102,7 +105,9 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
         !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile))
       return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (lo planes)");
   }
-  p.k_blocks = ld / BK;
+  const int k_valid = (g_gemm_k_valid > 0 && g_gemm_k_valid <= ld) ? g_gemm_k_valid : ld;
+  g_gemm_k_valid = 0;
+  p.k_blocks = ceil_div(k_valid, BK);
   p.kc = std::max(1, g_promote_k / BK);
   p.dbg = g_dbg_flags;
   if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (outputs)");

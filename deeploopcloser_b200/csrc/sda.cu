@@ -22,6 +22,10 @@ struct dlc_sda {
 
 using namespace dlc;
 
+namespace dlc {
+extern thread_local int g_gemm_k_valid;  // planes.cu
+}
+
 namespace {
 int out_pad(int n) {
   // Output width padded so that (a) it is the next layer's K (multiple of 64) and (b) a 32-multiple accumulator
@@ -139,6 +143,7 @@ extern "C" int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo
     const bool last = l + 1 == h->n_layers;
     void* o_hi = last ? nullptr : buf_hi[l & 1];
     void* o_lo = last ? nullptr : buf_lo[l & 1];
+    g_gemm_k_valid = h->dims[l];  // columns dims[l]..ld of both operands are zero padding
     int rc = dlc_gemm_planes(a_hi, a_lo, h->w_hi[l], h->w_lo[l], rows, h->dims[l + 1], h->n_pad[l], h->ld[l],
                              h->bias[l], DLC_ACT_SIGMOID, h->precision, last ? out_dev : nullptr, h->dims[l + 1], o_hi,
                              o_lo, h->n_pad[l], stream);

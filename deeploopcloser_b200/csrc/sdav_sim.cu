@@ -104,6 +104,8 @@ struct GramParams {
   float* S;           // [N, N]
   GramControl* ctl;   // NULL: always enabled
   int want_refine;    // this launch runs only when ctl->use_refine == want_refine
+  int col_stride;     // accumulator columns per frame on the N side: P when the B planes are packed P rows per
+                      // frame (even P < 32; n_tile = 8 P, no MMA work on pad rows), else 32
 };
 
 // score of one frame pair from the per-row matches: sum_k (a + b ln |p_ik - p_j,bj(k)|), warp-wide
@@ -162,6 +164,7 @@ struct GramPolicy {
   static __device__ __forceinline__ bool enabled(const Params& p) {
     return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
   }
+  static __device__ __forceinline__ int chunk_stride(const Params& p) { return p.col_stride; }
   static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
     return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
   }
@@ -234,6 +237,7 @@ struct GramRefinePolicy {
   static __device__ __forceinline__ bool enabled(const Params& p) {
     return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
   }
+  static __device__ __forceinline__ int chunk_stride(const Params& p) { return p.col_stride; }
   static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
     return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
   }
@@ -464,8 +468,10 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
 }
 
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ctl, off_probe, off_gaps, total;
+  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ctl, off_probe, off_gaps, total;
   int ld, rows_pad, max_tiles;
+  int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
+  int rows_b;      // rows of the N-side planes
 };
 static SimWorkspace sim_layout(int N, int P, int D) {
   SimWorkspace w{};
@@ -481,6 +487,18 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   const size_t plane = static_cast<size_t>(w.rows_pad) * w.ld * 2;
   w.off_hi = take(plane);
   w.off_lo = take(plane);
+  // N-side planes packed P rows per frame when that keeps UMMA's N = 8 P a multiple of 16 (even P): the MMA then
+  // does no work on the 32 - P pad rows of every frame column block. Otherwise the N side reads the M-side planes.
+  w.col_stride = (P < kFrameRows && (P & 1) == 0) ? P : kFrameRows;
+  w.rows_b = w.col_stride == kFrameRows ? w.rows_pad : N * P;
+  if (w.col_stride != kFrameRows) {
+    const size_t plane_b = static_cast<size_t>(w.rows_b) * w.ld * 2;
+    w.off_bhi = take(plane_b);
+    w.off_blo = take(plane_b);
+  } else {
+    w.off_bhi = w.off_hi;
+    w.off_blo = w.off_lo;
+  }
   w.off_part = take(sizeof(double) * kColSumSlabs * D);
   w.off_w = take(sizeof(double) * D);
   w.off_sqn = take(sizeof(float) * w.rows_pad);
@@ -500,12 +518,14 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
   CUtensorMap ta0, ta1, tb0, tb1;
   const void* hi = ws + L.off_hi;
   const void* lo = ws + L.off_lo;
+  const void* bhi = ws + L.off_bhi;
+  const void* blo = ws + L.off_blo;
   if (!make_tmap_k_major(&ta0, hi, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb0, hi, 0, L.ld, L.rows_pad, L.ld, BK, kMaxTileN) ||
+      !make_tmap_k_major(&tb0, bhi, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile) ||
       !make_tmap_k_major(&ta1, lo, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb1, lo, 0, L.ld, L.rows_pad, L.ld, BK, kMaxTileN))
+      !make_tmap_k_major(&tb1, blo, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
-  p.k_blocks = L.ld / BK;
+  p.k_blocks = ceil_div(p.D, BK);  // K blocks that hold data: the planes are zero from D to ld
   p.kc = std::max(1, g_promote_k / BK);
   if (p.num_tiles == 0) return DLC_OK;  // a part that owns no tile (more parts than M tiles)
   const int grid = std::min(p.num_tiles, sm_count());
@@ -598,6 +618,10 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   if (int rc = dlc_split_planes(desc_dev, DLC_F32, static_cast<int>(rows), D, D, P, kFrameRows, ws + L.off_hi,
                                 ws + L.off_lo, L.ld, stream))
     return rc;
+  if (L.col_stride != kFrameRows)
+    if (int rc = dlc_split_planes(desc_dev, DLC_F32, static_cast<int>(rows), D, D, 1, 1, ws + L.off_bhi,
+                                  ws + L.off_blo, L.ld, stream))
+      return rc;
   // 2. dataset mean -> distinctive weights w; 3. per-row squared norms and projections p = h . w
   if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
     w = const_cast<double*>(w_dev);
@@ -617,7 +641,8 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
 
   // 5. Gram + argmin + score
   GramParams p{};
-  p.n_tile = kMaxTileN;
+  p.col_stride = L.col_stride;
+  p.n_tile = kFramesPerNTile * L.col_stride;  // 256, or 240 for 30 patches per frame
   p.ab_fmt = 0;
   p.tiles = reinterpret_cast<const int2*>(ws + L.off_tiles);
   p.num_tiles = static_cast<int>(tiles.size());
