@@ -85,6 +85,19 @@ struct BiasActPolicy {
     const int total = p.m_tiles * p.n_tiles;
     return cta < total ? (total - cta + ncta - 1) / ncta : 0;
   }
+  // CTA-pair kernel (gemm_pair_sm100.cuh): a pair covers two adjacent 128-row tiles; tc.mt = the first of them
+  static __device__ __forceinline__ int num_tiles_pair(const Params& p, int cluster, int nclusters) {
+    const int total = ((p.m_tiles + 1) >> 1) * p.n_tiles;
+    return cluster < total ? (total - cluster + nclusters - 1) / nclusters : 0;
+  }
+  static __device__ __forceinline__ TileCoord tile_pair(const Params& p, int cluster, int nclusters, int i) {
+    const int t = cluster + i * nclusters;
+    TileCoord tc;
+    const int mp = t / p.n_tiles;
+    tc.mt = 2 * mp;
+    tc.nt = t - mp * p.n_tiles;
+    return tc;
+  }
   // N fastest: the CTAs running concurrently share one A row-block (read from HBM once, then L2).
   static __device__ __forceinline__ TileCoord tile(const Params& p, int cta, int ncta, int i) {
     const int t = cta + i * ncta;

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "bias_act.cuh"
+#include "gemm_pair_sm100.cuh"
 #include "util.h"
 
 namespace dlc {
@@ -85,9 +86,18 @@ int g_promote_k = 256;
 // Valid K of the next dlc_gemm_planes call on this thread (0 = the whole ld). Callers that know their operands are zero
 // beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
 thread_local int g_gemm_k_valid = 0;
-int g_tma_store = 1;  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
+int g_tma_store = 1;
+static int g_cta_pair = 1;  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern int g_sim_mgroup;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
+
+template <class Policy>
+static cudaError_t launch_gemm_pair_if(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                                       const CUtensorMap& b1, const BiasActParams& p, int clusters,
+                                       cudaStream_t stream) {
+  if constexpr (Policy::Cfg::NPROD == 3) return launch_gemm_pair<Policy>(a0, a1, b0, b1, p, clusters, stream);
+  else return cudaErrorInvalidValue;
+}
 
 template <class Policy>
 static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int m, int n_pad,
@@ -112,8 +122,19 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   p.dbg = g_dbg_flags;
   if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  cudaError_t e;
+  // CTA pairs (cta_group::2) for large 3-product contractions: each CTA stages half of the B tile, see
+  // gemm_pair_sm100.cuh. Needs an even split of n_tile into UMMA-legal halves and enough tiles to fill the GPU.
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  if (split && g_cta_pair && p.n_tile % 32 == 0 && (pair_tiles >= sm_count() / 2 || g_cta_pair == 2)) {
+    if (!make_tmap_k_major(&tb0, b_hi, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile / 2) ||
+        !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile / 2))
+      return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (pair B)");
+    e = launch_gemm_pair_if<Policy>(ta0, ta1, tb0, tb1, p, std::min(pair_tiles, sm_count() / 2), stream);
+  } else {
+    const int grid = total < sm_count() ? total : sm_count();
+    e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  }
   if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_gemm_planes: launch failed: %s", cudaGetErrorString(e));
   return DLC_OK;
 }
@@ -131,6 +152,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 3) {
     g_dbg_flags = value;
+    return DLC_OK;
+  }
+  if (key == 6) {  // 0: never, 1: when the problem fills the GPU with pairs, 2: whenever the shape allows (tests)
+    g_cta_pair = value;
     return DLC_OK;
   }
   if (key == 5) {

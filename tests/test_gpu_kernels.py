@@ -533,3 +533,31 @@ def test_sharded_sequence_pipeline_single_rank(cuda):
     assert torch.equal(ra["similarity"], rb["similarity"]) and torch.equal(ra["candidates"][1], rb["candidates"][1])
     assert ShardedSequencePipeline.frame_block(1063, 7, 8) == (931, 1063, 133)
     assert ShardedSequencePipeline.frame_block(5, 3, 4) == (5, 5, 2)        # more ranks than needed: empty block
+
+
+@pytest.mark.parametrize("m,k,n", [(3, 2, 2), (130, 200, 96), (257, 2500, 300), (700, 1681, 2500), (1000, 70, 520)])
+@pytest.mark.parametrize("bk", [32, 64])
+def test_cta_pair_kernel_vs_oracle(cuda, m, k, n, bk):
+    """The cta_group::2 kernel (two CTAs share one 256-row MMA, each staging half of the B tile) forced onto small and
+    ragged shapes: odd numbers of 128-row tiles (the peer CTA's tile is entirely out of range), N tiles of 96 / 64 /
+    256 columns, K not a multiple of the block."""
+    from deeploopcloser_b200 import _lib, ops
+    rng = np.random.default_rng(m + k + n)
+    a = rng.uniform(0, 1, (m, k))
+    b = rng.standard_normal((k, n))
+    bias = rng.standard_normal(n)
+    ref = 1.0 / (1.0 + np.exp(-(a @ b + bias)))
+    args = (torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda())
+    _lib.call("dlc_debug_set", 0, bk)
+    try:
+        _lib.call("dlc_debug_set", 6, 0)
+        single = ops.matmul(*args, act="sigmoid", precision="fp16x2").cpu().numpy()
+        _lib.call("dlc_debug_set", 6, 2)
+        out = ops.matmul(*args, act="sigmoid", precision="fp16x2").cpu().numpy()
+    finally:
+        _lib.call("dlc_debug_set", 6, 1)
+        _lib.call("dlc_debug_set", 0, 32)
+    assert np.array_equal(out, single)        # same K order and accumulation chunks as the single-CTA kernel
+    err = float(np.max(np.abs(out - ref)))
+    print("pair kernel", (m, k, n), "bk", bk, "max abs err", err)
+    assert err < 5e-5          # float32 accumulation of a sigmoid argument of magnitude up to ~50 * 30

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; tail -3 gpurun_out/pytest.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks']['sm_mhz'], d['roofline']['ms_per_launch'], d['roofline']['frac'], d['stages_ms'])"
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -s -k "cta_pair" > gpurun_out/pytest_pair.log 2>&1; echo "exit $?"; grep "pair kernel\|passed\|failed\|Error" gpurun_out/pytest_pair.log | tail -14
+timeout 600 python tools/sweep_encoder.py > gpurun_out/sweep_encoder.log 2>&1; tail -6 gpurun_out/sweep_encoder.log

@@ -31,8 +31,15 @@ def timed(reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-for bk, pk, tma in [(32, 256, 1), (32, 256, 0), (64, 256, 1), (32, 512, 1), (32, 128, 1), (32, 256, 1)]:
-    _lib.call("dlc_debug_set", 0, bk)
-    _lib.call("dlc_debug_set", 2, pk)
-    _lib.call("dlc_debug_set", 5, tma)
-    print(json.dumps({"split_bk": bk, "promote_k": pk, "tma_store": tma, "encode_ms": timed()}))
+configs = [(32, 256, 1, 1), (64, 256, 1, 1), (32, 256, 1, 0), (64, 256, 1, 0), (32, 256, 0, 1)]
+best = {c: 1e9 for c in configs}
+for _ in range(4):                       # interleaved rounds: the power-capped clock drifts within a run
+    for c in configs:
+        bk, pk, tma, pair = c
+        _lib.call("dlc_debug_set", 0, bk)
+        _lib.call("dlc_debug_set", 2, pk)
+        _lib.call("dlc_debug_set", 5, tma)
+        _lib.call("dlc_debug_set", 6, pair)
+        best[c] = min(best[c], timed(10))
+for (bk, pk, tma, pair), ms in best.items():
+    print(json.dumps({"split_bk": bk, "promote_k": pk, "tma_store": tma, "cta_pair": pair, "encode_ms_best_of_4": ms}))
