@@ -351,8 +351,8 @@ def run_ours(args):
                             "sample": "failed: %r" % (e,)}
 
     if rank == 0:
-        # gather, 5 layers, similarity (split, colsum, weights, rowstats, [probe, finalize, gated twin], gram), top-k
-        launches_per_step = 1 + len(DIMS) - 1 + (8 if args.sim_precision in ("auto", "fp16r") else 5) + 1
+        # gather, 5 layers, similarity (colsum, weights, prep_rows, [probe, finalize, gated twin], gram), top-k
+        launches_per_step = 1 + len(DIMS) - 1 + (7 if args.sim_precision in ("auto", "fp16r") else 4) + 1
         line = {"metric": "loop-query frames/sec (encode+match)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo split operands, f32 accumulate" if

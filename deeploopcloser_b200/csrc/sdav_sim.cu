@@ -77,6 +77,70 @@ rowstats_kernel(const float* __restrict__ H, int N, int P, int D, const double* 
   }
 }
 
+// One pass over the descriptors for everything the Gram kernel needs per row: the M-side operand planes (frames
+// re-grouped P -> 32 rows, pad rows zero), the N-side planes (packed P rows per frame, when they are separate), the
+// squared norm and the projection p = h . w. One warp per PADDED row; replaces two split passes + rowstats_kernel
+// (three reads of the 0.3 GB descriptor array) with one.
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
+                 __half* __restrict__ a_hi, __half* __restrict__ a_lo, __half* __restrict__ b_hi,
+                 __half* __restrict__ b_lo, int ld, float* __restrict__ sqn, double* __restrict__ pw) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N * kFrameRows) return;
+  const int f = warp / kFrameRows, k = warp % kFrameRows;
+  const bool valid = k < P;
+  const int64_t r = static_cast<int64_t>(f) * P + k;          // source row / N-side plane row
+  const float* h = H + r * D;
+  const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
+  double n2 = 0.0, pr = 0.0;
+  for (int c0 = lane * 8; c0 < ld; c0 += 256) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+    if (valid) {
+      if (vec && c0 + 8 <= D) {
+        const float4 u = *reinterpret_cast<const float4*>(h + c0);
+        const float4 v = *reinterpret_cast<const float4*>(h + c0 + 4);
+        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+        x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < D) x[j] = h[c0 + j];
+      }
+    }
+    __align__(16) __half hh[8];
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      split_f32(x[j], hh[j], ll[j]);
+      if (valid && c0 + j < D) {
+        const double xd = static_cast<double>(x[j]);
+        n2 += xd * xd;
+        pr += xd * w[c0 + j];
+      }
+    }
+    const int64_t oa = static_cast<int64_t>(warp) * ld + c0;
+    *reinterpret_cast<uint4*>(a_hi + oa) = *reinterpret_cast<const uint4*>(hh);
+    if (a_lo) *reinterpret_cast<uint4*>(a_lo + oa) = *reinterpret_cast<const uint4*>(ll);
+    if (b_hi && valid) {
+      const int64_t ob = r * ld + c0;
+      *reinterpret_cast<uint4*>(b_hi + ob) = *reinterpret_cast<const uint4*>(hh);
+      if (b_lo) *reinterpret_cast<uint4*>(b_lo + ob) = *reinterpret_cast<const uint4*>(ll);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+    pr += __shfl_xor_sync(0xffffffffu, pr, off);
+  }
+  if (lane == 0) {
+    sqn[warp] = valid ? static_cast<float>(n2) : INFINITY;
+    pw[warp] = pr;
+  }
+}
+
 // ---------------- Gram + argmin + score epilogue ----------------
 extern int g_promote_k;  // planes.cu
 
@@ -614,22 +678,22 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
   static thread_local std::vector<int2> tiles;
   if (!g_gram_only) {
-  // 1. operand planes: frames padded P -> 32 rows, K padded to a multiple of 64 (zeros)
-  if (int rc = dlc_split_planes(desc_dev, DLC_F32, static_cast<int>(rows), D, D, P, kFrameRows, ws + L.off_hi,
-                                ws + L.off_lo, L.ld, stream))
-    return rc;
-  if (L.col_stride != kFrameRows)
-    if (int rc = dlc_split_planes(desc_dev, DLC_F32, static_cast<int>(rows), D, D, 1, 1, ws + L.off_bhi,
-                                  ws + L.off_blo, L.ld, stream))
-      return rc;
-  // 2. dataset mean -> distinctive weights w; 3. per-row squared norms and projections p = h . w
+  // 1. dataset mean -> distinctive weights w
   if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
     w = const_cast<double*>(w_dev);
   } else {
     colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
     weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w);
   }
-  rowstats_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(desc_dev, N, P, D, w, sqn, pw);
+  // 2. one pass: operand planes (M side: frames padded P -> 32 rows; N side: packed P rows per frame when separate;
+  //    K padded with zeros), per-row squared norms and projections p = h . w
+  {
+    const bool sep = L.col_stride != kFrameRows;
+    prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
+        desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi), reinterpret_cast<__half*>(ws + L.off_lo),
+        sep ? reinterpret_cast<__half*>(ws + L.off_bhi) : nullptr,
+        sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw);
+  }
   DLC_CUDA(cudaGetLastError());
 
   // 4. tile work list (host-built, tiny) -> device
