@@ -95,10 +95,93 @@ topk_rows_kernel(const float* __restrict__ scores, const int64_t* __restrict__ c
   }
 }
 
+// Same selection for rows of at most 32 * kRegCols columns without an index map: the row is read ONCE into registers
+// (lane l holds columns l, l + 32, ...) and the k selection passes run on registers.
+constexpr int kRegCols = 40;
+template <bool LARGEST>
+__global__ void __launch_bounds__(128)
+topk_rows_reg_kernel(const float* __restrict__ scores, int rows, int cols, int ld, int k, int exclude_band,
+                     float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* srow = scores + static_cast<int64_t>(row) * ld;
+  const float worst = LARGEST ? -INFINITY : INFINITY;
+  float v[kRegCols];
+#pragma unroll
+  for (int t = 0; t < kRegCols; ++t) {
+    const int c = lane + 32 * t;
+    float s = worst;
+    bool ok = c < cols;
+    if (ok && exclude_band >= 0) {
+      const int d = c - row;
+      ok = (d < 0 ? -d : d) > exclude_band;
+    }
+    if (ok) s = srow[c];
+    // entries that can never be selected are parked at NaN: excluded, out of range, or NaN in the input
+    v[t] = (ok && s == s) ? s : __int_as_float(0x7fc00000);
+  }
+  for (int sel = 0; sel < k; ++sel) {
+    float bs = worst;
+    int bi = 0x7fffffff;
+    bool found = false;
+#pragma unroll
+    for (int t = 0; t < kRegCols; ++t) {
+      const float s = v[t];
+      if (s == s && (!found || (LARGEST ? s > bs : s < bs))) {  // columns ascend with t: strict keeps the lowest
+        bs = s;
+        bi = lane + 32 * t;
+        found = true;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      const int of = __shfl_xor_sync(0xffffffffu, static_cast<int>(found), off);
+      if (of && (!found || better<LARGEST>(os, oi, bs, bi))) {
+        bs = os;
+        bi = oi;
+        found = true;
+      }
+    }
+    const int64_t o = static_cast<int64_t>(row) * k + sel;
+    if (!found) {
+      if (lane == 0)
+        for (int t = sel; t < k; ++t) {
+          out_scores[static_cast<int64_t>(row) * k + t] = worst;
+          out_idx[static_cast<int64_t>(row) * k + t] = -1;
+        }
+      break;
+    }
+    if (lane == 0) {
+      out_scores[o] = bs;
+      out_idx[o] = bi;
+    }
+    // retire the winner in the lane that holds it
+    if ((bi & 31) == lane) {
+      const int tt = bi >> 5;
+#pragma unroll
+      for (int t = 0; t < kRegCols; ++t)
+        if (t == tt) v[t] = __int_as_float(0x7fc00000);
+    }
+  }
+}
+
 int topk_rows_impl(const float* scores, const int64_t* cand_idx, int rows, int cols, int ld, int k, int largest,
                    int exclude_band, const float* row_add, float scale, float* out_scores, int64_t* out_idx,
                    cudaStream_t stream) {
   if (rows == 0) return DLC_OK;
+  if (!cand_idx && !row_add && scale == 1.0f && cols <= 32 * kRegCols) {  // the loop-candidate case: S is [N, N]
+    const int grid = ceil_div(rows, 4);
+    if (largest)
+      topk_rows_reg_kernel<true><<<grid, 128, 0, stream>>>(scores, rows, cols, ld, k, exclude_band, out_scores, out_idx);
+    else
+      topk_rows_reg_kernel<false><<<grid, 128, 0, stream>>>(scores, rows, cols, ld, k, exclude_band, out_scores, out_idx);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_topk_rows: launch failed: %s", cudaGetErrorString(e));
+    return DLC_OK;
+  }
   const int block = 256;
   const int grid = ceil_div(rows, block / 32);
   if (largest)
