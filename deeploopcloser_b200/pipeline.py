@@ -43,7 +43,7 @@ class LoopClosurePipeline:
     def run_host_stream(self, batches, k=10, exclude_band=0):
         """Process a stream of HOST batches [(frames uint8 [B,H,W], xy float32 [B,P,2]), ...] (pinned torch tensors)
         end to end and return the candidate lists [(scores [B,k], idx [B,k]), ...] in pinned host memory (views of a
-        buffer owned by the pipeline: valid until the next call with the same stream length).
+        buffer owned by the pipeline: valid until the next call).
         The upload of batch i+1 runs on a copy stream while batch i computes (double-buffered device inputs), the
         candidate lists come back with asynchronous D2H copies; one synchronisation at the end."""
         batches = list(batches)
@@ -83,11 +83,12 @@ class LoopClosurePipeline:
             consumed[slot] = ev
             # pinned result buffers for the whole stream, allocated once per shape (cudaHostAlloc per batch would
             # serialise the pipeline)
-            shape = (len(batches),) + tuple(r["candidates"][0].shape)
+            per = tuple(r["candidates"][0].shape)
             pool = getattr(self, "_pinned_out", None)
-            if pool is None or pool[0].shape != shape:
-                pool = self._pinned_out = (torch.empty(shape, dtype=torch.float32).pin_memory(),
-                                           torch.empty(shape, dtype=torch.int64).pin_memory())
+            if pool is None or tuple(pool[0].shape[1:]) != per or pool[0].shape[0] < len(batches):
+                slots = max(64, len(batches))            # grow-only, so a longer stream does not re-allocate each call
+                pool = self._pinned_out = (torch.empty((slots,) + per, dtype=torch.float32).pin_memory(),
+                                           torch.empty((slots,) + per, dtype=torch.int64).pin_memory())
             s_h, i_h = pool[0][i], pool[1][i]
             s_h.copy_(r["candidates"][0], non_blocking=True)
             i_h.copy_(r["candidates"][1], non_blocking=True)
