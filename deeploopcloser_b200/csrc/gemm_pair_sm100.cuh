@@ -83,7 +83,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int my_tiles = Policy::num_tiles_pair(p, cluster, nclusters);
+  const int my_tiles = Policy::enabled(p) ? Policy::num_tiles_pair(p, cluster, nclusters) : 0;
   const int k_blocks = p.k_blocks;
   const int kc = p.kc > 0 ? p.kc : k_blocks;
   const int n_chunks = (k_blocks + kc - 1) / kc;
@@ -168,7 +168,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue));
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
-    const int n_cchunks = n_tile >> 5;
+    const int cstride = policy_chunk_stride<Policy>::get(p);
+    const int n_cchunks = n_tile / cstride;
     typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -180,12 +181,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&tfull[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) +
-                               (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(half * 128);
+                               (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(half * 4 * cstride);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           if (half * 4 + cc < n_cchunks) {
             uint32_t v[32];
-            tmem_ld_x32(taddr + cc * 32, v);
+            tmem_ld_x32(taddr + cc * cstride, v);
             tmem_ld_wait();
             if (ch == 0) {
 #pragma unroll

@@ -87,7 +87,8 @@ int g_promote_k = 256;
 // beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
 thread_local int g_gemm_k_valid = 0;
 int g_tma_store = 1;
-static int g_cta_pair = 1;  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
+int g_cta_pair = 1;
+int g_gram_pair = 1;  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern int g_sim_mgroup;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
@@ -152,6 +153,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 3) {
     g_dbg_flags = value;
+    return DLC_OK;
+  }
+  if (key == 7) {
+    g_gram_pair = value ? 1 : 0;
     return DLC_OK;
   }
   if (key == 6) {  // 0: never, 1: when the problem fills the GPU with pairs, 2: whenever the shape allows (tests)

@@ -17,7 +17,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "gemm_sm100.cuh"
+#include "gemm_pair_sm100.cuh"
 #include "util.h"
 
 namespace dlc {
@@ -159,6 +159,8 @@ struct GramParams {
   int n_tile, k_blocks, ab_fmt, kc;
   const int2* tiles;  // (mt, nt) work list in L2-friendly order
   int num_tiles;
+  const int2* pair_tiles;  // CTA-pair kernel: (first of two adjacent M tiles, nt)
+  int num_pair_tiles;
   int N, P, D;
   const float* desc;  // [N, P, D] float32 descriptors (exact refinement reads them)
   const float* sqn;   // [N*32]
@@ -229,6 +231,16 @@ struct GramPolicy {
     return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
   }
   static __device__ __forceinline__ int chunk_stride(const Params& p) { return p.col_stride; }
+  static __device__ __forceinline__ int num_tiles_pair(const Params& p, int cluster, int nclusters) {
+    return cluster < p.num_pair_tiles ? (p.num_pair_tiles - cluster + nclusters - 1) / nclusters : 0;
+  }
+  static __device__ __forceinline__ TileCoord tile_pair(const Params& p, int cluster, int nclusters, int i) {
+    const int2 t = __ldg(p.pair_tiles + cluster + i * nclusters);
+    TileCoord tc;
+    tc.mt = t.x;
+    tc.nt = t.y;
+    return tc;
+  }
   static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
     return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
   }
@@ -302,6 +314,16 @@ struct GramRefinePolicy {
     return p.ctl == nullptr || p.ctl->use_refine == p.want_refine;
   }
   static __device__ __forceinline__ int chunk_stride(const Params& p) { return p.col_stride; }
+  static __device__ __forceinline__ int num_tiles_pair(const Params& p, int cluster, int nclusters) {
+    return cluster < p.num_pair_tiles ? (p.num_pair_tiles - cluster + nclusters - 1) / nclusters : 0;
+  }
+  static __device__ __forceinline__ TileCoord tile_pair(const Params& p, int cluster, int nclusters, int i) {
+    const int2 t = __ldg(p.pair_tiles + cluster + i * nclusters);
+    TileCoord tc;
+    tc.mt = t.x;
+    tc.nt = t.y;
+    return tc;
+  }
   static __device__ __forceinline__ int num_tiles(const Params& p, int cta, int ncta) {
     return cta < p.num_tiles ? (p.num_tiles - cta + ncta - 1) / ncta : 0;
   }
@@ -511,28 +533,38 @@ __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* g
 
 // Work list: super-blocks of g_sim_mgroup M tiles; inside a super-block N tile outermost so the ~148 concurrently
 // running tiles touch g_sim_mgroup A row-blocks and ~148/g_sim_mgroup B row-blocks (fits L2) instead of streaming all of H.
-static void build_tile_list(int N, int full, int part, int n_parts, std::vector<int2>& out) {
+static void build_tile_list(int N, int full, int part, int n_parts, std::vector<int2>& out,
+                            std::vector<int2>& out_pairs) {
   const int m_tiles = ceil_div(N, kFramesPerMTile), n_tiles = ceil_div(N, kFramesPerNTile);
+  const int m_pairs = (m_tiles + 1) / 2;
   out.clear();
-  // M tiles owned by this part: every n_parts-th one (interleaved, so the triangle's long and short rows are
-  // dealt evenly), grouped into super-blocks of g_sim_mgroup owned tiles.
+  out_pairs.clear();
+  // Ownership is dealt in PAIRS of adjacent M tiles (what one CTA pair computes): every n_parts-th pair, interleaved
+  // so the triangle's long and short rows are spread evenly; super-blocks of g_sim_mgroup M tiles for L2 locality.
   std::vector<int> owned;
-  for (int mt = part; mt < m_tiles; mt += n_parts) owned.push_back(mt);
-  for (size_t g0 = 0; g0 < owned.size(); g0 += g_sim_mgroup) {
-    const size_t g1 = std::min(g0 + static_cast<size_t>(g_sim_mgroup), owned.size());
+  for (int q = part; q < m_pairs; q += n_parts) owned.push_back(q);
+  const size_t group = std::max(1, g_sim_mgroup / 2);
+  for (size_t g0 = 0; g0 < owned.size(); g0 += group) {
+    const size_t g1 = std::min(g0 + group, owned.size());
     for (int nt = 0; nt < n_tiles; ++nt)
       for (size_t g = g0; g < g1; ++g) {
-        const int mt = owned[g];
-        const int fa_min = mt * kFramesPerMTile;
+        const int q = owned[g];
         const int fb_max = std::min(nt * kFramesPerNTile + kFramesPerNTile - 1, N - 1);
-        // upper-triangle mode needs a pair fa < fb, or the diagonal block (to write the -1 fill)
-        if (full || fb_max >= fa_min) out.push_back(make_int2(mt, nt));
+        bool any = false;
+        for (int mt = 2 * q; mt < std::min(2 * q + 2, m_tiles); ++mt) {
+          // upper-triangle mode needs a pair fa < fb, or the diagonal block (to write the -1 fill)
+          if (full || fb_max >= mt * kFramesPerMTile) {
+            out.push_back(make_int2(mt, nt));
+            any = true;
+          }
+        }
+        if (any) out_pairs.push_back(make_int2(2 * q, nt));
       }
   }
 }
 
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ctl, off_probe, off_gaps, total;
+  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_ctl, off_probe, off_gaps, total;
   int ld, rows_pad, max_tiles;
   int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
   int rows_b;      // rows of the N-side planes
@@ -568,6 +600,7 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_sqn = take(sizeof(float) * w.rows_pad);
   w.off_pw = take(sizeof(double) * w.rows_pad);
   w.off_tiles = take(sizeof(int2) * w.max_tiles);
+  w.off_ptiles = take(sizeof(int2) * w.max_tiles);
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
   w.off_gaps = take(sizeof(float) * kProbeSamples);
@@ -594,6 +627,27 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
   if (p.num_tiles == 0) return DLC_OK;  // a part that owns no tile (more parts than M tiles)
   const int grid = std::min(p.num_tiles, sm_count());
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_sdav_similarity: launch failed: %s", cudaGetErrorString(e));
+  return DLC_OK;
+}
+
+// The same launch on CTA pairs (gemm_pair_sm100.cuh): each CTA stages half of the N tile.
+extern int g_cta_pair;   // planes.cu
+extern int g_gram_pair;  // planes.cu
+template <class Policy>
+static int run_gram_pair(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t stream) {
+  constexpr int BK = Policy::Cfg::BK;
+  CUtensorMap ta0, ta1, tb0, tb1;
+  if (!make_tmap_k_major(&ta0, ws + L.off_hi, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
+      !make_tmap_k_major(&tb0, ws + L.off_bhi, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile / 2) ||
+      !make_tmap_k_major(&ta1, ws + L.off_lo, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
+      !make_tmap_k_major(&tb1, ws + L.off_blo, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile / 2))
+    return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
+  p.k_blocks = ceil_div(p.D, BK);
+  p.kc = std::max(1, g_promote_k / BK);
+  if (p.num_pair_tiles == 0) return DLC_OK;  // a part that owns no tile
+  const int clusters = std::min(p.num_pair_tiles, sm_count() / 2);
+  cudaError_t e = launch_gemm_pair<Policy>(ta0, ta1, tb0, tb1, p, clusters, stream);
   if (e != cudaSuccess) return fail(DLC_ECUDA, "dlc_sdav_similarity: launch failed: %s", cudaGetErrorString(e));
   return DLC_OK;
 }
@@ -676,7 +730,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   double* w = reinterpret_cast<double*>(ws + L.off_w);
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
-  static thread_local std::vector<int2> tiles;
+  static thread_local std::vector<int2> tiles, pair_tiles;
   if (!g_gram_only) {
   // 1. dataset mean -> distinctive weights w
   if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
@@ -697,7 +751,9 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   DLC_CUDA(cudaGetLastError());
 
   // 4. tile work list (host-built, tiny) -> device
-  build_tile_list(N, full_asymmetric, part, n_parts, tiles);
+  build_tile_list(N, full_asymmetric, part, n_parts, tiles, pair_tiles);
+  DLC_CUDA(cudaMemcpyAsync(ws + L.off_ptiles, pair_tiles.data(), sizeof(int2) * pair_tiles.size(),
+                           cudaMemcpyHostToDevice, s));
   // a part of the matrix: entries other parts own stay zero, so the parts combine with a sum (all-reduce)
   if (n_parts > 1) DLC_CUDA(cudaMemsetAsync(S_dev, 0, sizeof(float) * static_cast<size_t>(N) * N, s));
   DLC_CUDA(cudaMemcpyAsync(ws + L.off_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
@@ -710,6 +766,8 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.ab_fmt = 0;
   p.tiles = reinterpret_cast<const int2*>(ws + L.off_tiles);
   p.num_tiles = static_cast<int>(tiles.size());
+  p.pair_tiles = reinterpret_cast<const int2*>(ws + L.off_ptiles);
+  p.num_pair_tiles = static_cast<int>(pair_tiles.size());
   p.N = N;
   p.P = P;
   p.D = D;
@@ -722,7 +780,13 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.S = S_dev;
   p.ctl = nullptr;
   p.want_refine = 0;
-  if (precision == DLC_PREC_FP16X2) return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+  if (precision == DLC_PREC_FP16X2) {
+    // enough pair tiles to fill the GPU and an N tile that splits into two UMMA-legal halves: CTA pairs
+    if (g_cta_pair && g_gram_pair && p.n_tile >= 32 && p.n_tile % 16 == 0 && (p.n_tile / 2) % 8 == 0 &&
+        (p.num_pair_tiles >= sm_count() / 2 || g_cta_pair == 2))
+      return run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s);
+    return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+  }
   if (precision == DLC_PREC_FP16) return run_gram<GramPolicy<64, 1>>(L, ws, p, s);
 
   // DLC_PREC_AUTO / DLC_PREC_FP16_REFINED: probe the single-product error on the data, then launch both kernels; the

@@ -561,3 +561,21 @@ def test_cta_pair_kernel_vs_oracle(cuda, m, k, n, bk):
     err = float(np.max(np.abs(out - ref)))
     print("pair kernel", (m, k, n), "bk", bk, "max abs err", err)
     assert err < 5e-5          # float32 accumulation of a sigmoid argument of magnitude up to ~50 * 30
+
+
+@pytest.mark.parametrize("n,p,d", [(9, 30, 2500), (21, 30, 300), (2, 30, 64), (33, 6, 128), (17, 5, 96)])
+def test_similarity_cta_pair_equals_single(cuda, n, p, d):
+    """The SDAV Gram kernel on CTA pairs (each CTA stages half of the 240-column N tile) gives bit-identical scores
+    to the single-CTA kernel, including odd numbers of M tiles and the 32-stride fallback (odd P)."""
+    from deeploopcloser_b200 import _lib, ops
+    rng = np.random.default_rng(n * 7 + p)
+    desc = torch.from_numpy(rng.uniform(0, 1, (n, p, d)).astype(np.float32)).cuda()
+    try:
+        _lib.call("dlc_debug_set", 6, 0)
+        single = ops.sdav_similarity(desc).clone()
+        _lib.call("dlc_debug_set", 6, 2)
+        pair = ops.sdav_similarity(desc).clone()
+        parts = torch.stack([ops.sdav_similarity_part(desc, q, 3).clone() for q in range(3)]).sum(0)
+    finally:
+        _lib.call("dlc_debug_set", 6, 1)
+    assert torch.equal(pair, single) and torch.equal(parts, single)

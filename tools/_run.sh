@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -x -q -m gpu -k "pipeline or smoke or host" > gpurun_out/pytest.log 2>&1; tail -2 gpurun_out/pytest.log
-for i in 1 2; do timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e'], d['clocks']['sm_mhz'])"; done
+timeout 600 python tools/sweep_step_pair.py > gpurun_out/sweep_step_pair.log 2>&1; tail -3 gpurun_out/sweep_step_pair.log
