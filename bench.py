@@ -307,10 +307,12 @@ def run_ours(args):
         achieved = GRAM_FLOP / (gram_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_gram_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture per kernel
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            tj = tj.get("GramRefinePolicy" if products == 1 else "GramPolicy<32,3>", tj if "dram_bytes_read" in tj else None)
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roof = {"kernel": "gemm_tc_kernel<%s> (SDAV Gram + argmin + score)" % (
                     "GramRefinePolicy" if products == 1 else "GramPolicy<32,3>"), "bound": "tensor",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
@@ -351,8 +353,8 @@ def run_ours(args):
                             "sample": "failed: %r" % (e,)}
 
     if rank == 0:
-        # gather, 5 layers, similarity (colsum, weights, prep_rows, [probe, finalize, gated twin], gram), top-k
-        launches_per_step = 1 + len(DIMS) - 1 + (7 if args.sim_precision in ("auto", "fp16r") else 4) + 1
+        # gather, 5 layers, similarity (colsum, weights, prep_rows, [rep_mask, probe, finalize, gated twin], gram), top-k
+        launches_per_step = 1 + len(DIMS) - 1 + (8 if args.sim_precision in ("auto", "fp16r") else 4) + 1
         line = {"metric": "loop-query frames/sec (encode+match)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo split operands, f32 accumulate" if
@@ -380,7 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"], help="encoder arithmetic")
-    ap.add_argument("--sim-precision", default="fp16x2", choices=["auto", "fp16r", "fp16x2", "fp16"],
+    ap.add_argument("--sim-precision", default="auto", choices=["auto", "fp16r", "fp16x2", "fp16"],
                     help="SDAV score-matrix arithmetic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", default="48,4800", type=lambda v: tuple(int(t) for t in v.split(",")),

@@ -84,7 +84,8 @@ rowstats_kernel(const float* __restrict__ H, int N, int P, int D, const double* 
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
                  __half* __restrict__ a_hi, __half* __restrict__ a_lo, __half* __restrict__ b_hi,
-                 __half* __restrict__ b_lo, int ld, float* __restrict__ sqn, double* __restrict__ pw) {
+                 __half* __restrict__ b_lo, int ld, float* __restrict__ sqn, double* __restrict__ pw,
+                 unsigned long long* __restrict__ sig) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N * kFrameRows) return;
@@ -94,6 +95,7 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
+  uint32_t s1 = 0, s2 = 0;  // order-independent 64-bit signature of the row's bit pattern (duplicate detection)
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     float x[8];
 #pragma unroll
@@ -119,6 +121,9 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
         const double xd = static_cast<double>(x[j]);
         n2 += xd * xd;
         pr += xd * w[c0 + j];
+        const uint32_t bits = __float_as_uint(x[j]);
+        s1 += bits * (2654435761u * static_cast<uint32_t>(c0 + j) + 0x9e3779b9u);
+        s2 += (bits ^ (bits >> 15)) * (40503u * static_cast<uint32_t>(c0 + j) + 2246822519u) + bits;
       }
     }
     const int64_t oa = static_cast<int64_t>(warp) * ld + c0;
@@ -134,11 +139,45 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   for (int off = 16; off > 0; off >>= 1) {
     n2 += __shfl_xor_sync(0xffffffffu, n2, off);
     pr += __shfl_xor_sync(0xffffffffu, pr, off);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
   }
   if (lane == 0) {
     sqn[warp] = valid ? static_cast<float>(n2) : INFINITY;
     pw[warp] = pr;
+    sig[warp] = (static_cast<unsigned long long>(s1) << 32) | s2;
   }
+}
+
+// rep_mask[f]: bit c set iff patch row c of frame f is not bit-identical to an earlier row of the same frame.
+// Duplicate patches are common (keypoints near a corner are all shifted onto the same corner patch); their squared
+// distances to any row are bit-identical in every arithmetic, np.argmin keeps the first of them, and so does the
+// strict '<' scan of the kernels - they never need the exact re-evaluation. One warp per frame (lane = row);
+// matching signatures are confirmed by comparing the rows.
+__global__ void __launch_bounds__(256)
+rep_mask_kernel(const float* __restrict__ H, int N, int P, int D, const unsigned long long* __restrict__ sig,
+                uint32_t* __restrict__ rep_mask) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= N) return;
+  const unsigned long long my = lane < P ? sig[f * kFrameRows + lane] : 0ull;
+  uint32_t rep = 0;
+  for (int c = 0; c < P; ++c) {
+    const unsigned long long sc = __shfl_sync(0xffffffffu, my, c);
+    uint32_t cand = __ballot_sync(0xffffffffu, lane < c && my == sc) & rep;  // earlier representatives, same signature
+    bool dup = false;
+    while (cand && !dup) {
+      const int e = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float* a = H + (static_cast<int64_t>(f) * P + c) * D;
+      const float* b = H + (static_cast<int64_t>(f) * P + e) * D;
+      bool same = true;
+      for (int i = lane; i < D; i += 32) same = same && (__float_as_uint(a[i]) == __float_as_uint(b[i]));
+      dup = __all_sync(0xffffffffu, same);
+    }
+    if (!dup) rep |= 1u << c;
+  }
+  if (lane == 0) rep_mask[f] = rep;
 }
 
 // ---------------- Gram + argmin + score epilogue ----------------
@@ -170,6 +209,7 @@ struct GramParams {
   float* S;           // [N, N]
   GramControl* ctl;   // NULL: always enabled
   int want_refine;    // this launch runs only when ctl->use_refine == want_refine
+  const uint32_t* rep_mask;  // [N] bit c set = row c of the frame is the FIRST of its class of bit-identical rows
   int col_stride;     // accumulator columns per frame on the N side: P when the B planes are packed P rows per
                       // frame (even P < 32; n_tile = 8 P, no MMA work on pad rows), else 32
 };
@@ -215,6 +255,46 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ a, const fl
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
   return acc0;
+}
+
+// exact squared distances of row a to TWO rows at once (a is read once): the usual refinement case
+__device__ __forceinline__ void exact_d2_pair(const float* __restrict__ a, const float* __restrict__ b0,
+                                              const float* __restrict__ b1, int D, int lane, double& r0, double& r1) {
+  double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+  if ((D & 3) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* p4 = reinterpret_cast<const float4*>(b0);
+    const float4* q4 = reinterpret_cast<const float4*>(b1);
+    const int n4 = D >> 2;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 x = __ldg(a4 + i), y = __ldg(p4 + i), z = __ldg(q4 + i);
+      double d;
+      d = static_cast<double>(x.x - y.x); s0 = fma(d, d, s0);
+      d = static_cast<double>(x.y - y.y); s1 = fma(d, d, s1);
+      d = static_cast<double>(x.z - y.z); s0 = fma(d, d, s0);
+      d = static_cast<double>(x.w - y.w); s1 = fma(d, d, s1);
+      d = static_cast<double>(x.x - z.x); t0 = fma(d, d, t0);
+      d = static_cast<double>(x.y - z.y); t1 = fma(d, d, t1);
+      d = static_cast<double>(x.z - z.z); t0 = fma(d, d, t0);
+      d = static_cast<double>(x.w - z.w); t1 = fma(d, d, t1);
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) {
+      const double d = static_cast<double>(a[i] - b0[i]), e = static_cast<double>(a[i] - b1[i]);
+      s0 = fma(d, d, s0);
+      t0 = fma(e, e, t0);
+    }
+  }
+  s0 += s1;
+  t0 += t1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+    t0 += __shfl_xor_sync(0xffffffffu, t0, off);
+  }
+  r0 = s0;
+  r1 = t0;
 }
 
 // ---- (A) three fp16 products + two-level accumulation: every Gram entry good to ~1e-7 relative
@@ -384,7 +464,10 @@ struct GramRefinePolicy {
       for (int j = 0; j < 32; ++j)
         if (d[j] <= lim) m |= 1u << j;
       bj[SLOT] = b;
-      mk[SLOT] = (lane < p.P && (m & (m - 1)) != 0) ? m : 0u;  // more than one candidate inside the margin
+      // candidates inside the margin, one per class of bit-identical rows (the first minimum b is always the first
+      // of its class): more than one left = the row needs the exact re-evaluation
+      m &= __ldg(p.rep_mask + fb);
+      mk[SLOT] = (lane < p.P && (m & (m - 1)) != 0) ? m : 0u;
     }
     __device__ __forceinline__ void end_tile(TileCoord) {}
 
@@ -410,12 +493,28 @@ struct GramRefinePolicy {
           double best = INFINITY;
           int bx = 0;
           while (m) {  // ascending j + strict '<'  ->  first exact minimum, like np.argmin
-            const int j = __ffs(m) - 1;
+            const int j0 = __ffs(m) - 1;
             m &= m - 1;
-            const double dd = exact_d2(arow, bbase + static_cast<int64_t>(j) * p.D, p.D, lane);
-            if (dd < best) {
-              best = dd;
-              bx = j;
+            if (m) {     // two candidates per pass over the row
+              const int j1 = __ffs(m) - 1;
+              m &= m - 1;
+              double e0, e1;
+              exact_d2_pair(arow, bbase + static_cast<int64_t>(j0) * p.D, bbase + static_cast<int64_t>(j1) * p.D, p.D,
+                            lane, e0, e1);
+              if (e0 < best) {
+                best = e0;
+                bx = j0;
+              }
+              if (e1 < best) {
+                best = e1;
+                bx = j1;
+              }
+            } else {
+              const double dd = exact_d2(arow, bbase + static_cast<int64_t>(j0) * p.D, p.D, lane);
+              if (dd < best) {
+                best = dd;
+                bx = j0;
+              }
             }
           }
           if (lane == L) bj[SLOT] = bx;
@@ -436,7 +535,7 @@ struct GramRefinePolicy {
 };
 
 // ---- probe: estimate the single-product error and the share of rows it would leave ambiguous
-constexpr int kProbeSamples = 2048;
+constexpr int kProbeSamples = 1024;
 struct ProbeAccum {
   double sum_err2;        // sum over sampled (row, candidate) of (approximate - exact squared distance)^2
   unsigned long long n_err;
@@ -450,21 +549,25 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
-// one warp per sample: a random row k of frame fa against all P rows of a random other frame fb
-__global__ void __launch_bounds__(256)
-gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, ProbeAccum* acc, float* gaps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// one CTA per sample: a random row k of frame fa against all P rows of a random other frame fb (warp j = row j)
+__global__ void __launch_bounds__(1024)
+gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const uint32_t* __restrict__ rep_mask,
+                  ProbeAccum* acc, float* gaps) {
+  __shared__ double s_e[32];
+  __shared__ double s_d[32];
+  const int sample = blockIdx.x;
+  const int j = threadIdx.x >> 5;  // candidate row of frame fb handled by this warp
   const int lane = threadIdx.x & 31;
-  if (warp >= kProbeSamples) return;
-  const uint32_t h = hash_u32(0x9e3779b9u * (warp + 1));
+  const uint32_t h = hash_u32(0x9e3779b9u * (sample + 1));
   const int fa = h % N;
   int fb = hash_u32(h) % N;
   if (fb == fa) fb = (fb + 1) % N;
   const int k = hash_u32(h ^ 0x5bd1e995u) % P;
-  const float* a = desc + (static_cast<int64_t>(fa) * P + k) * D;
-  double row_err2 = 0.0;
-  double d1 = INFINITY, d2 = INFINITY;
-  for (int j = 0; j < P; ++j) {
+  const uint32_t rep = rep_mask[fb];
+  // a bit-identical copy of an earlier row never needs refinement: only class representatives take part
+  const bool active = j < P && ((rep >> j) & 1u);
+  if (active) {
+    const float* a = desc + (static_cast<int64_t>(fa) * P + k) * D;
     const float* b = desc + (static_cast<int64_t>(fb) * P + j) * D;
     double g = 0.0, gr = 0.0, nb = 0.0;
     for (int c = lane; c < D; c += 32) {
@@ -479,22 +582,38 @@ gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, ProbeAccu
       gr += __shfl_xor_sync(0xffffffffu, gr, off);
       nb += __shfl_xor_sync(0xffffffffu, nb, off);
     }
-    const double e = 2.0 * (g - gr);  // error of the approximate squared distance n_j - 2 G
-    row_err2 += e * e;
-    const double dist = nb - 2.0 * g;
-    if (dist < d1) {
-      d2 = d1;
-      d1 = dist;
-    } else if (dist < d2) {
-      d2 = dist;
+    if (lane == 0) {
+      s_e[j] = 2.0 * (g - gr);  // error of the approximate squared distance n_j - 2 G
+      s_d[j] = nb - 2.0 * g;
     }
   }
-  if (lane == 0) {
-    atomicAdd(&acc->sum_err2, row_err2);
-    atomicAdd(&acc->n_err, static_cast<unsigned long long>(P));
-    const double mean_row = row_err2 / P;
-    atomicMax(&acc->max_row_bits, static_cast<unsigned long long>(__double_as_longlong(mean_row)));  // >= 0: bit order = value order
-    gaps[warp] = static_cast<float>(d2 - d1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // The single-product error of a squared distance has a large COMMON part (saturated values just below 1 round
+    // up to 1.0 in fp16: every Gram entry of the row is biased the same way) that cancels in the comparison of two
+    // candidates of the same row. What decides an argmin is the error of a DIFFERENCE d_a - d_b, i.e. the spread of
+    // the errors around their row mean: accumulate sum_j (e_j - mean_j e)^2.
+    double sum_e = 0.0, sum_e2 = 0.0, d1 = INFINITY, d2 = INFINITY;
+    int n_rep = 0;
+    for (int c = 0; c < P; ++c) {
+      if (!((rep >> c) & 1u)) continue;
+      ++n_rep;
+      sum_e += s_e[c];
+      sum_e2 += s_e[c] * s_e[c];
+      const double dist = s_d[c];
+      if (dist < d1) {
+        d2 = d1;
+        d1 = dist;
+      } else if (dist < d2) {
+        d2 = dist;
+      }
+    }
+    const double centered = n_rep > 1 ? fmax(sum_e2 - sum_e * sum_e / n_rep, 0.0) : 0.0;  // sum (e - mean)^2
+    atomicAdd(&acc->sum_err2, centered);
+    atomicAdd(&acc->n_err, static_cast<unsigned long long>(n_rep > 1 ? n_rep - 1 : 0));
+    const double var_row = n_rep > 1 ? centered / (n_rep - 1) : 0.0;
+    atomicMax(&acc->max_row_bits, static_cast<unsigned long long>(__double_as_longlong(var_row)));  // >= 0: bit order = value order
+    gaps[sample] = static_cast<float>(d2 - d1);
   }
 }
 __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* gaps, const float* sqn, int rows_pad,
@@ -513,9 +632,10 @@ __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* g
     if ((r % kFrameRows) < P) nmax = fmaxf(nmax, sqn[r]);
   atomicMax(reinterpret_cast<int*>(&s_nmax), __float_as_int(nmax));  // non-negative floats order like ints
   __syncthreads();
-  // >= 8 sigma of the operand-rounding error (global and worst sampled row) plus an allowance for the tensor core's
-  // truncating fp32 accumulation (differential part ~1e-6 of the largest Gram entry)
-  const float margin = static_cast<float>(fmax(8.0 * rms, 4.0 * rms_max)) + 4e-6f * s_nmax;
+  // The gap between two candidates carries the difference of two such errors (std sqrt(2) sigma): the margin is
+  // >= 8 standard deviations of that difference (global estimate; >= 4 for the worst sampled row) plus an allowance
+  // for the tensor core's truncating fp32 accumulation (differential part ~1e-6 of the largest Gram entry)
+  const float margin = static_cast<float>(1.41421356 * fmax(8.0 * rms, 4.0 * rms_max)) + 4e-6f * s_nmax;
   int cnt = 0;
   for (int i = threadIdx.x; i < kProbeSamples; i += blockDim.x) cnt += gaps[i] < margin ? 1 : 0;
   atomicAdd(&s_cnt, cnt);
@@ -564,7 +684,7 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
 }
 
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_ctl, off_probe, off_gaps, total;
+  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_sig, off_rep, off_ctl, off_probe, off_gaps, total;
   int ld, rows_pad, max_tiles;
   int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
   int rows_b;      // rows of the N-side planes
@@ -601,6 +721,8 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_pw = take(sizeof(double) * w.rows_pad);
   w.off_tiles = take(sizeof(int2) * w.max_tiles);
   w.off_ptiles = take(sizeof(int2) * w.max_tiles);
+  w.off_sig = take(sizeof(unsigned long long) * w.rows_pad);
+  w.off_rep = take(sizeof(uint32_t) * N);
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
   w.off_gaps = take(sizeof(float) * kProbeSamples);
@@ -660,10 +782,10 @@ using namespace dlc;
 // and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
 static int g_gram_only = 0;
 // AUTO uses the one-product + refinement kernel only when the probe expects at most this share of rows to need the
-// exact re-evaluation. Measured on B200 (1063 frames): refinement costs ~10 us per 1000 flagged rows per SM because
-// each candidate streams two 10 KB float32 rows; at 2.8 % flagged rows it is slower (6.6 ms) than three products
-// (5.4 ms), at <= 0.4 % it wins (< 2.5 ms).
-static float g_max_flag_frac = 0.004f;
+// exact re-evaluation. Measured on B200 (1063 frames, 17 M row-vs-frame decisions): the refinement costs ~11 us per
+// 1000 flagged rows (each candidate streams 10 KB float32 rows from L2), i.e. ~0.2 ms per 0.1 % of flagged rows,
+// against ~3 ms saved by issuing one tensor product instead of three: break-even near 1.5 %.
+static float g_max_flag_frac = 0.012f;
 extern "C" int dlc_sdav_debug_gram_only(int on) {
   g_gram_only = on ? 1 : 0;
   return DLC_OK;
@@ -730,6 +852,8 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   double* w = reinterpret_cast<double*>(ws + L.off_w);
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
+  unsigned long long* sig = reinterpret_cast<unsigned long long*>(ws + L.off_sig);
+  uint32_t* rep = reinterpret_cast<uint32_t*>(ws + L.off_rep);
   static thread_local std::vector<int2> tiles, pair_tiles;
   if (!g_gram_only) {
   // 1. dataset mean -> distinctive weights w
@@ -746,7 +870,9 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
     prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
         desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi), reinterpret_cast<__half*>(ws + L.off_lo),
         sep ? reinterpret_cast<__half*>(ws + L.off_bhi) : nullptr,
-        sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw);
+        sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw, sig);
+    if (precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED)
+      rep_mask_kernel<<<ceil_div(N, 8), 256, 0, s>>>(desc_dev, N, P, D, sig, rep);
   }
   DLC_CUDA(cudaGetLastError());
 
@@ -761,6 +887,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
 
   // 5. Gram + argmin + score
   GramParams p{};
+  p.rep_mask = rep;
   p.col_stride = L.col_stride;
   p.n_tile = kFramesPerNTile * L.col_stride;  // 256, or 240 for 30 patches per frame
   p.ab_fmt = 0;
@@ -798,7 +925,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
     float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
     DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
     if (N >= 2) {
-      gram_probe_kernel<<<ceil_div(kProbeSamples, 8), 256, 0, s>>>(desc_dev, N, P, D, acc, gaps);
+      gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_dev, N, P, D, rep, acc, gaps);
     } else {
       DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
     }

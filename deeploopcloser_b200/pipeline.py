@@ -7,12 +7,12 @@ from . import ops
 
 class LoopClosurePipeline:
     def __init__(self, dims=(1681, 2500, 2500, 2500, 2500, 2500), precision="fp16x2", patch=41, swap_xy_quirk=True,
-                 mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="fp16x2"):
+                 mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="auto"):
         self.dims = list(dims)
         self.precision = precision
-        # "fp16x2": three-product Gram (default). "auto": a device-side probe picks one fp16 product + exact
-        # refinement of ambiguous rows when very few rows need it (well separated patches), else the three-product
-        # kernel. "fp16r": always refine (most exact, slower when many rows are near-ties).
+        # "auto" (default): a device-side probe picks one fp16 product + exact refinement of the ambiguous rows when
+        # few rows need it (< 1.2 %; bit-identical duplicate patches never do), else the three-product kernel.
+        # "fp16x2": always three products. "fp16r": always refine (most exact, slower when many rows are near-ties).
         self.sim_precision = sim_precision
         self.patch = patch
         self.swap_xy_quirk = swap_xy_quirk
