@@ -11,7 +11,9 @@
 //           empty[s]  per CTA; arrived by the leader's MMA commit, multicast to both CTAs
 //           tfull[a]  per CTA; same multicast commit
 //           tempty[a] leader only; 16 arrivals = the 8 epilogue warps of each CTA (remote arrive from the peer)
-// Only policies with two-level accumulation (kPromote) are supported; tiles come from Policy::tile_pair().
+// The epilogue always drains the accumulator into registers first (the two-level accumulation path; with one K
+// chunk - kc >= k_blocks, what one-product policies pass - that is a plain copy that hands the TMEM buffer back at
+// once). NPROD = 1 policies stage and multiply one plane per operand. Tiles come from Policy::tile_pair().
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -23,7 +25,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ typename Policy::Params p) {
   using Cfg = typename Policy::Cfg;
-  static_assert(Policy::kPromote && Cfg::NPROD == 3, "the pair kernel implements the 3-product, two-level path");
+  static_assert(Cfg::NPROD == 3 ? Policy::kPromote : !Policy::kPromote,
+                "3-product policies use two-level accumulation, 1-product policies plain accumulation");
+  constexpr int kPl = Cfg::kPlanes;
   static_assert(!policy_im2col_a<Policy>::value, "implicit-GEMM operands are not supported by the pair kernel");
   constexpr int BK = Cfg::BK;
   constexpr int SMAX = Cfg::kMaxStages;
@@ -44,7 +48,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int n_tile = p.n_tile;
   const int half_n = n_tile >> 1;                         // B rows staged by each CTA
   const int b_plane_bytes = half_n * BK * 2;
-  const int stage_bytes = 2 * Cfg::kABytes + 2 * b_plane_bytes;
+  const int stage_bytes = kPl * (Cfg::kABytes + b_plane_bytes);
   int S = ring_bytes<Policy>() / stage_bytes;
   S = S < SMAX ? S : SMAX;
 
@@ -57,9 +61,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB0);
-    tma_prefetch_desc(&tmB1);
+    if (kPl == 2) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmB1);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -85,7 +91,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int my_tiles = Policy::enabled(p) ? Policy::num_tiles_pair(p, cluster, nclusters) : 0;
   const int k_blocks = p.k_blocks;
-  const int kc = p.kc > 0 ? p.kc : k_blocks;
+  const int kc = Policy::kPromote ? (p.kc > 0 ? p.kc : k_blocks) : k_blocks;
   const int n_chunks = (k_blocks + kc - 1) / kc;
 
   if (warp < 4) {
@@ -106,10 +112,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (leader) mbar_arrive_expect_tx(&full[stage], tx_pair);
             uint8_t* st = smem + stage * stage_bytes;
             tma_load_2d_pair(st, &tmA0, lbar, kb * BK, m0, Policy::kHintA);
-            tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
-            uint8_t* sb = st + 2 * Cfg::kABytes;
+            if (kPl == 2) tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
+            uint8_t* sb = st + kPl * Cfg::kABytes;
             tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
-            tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
+            if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
@@ -137,18 +143,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
               const uint32_t a_lo = a_hi + Cfg::kABytes;
-              const uint32_t b_hi = a_hi + 2 * Cfg::kABytes;
+              const uint32_t b_hi = a_hi + kPl * Cfg::kABytes;
               const uint32_t b_lo = b_hi + b_plane_bytes;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 const uint32_t koff = k * 32;
                 const uint64_t dah = make_smem_desc(a_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
                 const uint64_t dbh = make_smem_desc(b_hi + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-                const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-                const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-                umma_f16_pair(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
-                umma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
-                umma_f16_pair(d_tmem, dah, dbh, idesc, 1u);
+                if (Cfg::NPROD == 3) {
+                  const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+                  const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
+                  umma_f16_pair(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+                  umma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
+                  umma_f16_pair(d_tmem, dah, dbh, idesc, 1u);
+                } else {
+                  umma_f16_pair(d_tmem, dah, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+                }
               }
               umma_commit_pair(&empty[stage], 0x3);  // both CTAs' slots are free once these MMAs have read them
               if (++stage == S) {

@@ -90,6 +90,7 @@ int g_tma_store = 1;
 int g_cta_pair = 1;
 int g_gram_pair = 1;  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern int g_sim_mgroup;  // sdav_sim.cu
+extern int g_refine_cap;  // sdav_sim.cu
 static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
 template <class Policy>
@@ -173,6 +174,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 2 && value >= 32) {
     g_promote_k = value;
+    return DLC_OK;
+  }
+  if (key == 8) {  // capacity of the deferred-refinement list of the SDAV score kernel (-1: default, 0: refine in place)
+    g_refine_cap = value;
     return DLC_OK;
   }
   return fail(DLC_EINVAL, "dlc_debug_set: unknown key/value %d/%d", key, value);

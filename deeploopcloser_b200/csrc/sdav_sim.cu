@@ -25,7 +25,7 @@ namespace dlc {
 constexpr int kFrameRows = 32;                          // padded patch rows per frame
 constexpr int kFramesPerMTile = kTileM / kFrameRows;    // 4
 constexpr int kFramesPerNTile = kMaxTileN / kFrameRows; // 8
-int g_sim_mgroup = 8;                                   // M tiles per L2 super-block of the tile order (dlc_debug_set key 4)
+int g_sim_mgroup = 32;                                  // M tiles per L2 super-block of the tile order (dlc_debug_set key 4)
 
 // ---------------- column mean -> distinctive weights (deterministic two-stage reduction) ----------------
 constexpr int kColSumSlabs = 128;
@@ -190,8 +190,20 @@ struct GramControl {
   float margin;         // candidates within `margin` of the approximate minimum are re-evaluated exactly
   float sigma;          // estimated std of the approximate squared-distance error (diagnostic)
   float flagged_frac;   // estimated fraction of rows needing refinement (diagnostic)
-  unsigned long long flagged_rows;   // counted by the refine kernel (diagnostic)
+  unsigned long long flagged_rows;   // counted by the refine kernels (diagnostic)
   unsigned long long refined_cands;  // "
+  unsigned int n_entries;            // frame pairs the Gram kernel deferred to gram_refine_fix_kernel (may exceed the capacity)
+  unsigned int pad_;
+};
+
+// A frame pair with at least one ambiguous row, handed from the Gram epilogue to gram_refine_fix_kernel: the
+// approximate match of every row and, for the ambiguous rows, the candidates inside the margin.
+struct RefineEntry {
+  int fa, fb;
+  uint32_t flagged;   // ballot of the lanes (rows of fa) that need the exact re-evaluation
+  uint32_t pad_;
+  uint8_t bj[32];     // approximate argmin per row
+  uint32_t mk[32];    // candidate mask per row (0 = row is not ambiguous)
 };
 
 struct GramParams {
@@ -212,6 +224,8 @@ struct GramParams {
   const uint32_t* rep_mask;  // [N] bit c set = row c of the frame is the FIRST of its class of bit-identical rows
   int col_stride;     // accumulator columns per frame on the N side: P when the B planes are packed P rows per
                       // frame (even P < 32; n_tile = 8 P, no MMA work on pad rows), else 32
+  RefineEntry* work;  // deferred-refinement work list (NULL: refine inside the epilogue)
+  int work_cap;       // entries the list holds; pairs beyond it are refined inside the epilogue
 };
 
 // score of one frame pair from the per-row matches: sum_k (a + b ln |p_ik - p_j,bj(k)|), warp-wide
@@ -377,6 +391,51 @@ struct GramPolicy {
   };
 };
 
+// Exact re-evaluation of the ambiguous rows of frame pair (fa, fb): `fl` = ballot of the lanes (rows of fa) whose
+// candidate mask `mk` holds more than one class of rows of fb inside the margin. Returns this lane's match.
+__device__ __forceinline__ int refine_rows(const GramParams& p, int fa, int fb, int lane, uint32_t fl, uint32_t my_mk,
+                                           int my_bj) {
+  if (lane == 0 && p.ctl) atomicAdd(&p.ctl->flagged_rows, static_cast<unsigned long long>(__popc(fl)));
+  const float* abase = p.desc + static_cast<int64_t>(fa) * p.P * p.D;
+  const float* bbase = p.desc + static_cast<int64_t>(fb) * p.P * p.D;
+  while (fl) {
+    const int L = __ffs(fl) - 1;
+    fl &= fl - 1;
+    uint32_t m = __shfl_sync(0xffffffffu, my_mk, L);
+    if (lane == 0 && p.ctl) atomicAdd(&p.ctl->refined_cands, static_cast<unsigned long long>(__popc(m)));
+    const float* arow = abase + static_cast<int64_t>(L) * p.D;
+    double best = INFINITY;
+    int bx = 0;
+    while (m) {  // ascending j + strict '<'  ->  first exact minimum, like np.argmin
+      const int j0 = __ffs(m) - 1;
+      m &= m - 1;
+      if (m) {     // two candidates per pass over the row
+        const int j1 = __ffs(m) - 1;
+        m &= m - 1;
+        double e0, e1;
+        exact_d2_pair(arow, bbase + static_cast<int64_t>(j0) * p.D, bbase + static_cast<int64_t>(j1) * p.D, p.D, lane,
+                      e0, e1);
+        if (e0 < best) {
+          best = e0;
+          bx = j0;
+        }
+        if (e1 < best) {
+          best = e1;
+          bx = j1;
+        }
+      } else {
+        const double dd = exact_d2(arow, bbase + static_cast<int64_t>(j0) * p.D, p.D, lane);
+        if (dd < best) {
+          best = dd;
+          bx = j0;
+        }
+      }
+    }
+    if (lane == L) my_bj = bx;
+  }
+  return my_bj;
+}
+
 // ---- (B) one fp16 product + exact refinement. The single-product Gram entry carries the fp16 rounding of the
 // operands (std `sigma` on the squared distance, estimated by the probe). A row whose runner-up lies within
 // `margin` (>= 8 sigma) of the approximate minimum is re-evaluated: the candidates inside the margin get their exact
@@ -479,46 +538,28 @@ struct GramRefinePolicy {
         return;
       }
       if (!chunk_active(fb)) return;
-      uint32_t fl = __ballot_sync(0xffffffffu, mk[SLOT] != 0);
+      const uint32_t fl = __ballot_sync(0xffffffffu, mk[SLOT] != 0);
       if (fl) {
-        if (lane == 0 && p.ctl) atomicAdd(&p.ctl->flagged_rows, static_cast<unsigned long long>(__popc(fl)));
-        const float* abase = p.desc + static_cast<int64_t>(fa) * p.P * p.D;
-        const float* bbase = p.desc + static_cast<int64_t>(fb) * p.P * p.D;
-        while (fl) {
-          const int L = __ffs(fl) - 1;
-          fl &= fl - 1;
-          uint32_t m = __shfl_sync(0xffffffffu, mk[SLOT], L);
-          if (lane == 0 && p.ctl) atomicAdd(&p.ctl->refined_cands, static_cast<unsigned long long>(__popc(m)));
-          const float* arow = abase + static_cast<int64_t>(L) * p.D;
-          double best = INFINITY;
-          int bx = 0;
-          while (m) {  // ascending j + strict '<'  ->  first exact minimum, like np.argmin
-            const int j0 = __ffs(m) - 1;
-            m &= m - 1;
-            if (m) {     // two candidates per pass over the row
-              const int j1 = __ffs(m) - 1;
-              m &= m - 1;
-              double e0, e1;
-              exact_d2_pair(arow, bbase + static_cast<int64_t>(j0) * p.D, bbase + static_cast<int64_t>(j1) * p.D, p.D,
-                            lane, e0, e1);
-              if (e0 < best) {
-                best = e0;
-                bx = j0;
-              }
-              if (e1 < best) {
-                best = e1;
-                bx = j1;
-              }
-            } else {
-              const double dd = exact_d2(arow, bbase + static_cast<int64_t>(j0) * p.D, p.D, lane);
-              if (dd < best) {
-                best = dd;
-                bx = j0;
-              }
+        // Ambiguous rows: hand the pair to gram_refine_fix_kernel (one short burst of stores) - re-evaluating here
+        // stalls this warp for microseconds per row on 10 KB row reads, the accumulator double buffer runs dry and
+        // the tensor pipe idles (measured: 1.4 ms of Gram + 1.4 ms of stalls on the bench workload).
+        if (p.work) {
+          unsigned int slot = 0;
+          if (lane == 0) slot = atomicAdd(&p.ctl->n_entries, 1u);
+          slot = __shfl_sync(0xffffffffu, slot, 0);
+          if (slot < static_cast<unsigned int>(p.work_cap)) {
+            RefineEntry* e = p.work + slot;
+            if (lane == 0) {
+              e->fa = fa;
+              e->fb = fb;
+              e->flagged = fl;
             }
+            e->bj[lane] = static_cast<uint8_t>(bj[SLOT]);
+            e->mk[lane] = mk[SLOT];
+            return;
           }
-          if (lane == L) bj[SLOT] = bx;
         }
+        bj[SLOT] = refine_rows(p, fa, fb, lane, fl, mk[SLOT], bj[SLOT]);  // list full (or absent): refine in place
       }
       pair_score(p, fa, fb, lane, pa, bj[SLOT]);
     }
@@ -533,6 +574,25 @@ struct GramRefinePolicy {
     __device__ __forceinline__ void finish() {}
   };
 };
+
+// Second pass of mode (B): one warp per deferred frame pair re-evaluates its ambiguous rows exactly and writes the
+// pair's score. Thousands of independent warps keep the row reads in flight (the list is in tile order, so
+// neighbouring entries share frames and the reads mostly hit L2); same arithmetic as the in-epilogue path.
+constexpr int kFixThreads = 256;
+__global__ void __launch_bounds__(kFixThreads, 4) gram_refine_fix_kernel(const GramParams p) {
+  if (p.ctl->use_refine != p.want_refine) return;
+  const unsigned int n = min(p.ctl->n_entries, static_cast<unsigned int>(p.work_cap));
+  const int lane = threadIdx.x & 31;
+  const unsigned int warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const RefineEntry* e = p.work + i;
+    const int fa = e->fa, fb = e->fb;
+    const uint32_t fl = e->flagged;
+    const double pa = p.pw[fa * kFrameRows + lane];
+    const int bj = refine_rows(p, fa, fb, lane, fl, e->mk[lane], e->bj[lane]);
+    pair_score(p, fa, fb, lane, pa, bj);
+  }
+}
 
 // ---- probe: estimate the single-product error and the share of rows it would leave ambiguous
 constexpr int kProbeSamples = 1024;
@@ -648,6 +708,7 @@ __global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* g
     ctl->use_refine = force >= 0 ? force : (frac <= max_flag_frac ? 1 : 0);
     ctl->flagged_rows = 0;
     ctl->refined_cands = 0;
+    ctl->n_entries = 0;
   }
 }
 
@@ -683,11 +744,14 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
   }
 }
 
+constexpr int64_t kMaxRefineEntries = 1 << 18;
+int g_refine_cap = -1;  // developer override of the list capacity (dlc_debug_set key 8; 0 = refine in the epilogue)
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_sig, off_rep, off_ctl, off_probe, off_gaps, total;
+  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_sig, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
   int ld, rows_pad, max_tiles;
   int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
   int rows_b;      // rows of the N-side planes
+  int work_cap;    // entries of the deferred-refinement list
 };
 static SimWorkspace sim_layout(int N, int P, int D) {
   SimWorkspace w{};
@@ -726,6 +790,10 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
   w.off_gaps = take(sizeof(float) * kProbeSamples);
+  // deferred refinement: auto mode selects the one-product kernel only below ~1 % ambiguous rows, so a quarter of a
+  // million ambiguous PAIRS (46 MB) covers sequences of thousands of frames; beyond it the epilogue refines in place
+  w.work_cap = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(N) * N, kMaxRefineEntries));
+  w.off_work = take(sizeof(RefineEntry) * static_cast<size_t>(w.work_cap));
   w.total = o;
   (void)P;
   return w;
@@ -907,14 +975,13 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.S = S_dev;
   p.ctl = nullptr;
   p.want_refine = 0;
-  if (precision == DLC_PREC_FP16X2) {
-    // enough pair tiles to fill the GPU and an N tile that splits into two UMMA-legal halves: CTA pairs
-    if (g_cta_pair && g_gram_pair && p.n_tile >= 32 && p.n_tile % 16 == 0 && (p.n_tile / 2) % 8 == 0 &&
-        (p.num_pair_tiles >= sm_count() / 2 || g_cta_pair == 2))
-      return run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s);
-    return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
-  }
-  if (precision == DLC_PREC_FP16) return run_gram<GramPolicy<64, 1>>(L, ws, p, s);
+  // enough pair tiles to fill the GPU and an N tile that splits into two UMMA-legal halves: CTA pairs
+  const bool pairs = g_cta_pair && g_gram_pair && p.n_tile >= 32 && p.n_tile % 16 == 0 && (p.n_tile / 2) % 8 == 0 &&
+                     (p.num_pair_tiles >= sm_count() / 2 || g_cta_pair == 2);
+  if (precision == DLC_PREC_FP16X2)
+    return pairs ? run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s) : run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+  if (precision == DLC_PREC_FP16)
+    return pairs ? run_gram_pair<GramPolicy<64, 1>>(L, ws, p, s) : run_gram<GramPolicy<64, 1>>(L, ws, p, s);
 
   // DLC_PREC_AUTO / DLC_PREC_FP16_REFINED: probe the single-product error on the data, then launch both kernels; the
   // device-side control block lets exactly one of them run (no host round trip).
@@ -934,9 +1001,17 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
     DLC_CUDA(cudaGetLastError());
   }
   p.want_refine = 1;
-  if (int rc = run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
+  p.work_cap = g_refine_cap >= 0 ? std::min(g_refine_cap, L.work_cap) : L.work_cap;
+  p.work = p.work_cap > 0 ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
+  if (g_gram_only) DLC_CUDA(cudaMemsetAsync(&ctl->n_entries, 0, sizeof(unsigned int), s));  // else reset by the probe
+  if (int rc = pairs ? run_gram_pair<GramRefinePolicy>(L, ws, p, s) : run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
+  if (p.work) {
+    gram_refine_fix_kernel<<<4 * sm_count(), kFixThreads, 0, s>>>(p);
+    DLC_CUDA(cudaGetLastError());
+  }
+  p.work = nullptr;
   p.want_refine = 0;
-  return run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+  return pairs ? run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s) : run_gram<GramPolicy<32, 3>>(L, ws, p, s);
 }
 
 // Diagnostics of the last AUTO / FP16_REFINED call that used this workspace: out_host[0..5] = use_refine, margin,

@@ -563,6 +563,55 @@ def test_cta_pair_kernel_vs_oracle(cuda, m, k, n, bk):
     assert err < 5e-5          # float32 accumulation of a sigmoid argument of magnitude up to ~50 * 30
 
 
+def _near_tie_frames(seed, n=12, p=30, d=1024):
+    rng = np.random.default_rng(seed)
+    desc = rng.uniform(0.05, 0.95, (n, p, d)).astype(np.float32)
+    for f in range(1, n):           # frame f holds near-copies of patches of frame 0, in pairs 1e-4 apart
+        for k in range(0, p, 2):
+            base = desc[0, (k + f) % p]
+            desc[f, k] = base + 3e-3 * rng.standard_normal(d).astype(np.float32)
+            desc[f, k + 1] = desc[f, k] + 2e-5 * rng.standard_normal(d).astype(np.float32)
+    return np.clip(desc, 0, 1)
+
+
+@pytest.mark.parametrize("pair_mode", [0, 2])
+def test_similarity_deferred_refinement_equals_in_place(cuda, pair_mode):
+    """fp16r: ambiguous frame pairs are handed to a second kernel through a work list; a full list falls back to the
+    re-evaluation inside the Gram epilogue. All three routes (deferred, in place, list of 3 entries) must give the
+    same bits and the same flagged-row count, on single CTAs and on CTA pairs."""
+    from deeploopcloser_b200 import _lib, ops
+    desc = torch.from_numpy(_near_tie_frames(7)).cuda()
+    n, p, d = desc.shape
+    out, flagged = {}, {}
+    try:
+        _lib.call("dlc_debug_set", 6, pair_mode)
+        for cap in (-1, 0, 3):
+            _lib.call("dlc_debug_set", 8, cap)
+            out[cap] = ops.sdav_similarity(desc, precision="fp16r").clone()
+            flagged[cap] = ops.sdav_similarity_stats(n, p, d)["flagged_rows"]
+    finally:
+        _lib.call("dlc_debug_set", 8, -1)
+        _lib.call("dlc_debug_set", 6, 1)
+    assert flagged[-1] > 3 and flagged[0] == flagged[-1] and flagged[3] == flagged[-1]
+    assert torch.equal(out[0], out[-1]) and torch.equal(out[3], out[-1])
+    _check_similarity(out[-1].cpu().numpy(), desc.cpu().numpy(), False)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp16r"])
+def test_similarity_one_product_cta_pair_equals_single(cuda, precision):
+    from deeploopcloser_b200 import _lib, ops
+    rng = np.random.default_rng(11)
+    desc = torch.from_numpy(rng.uniform(0, 1, (37, 30, 300)).astype(np.float32)).cuda()
+    try:
+        _lib.call("dlc_debug_set", 6, 0)
+        single = ops.sdav_similarity(desc, precision=precision).clone()
+        _lib.call("dlc_debug_set", 6, 2)
+        pair = ops.sdav_similarity(desc, precision=precision).clone()
+    finally:
+        _lib.call("dlc_debug_set", 6, 1)
+    assert torch.equal(pair, single)
+
+
 @pytest.mark.parametrize("n,p,d", [(9, 30, 2500), (21, 30, 300), (2, 30, 64), (33, 6, 128), (17, 5, 96)])
 def test_similarity_cta_pair_equals_single(cuda, n, p, d):
     """The SDAV Gram kernel on CTA pairs (each CTA stages half of the 240-column N tile) gives bit-identical scores
