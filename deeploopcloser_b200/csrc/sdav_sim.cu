@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
                  __half* __restrict__ a_hi, __half* __restrict__ a_lo, __half* __restrict__ b_hi,
                  __half* __restrict__ b_lo, int ld, float* __restrict__ sqn, double* __restrict__ pw,
-                 unsigned long long* __restrict__ sig) {
+                 unsigned int* __restrict__ nmax_bits) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N * kFrameRows) return;
@@ -95,7 +95,6 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
-  uint32_t s1 = 0, s2 = 0;  // order-independent 64-bit signature of the row's bit pattern (duplicate detection)
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     float x[8];
 #pragma unroll
@@ -121,9 +120,6 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
         const double xd = static_cast<double>(x[j]);
         n2 += xd * xd;
         pr += xd * w[c0 + j];
-        const uint32_t bits = __float_as_uint(x[j]);
-        s1 += bits * (2654435761u * static_cast<uint32_t>(c0 + j) + 0x9e3779b9u);
-        s2 += (bits ^ (bits >> 15)) * (40503u * static_cast<uint32_t>(c0 + j) + 2246822519u) + bits;
       }
     }
     const int64_t oa = static_cast<int64_t>(warp) * ld + c0;
@@ -139,45 +135,92 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   for (int off = 16; off > 0; off >>= 1) {
     n2 += __shfl_xor_sync(0xffffffffu, n2, off);
     pr += __shfl_xor_sync(0xffffffffu, pr, off);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
   }
   if (lane == 0) {
     sqn[warp] = valid ? static_cast<float>(n2) : INFINITY;
     pw[warp] = pr;
-    sig[warp] = (static_cast<unsigned long long>(s1) << 32) | s2;
+    // largest squared norm (the probe's margin scales an allowance with it); non-negative floats order like their
+    // bit patterns, and the plain read first keeps all but a few rows off the atomic
+    if (nmax_bits && valid) {
+      const unsigned int bits = __float_as_uint(static_cast<float>(n2));
+      if (bits > *reinterpret_cast<volatile unsigned int*>(nmax_bits)) atomicMax(nmax_bits, bits);
+    }
+  }
+}
+
+// Residual planes only (lo = fp16(x - fp16(x))), for the three-product kernel when the precision probe decided
+// against the one-product kernel: launched after the probe and skipped (device-side gate) otherwise, so the common
+// one-product path never writes the 0.3 GB of residual planes. Same indexing as prep_rows_kernel.
+struct GramControl;
+__device__ __forceinline__ bool lo_planes_wanted(const GramControl* ctl);
+__global__ void __launch_bounds__(256)
+lo_planes_kernel(const float* __restrict__ H, int N, int P, int D, __half* __restrict__ a_lo,
+                 __half* __restrict__ b_lo, int ld, const GramControl* __restrict__ ctl) {
+  if (!lo_planes_wanted(ctl)) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N * kFrameRows) return;
+  const int f = warp / kFrameRows, k = warp % kFrameRows;
+  const bool valid = k < P;
+  const int64_t r = static_cast<int64_t>(f) * P + k;
+  const float* h = H + r * D;
+  for (int c0 = lane * 8; c0 < ld; c0 += 256) {
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = (valid && c0 + j < D) ? h[c0 + j] : 0.0f;
+      __half hh;
+      split_f32(x, hh, ll[j]);
+    }
+    *reinterpret_cast<uint4*>(a_lo + static_cast<int64_t>(warp) * ld + c0) = *reinterpret_cast<const uint4*>(ll);
+    if (b_lo && valid) *reinterpret_cast<uint4*>(b_lo + r * ld + c0) = *reinterpret_cast<const uint4*>(ll);
   }
 }
 
 // rep_mask[f]: bit c set iff patch row c of frame f is not bit-identical to an earlier row of the same frame.
 // Duplicate patches are common (keypoints near a corner are all shifted onto the same corner patch); their squared
 // distances to any row are bit-identical in every arithmetic, np.argmin keeps the first of them, and so does the
-// strict '<' scan of the kernels - they never need the exact re-evaluation. One warp per frame (lane = row);
-// matching signatures are confirmed by comparing the rows.
-__global__ void __launch_bounds__(256)
-rep_mask_kernel(const float* __restrict__ H, int N, int P, int D, const unsigned long long* __restrict__ sig,
-                uint32_t* __restrict__ rep_mask) {
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// strict '<' scan of the kernels - they never need the exact re-evaluation. One CTA per frame, warp c = row c:
+// lane e < c compares the first elements of rows e and c, only rows with an equal prefix are compared in full.
+constexpr int kRepPrefix = 32;
+__global__ void __launch_bounds__(1024)
+rep_mask_kernel(const float* __restrict__ H, int N, int P, int D, uint32_t* __restrict__ rep_mask) {
+  __shared__ uint32_t s_rep;
+  const int f = blockIdx.x;
+  const int c = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (f >= N) return;
-  const unsigned long long my = lane < P ? sig[f * kFrameRows + lane] : 0ull;
-  uint32_t rep = 0;
-  for (int c = 0; c < P; ++c) {
-    const unsigned long long sc = __shfl_sync(0xffffffffu, my, c);
-    uint32_t cand = __ballot_sync(0xffffffffu, lane < c && my == sc) & rep;  // earlier representatives, same signature
+  if (threadIdx.x == 0) s_rep = 0;
+  __syncthreads();
+  if (c < P) {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + c) * D);
+    uint32_t diff = 1;
+    if (lane < c) {  // branch-free accumulation: the loads of the prefix are independent and issue back to back
+      const uint32_t* b = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + lane) * D);
+      const int n = D < kRepPrefix ? D : kRepPrefix;
+      diff = 0;
+      for (int i = 0; i < n; ++i) diff |= a[i] ^ b[i];
+    }
+    uint32_t cand = __ballot_sync(0xffffffffu, diff == 0);
     bool dup = false;
     while (cand && !dup) {
       const int e = __ffs(cand) - 1;
       cand &= cand - 1;
-      const float* a = H + (static_cast<int64_t>(f) * P + c) * D;
-      const float* b = H + (static_cast<int64_t>(f) * P + e) * D;
-      bool same = true;
-      for (int i = lane; i < D; i += 32) same = same && (__float_as_uint(a[i]) == __float_as_uint(b[i]));
-      dup = __all_sync(0xffffffffu, same);
+      const uint32_t* b = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + e) * D);
+      dup = true;
+      for (int base = 0; base < D && dup; base += 32 * 8) {  // 8 independent loads per lane, then one vote
+        uint32_t d = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = base + u * 32 + lane;
+          if (i < D) d |= a[i] ^ b[i];
+        }
+        dup = !__any_sync(0xffffffffu, d != 0);
+      }
     }
-    if (!dup) rep |= 1u << c;
+    if (!dup && lane == 0) atomicOr(&s_rep, 1u << c);
   }
-  if (lane == 0) rep_mask[f] = rep;
+  __syncthreads();
+  if (threadIdx.x == 0) rep_mask[f] = s_rep;
 }
 
 // ---------------- Gram + argmin + score epilogue ----------------
@@ -195,6 +238,8 @@ struct GramControl {
   unsigned int n_entries;            // frame pairs the Gram kernel deferred to gram_refine_fix_kernel (may exceed the capacity)
   unsigned int pad_;
 };
+
+__device__ __forceinline__ bool lo_planes_wanted(const GramControl* ctl) { return ctl->use_refine == 0; }
 
 // A frame pair with at least one ambiguous row, handed from the Gram epilogue to gram_refine_fix_kernel: the
 // approximate match of every row and, for the ambiguous rows, the candidates inside the margin.
@@ -600,6 +645,8 @@ struct ProbeAccum {
   double sum_err2;        // sum over sampled (row, candidate) of (approximate - exact squared distance)^2
   unsigned long long n_err;
   unsigned long long max_row_bits;
+  unsigned int nmax_bits;   // largest squared row norm (float bits), written by prep_rows_kernel
+  unsigned int pad_;
 };
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
   x ^= x >> 16;
@@ -629,22 +676,36 @@ gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const uin
   if (active) {
     const float* a = desc + (static_cast<int64_t>(fa) * P + k) * D;
     const float* b = desc + (static_cast<int64_t>(fb) * P + j) * D;
-    double g = 0.0, gr = 0.0, nb = 0.0;
-    for (int c = lane; c < D; c += 32) {
-      const float x = a[c], y = b[c];
-      g = fma(static_cast<double>(x), static_cast<double>(y), g);
-      gr = fma(static_cast<double>(__half2float(__float2half_rn(x))), static_cast<double>(__half2float(__float2half_rn(y))), gr);
-      nb = fma(static_cast<double>(y), static_cast<double>(y), nb);
+    // err  = sum_c x y - fp16(x) fp16(y) = sum_c (x - xh) y + xh (y - yh): both residuals are exact in float32 and the
+    //        sum is a statistic (three digits are plenty) -> float32 throughout, no float64 conversions;
+    // dist = sum_c y (y - 2 x)  (squared distance up to the row constant): float32 partial sums of four elements,
+    //        added in float64 (absolute error ~1e-5 on values ~1e3; it is compared with a margin ~1e-2).
+    float err = 0.0f;
+    double dist = 0.0;
+    auto term = [&](float x, float y) -> float {
+      const float xh = __half2float(__float2half_rn(x)), yh = __half2float(__float2half_rn(y));
+      err = fmaf(x - xh, y, fmaf(xh, y - yh, err));
+      return y * (y - 2.0f * x);
+    };
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(desc) & 15) == 0) {
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll 4
+      for (int c = lane; c < (D >> 2); c += 32) {
+        const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
+        dist += static_cast<double>((term(x.x, y.x) + term(x.y, y.y)) + (term(x.z, y.z) + term(x.w, y.w)));
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) dist += static_cast<double>(term(a[c], b[c]));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, off);
-      gr += __shfl_xor_sync(0xffffffffu, gr, off);
-      nb += __shfl_xor_sync(0xffffffffu, nb, off);
+      err += __shfl_xor_sync(0xffffffffu, err, off);
+      dist += __shfl_xor_sync(0xffffffffu, dist, off);
     }
     if (lane == 0) {
-      s_e[j] = 2.0 * (g - gr);  // error of the approximate squared distance n_j - 2 G
-      s_d[j] = nb - 2.0 * g;
+      s_e[j] = 2.0 * static_cast<double>(err);  // error of the approximate squared distance n_j - 2 G
+      s_d[j] = dist;
     }
   }
   __syncthreads();
@@ -676,22 +737,14 @@ gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const uin
     gaps[sample] = static_cast<float>(d2 - d1);
   }
 }
-__global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* gaps, const float* sqn, int rows_pad,
-                                           int P, float max_flag_frac, int force, GramControl* ctl) {
+__global__ void gram_probe_finalize_kernel(const ProbeAccum* acc, const float* gaps, float max_flag_frac, int force,
+                                           GramControl* ctl) {
   __shared__ int s_cnt;
-  __shared__ float s_nmax;
-  if (threadIdx.x == 0) {
-    s_cnt = 0;
-    s_nmax = 0.0f;
-  }
+  if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   const double rms = sqrt(acc->sum_err2 / static_cast<double>(acc->n_err > 0 ? acc->n_err : 1));
   const double rms_max = sqrt(__longlong_as_double(static_cast<long long>(acc->max_row_bits)));
-  float nmax = 0.0f;
-  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x)
-    if ((r % kFrameRows) < P) nmax = fmaxf(nmax, sqn[r]);
-  atomicMax(reinterpret_cast<int*>(&s_nmax), __float_as_int(nmax));  // non-negative floats order like ints
-  __syncthreads();
+  const float s_nmax = __uint_as_float(acc->nmax_bits);
   // The gap between two candidates carries the difference of two such errors (std sqrt(2) sigma): the margin is
   // >= 8 standard deviations of that difference (global estimate; >= 4 for the worst sampled row) plus an allowance
   // for the tensor core's truncating fp32 accumulation (differential part ~1e-6 of the largest Gram entry)
@@ -747,7 +800,7 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
 constexpr int64_t kMaxRefineEntries = 1 << 18;
 int g_refine_cap = -1;  // developer override of the list capacity (dlc_debug_set key 8; 0 = refine in the epilogue)
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_sig, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
+  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
   int ld, rows_pad, max_tiles;
   int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
   int rows_b;      // rows of the N-side planes
@@ -785,7 +838,6 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_pw = take(sizeof(double) * w.rows_pad);
   w.off_tiles = take(sizeof(int2) * w.max_tiles);
   w.off_ptiles = take(sizeof(int2) * w.max_tiles);
-  w.off_sig = take(sizeof(unsigned long long) * w.rows_pad);
   w.off_rep = take(sizeof(uint32_t) * N);
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
@@ -920,7 +972,6 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   double* w = reinterpret_cast<double*>(ws + L.off_w);
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
-  unsigned long long* sig = reinterpret_cast<unsigned long long*>(ws + L.off_sig);
   uint32_t* rep = reinterpret_cast<uint32_t*>(ws + L.off_rep);
   static thread_local std::vector<int2> tiles, pair_tiles;
   if (!g_gram_only) {
@@ -932,15 +983,38 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
     weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w);
   }
   // 2. one pass: operand planes (M side: frames padded P -> 32 rows; N side: packed P rows per frame when separate;
-  //    K padded with zeros), per-row squared norms and projections p = h . w
+  //    K padded with zeros), per-row squared norms and projections p = h . w. With a precision probe (auto / fp16r)
+  //    the residual planes are written later and only if the probe picks the three-product kernel.
   {
     const bool sep = L.col_stride != kFrameRows;
+    const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
+    const bool lo_now = precision == DLC_PREC_FP16X2;
+    ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
+    if (probe) DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
     prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
-        desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi), reinterpret_cast<__half*>(ws + L.off_lo),
+        desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi),
+        lo_now ? reinterpret_cast<__half*>(ws + L.off_lo) : nullptr,
         sep ? reinterpret_cast<__half*>(ws + L.off_bhi) : nullptr,
-        sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw, sig);
-    if (precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED)
-      rep_mask_kernel<<<ceil_div(N, 8), 256, 0, s>>>(desc_dev, N, P, D, sig, rep);
+        sep && lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw,
+        probe ? &acc->nmax_bits : nullptr);
+    // 3. precision probe: classes of bit-identical rows, then the single-product error on sampled rows -> margin and
+    //    the device-side choice between the two Gram kernels
+    if (probe) {
+      GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
+      float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
+      rep_mask_kernel<<<N, 1024, 0, s>>>(desc_dev, N, P, D, rep);
+      if (N >= 2) {
+        gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_dev, N, P, D, rep, acc, gaps);
+      } else {
+        DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
+      }
+      gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, g_max_flag_frac,
+                                                   precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
+      if (precision == DLC_PREC_AUTO)  // fp16r never runs the three-product kernel
+        lo_planes_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
+            desc_dev, N, P, D, reinterpret_cast<__half*>(ws + L.off_lo),
+            sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, ctl);
+    }
   }
   DLC_CUDA(cudaGetLastError());
 
@@ -987,19 +1061,6 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   // device-side control block lets exactly one of them run (no host round trip).
   GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
   p.ctl = ctl;
-  if (!g_gram_only) {
-    ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
-    float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
-    DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
-    if (N >= 2) {
-      gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_dev, N, P, D, rep, acc, gaps);
-    } else {
-      DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
-    }
-    gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, sqn, L.rows_pad, P, g_max_flag_frac,
-                                                 precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
-    DLC_CUDA(cudaGetLastError());
-  }
   p.want_refine = 1;
   p.work_cap = g_refine_cap >= 0 ? std::min(g_refine_cap, L.work_cap) : L.work_cap;
   p.work = p.work_cap > 0 ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
