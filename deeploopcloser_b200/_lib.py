@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("DLC_LIB_PATH") or os.path.join(_HERE, "libdlc.so")  #
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP16, PREC_FP16X2, PREC_BF16, PREC_AUTO, PREC_FP16_REFINED = 0, 1, 2, 3, 4
-F32, F64, F16, BF16, U8 = 0, 1, 2, 3, 4
+F32, F64, F16, BF16, U8, I32 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 METRIC_COS, METRIC_DOT, METRIC_L2 = 0, 1, 2
 
@@ -64,6 +64,8 @@ PROTOTYPES = {
     "dlc_match_threshold": (_i, [_p, _p, _i, _f, _i, _i64, _p, _p, _p, _p, _sz, _p]),
     "dlc_hamming_workspace_bytes": (_sz, [_i, _i]),
     "dlc_hamming_matrix": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
+    "dlc_matrix_image_workspace_bytes": (_sz, []),
+    "dlc_matrix_image": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_cnnvtl_create": (_i, [C.POINTER(_p), _i, _i, _i]),
     "dlc_cnnvtl_destroy": (_i, [_p]),
     "dlc_cnnvtl_set_conv": (_i, [_p, _i, _p, _p]),

@@ -26,6 +26,17 @@ class DistanceCalculator:
 
 
 def distance_image(distance_matrix):
-    """255 - D / max * 255 (create_distance_matrix.py:40)."""
-    m = np.asarray(distance_matrix, dtype=np.float64)
-    return 255 - m / m.max() * 255
+    """Hamming matrix -> uint8 image on the B200: 255 - D / max * 255 (create_distance_matrix.py:40) and cv2.imwrite's
+    float64 -> uint8 conversion (:41). Accepts a NumPy array or a CUDA int32 tensor; returns NumPy."""
+    import torch
+
+    from . import _cuda, ops
+    _cuda.require_cuda()
+    m = distance_matrix
+    if not isinstance(m, torch.Tensor):
+        m = np.asarray(m)
+        if m.size and (m.min() < -2 ** 31 or m.max() >= 2 ** 31):
+            raise ValueError("distances must fit int32")
+        m = torch.from_numpy(np.ascontiguousarray(m, dtype=np.int32))
+    m = m.to(device="cuda", dtype=torch.int32).contiguous()
+    return ops.matrix_image(m, ops.IMG_DISTANCE).cpu().numpy()

@@ -244,6 +244,28 @@ def hamming_matrix(desc, signed_bin_quirk=True):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ matrix -> image
+IMG_SIMILARITY, IMG_DISTANCE = 0, 1
+
+
+def matrix_image(m, mode, truncate_int=False):
+    """Score matrix (float32) or Hamming matrix (int32) [rows, cols] on the device -> uint8 image, the tail of
+    create_similarity_matrix.py:41-48 / create_distance_matrix.py:40-41 (see dlc_matrix_image)."""
+    _check_cuda(m)
+    if m.dtype == torch.float32:
+        dtype = _lib.F32
+    elif m.dtype == torch.int32:
+        dtype = _lib.I32
+    else:
+        raise ValueError("expected a float32 or int32 matrix")
+    rows, cols = m.shape
+    out = torch.empty((rows, cols), dtype=torch.uint8, device=m.device)
+    ws, ws_bytes = _ws.get(_lib.call("dlc_matrix_image_workspace_bytes"))
+    _lib.call("dlc_matrix_image", ptr(m), dtype, rows, cols, int(mode), int(bool(truncate_int)), ptr(out), ws,
+              ws_bytes, stream_ptr())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ fused conv head
 class CnnVtlHead:
     """Owner of a dlc_cnnvtl handle: packed conv filters and the kept-column tables live on the device."""

@@ -62,8 +62,36 @@ class SimilarityCalculator:
         return s.cpu().numpy(), i.cpu().numpy()
 
 
-def similarity_image(similarity_matrix):
-    """min-max normalisation to 0..255 (create_similarity_matrix.py:41-45)."""
-    m = np.asarray(similarity_matrix, dtype=np.float64)
-    move = 0 - m.min()
-    return 255 * ((m + move) / (m.max() + move))
+def similarity_image(similarity_matrix, reference_int=True):
+    """Score matrix -> uint8 image on the B200: min-max normalisation to 0..255 (create_similarity_matrix.py:41-45)
+    and cv2.imwrite's float64 -> uint8 conversion (:48). reference_int=True first truncates the scores toward zero,
+    as the reference's int64 matrix does on store (:31). Accepts a NumPy array or a CUDA tensor; returns NumPy."""
+    import torch
+
+    from . import _cuda, ops
+    _cuda.require_cuda()
+    m = similarity_matrix
+    if not isinstance(m, torch.Tensor):
+        m = torch.from_numpy(np.ascontiguousarray(m, dtype=np.float32))
+    m = m.to(device="cuda", dtype=torch.float32).contiguous()
+    return ops.matrix_image(m, ops.IMG_SIMILARITY, truncate_int=reference_int).cpu().numpy()
+
+
+def write_png(path, image_u8):
+    """8-bit grey PNG (what cv2.imwrite produces for the reference's matrices); pure zlib, no OpenCV needed."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(image_u8, dtype=np.uint8)
+    if img.ndim != 2:
+        raise ValueError("expected a [rows, cols] uint8 image")
+    h, w = img.shape
+
+    def chunk(tag, data):
+        body = tag + data
+        return struct.pack(">I", len(data)) + body + struct.pack(">I", zlib.crc32(body) & 0xFFFFFFFF)
+
+    raw = b"".join(b"\x00" + img[r].tobytes() for r in range(h))          # filter type 0 per scanline
+    png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) +
+           chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+    with open(str(path), "wb") as f:
+        f.write(png)

@@ -45,6 +45,7 @@ extern "C" {
 #define DLC_F16 2
 #define DLC_BF16 3
 #define DLC_U8 4
+#define DLC_I32 5
 
 /* activations of dlc_gemm_planes */
 #define DLC_ACT_NONE 0
@@ -285,6 +286,21 @@ int dlc_train_sgd(double* w_dev, const void* grad_dev, int grad_dtype, int64_t n
 /* out = (dx + extra) * keep[r % mask_rows]: gradient through x_l = h_{l-1} * mask_l (+ the label gradient). */
 int dlc_train_mask_grad(const float* dx_dev, const float* extra_dev, const float* keep_dev, int R, int C,
                         int mask_rows, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Matrix -> 8-bit image: the tails of src/sdav/create_similarity_matrix.py:41-48 (DLC_IMG_SIMILARITY:
+ * 255 * ((M - min) / (max - min)), written as in the reference: move = 0 - min, divide = max + move) and of
+ * src/cnn_vtl/create_distance_matrix.py:40-41 (DLC_IMG_DISTANCE: 255 - M / max * 255), followed by cv2.imwrite's
+ * float64 -> uint8 conversion (round half to even, clamp to 0..255). m_dev [rows, cols] DLC_F32 (scores) or DLC_I32
+ * (Hamming distances); truncate_int != 0 truncates float scores toward zero first, as the reference's int64 matrix
+ * (np.full([n, n], -1), :31) does on store. Non-finite scores stay out of the range and saturate (+inf -> 255).
+ * Float64 arithmetic in the reference's operation order. out_dev uint8 [rows, cols].
+ * ------------------------------------------------------------------------------------------------------------ */
+#define DLC_IMG_SIMILARITY 0
+#define DLC_IMG_DISTANCE 1
+size_t dlc_matrix_image_workspace_bytes(void);
+int dlc_matrix_image(const void* m_dev, int dtype, int rows, int cols, int mode, int truncate_int, uint8_t* out_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,8 +88,58 @@ def golden_misc():
                         tw_expected=expected)
 
 
+def _exec_reference_lines(path, first, last, env):
+    """Runs lines first..last (1-based, inclusive) of a reference script - the scripts themselves cannot be imported
+    (hard-coded paths, TensorFlow) - in `env`, so the fixture holds what the reference's own statements compute."""
+    with open(os.path.join(REF, path)) as f:
+        lines = f.readlines()[first - 1:last]
+    exec(compile("".join(lines), path, "exec"), env)
+    return env
+
+
+def golden_images():
+    """create_similarity_matrix.py:31,41-45 + :48 and create_distance_matrix.py:31,40-41: the reference's int64
+    matrix, its normalisation lines executed verbatim, and the real cv2.imwrite -> imread round trip."""
+    import tempfile
+
+    import cv2
+    g = np.load(os.path.join(HERE, "similarity.npz"))
+    h = np.load(os.path.join(HERE, "hamming.npz"))
+    out = {}
+    tmp = tempfile.mkdtemp()
+    rng = np.random.default_rng(3)
+    big = rng.normal(-300.0, 120.0, (37, 37))
+    big = (big + big.T) / 2
+    for name, S in (("a", g["S_a"]), ("b", g["S_b"]), ("r", big)):
+        S = np.array(S, dtype=np.float64)
+        n = len(S)
+        similarity_matrix = np.full([n, n], -1)                       # :31 (int64)
+        for i in range(n):
+            for j in range(i + 1, n):
+                similarity_matrix[i, j] = S[i, j]                     # :36-37, float -> int64 store
+                similarity_matrix[j, i] = S[i, j]
+        env = _exec_reference_lines("src/sdav/create_similarity_matrix.py", 41, 45,
+                                    {"similarity_matrix": similarity_matrix, "np": np})
+        path = os.path.join(tmp, "s.png")
+        cv2.imwrite(path, env["similarity_img"])                      # :48
+        out["sim_scores_" + name] = np.where(np.eye(n, dtype=bool), -1.0, np.triu(S, 1) + np.triu(S, 1).T)
+        out["sim_int_" + name] = similarity_matrix
+        out["sim_img_f64_" + name] = env["similarity_img"]
+        out["sim_png_" + name] = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    distance_matrix = np.full([len(h["D"]), len(h["D"])], -1)         # :31
+    distance_matrix[:, :] = h["D"]
+    env = _exec_reference_lines("src/cnn_vtl/create_distance_matrix.py", 40, 40,
+                                {"distance_matrix": distance_matrix, "np": np})
+    path = os.path.join(tmp, "d.png")
+    cv2.imwrite(path, env["distance_img"])                            # :41
+    out["dist_D"] = h["D"]
+    out["dist_img_f64"] = env["distance_img"]
+    out["dist_png"] = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    np.savez_compressed(os.path.join(HERE, "images.npz"), **out)
+
+
 if __name__ == "__main__":
-    golden_patches(); golden_similarity(); golden_hamming(); golden_misc()
+    golden_patches(); golden_similarity(); golden_hamming(); golden_misc(); golden_images()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -173,3 +173,67 @@ def test_streaming_loop_closer(cuda):
     assert np.array_equal(i1[:, 0].cpu().numpy(), np.arange(8))
     assert np.all(np.abs(s1[:, 0].cpu().numpy() - 1.0) < 2e-3)
     assert len(sl.db.local) == 16
+
+
+def test_matrix_images_match_reference(cuda, golden_dir):
+    """a6 / a10 tails on the device (dlc_matrix_image) vs fixtures made by executing the reference's normalisation
+    lines verbatim + the real cv2.imwrite: pixels identical."""
+    from deeploopcloser_b200.distance import distance_image
+    from deeploopcloser_b200.similarity import similarity_image
+    g = np.load(golden_dir + "/images.npz")
+    for name in "abr":
+        scores = g["sim_scores_" + name]
+        # the product's scores are float32: use float32-representable inputs whose truncation is unambiguous
+        s32 = scores.astype(np.float32)
+        if np.array_equal(np.trunc(s32.astype(np.float64)), g["sim_int_" + name]):
+            assert np.array_equal(similarity_image(s32), g["sim_png_" + name]), name
+        assert np.array_equal(similarity_image(g["sim_int_" + name].astype(np.float32)), g["sim_png_" + name]), name
+    assert np.array_equal(distance_image(g["dist_D"]), g["dist_png"])
+
+
+def test_matrix_image_edge_cases(cuda):
+    import torch
+
+    from deeploopcloser_b200 import ops
+    from oracle import images as o_img
+    # +inf (a matched pair of identical patches) saturates and leaves the range of the finite scores alone
+    s = np.array([[-1, -400.7, np.inf], [-400.7, -1, -20.2], [np.inf, -20.2, -1]], dtype=np.float32)
+    img = ops.matrix_image(torch.from_numpy(s).cuda(), ops.IMG_SIMILARITY, truncate_int=True).cpu().numpy()
+    finite = np.where(np.isfinite(s), s, -1).astype(np.float64)
+    ref = o_img.imwrite_u8(o_img.similarity_image_f64(o_img.to_reference_int(finite)))
+    assert img[0, 2] == 255 and img[2, 0] == 255
+    m = np.isfinite(s)
+    assert np.array_equal(img[m], ref[m])
+    # without truncation, constant matrix (0 / 0 -> black), empty matrix
+    r = np.random.default_rng(1).normal(0, 50, (33, 65)).astype(np.float32)
+    img = ops.matrix_image(torch.from_numpy(r).cuda(), ops.IMG_SIMILARITY).cpu().numpy()
+    assert np.array_equal(img, o_img.imwrite_u8(o_img.similarity_image_f64(r.astype(np.float64))))
+    c = torch.full((4, 4), 7.0, device="cuda")
+    assert int(ops.matrix_image(c, ops.IMG_SIMILARITY).max()) == 0
+    assert ops.matrix_image(torch.empty((0, 5), dtype=torch.int32, device="cuda"), ops.IMG_DISTANCE).shape == (0, 5)
+    d = np.random.default_rng(2).integers(0, 9000, (130, 130)).astype(np.int32)
+    img = ops.matrix_image(torch.from_numpy(d).cuda(), ops.IMG_DISTANCE).cpu().numpy()
+    assert np.array_equal(img, o_img.imwrite_u8(o_img.distance_image_f64(d.astype(np.int64))))
+
+
+def test_create_matrix_scripts(cuda, tmp_path):
+    """The two script drop-ins end to end on synthetic frames: dataset directory in, PNG out, image == oracle."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import images as o_img
+    from src.cnn_vtl import create_distance_matrix
+    from src.sdav import create_similarity_matrix
+    rng = np.random.default_rng(5)
+    data = tmp_path / "frames"
+    data.mkdir()
+    for i in range(5):
+        cv2.imwrite(str(data / ("f%03d.png" % i)), rng.integers(0, 256, (96, 128, 3), dtype=np.uint8))
+    S = create_similarity_matrix.main([str(data), str(tmp_path / "s.png"), "--keypoints", "seeded"])
+    assert S.dtype == np.int64 and S.shape == (5, 5) and np.all(np.diag(S) == -1) and np.array_equal(S, S.T)
+    finite = np.isfinite(S.astype(np.float64)).all()
+    png = cv2.imread(str(tmp_path / "s.png"), cv2.IMREAD_GRAYSCALE)
+    if finite:
+        assert np.array_equal(png, o_img.imwrite_u8(o_img.similarity_image_f64(S)))
+    D = create_distance_matrix.main([str(data), str(tmp_path / "d.png")])
+    assert D.shape == (5, 5) and np.all(np.diag(D) == 0)
+    png = cv2.imread(str(tmp_path / "d.png"), cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(png, o_img.imwrite_u8(o_img.distance_image_f64(D)))

@@ -3,6 +3,7 @@ tests/golden/make_golden.py) and against its own algebraic restatements."""
 import warnings
 
 import numpy as np
+import pytest
 
 from oracle import cnnvtl as o_cnn
 from oracle import hamming as o_ham
@@ -141,3 +142,30 @@ def test_sda_oracle_matches_torch():
     for w, b in zip(ws, bs):
         h = torch.sigmoid(h @ torch.from_numpy(w) + torch.from_numpy(b))
     assert np.max(np.abs(h.numpy() - o_sda.sda_forward(x, ws, bs))) <= 1e-14
+
+
+def test_image_oracle_matches_reference_lines_and_cv2(golden_dir):
+    """oracle/images.py vs fixtures made by executing create_similarity_matrix.py:41-45 / create_distance_matrix.py:40
+    verbatim and round-tripping through the real cv2.imwrite (tests/golden/make_golden.py::golden_images)."""
+    from oracle import images as o_img
+    g = np.load(golden_dir + "/images.npz")
+    for name in "abr":
+        m = o_img.to_reference_int(g["sim_scores_" + name])
+        assert np.array_equal(m, g["sim_int_" + name])
+        f = o_img.similarity_image_f64(m)
+        assert np.array_equal(f, g["sim_img_f64_" + name])
+        assert np.array_equal(o_img.imwrite_u8(f), g["sim_png_" + name])
+    f = o_img.distance_image_f64(g["dist_D"])
+    assert np.array_equal(f, g["dist_img_f64"])
+    assert np.array_equal(o_img.imwrite_u8(f), g["dist_png"])
+    assert np.array_equal(o_img.imwrite_u8(np.array([0.5, 1.5, 2.5, -3.0, 300.0, np.nan])), [0, 2, 2, 0, 255, 0])
+
+
+def test_write_png_round_trip(tmp_path):
+    """The pure-zlib PNG writer produces a file OpenCV reads back bit for bit (skipped without cv2)."""
+    cv2 = pytest.importorskip("cv2")
+    from deeploopcloser_b200.similarity import write_png
+    img = np.random.default_rng(0).integers(0, 256, (37, 53), dtype=np.uint8)
+    path = str(tmp_path / "m.png")
+    write_png(path, img)
+    assert np.array_equal(cv2.imread(path, cv2.IMREAD_GRAYSCALE), img)
