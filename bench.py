@@ -222,7 +222,8 @@ def run_ours(args):
 
     frames_h, xy_h = synthetic_inputs(100 + rank)
     ws, bs = reference_weights()
-    pipe = LoopClosurePipeline(DIMS, precision=args.precision, sim_precision=args.sim_precision)
+    pipe = LoopClosurePipeline(DIMS, precision=args.precision, sim_precision=args.sim_precision,
+                               raw_pixels=not args.split_pixel_input)
     pipe.set_weights(ws, bs)
     frames_pin = torch.from_numpy(frames_h).pin_memory()
     xy_pin = torch.from_numpy(xy_h).pin_memory()
@@ -361,6 +362,7 @@ def run_ours(args):
                 args.precision == "fp16x2" else "f16 operands, f32 accumulate", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "precision": args.precision, "sim_precision": args.sim_precision,
                            "weights": "N(0,1) init (reference default, no checkpoint shipped)",
+                           "layer0_input": "pixel/255 hi/lo planes (3 products)" if args.split_pixel_input else "exact 8-bit pixel plane, 1/255 folded into layer 0 (2 products)",
                            "k": K_CAND, "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the 126 MB L2; no explicit flush",
                            "multi_gpu": "independent sequence per rank, no collective"},
                 "e2e": {"value": e2e_value, "unit": "frames/s",
@@ -385,6 +387,8 @@ def main():
     ap.add_argument("--sim-precision", default="auto", choices=["auto", "fp16r", "fp16x2", "fp16"],
                     help="SDAV score-matrix arithmetic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-pixel-input", action="store_true",
+                    help="A/B: feed layer 0 pixel/255 as hi/lo planes (3 products) instead of exact pixel values (2)")
     ap.add_argument("--cpu-sample", default="48,4800", type=lambda v: tuple(int(t) for t in v.split(",")),
                     help="reference arm: frames encoded, frame pairs scored per step")
     args = ap.parse_args()

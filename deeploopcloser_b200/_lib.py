@@ -41,9 +41,11 @@ PROTOTYPES = {
     "dlc_pack_weight_planes": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_gemm_planes": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
     "dlc_patch_gather": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _i, _p]),
+    "dlc_patch_gather_u8": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _i, _p]),
     "dlc_patch_gather_f64": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "dlc_sda_create": (_i, [C.POINTER(_p), _i, C.POINTER(_i), _i]),
     "dlc_sda_destroy": (_i, [_p]),
+    "dlc_sda_set_input_u8": (_i, [_p, _i]),
     "dlc_sda_set_layer": (_i, [_p, _i, _p, _p]),
     "dlc_sda_workspace_bytes": (_sz, [_p, _i]),
     "dlc_sda_encode": (_i, [_p, _p, _p, _i, _p, _p, _sz, _p]),

@@ -19,6 +19,7 @@ struct BiasActParams {
   int m_tiles, n_tiles;
   int M, N;
   const float* bias;
+  float alpha = 1.0f;  // z = alpha * acc + bias (one fused rounding; alpha = 1 is bit-identical to acc + bias)
   int act;
   float* out_f32;
   int out_ld;
@@ -32,6 +33,7 @@ struct BiasActParams {
   int use_tma_store;
   alignas(64) CUtensorMap tm_out_hi;
   alignas(64) CUtensorMap tm_out_lo;
+  // cv_a_lo_zero: the A operand is exact in fp16, no residual plane (any BiasActPolicy)
   // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
   int cv_implicit, cv_a_lo_zero, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
   // ---- CONV only: descriptor tail. Row m = output pixel of image m / cv_ohw; the per-image min / max of every conv
@@ -78,6 +80,7 @@ struct BiasActPolicy {
   static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
   static constexpr int kEpiWarps = 4;
   static __device__ __forceinline__ bool enabled(const Params&) { return true; }
+  static __device__ __forceinline__ bool a_lo_zero(const Params& p) { return p.cv_a_lo_zero != 0; }
   static constexpr uint64_t kHintA = kEvictNormal;
   static constexpr uint64_t kHintB = kEvictLast;  // weights are re-read by every M tile: keep them in L2
 
@@ -177,7 +180,7 @@ struct BiasActPolicy {
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float z = v[j] + b[j];
+        float z = fmaf(v[j], p.alpha, b[j]);
         if (ACT == DLC_ACT_SIGMOID) z = __fdividef(1.0f, 1.0f + __expf(-z));
         else if (ACT == DLC_ACT_RELU) z = fmaxf(z, 0.0f);
         h[j] = z;

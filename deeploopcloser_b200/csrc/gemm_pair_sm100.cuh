@@ -48,7 +48,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int n_tile = p.n_tile;
   const int half_n = n_tile >> 1;                         // B rows staged by each CTA
   const int b_plane_bytes = half_n * BK * 2;
-  const int stage_bytes = kPl * (Cfg::kABytes + b_plane_bytes);
+  const bool a_lo_zero = policy_a_lo_zero<Policy>::get(p);   // A exact in fp16: no residual plane, two products
+  const int a_planes = a_lo_zero ? 1 : kPl;
+  const int stage_bytes = a_planes * Cfg::kABytes + kPl * b_plane_bytes;
   int S = ring_bytes<Policy>() / stage_bytes;
   S = S < SMAX ? S : SMAX;
 
@@ -112,8 +114,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (leader) mbar_arrive_expect_tx(&full[stage], tx_pair);
             uint8_t* st = smem + stage * stage_bytes;
             tma_load_2d_pair(st, &tmA0, lbar, kb * BK, m0, Policy::kHintA);
-            if (kPl == 2) tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
-            uint8_t* sb = st + kPl * Cfg::kABytes;
+            if (kPl == 2 && !a_lo_zero) tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
+            uint8_t* sb = st + a_planes * Cfg::kABytes;
             tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
             if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
             if (++stage == S) {
@@ -143,7 +145,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               tc_fence_after();
               const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
               const uint32_t a_lo = a_hi + Cfg::kABytes;
-              const uint32_t b_hi = a_hi + kPl * Cfg::kABytes;
+              const uint32_t b_hi = a_hi + a_planes * Cfg::kABytes;
               const uint32_t b_lo = b_hi + b_plane_bytes;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -153,8 +155,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 if (Cfg::NPROD == 3) {
                   const uint64_t dal = make_smem_desc(a_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
                   const uint64_t dbl = make_smem_desc(b_lo + koff, Cfg::kSBO, Cfg::kSwizzleMode);
-                  umma_f16_pair(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
-                  umma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
+                  if (!a_lo_zero) {
+                    umma_f16_pair(d_tmem, dal, dbh, idesc, (kk | k) != 0 ? 1u : 0u);
+                    umma_f16_pair(d_tmem, dah, dbl, idesc, 1u);
+                  } else {
+                    umma_f16_pair(d_tmem, dah, dbl, idesc, (kk | k) != 0 ? 1u : 0u);
+                  }
                   umma_f16_pair(d_tmem, dah, dbh, idesc, 1u);
                 } else {
                   umma_f16_pair(d_tmem, dah, dbh, idesc, (kk | k) != 0 ? 1u : 0u);

@@ -97,6 +97,18 @@ struct policy_im2col_a : std::false_type {};
 template <class P>
 struct policy_im2col_a<P, std::enable_if_t<P::kIm2colA>> : std::true_type {};
 
+// Optional policy member `static bool a_lo_zero(const Params&)` (3-product policies): the A operand of this launch is
+// exactly representable in fp16 (8-bit pixel values), so its residual plane is neither staged nor multiplied -
+// two products per K step instead of three.
+template <class P, class = void>
+struct policy_a_lo_zero {
+  static __device__ __forceinline__ bool get(const typename P::Params&) { return false; }
+};
+template <class P>
+struct policy_a_lo_zero<P, std::void_t<decltype(P::a_lo_zero(std::declval<const typename P::Params&>()))>> {
+  static __device__ __forceinline__ bool get(const typename P::Params& p) { return P::Cfg::NPROD == 3 && P::a_lo_zero(p); }
+};
+
 // Optional policy member `static constexpr bool kAltTiles = true` (two-level-accumulation policies): when the
 // accumulator is at most 128 columns wide and the whole K range is one chunk, the two groups of four epilogue warps
 // take alternate tiles (group g owns TMEM buffer g) instead of splitting the columns of every tile, so a narrow,
@@ -203,10 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   void* scratch = scratch_b;
   uint8_t* smem = scratch_b + policy_scratch<Policy>::value;  // scratch sizes are multiples of 1024
 
-  // cv_a_lo_zero (im2col policies): the A operand is exactly representable in fp16 (8-bit pixels), so its residual
-  // plane is neither staged nor multiplied
-  bool a_lo_zero = false;
-  if constexpr (policy_im2col_a<Policy>::value) a_lo_zero = Cfg::NPROD == 3 && p.cv_a_lo_zero != 0;
+  // the A operand is exactly representable in fp16 (8-bit pixels): its residual plane is neither staged nor multiplied
+  const bool a_lo_zero = policy_a_lo_zero<Policy>::get(p);
   const int a_planes = a_lo_zero ? 1 : Cfg::kPlanes;
   const int stage_bytes = Cfg::stage_bytes(p.n_tile, a_planes);
   const int S = Cfg::stages(p.n_tile, a_planes, ring_bytes<Policy>());

@@ -53,9 +53,11 @@ constexpr int kThreadsPerPatch = 64;
 __global__ void __launch_bounds__(kPatchesPerCta* kThreadsPerPatch)
 patch_gather_planes_kernel(const uint8_t* __restrict__ img, int H, int W, const float* __restrict__ xy, int P,
                            int64_t n_patches, int patch, int swap_xy_quirk, __half* __restrict__ out_hi,
-                           __half* __restrict__ out_lo, int ld) {
+                           __half* __restrict__ out_lo, int ld, int raw) {
   __shared__ uint32_t lut[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_pixel_lut[i];
+  // raw: the plane holds the pixel value itself (0..255, exact in fp16; the encoder folds the 1/255 into layer 0)
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    lut[i] = raw ? static_cast<uint32_t>(__half_as_ushort(__int2half_rn(i))) : g_pixel_lut[i];
   __syncthreads();
   const int64_t pidx = static_cast<int64_t>(blockIdx.x) * kPatchesPerCta + threadIdx.x / kThreadsPerPatch;  // b * P + p
   if (pidx >= n_patches) return;
@@ -136,7 +138,21 @@ extern "C" int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, con
   const int grid = static_cast<int>((n_patches + kPatchesPerCta - 1) / kPatchesPerCta);
   patch_gather_planes_kernel<<<grid, kPatchesPerCta * kThreadsPerPatch, 0, as_stream(stream)>>>(
       img_dev, H, W, xy_dev, P, n_patches, patch, swap_xy_quirk, static_cast<__half*>(out_hi_dev),
-      static_cast<__half*>(out_lo_dev), ld);
+      static_cast<__half*>(out_lo_dev), ld, 0);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+extern "C" int dlc_patch_gather_u8(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
+                                   int swap_xy_quirk, void* out_dev, int ld, void* stream) {
+  if (int rc = check_patch_args(img_dev, B, H, W, xy_dev, P, patch)) return rc;
+  DLC_CHECK_ARG(out_dev || B == 0);
+  DLC_CHECK_ARG(ld >= patch * patch && ld % 8 == 0);
+  if (B == 0) return DLC_OK;
+  const int64_t n_patches = static_cast<int64_t>(B) * P;
+  const int grid = static_cast<int>((n_patches + kPatchesPerCta - 1) / kPatchesPerCta);
+  patch_gather_planes_kernel<<<grid, kPatchesPerCta * kThreadsPerPatch, 0, as_stream(stream)>>>(
+      img_dev, H, W, xy_dev, P, n_patches, patch, swap_xy_quirk, static_cast<__half*>(out_dev), nullptr, ld, 1);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }

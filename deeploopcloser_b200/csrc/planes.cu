@@ -86,6 +86,9 @@ int g_promote_k = 256;
 // Valid K of the next dlc_gemm_planes call on this thread (0 = the whole ld). Callers that know their operands are zero
 // beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
 thread_local int g_gemm_k_valid = 0;
+// Scale of the accumulator before the bias of the next dlc_gemm_planes call on this thread (z = alpha * acc + bias;
+// reset to 1 by the call). The SDA encoder's first layer on raw 8-bit pixels uses 1/256 (see dlc_sda_set_input_u8).
+thread_local float g_gemm_alpha = 1.0f;
 int g_tma_store = 1;
 int g_cta_pair = 1;
 int g_gram_pair = 1;  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
@@ -113,10 +116,14 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   ta1 = ta0;
   tb1 = tb0;
   if (split) {
-    if (!make_tmap_k_major(&ta1, a_lo, p.ab_fmt, ld, m, ld, BK, kTileM) ||
+    // a_lo == NULL: the A values are exact in fp16 (their residual is zero) -> two products instead of three
+    if ((a_lo && !make_tmap_k_major(&ta1, a_lo, p.ab_fmt, ld, m, ld, BK, kTileM)) ||
         !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile))
       return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (lo planes)");
+    p.cv_a_lo_zero = a_lo ? 0 : 1;
   }
+  p.alpha = g_gemm_alpha;
+  g_gemm_alpha = 1.0f;
   const int k_valid = (g_gemm_k_valid > 0 && g_gemm_k_valid <= ld) ? g_gemm_k_valid : ld;
   g_gemm_k_valid = 0;
   p.k_blocks = ceil_div(k_valid, BK);
@@ -237,7 +244,7 @@ extern "C" int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const
   DLC_CHECK_ARG(ld > 0 && ld % 64 == 0);
   DLC_CHECK_ARG(act == DLC_ACT_NONE || act == DLC_ACT_SIGMOID || act == DLC_ACT_RELU);
   DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2 || precision == DLC_PREC_BF16);
-  DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || (a_lo_dev && b_lo_dev));
+  DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || b_lo_dev);  // a_lo_dev == NULL: A is exact in fp16
   DLC_CHECK_ARG(out_f32_dev || out_hi_dev);
   DLC_CHECK_ARG(!out_f32_dev || out_ld >= n);
   DLC_CHECK_ARG(!out_hi_dev || (out_plane_ld >= 32 && out_plane_ld % 8 == 0));

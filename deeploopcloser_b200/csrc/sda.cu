@@ -18,12 +18,14 @@ struct dlc_sda {
   std::vector<void*> w_lo;
   std::vector<float*> bias;  // [n_pad[l]]
   std::vector<bool> is_set;
+  bool input_u8 = false;     // x planes hold raw pixel values 0..255 (dlc_sda_set_input_u8)
 };
 
 using namespace dlc;
 
 namespace dlc {
 extern thread_local int g_gemm_k_valid;  // planes.cu
+extern thread_local float g_gemm_alpha;  // planes.cu
 }
 
 namespace {
@@ -80,6 +82,16 @@ extern "C" int dlc_sda_destroy(dlc_sda* h) {
   return DLC_OK;
 }
 
+extern "C" int dlc_sda_set_input_u8(dlc_sda* h, int on) {
+  DLC_CHECK_ARG(h);
+  const bool want = on != 0;
+  if (want != h->input_u8) {
+    h->input_u8 = want;
+    h->is_set[0] = false;  // layer 0 is packed differently: dlc_sda_set_layer(h, 0, ...) again
+  }
+  return DLC_OK;
+}
+
 extern "C" int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const double* b_host) {
   DLC_CHECK_ARG(h && w_host && b_host);
   DLC_CHECK_ARG(l >= 0 && l < h->n_layers);
@@ -87,6 +99,15 @@ extern "C" int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const 
   double* w_dev = nullptr;
   const size_t wbytes = sizeof(double) * static_cast<size_t>(k) * n;
   DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&w_dev), wbytes));
+  // Raw-pixel input: sigmoid((p / 255) W + b) = sigmoid((p (W * 256/255)) / 256 + b). The pixel values are exact in
+  // fp16, the weights keep their magnitude (hi/lo split stays in the normal fp16 range) and the 1/256 in the epilogue
+  // is exact - layer 0 needs two tensor-core products per K step instead of three.
+  std::vector<double> scaled;
+  if (l == 0 && h->input_u8) {
+    scaled.resize(static_cast<size_t>(k) * n);
+    for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = w_host[i] * (256.0 / 255.0);
+    w_host = scaled.data();
+  }
   cudaError_t e = cudaMemcpy(w_dev, w_host, wbytes, cudaMemcpyHostToDevice);
   int rc = DLC_OK;
   if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_sda_set_layer: H2D copy failed: %s", cudaGetErrorString(e));
@@ -123,7 +144,7 @@ extern "C" int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo
                               void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(h && x_hi_dev && out_dev);
   DLC_CHECK_ARG(rows > 0);
-  DLC_CHECK_ARG(h->precision != DLC_PREC_FP16X2 || x_lo_dev);
+  DLC_CHECK_ARG(h->precision != DLC_PREC_FP16X2 || x_lo_dev || h->input_u8);
   for (int l = 0; l < h->n_layers; ++l)
     if (!h->is_set[l]) return fail(DLC_EINVAL, "dlc_sda_encode: layer %d has no weights (dlc_sda_set_layer)", l);
   if (ws_bytes < dlc_sda_workspace_bytes(h, rows) || (h->n_layers > 1 && !ws_dev))
@@ -138,12 +159,13 @@ extern "C" int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo
   void* buf_lo[2] = {split ? base + plane : nullptr, split ? base + plane * 3 : nullptr};
 
   const void* a_hi = x_hi_dev;
-  const void* a_lo = x_lo_dev;
+  const void* a_lo = h->input_u8 ? nullptr : x_lo_dev;  // raw pixels are exact in fp16: no residual plane
   for (int l = 0; l < h->n_layers; ++l) {
     const bool last = l + 1 == h->n_layers;
     void* o_hi = last ? nullptr : buf_hi[l & 1];
     void* o_lo = last ? nullptr : buf_lo[l & 1];
     g_gemm_k_valid = h->dims[l];  // columns dims[l]..ld of both operands are zero padding
+    if (l == 0 && h->input_u8) g_gemm_alpha = 1.0f / 256.0f;
     int rc = dlc_gemm_planes(a_hi, a_lo, h->w_hi[l], h->w_lo[l], rows, h->dims[l + 1], h->n_pad[l], h->ld[l],
                              h->bias[l], DLC_ACT_SIGMOID, h->precision, last ? out_dev : nullptr, h->dims[l + 1], o_hi,
                              o_lo, h->n_pad[l], stream);

@@ -106,6 +106,19 @@ def patch_gather(img, xy, patch=41, swap_xy_quirk=True, need_lo=True):
     return hi, lo
 
 
+def patch_gather_u8(img, xy, patch=41, swap_xy_quirk=True):
+    """img uint8 [B,H,W], xy float32 [B,P,2] -> ONE fp16 plane [B*P, ld(patch^2)] of raw pixel values 0..255 (exact
+    in fp16), the input of an SdaEncoder(input_u8=True)."""
+    _check_cuda(img, xy)
+    B, H, W = img.shape
+    P = xy.shape[1]
+    ld = _lib.plane_ld(patch * patch)
+    out = torch.empty((B * P, ld), dtype=torch.float16, device=img.device)
+    _lib.call("dlc_patch_gather_u8", ptr(img), B, H, W, ptr(xy), P, patch, int(bool(swap_xy_quirk)), ptr(out), ld,
+              stream_ptr())
+    return out
+
+
 def patch_gather_f64(img, xy, patch=41, swap_xy_quirk=True):
     _check_cuda(img, xy)
     B, H, W = img.shape
@@ -120,12 +133,17 @@ def patch_gather_f64(img, xy, patch=41, swap_xy_quirk=True):
 class SdaEncoder:
     """Owner of a dlc_sda handle (packed weights live on the device)."""
 
-    def __init__(self, dims, precision="fp16x2"):
+    def __init__(self, dims, precision="fp16x2", input_u8=False):
+        """input_u8: the planes given to encode_planes hold raw pixel values (patch_gather_u8); the /255 of the
+        reference's parser is folded into layer 0, which then needs two tensor-core products instead of three."""
         self.dims = [int(d) for d in dims]
         self.precision = precision
+        self.input_u8 = bool(input_u8)
         self._h = C.c_void_p()
         arr = (C.c_int * len(self.dims))(*self.dims)
         _lib.call("dlc_sda_create", C.byref(self._h), len(self.dims) - 1, arr, precision_code(precision))
+        if self.input_u8:
+            _lib.call("dlc_sda_set_input_u8", self._h, 1)
         self._ws = Workspace()
 
     def set_layer(self, l, w, b):

@@ -7,7 +7,7 @@ from . import ops
 
 class LoopClosurePipeline:
     def __init__(self, dims=(1681, 2500, 2500, 2500, 2500, 2500), precision="fp16x2", patch=41, swap_xy_quirk=True,
-                 mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="auto"):
+                 mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="auto", raw_pixels=True):
         self.dims = list(dims)
         self.precision = precision
         # "auto" (default): a device-side probe picks one fp16 product + exact refinement of the ambiguous rows when
@@ -17,7 +17,10 @@ class LoopClosurePipeline:
         self.patch = patch
         self.swap_xy_quirk = swap_xy_quirk
         self.sim_args = dict(mu=mu, sigma=sigma, a=a, b=b)
-        self.encoder = ops.SdaEncoder(self.dims, precision)
+        # raw_pixels: the patch planes hold pixel values 0..255 (exact in fp16) and layer 0 absorbs the /255 of
+        # CvInputParser.py:27 - no input rounding, and two tensor-core products for layer 0 instead of three
+        self.raw_pixels = bool(raw_pixels)
+        self.encoder = ops.SdaEncoder(self.dims, precision, input_u8=self.raw_pixels)
 
     def set_weights(self, weights, biases):
         for l, (w, b) in enumerate(zip(weights, biases)):
@@ -25,8 +28,10 @@ class LoopClosurePipeline:
 
     def encode(self, frames, xy):
         """frames uint8 [B,H,W] (CUDA), xy float32 [B,P,2] (CUDA) -> float32 [B*P, D] descriptors."""
-        split = self.precision == "fp16x2"
-        hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=split)
+        if self.raw_pixels:
+            hi, lo = ops.patch_gather_u8(frames, xy, self.patch, self.swap_xy_quirk), None
+        else:
+            hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=self.precision == "fp16x2")
         return self.encoder.encode_planes(hi, lo, hi.shape[0])
 
     def match(self, desc, n_frames, k=10, exclude_band=0):

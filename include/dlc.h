@@ -91,7 +91,8 @@ int dlc_pack_weight_planes(const void* w_dev, int src_dtype, int k, int n, int n
 /* out = act(A * B^T + bias):  A planes [m, ld] , B planes [n_pad, ld] (n_pad multiple of n_tile), k = ld.
  * Outputs (each optional): out_f32_dev [m, n] with pitch out_ld; out_hi/out_lo planes [m, out_plane_ld] whose
  * columns >= n are written as zero (so they can feed the next contraction directly).
- * precision: DLC_PREC_FP16 (lo planes ignored), DLC_PREC_FP16X2, DLC_PREC_BF16 (planes hold bf16).
+ * precision: DLC_PREC_FP16 (lo planes ignored), DLC_PREC_FP16X2, DLC_PREC_BF16 (planes hold bf16). With
+ * DLC_PREC_FP16X2, a_lo_dev == NULL declares the A values exact in fp16 (two products per K step instead of three).
  * Replaces: TensorWrapper.matmul/add/sigmoid (src/utils/TensorflowWrapper.py:57-78) and tf.layers.conv2d's
  * matmul core (src/cnn_vtl/network/cnn_vtl.py:33-93). */
 int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const void* b_hi_dev, const void* b_lo_dev, int m,
@@ -108,6 +109,10 @@ int dlc_gemm_planes(const void* a_hi_dev, const void* a_lo_dev, const void* b_hi
 /* fp16 planes [B*P, ld] (ld = dlc_plane_ld(patch*patch)), value = pixel/255 split into hi/lo. lo may be NULL. */
 int dlc_patch_gather(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
                      int swap_xy_quirk, void* out_hi_dev, void* out_lo_dev, int ld, void* stream);
+/* One fp16 plane [B*P, ld] holding the pixel VALUE (0..255, exact in fp16) instead of pixel/255: input of an encoder
+ * in raw-pixel mode (dlc_sda_set_input_u8), which folds the /255.0 of CvInputParser.py:27 into its first layer. */
+int dlc_patch_gather_u8(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
+                        int swap_xy_quirk, void* out_dev, int ld, void* stream);
 /* float64 [B*P, patch*patch], bit-identical to the reference's ndarray. */
 int dlc_patch_gather_f64(const uint8_t* img_dev, int B, int H, int W, const float* xy_dev, int P, int patch,
                          int swap_xy_quirk, double* out_dev, void* stream);
@@ -121,6 +126,11 @@ typedef struct dlc_sda dlc_sda;
 /* dims has n_layers+1 entries (1681,2500,2500,2500,2500,2500 for SDAV; in,hidden for one DA). */
 int dlc_sda_create(dlc_sda** h, int n_layers, const int* dims, int precision);
 int dlc_sda_destroy(dlc_sda* h);
+/* Raw-pixel input mode (call before dlc_sda_set_layer(h, 0, ...); changing it un-sets layer 0): the x planes given to
+ * dlc_sda_encode hold pixel values 0..255 (dlc_patch_gather_u8; exact in fp16, x_lo_dev is ignored) and layer 0
+ * evaluates sigmoid((p / 255) W + b) as sigmoid((p (W * 256/255)) / 256 + b): two tensor-core products per K step
+ * instead of three, and no rounding of the input at all. */
+int dlc_sda_set_input_u8(dlc_sda* h, int on);
 /* W_host [dims[l], dims[l+1]] row-major float64, b_host [dims[l+1]] float64 (the reference's variable layout). */
 int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const double* b_host);
 /* bytes of scratch needed to encode `rows` patch rows */

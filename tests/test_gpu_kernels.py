@@ -628,3 +628,61 @@ def test_similarity_cta_pair_equals_single(cuda, n, p, d):
     finally:
         _lib.call("dlc_debug_set", 6, 1)
     assert torch.equal(pair, single) and torch.equal(parts, single)
+
+
+# ------------------------------------------------------------------------------------------- raw-pixel encoder input
+def test_patch_gather_u8_golden(cuda, golden_dir):
+    """dlc_patch_gather_u8: the plane holds the pixel VALUE of the reference's patches, exactly."""
+    from deeploopcloser_b200 import ops
+    g = np.load(golden_dir + "/patches.npz")
+    out = ops.patch_gather_u8(torch.from_numpy(g["img"]).cuda(), torch.from_numpy(g["xy"]).cuda()).double().cpu().numpy()
+    assert out.shape == (60, 1728)
+    assert np.array_equal(out[:, :1681], np.rint(g["out"].reshape(60, 1681) * 255.0))
+    assert np.all(out[:, 1681:] == 0)
+
+
+@pytest.mark.parametrize("dims,frames,pair_mode", [([1681, 256, 128], 3, 1), ([1681, 2500, 300], 9, 2),
+                                                    ([1681, 256, 128], 10, 2), ([1681, 128], 2, 1)])
+def test_encoder_raw_pixel_mode(cuda, dims, frames, pair_mode):
+    """SdaEncoder(input_u8=True): sigmoid((p / 255) W + b) evaluated as sigmoid((p (W 256/255)) / 256 + b) with the
+    pixel plane exact in fp16 and TWO tensor-core products in layer 0. Same tolerance as the split-input path (1e-3 on
+    the reference's saturating N(0,1) weights) and at least as accurate; single-CTA and CTA-pair kernels."""
+    from deeploopcloser_b200 import _lib, ops
+    rng = np.random.default_rng(len(dims) * 100 + frames)
+    H, W, P = 96, 128, 30
+    img = rng.integers(0, 256, (frames, H, W), dtype=np.uint8)
+    xy = np.stack([rng.uniform(0, W, (frames, P)), rng.uniform(0, H, (frames, P))], -1).astype(np.float32)
+    ws, bs = o_sda.make_weights(dims, seed=3, scale="normal")
+    bs = [b + 0.1 * rng.standard_normal(b.shape) for b in bs]
+    x = np.concatenate([o_patch.extract_patches(img[i], xy[i]) for i in range(frames)])
+    ref = o_sda.sda_forward(x, ws, bs)
+    img_d, xy_d = torch.from_numpy(img).cuda(), torch.from_numpy(xy).cuda()
+    errs = {}
+    try:
+        _lib.call("dlc_debug_set", 6, pair_mode)
+        for raw in (True, False):
+            enc = ops.SdaEncoder(dims, "fp16x2", input_u8=raw)
+            for l, (w, b) in enumerate(zip(ws, bs)):
+                enc.set_layer(l, w, b)
+            if raw:
+                out = enc.encode_planes(ops.patch_gather_u8(img_d, xy_d), None, frames * P)
+            else:
+                hi, lo = ops.patch_gather(img_d, xy_d)
+                out = enc.encode_planes(hi, lo, frames * P)
+            errs[raw] = float(np.max(np.abs(out.cpu().numpy() - ref)))
+            enc.close()
+    finally:
+        _lib.call("dlc_debug_set", 6, 1)
+    print("raw-pixel encoder", dims, "max abs err raw / split input:", errs[True], errs[False])
+    assert errs[True] <= TOL and errs[True] <= 2.0 * errs[False] + 1e-6
+
+
+def test_encoder_raw_pixel_mode_needs_layer0_again(cuda):
+    from deeploopcloser_b200 import _lib, ops
+    enc = ops.SdaEncoder([1681, 64], "fp16x2")
+    enc.set_layer(0, np.zeros((1681, 64)), np.zeros(64))
+    _lib.call("dlc_sda_set_input_u8", enc._h, 1)          # layer 0 is packed differently: must be set again
+    x = torch.zeros((30, 1728), dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError):
+        enc.encode_planes(x, None, 30)
+    enc.close()
