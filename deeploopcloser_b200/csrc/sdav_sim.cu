@@ -906,8 +906,8 @@ static int g_gram_only = 0;
 // 1000 flagged rows (each candidate streams 10 KB float32 rows from L2), i.e. ~0.2 ms per 0.1 % of flagged rows,
 // against ~3 ms saved by issuing one tensor product instead of three: break-even near 1.5 %.
 static float g_max_flag_frac = 0.012f;
-extern "C" int dlc_sdav_debug_gram_only(int on) {
-  g_gram_only = on ? 1 : 0;
+extern "C" int dlc_sdav_debug_gram_only(int on) {  // 2: additionally skip the second (refinement) pass - timing only
+  g_gram_only = on;
   return DLC_OK;
 }
 
@@ -1066,7 +1066,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.work = p.work_cap > 0 ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
   if (g_gram_only) DLC_CUDA(cudaMemsetAsync(&ctl->n_entries, 0, sizeof(unsigned int), s));  // else reset by the probe
   if (int rc = pairs ? run_gram_pair<GramRefinePolicy>(L, ws, p, s) : run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
-  if (p.work) {
+  if (p.work && g_gram_only != 2) {
     gram_refine_fix_kernel<<<4 * sm_count(), kFixThreads, 0, s>>>(p);
     DLC_CUDA(cudaGetLastError());
   }
