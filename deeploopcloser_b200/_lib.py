@@ -42,6 +42,8 @@ PROTOTYPES = {
     "dlc_gemm_planes": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _p]),
     "dlc_patch_gather": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_patch_gather_u8": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _i, _p]),
+    "dlc_surf_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dlc_surf_detect": (_i, [_p, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
     "dlc_patch_gather_f64": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "dlc_sda_create": (_i, [C.POINTER(_p), _i, C.POINTER(_i), _i]),
     "dlc_sda_destroy": (_i, [_p]),

@@ -1,0 +1,425 @@
+// f3: the keypoint detector in front of the patch gather - get_top_n_key_points
+// (src/sdav/input/CvInputParser.py:36-46: cv2.xfeatures2d.SURF_create().detect, sort by -response, first n).
+// The arithmetic of that call lives in opencv-contrib 3.4.2's non-free xfeatures2d module, which is neither in the
+// reference tree nor in this image: PARITY UNPINNED. This file implements the published fast-Hessian detector
+// (Bay et al., CVIU 2008) with that implementation's documented constants; oracle/surf.py is the same algorithm in
+// NumPy and the two agree bit for bit (every float operation below is an explicitly rounded intrinsic, no FMA
+// contraction, same operation order as the oracle).
+//
+// Bytes-bound pipeline, one batch of frames per call:
+//   integral image (row scan, then column scan by strips)                      int32 [B, H+1, W+1]
+//   per octave: box-filter Hessian determinant of its n_layers + 2 layers      float [B, layers, H/step, W/step]
+//   per octave: strict 3x3x3 maxima of the middle layers above the threshold, quadratic interpolation, orientation-
+//               window test -> appended to a per-frame candidate list
+//   per frame : n best candidates by (response desc, detection order asc) -> xy [B, n, 2]
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "util.h"
+
+namespace dlc {
+
+constexpr int kSurfMaxLayers = 6;     // n_layers + 2 per octave
+constexpr int kSurfMaxOctaves = 5;
+constexpr int kSurfCap = 16384;       // candidates kept per frame
+constexpr int kOriRadius = 6;
+
+struct SurfBox {
+  int x1, y1, x2, y2;
+  float w;
+};
+struct SurfLayer {
+  int size, ni, nj, margin;
+  SurfBox dx[3], dy[3], dxy[4];
+};
+struct SurfOctave {
+  int step, rows, cols, n;            // det arrays are [n][rows][cols]
+  int64_t det_off;                    // float offset of this octave inside a frame's det block
+  SurfLayer layer[kSurfMaxLayers];
+};
+
+// ---------------------------------------------------------------- integral image
+__global__ void __launch_bounds__(256)
+surf_integral_rows_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int32_t* __restrict__ sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * H) return;
+  const int b = warp / H, r = warp - b * H;
+  const uint8_t* src = img + (static_cast<int64_t>(b) * H + r) * W;
+  int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * (W + 1);
+  int32_t* dst = frame + static_cast<int64_t>(r + 1) * (W + 1);
+  if (r == 0)
+    for (int c = lane; c <= W; c += 32) frame[c] = 0;
+  if (lane == 0) dst[0] = 0;
+  int carry = 0;
+  for (int c0 = 0; c0 < W; c0 += 32) {
+    const int c = c0 + lane;
+    int v = c < W ? src[c] : 0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += t;
+    }
+    if (c < W) dst[c + 1] = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+// strip of 32 columns x all rows per CTA; warp w owns a block of consecutive rows, lane = column
+__global__ void __launch_bounds__(1024)
+surf_integral_cols_kernel(int B, int H, int W, int32_t* __restrict__ sum) {
+  __shared__ int s_tot[32][33];
+  const int strips = (W + 31) / 32;
+  const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = 1 + strip * 32 + lane;
+  const int per = (H + 31) / 32;
+  const int r0 = 1 + w * per, r1 = min(H + 1, r0 + per);
+  int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * (W + 1);
+  int acc = 0;
+  if (c <= W)
+    for (int r = r0; r < r1; ++r) acc += frame[static_cast<int64_t>(r) * (W + 1) + c];
+  s_tot[w][lane] = acc;
+  __syncthreads();
+  int off = 0;
+  for (int k = 0; k < w; ++k) off += s_tot[k][lane];
+  if (c <= W)
+    for (int r = r0; r < r1; ++r) {
+      const int64_t i = static_cast<int64_t>(r) * (W + 1) + c;
+      off += frame[i];
+      frame[i] = off;
+    }
+}
+
+// ---------------------------------------------------------------- Hessian determinant
+template <int N>
+__device__ __forceinline__ float haar(const int32_t* __restrict__ org, int pitch, const SurfBox (&f)[N]) {
+  double d = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const int s = __ldg(org + f[k].y1 * pitch + f[k].x1) + __ldg(org + f[k].y2 * pitch + f[k].x2) -
+                  __ldg(org + f[k].y2 * pitch + f[k].x1) - __ldg(org + f[k].y1 * pitch + f[k].x2);
+    d = __dadd_rn(d, static_cast<double>(__fmul_rn(__int2float_rn(s), f[k].w)));
+  }
+  return __double2float_rn(d);
+}
+
+__global__ void __launch_bounds__(256)
+surf_det_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc,
+                int64_t det_frame_stride, float* __restrict__ det) {
+  const int l = blockIdx.y, b = blockIdx.z;
+  const SurfLayer& L = oc.layer[l];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= oc.rows * oc.cols) return;
+  const int r = idx / oc.cols, c = idx - r * oc.cols;
+  const int i = r - L.margin, j = c - L.margin;
+  float v = 0.0f;  // the filter does not fit here
+  if (i >= 0 && i < L.ni && j >= 0 && j < L.nj) {
+    const int pitch = W + 1;
+    const int32_t* org = sum + static_cast<int64_t>(b) * (H + 1) * pitch + static_cast<int64_t>(i) * oc.step * pitch +
+                         j * oc.step;
+    const float dx = haar<3>(org, pitch, L.dx);
+    const float dy = haar<3>(org, pitch, L.dy);
+    const float dxy = haar<4>(org, pitch, L.dxy);
+    v = __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
+  }
+  det[static_cast<int64_t>(b) * det_frame_stride + oc.det_off + static_cast<int64_t>(l) * oc.rows * oc.cols + idx] = v;
+}
+
+// ---------------------------------------------------------------- maxima
+// Gaussian elimination with partial pivoting, float64, the oracle's operation order (solve3 in oracle/surf.py)
+__device__ __forceinline__ bool solve3(double (&M)[3][4], double (&x)[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int p = k;
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r)
+      if (fabs(M[r][k]) > fabs(M[p][k])) p = r;
+    if (M[p][k] == 0.0) return false;
+    if (p != k) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double t = M[k][c];
+        M[k][c] = M[p][c];
+        M[p][c] = t;
+      }
+    }
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r) {
+      const double f = __ddiv_rn(M[r][k], M[k][k]);
+#pragma unroll
+      for (int c = k; c < 4; ++c) M[r][c] = __dsub_rn(M[r][c], __dmul_rn(f, M[k][c]));
+    }
+  }
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    double s = M[k][3];
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) s = __dsub_rn(s, __dmul_rn(M[k][c], x[c]));
+    x[k] = __ddiv_rn(s, M[k][k]);
+  }
+  return true;
+}
+
+__device__ __forceinline__ int round_half_even(float v) { return __float2int_rn(v); }
+
+// the orientation stage of the reference implementation drops a keypoint when no gradient sample of its radius-6s
+// disc fits inside the image
+__device__ bool orientation_samplable(float x, float y, float size, int H, int W) {
+  const float s = __fdiv_rn(__fmul_rn(size, 1.2f), 9.0f);
+  const int grad = 2 * round_half_even(__fmul_rn(2.0f, s));
+  if (H + 1 < grad || W + 1 < grad) return false;
+  const float half = __fdiv_rn(static_cast<float>(grad - 1), 2.0f);
+  for (int i = -kOriRadius; i <= kOriRadius; ++i)
+    for (int j = -kOriRadius; j <= kOriRadius; ++j)
+      if (i * i + j * j <= kOriRadius * kOriRadius) {
+        const int px = round_half_even(__fsub_rn(__fadd_rn(x, __fmul_rn(static_cast<float>(j), s)), half));
+        const int py = round_half_even(__fsub_rn(__fadd_rn(y, __fmul_rn(static_cast<float>(i), s)), half));
+        if (py >= 0 && py < H + 1 - grad && px >= 0 && px < W + 1 - grad) return true;
+      }
+  return false;
+}
+
+__global__ void __launch_bounds__(256)
+surf_maxima_kernel(const float* __restrict__ det, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
+                   int64_t det_frame_stride, float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys,
+                   int* __restrict__ count) {
+  const int l = 1 + blockIdx.y, b = blockIdx.z;   // middle layers 1 .. n - 2
+  const SurfLayer& L = oc.layer[l];
+  const int size = L.size;
+  const int margin = (oc.layer[l + 1].size / 2) / oc.step + 1;
+  const int wr = oc.rows - 2 * margin, wc = oc.cols - 2 * margin;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wr <= 0 || wc <= 0 || idx >= wr * wc) return;
+  const int i = margin + idx / wc, j = margin + idx % wc;
+  const int64_t plane = static_cast<int64_t>(oc.rows) * oc.cols;
+  const float* d1 = det + static_cast<int64_t>(b) * det_frame_stride + oc.det_off + l * plane +
+                    static_cast<int64_t>(i) * oc.cols + j;
+  const float val0 = d1[0];
+  if (!(val0 > thr)) return;
+  float N9[3][9];
+#pragma unroll
+  for (int dl = 0; dl < 3; ++dl)
+#pragma unroll
+    for (int di = 0; di < 3; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 3; ++dj)
+        N9[dl][di * 3 + dj] = d1[(dl - 1) * plane + (di - 1) * oc.cols + (dj - 1)];
+  bool is_max = true;
+#pragma unroll
+  for (int dl = 0; dl < 3; ++dl)
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+      if (!(dl == 1 && q == 4)) is_max = is_max && (val0 > N9[dl][q]);
+  if (!is_max) return;
+  const int sum_i = oc.step * (i - (size / 2) / oc.step);
+  const int sum_j = oc.step * (j - (size / 2) / oc.step);
+  const float cy = __fadd_rn(static_cast<float>(sum_i), __fmul_rn(static_cast<float>(size - 1), 0.5f));
+  const float cx = __fadd_rn(static_cast<float>(sum_j), __fmul_rn(static_cast<float>(size - 1), 0.5f));
+  const int ds = size - oc.layer[l - 1].size;
+  // negative first derivatives and the Hessian of the 3x3x3 neighbourhood (float32, as Vec3f / Matx33f)
+  const float bx = __fdiv_rn(-__fsub_rn(N9[1][5], N9[1][3]), 2.0f);
+  const float by = __fdiv_rn(-__fsub_rn(N9[1][7], N9[1][1]), 2.0f);
+  const float bs = __fdiv_rn(-__fsub_rn(N9[2][4], N9[0][4]), 2.0f);
+  const float axx = __fadd_rn(__fsub_rn(N9[1][3], __fmul_rn(2.0f, N9[1][4])), N9[1][5]);
+  const float ayy = __fadd_rn(__fsub_rn(N9[1][1], __fmul_rn(2.0f, N9[1][4])), N9[1][7]);
+  const float ass = __fadd_rn(__fsub_rn(N9[0][4], __fmul_rn(2.0f, N9[1][4])), N9[2][4]);
+  const float axy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[1][8], N9[1][6]), N9[1][2]), N9[1][0]), 4.0f);
+  const float axs = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][5], N9[2][3]), N9[0][5]), N9[0][3]), 4.0f);
+  const float ays = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][7], N9[2][1]), N9[0][7]), N9[0][1]), 4.0f);
+  double M[3][4] = {{axx, axy, axs, bx}, {axy, ayy, ays, by}, {axs, ays, ass, bs}};
+  double xd[3];
+  if (!solve3(M, xd)) return;
+  const float x0 = __double2float_rn(xd[0]), x1 = __double2float_rn(xd[1]), x2 = __double2float_rn(xd[2]);
+  if (!((x0 != 0.0f || x1 != 0.0f || x2 != 0.0f) && fabsf(x0) <= 1.0f && fabsf(x1) <= 1.0f && fabsf(x2) <= 1.0f)) return;
+  const float px = __fadd_rn(cx, __fmul_rn(x0, static_cast<float>(oc.step)));
+  const float py = __fadd_rn(cy, __fmul_rn(x1, static_cast<float>(oc.step)));
+  const float ksize = rintf(__fadd_rn(static_cast<float>(size), __fmul_rn(x2, static_cast<float>(ds))));
+  if (!orientation_samplable(px, py, ksize, H, W)) return;
+  const int slot = atomicAdd(count + b, 1);
+  if (slot >= kSurfCap) return;
+  // order: response descending, then detection order (octave, layer, row, column) ascending
+  const uint32_t order = (static_cast<uint32_t>(octave) << 29) | (static_cast<uint32_t>(l) << 26) |
+                         (static_cast<uint32_t>(i) << 13) | static_cast<uint32_t>(j);
+  cand[static_cast<int64_t>(b) * kSurfCap + slot] = make_float4(px, py, ksize, val0);
+  keys[static_cast<int64_t>(b) * kSurfCap + slot] =
+      (static_cast<unsigned long long>(__float_as_uint(val0)) << 32) | static_cast<unsigned long long>(~order);
+}
+
+// ---------------------------------------------------------------- n best per frame
+__global__ void __launch_bounds__(256)
+surf_top_kernel(const float4* __restrict__ cand, unsigned long long* __restrict__ keys, const int* __restrict__ count,
+                int H, int W, int top_n, float* __restrict__ xy, float* __restrict__ info, int* __restrict__ found) {
+  __shared__ unsigned long long s_key[8];
+  __shared__ int s_idx[8];
+  const int b = blockIdx.x;
+  const int total = count[b];
+  const int m = min(total, kSurfCap);
+  unsigned long long* k = keys + static_cast<int64_t>(b) * kSurfCap;
+  const float4* c = cand + static_cast<int64_t>(b) * kSurfCap;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int n = 0; n < top_n; ++n) {
+    unsigned long long best = 0ull;   // valid keys are > 0 (response > threshold > 0)
+    int bi = -1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const unsigned long long v = k[i];
+      if (v > best) {
+        best = v;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best) {   // keys are distinct (the order field is unique), no tie to break
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_key[w] = best;
+      s_idx[w] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < 8; ++q)
+        if (s_key[q] > best) {
+          best = s_key[q];
+          bi = s_idx[q];
+        }
+      float* o = xy + (static_cast<int64_t>(b) * top_n + n) * 2;
+      float* oi = info ? info + (static_cast<int64_t>(b) * top_n + n) * 2 : nullptr;
+      if (bi >= 0) {
+        const float4 v = c[bi];
+        o[0] = v.x;
+        o[1] = v.y;
+        if (oi) {
+          oi[0] = v.z;
+          oi[1] = v.w;
+        }
+        k[bi] = 0ull;  // taken
+      } else {         // fewer than top_n keypoints: the image centre, size / response 0 (found[b] tells)
+        o[0] = 0.5f * static_cast<float>(W - 1);
+        o[1] = 0.5f * static_cast<float>(H - 1);
+        if (oi) {
+          oi[0] = 0.0f;
+          oi[1] = 0.0f;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) found[b] = total;
+}
+
+// ---------------------------------------------------------------- host side
+static inline int cv_round(float v) { return static_cast<int>(nearbyint(static_cast<double>(v))); }
+static void resize_pattern(const int (*src)[5], int n, int size, SurfBox* dst) {
+  const float ratio = static_cast<float>(size) / 9.0f;
+  for (int k = 0; k < n; ++k) {
+    const int x1 = cv_round(ratio * src[k][0]), y1 = cv_round(ratio * src[k][1]);
+    const int x2 = cv_round(ratio * src[k][2]), y2 = cv_round(ratio * src[k][3]);
+    dst[k] = SurfBox{x1, y1, x2, y2, src[k][4] / (static_cast<float>(x2 - x1) * static_cast<float>(y2 - y1))};
+  }
+}
+
+struct SurfPlan {
+  int n_octaves;
+  SurfOctave oc[kSurfMaxOctaves];
+  int64_t det_floats_per_frame;
+  size_t off_sum, off_det, off_cand, off_keys, off_count, total;
+};
+static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
+  static const int dx_s[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
+  static const int dy_s[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
+  static const int dxy_s[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
+  SurfPlan p{};
+  p.n_octaves = n_octaves;
+  int64_t off = 0;
+  for (int o = 0; o < n_octaves; ++o) {
+    SurfOctave& oc = p.oc[o];
+    oc.step = 1 << o;
+    oc.rows = H / oc.step;
+    oc.cols = W / oc.step;
+    oc.n = n_layers + 2;
+    oc.det_off = off;
+    off += static_cast<int64_t>(oc.n) * oc.rows * oc.cols;
+    for (int l = 0; l < oc.n; ++l) {
+      SurfLayer& L = oc.layer[l];
+      L.size = (9 + 6 * l) << o;
+      const bool fits = L.size <= H && L.size <= W;
+      L.ni = fits ? 1 + (H - L.size) / oc.step : 0;
+      L.nj = fits ? 1 + (W - L.size) / oc.step : 0;
+      L.margin = (L.size / 2) / oc.step;
+      resize_pattern(dx_s, 3, L.size, L.dx);
+      resize_pattern(dy_s, 3, L.size, L.dy);
+      resize_pattern(dxy_s, 4, L.size, L.dxy);
+    }
+  }
+  p.det_floats_per_frame = off;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  p.off_sum = take(sizeof(int32_t) * static_cast<size_t>(B) * (H + 1) * (W + 1));
+  p.off_det = take(sizeof(float) * static_cast<size_t>(B) * off);
+  p.off_cand = take(sizeof(float4) * static_cast<size_t>(B) * kSurfCap);
+  p.off_keys = take(sizeof(unsigned long long) * static_cast<size_t>(B) * kSurfCap);
+  p.off_count = take(sizeof(int) * static_cast<size_t>(B));
+  p.total = o;
+  return p;
+}
+
+}  // namespace dlc
+
+using namespace dlc;
+
+static int check_surf_args(int B, int H, int W, int n_octaves, int n_layers) {
+  DLC_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && H < 8192 && W < 8192);  // row / column fit the 13-bit order fields
+  DLC_CHECK_ARG(n_octaves >= 1 && n_octaves <= kSurfMaxOctaves);
+  DLC_CHECK_ARG(n_layers >= 1 && n_layers + 2 <= kSurfMaxLayers);
+  return DLC_OK;
+}
+
+extern "C" size_t dlc_surf_workspace_bytes(int B, int H, int W, int n_octaves, int n_layers) {
+  if (B <= 0 || check_surf_args(B, H, W, n_octaves, n_layers) != DLC_OK) return 0;
+  return surf_plan(B, H, W, n_octaves, n_layers).total;
+}
+
+extern "C" int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, float hessian_threshold, int n_octaves,
+                               int n_layers, int top_n, float* xy_dev, float* info_dev, int32_t* found_dev,
+                               void* ws_dev, size_t ws_bytes, void* stream) {
+  if (int rc = check_surf_args(B, H, W, n_octaves, n_layers)) return rc;
+  DLC_CHECK_ARG(top_n >= 1 && hessian_threshold > 0.0f);
+  if (B == 0) return DLC_OK;
+  DLC_CHECK_ARG(img_dev && xy_dev && found_dev && ws_dev);
+  DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0);
+  const SurfPlan p = surf_plan(B, H, W, n_octaves, n_layers);
+  if (ws_bytes < p.total)
+    return fail(DLC_ENOMEM, "dlc_surf_detect: workspace of %zu bytes needed, %zu given", p.total, ws_bytes);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(ws_dev);
+  int32_t* sum = reinterpret_cast<int32_t*>(ws + p.off_sum);
+  float* det = reinterpret_cast<float*>(ws + p.off_det);
+  float4* cand = reinterpret_cast<float4*>(ws + p.off_cand);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + p.off_keys);
+  int* count = reinterpret_cast<int*>(ws + p.off_count);
+  DLC_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * B, s));
+  surf_integral_rows_kernel<<<ceil_div(B * H, 8), 256, 0, s>>>(img_dev, B, H, W, sum);
+  surf_integral_cols_kernel<<<B * ceil_div(W, 32), 1024, 0, s>>>(B, H, W, sum);
+  for (int o = 0; o < n_octaves; ++o) {
+    const SurfOctave& oc = p.oc[o];
+    const int cells = oc.rows * oc.cols;
+    if (cells == 0) continue;
+    surf_det_kernel<<<dim3(ceil_div(cells, 256), oc.n, B), 256, 0, s>>>(sum, H, W, oc, p.det_floats_per_frame, det);
+    surf_maxima_kernel<<<dim3(ceil_div(cells, 256), n_layers, B), 256, 0, s>>>(det, H, W, oc, o, p.det_floats_per_frame,
+                                                                             hessian_threshold, cand, keys, count);
+  }
+  surf_top_kernel<<<B, 256, 0, s>>>(cand, keys, count, H, W, top_n, xy_dev, info_dev, found_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}

@@ -1,8 +1,10 @@
 """Drop-in for `src.sdav.input.CvInputParser` (reference src/sdav/input/CvInputParser.py).
 `parse(image)` = top-n keypoints -> 41x41 patches around them (window shifted inside the image, rows indexed by x -
 the reference's quirk) -> / 255.0 -> float64 [n, 1681]. The gather + normalise runs on the B200
-(dlc_patch_gather_f64, bit-identical to the reference's NumPy result). Keypoint detection itself (OpenCV SURF,
-CvInputParser.py:36-46) is host code outside the accelerated path; `key_points=` lets callers inject keypoints."""
+(dlc_patch_gather_f64, bit-identical to the reference's NumPy result). Keypoint detection (OpenCV SURF in the
+reference, CvInputParser.py:36-46) runs on the B200 too (dlc_surf_detect, a restatement of the published fast-Hessian
+detector - parity against OpenCV's non-free module cannot be pinned here); `key_points=` lets callers inject their
+own keypoints."""
 import math
 
 import numpy as np
@@ -19,15 +21,45 @@ def _xy_array(key_points):
     return np.ascontiguousarray(arr, dtype=np.float32).reshape(-1, 2)
 
 
-def get_top_n_key_points(img, n):
-    """Top n SURF keypoints by response (CvInputParser.py:36-46). Needs opencv-contrib (non-free SURF)."""
-    import cv2
-    if not hasattr(cv2, "xfeatures2d") or not hasattr(cv2.xfeatures2d, "SURF_create"):
-        raise RuntimeError("cv2.xfeatures2d.SURF_create is unavailable in this OpenCV build; pass key_points= "
-                           "(an [n, 2] array of (x, y) centres or cv2.KeyPoint objects) instead")
-    key_points = list(cv2.xfeatures2d.SURF_create().detect(img, None))
-    key_points.sort(key=lambda kp: -kp.response)
-    return key_points[0:n]
+class KeyPoint:
+    """The attributes of cv2.KeyPoint that the reference reads (.pt, CvInputParser.py:111; .response, :44)."""
+    __slots__ = ("pt", "size", "response")
+
+    def __init__(self, x, y, size, response):
+        self.pt = (float(x), float(y))
+        self.size = float(size)
+        self.response = float(response)
+
+    def __repr__(self):
+        return "KeyPoint(pt=(%.3f, %.3f), size=%g, response=%g)" % (self.pt[0], self.pt[1], self.size, self.response)
+
+
+def get_top_n_key_points(img, n, detector="b200"):
+    """Top n SURF keypoints in descending response order (CvInputParser.py:36-46).
+    detector="b200" (default): the fast-Hessian detector on the GPU (dlc_surf_detect; SURF_create() defaults:
+    threshold 100, 4 octaves, 3 layers). It restates the published algorithm - OpenCV's non-free SURF is not available
+    to pin it against, so individual keypoints may differ from the reference's. detector="opencv": the reference's
+    own call, for environments whose OpenCV has xfeatures2d (host code, not accelerated)."""
+    if detector == "opencv":
+        import cv2
+        if not hasattr(cv2, "xfeatures2d") or not hasattr(cv2.xfeatures2d, "SURF_create"):
+            raise RuntimeError("cv2.xfeatures2d.SURF_create is unavailable in this OpenCV build")
+        key_points = list(cv2.xfeatures2d.SURF_create().detect(img, None))
+        key_points.sort(key=lambda kp: -kp.response)
+        return key_points[0:n]
+    if detector != "b200":
+        raise ValueError("detector must be 'b200' or 'opencv'")
+    import torch
+
+    from . import _cuda, ops
+    _cuda.require_cuda()
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    if img.ndim != 2:
+        raise ValueError("expected a single-channel (grayscale) image")
+    xy, info, found = ops.surf_detect(torch.from_numpy(img)[None].cuda(), top_n=int(n))
+    m = min(int(found[0].item()), int(n))           # like the reference: fewer than n when the image has fewer
+    xy, info = xy[0, :m].cpu().numpy(), info[0, :m].cpu().numpy()
+    return [KeyPoint(xy[i, 0], xy[i, 1], info[i, 0], info[i, 1]) for i in range(m)]
 
 
 def get_1d_boundaries(rect_shape, center_points, patch_size, axis):

@@ -93,6 +93,28 @@ def matmul(a, b, bias=None, act="none", precision="fp16x2"):
 
 
 # ------------------------------------------------------------------------------------------------ patches
+SURF_CANDIDATE_CAP = 16384
+_ws_surf = Workspace()
+
+
+def surf_detect(img, top_n=30, hessian_threshold=100.0, n_octaves=4, n_layers=3, chunk=64):
+    """img uint8 [B,H,W] (CUDA) -> (xy float32 [B,top_n,2], info float32 [B,top_n,2] = (size, response),
+    found int32 [B]): the top_n fast-Hessian keypoints of every frame, best response first (see dlc_surf_detect).
+    Frames are processed `chunk` at a time to bound the workspace (~10 MB per 640x480 frame)."""
+    _check_cuda(img)
+    assert img.dtype == torch.uint8 and img.dim() == 3
+    B, H, W = img.shape
+    xy = torch.empty((B, top_n, 2), dtype=torch.float32, device=img.device)
+    info = torch.empty((B, top_n, 2), dtype=torch.float32, device=img.device)
+    found = torch.empty((B,), dtype=torch.int32, device=img.device)
+    for b0 in range(0, B, chunk):
+        n = min(chunk, B - b0)
+        ws, ws_bytes = _ws_surf.get(_lib.call("dlc_surf_workspace_bytes", n, H, W, n_octaves, n_layers))
+        _lib.call("dlc_surf_detect", ptr(img[b0:b0 + n]), n, H, W, float(hessian_threshold), n_octaves, n_layers, top_n,
+                  ptr(xy[b0:b0 + n]), ptr(info[b0:b0 + n]), ptr(found[b0:b0 + n]), ws, ws_bytes, stream_ptr())
+    return xy, info, found
+
+
 def patch_gather(img, xy, patch=41, swap_xy_quirk=True, need_lo=True):
     """img uint8 [B,H,W], xy float32 [B,P,2] -> (hi, lo) planes [B*P, ld(patch^2)]."""
     _check_cuda(img, xy)

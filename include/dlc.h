@@ -118,6 +118,24 @@ int dlc_patch_gather_f64(const uint8_t* img_dev, int B, int H, int W, const floa
                          int swap_xy_quirk, double* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * f3  keypoint detector in front of the patch gather. Replaces get_top_n_key_points
+ *     (src/sdav/input/CvInputParser.py:36-46: cv2.xfeatures2d.SURF_create().detect(img), sort by -response, first n).
+ *     The fast-Hessian ("SURF") detector of Bay et al. with the documented constants of opencv-contrib 3.4.2 (9x9 base
+ *     box filters + 6 per layer, doubling per octave; det = Dxx Dyy - 0.81 Dxy^2; strict 3x3x3 maxima of the middle
+ *     layers; quadratic sub-sample interpolation; orientation-window test). That module is absent from the reference
+ *     tree and from this image: PARITY UNPINNED against OpenCV; bit-identical to oracle/surf.py.
+ * img_dev uint8 [B,H,W] -> xy_dev float32 [B, top_n, 2] (x = column, y = row; what dlc_patch_gather* consume), best
+ * response first, ties in detection order (octave, layer, row, column); info_dev (optional) float32 [B, top_n, 2] =
+ * (size, response); found_dev int32 [B] = keypoints found in the frame before the cut (entries beyond it are the
+ * image centre with response 0; more than 16384 means the candidate list overflowed and the selection is incomplete).
+ * SURF_create() defaults: hessian_threshold 100, n_octaves 4, n_layers 3.
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t dlc_surf_workspace_bytes(int B, int H, int W, int n_octaves, int n_layers);
+int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, float hessian_threshold, int n_octaves, int n_layers,
+                    int top_n, float* xy_dev, float* info_dev, int32_t* found_dev, void* ws_dev, size_t ws_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * a3/a4  SDA encoder forward: H_l = sigmoid(H_{l-1} W_l + b_l).
  *        Replaces SDAV.transform (src/sdav/network/SDAV.py:120-163, 293-302) and DA.transform
  *        (src/sdav/network/DenoisingAutoencoderVariant.py:116-119, 254-259).

@@ -686,3 +686,58 @@ def test_encoder_raw_pixel_mode_needs_layer0_again(cuda):
     with pytest.raises(RuntimeError):
         enc.encode_planes(x, None, 30)
     enc.close()
+
+
+# ------------------------------------------------------------------------------------------- keypoint detector (8f rank 3)
+def _surf_frames(kind, B, H, W, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = []
+    for _ in range(B):
+        img = np.full((H, W), 90.0) + rng.normal(0, 2.0, (H, W))
+        for _ in range(14):
+            s = rng.uniform(2.5, 9.0)
+            img += rng.choice([-1, 1]) * rng.uniform(40, 140) * np.exp(
+                -((xx - rng.uniform(0, W)) ** 2 + (yy - rng.uniform(0, H)) ** 2) / (2 * s * s))
+        out.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("kind,B,H,W", [("blobs", 3, 192, 240), ("noise", 2, 192, 240), ("blobs", 2, 101, 135),
+                                        ("noise", 1, 50, 61), ("blobs", 1, 480, 640)])
+def test_surf_detect_equals_oracle(cuda, kind, B, H, W):
+    """dlc_surf_detect == oracle/surf.py bit for bit: positions, sizes, responses, order and the keypoint count, for
+    blob and noise frames, sizes that are not multiples of the sampling steps and frames too small for the upper
+    octaves."""
+    from deeploopcloser_b200 import ops
+    from oracle import surf
+    frames = _surf_frames(kind, B, H, W, seed=H + B)
+    n = 30
+    xy, info, found = ops.surf_detect(torch.from_numpy(frames).cuda(), top_n=n)
+    xy, info, found = xy.cpu().numpy(), info.cpu().numpy(), found.cpu().numpy()
+    for b in range(B):
+        all_kp = surf.detect(frames[b])
+        ref = surf.top_n(all_kp, n)
+        assert found[b] == len(all_kp) <= ops.SURF_CANDIDATE_CAP, (found[b], len(all_kp))
+        m = len(ref)
+        assert np.array_equal(xy[b, :m], ref[:, 0:2].astype(np.float32))
+        assert np.array_equal(info[b, :m], ref[:, 2:4].astype(np.float32))
+        assert np.all(xy[b, m:] == [0.5 * (W - 1), 0.5 * (H - 1)]) and np.all(info[b, m:] == 0)
+        print("surf", kind, (H, W), "keypoints", len(all_kp), "top response", ref[0, 3] if m else None)
+
+
+def test_surf_feeds_the_parser(cuda):
+    """CvInputParser.parse(image) without injected keypoints: GPU detector -> GPU patch gather == the oracle chain."""
+    from oracle import surf
+    from src.sdav.input.CvInputParser import CvInputParser, get_top_n_key_points
+    img = _surf_frames("blobs", 1, 192, 240, seed=9)[0]
+    kps = get_top_n_key_points(img, 30)
+    ref = surf.top_n(surf.detect(img), 30)
+    assert len(kps) == len(ref) > 0
+    assert np.array_equal(np.array([kp.pt for kp in kps], dtype=np.float32), ref[:, :2].astype(np.float32))
+    assert all(kps[i].response >= kps[i + 1].response for i in range(len(kps) - 1))
+    out = CvInputParser(30, 41).parse(img)
+    want = o_patch.extract_patches(img, ref[:, :2].astype(np.float32))
+    assert np.array_equal(out, want)

@@ -169,3 +169,30 @@ def test_write_png_round_trip(tmp_path):
     path = str(tmp_path / "m.png")
     write_png(path, img)
     assert np.array_equal(cv2.imread(path, cv2.IMREAD_GRAYSCALE), img)
+
+
+def _blob_image(H, W, blobs, base=60.0):
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    img = np.full((H, W), base)
+    for bx, by, s, a in blobs:
+        img += a * np.exp(-((xx - bx) ** 2 + (yy - by) ** 2) / (2 * s * s))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def test_surf_oracle_recovers_synthetic_blobs():
+    """The detector oracle cannot be pinned against OpenCV's non-free SURF (absent here); what can be checked is the
+    geometry it must satisfy: Gaussian blobs are found at their centres (x = column, y = row, sub-pixel), with a size
+    that grows with the blob, strongest response first, bright and dark blobs alike, and nothing in a flat image."""
+    from oracle import surf
+    blobs = [(60.0, 50.0, 3.0, 150), (150.5, 100.25, 5.0, 120), (200.0, 150.0, 8.0, -50)]
+    kp = surf.top_n(surf.detect(_blob_image(192, 240, blobs)), 3)
+    assert len(kp) == 3 and np.all(np.diff(kp[:, 3]) <= 0)
+    for (bx, by, s, _), row in zip(blobs, kp):
+        assert abs(row[0] - bx) < 0.1 and abs(row[1] - by) < 0.1
+        assert 5.0 * s <= row[2] <= 6.5 * s
+    assert len(surf.detect(np.full((96, 128), 77, dtype=np.uint8))) == 0
+    # a blob smaller than the first middle layer (15 x 15 filter) has no scale-space maximum there
+    assert len(surf.detect(_blob_image(96, 128, [(64.0, 48.0, 2.0, 180)]))) == 0
+    # layer geometry: filter sizes of SURF_create() defaults
+    assert surf.layer_sizes() == [[9, 15, 21, 27, 33], [18, 30, 42, 54, 66], [36, 60, 84, 108, 132],
+                                  [72, 120, 168, 216, 264]]

@@ -1,5 +1,1 @@
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log > gpurun_out/r1_bench_1gpu_v3.json; python -c "import json; d=json.load(open('gpurun_out/r1_bench_1gpu_v3.json')); print(round(d['value']), round(d['ms_per_step'],3), d['e2e'], d['clocks'], d['roofline']['ms_per_launch'], d['roofline']['frac'], d['cpu_baseline']['value'], d['gpu_launches'], d['stages_ms'])"
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -1 gpurun_out/bench_reference.log | cut -c1-600
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_v7.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:prep_rows|gram_refine_fix|gram_probe_kernel|rep_mask|gemm_pair_kernel|colsum|patch_gather|topk' --launch-skip 15 -c 15 -o gpurun_out/prof_step_r1v7 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
-timeout 300 python -m pytest tests -q -m gpu -k "raw_pixel" -s 2>&1 | grep "raw-pixel encoder"
+timeout 900 python -m pytest tests -x -q -m gpu -k "surf" -s > gpurun_out/pytest_surf.log 2>&1; echo "exit $?"; grep -a "^surf\|passed\|failed\|Error\|assert" gpurun_out/pytest_surf.log | head -30
