@@ -6,12 +6,15 @@
 // NumPy and the two agree bit for bit (every float operation below is an explicitly rounded intrinsic, no FMA
 // contraction, same operation order as the oracle).
 //
-// Bytes-bound pipeline, one batch of frames per call:
+// One batch of frames per call:
 //   integral image (row scan, then column scan by strips)                      int32 [B, H+1, W+1]
-//   per octave: box-filter Hessian determinant of its n_layers + 2 layers      float [B, layers, H/step, W/step]
-//   per octave: strict 3x3x3 maxima of the middle layers above the threshold, quadratic interpolation, orientation-
-//               window test -> appended to a per-frame candidate list
+//   per octave, ONE kernel: box-filter Hessian determinant of its n_layers + 2 layers on a 32 x 32-sample tile (+ halo)
+//               into shared memory - the layers never exist in HBM - then the strict 3x3x3 maxima of the middle
+//               layers above the threshold, quadratic interpolation, orientation-window test -> appended to a
+//               per-frame candidate list
 //   per frame : n best candidates by (response desc, detection order asc) -> xy [B, n, 2]
+// Cost model: 32 integral-image lookups (L1 hits) per sample and layer, 5 x 1.33 layer-samples per pixel: the path is
+// bound by load instructions, not by HBM (the compulsory traffic is 1 B read + 8 B written/read per pixel).
 #include <math.h>
 #include <stdint.h>
 
@@ -35,8 +38,7 @@ struct SurfLayer {
   SurfBox dx[3], dy[3], dxy[4];
 };
 struct SurfOctave {
-  int step, rows, cols, n;            // det arrays are [n][rows][cols]
-  int64_t det_off;                    // float offset of this octave inside a frame's det block
+  int step, rows, cols, n;            // n layers of rows x cols samples
   SurfLayer layer[kSurfMaxLayers];
 };
 
@@ -93,38 +95,69 @@ surf_integral_cols_kernel(int B, int H, int W, int32_t* __restrict__ sum) {
 }
 
 // ---------------------------------------------------------------- Hessian determinant
-template <int N>
-__device__ __forceinline__ float haar(const int32_t* __restrict__ org, int pitch, const SurfBox (&f)[N]) {
+// Box sums of one pattern from the integral image. The three Dxx boxes share their rows and abut in x (and the Dyy
+// boxes transposed), the four Dxy boxes lie on a 4 x 4 grid of corners: 8 + 8 + 16 = 32 loads per sample instead of
+// 40 (surf_plan checks the structure). Every box sum is formed exactly in int32, then float(box) * w is added in
+// float64 in box order and rounded to float32 - the oracle's arithmetic.
+__device__ __forceinline__ float haar_acc(const int (&box)[4], const float (&w)[4], int n) {
   double d = 0.0;
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const int s = __ldg(org + f[k].y1 * pitch + f[k].x1) + __ldg(org + f[k].y2 * pitch + f[k].x2) -
-                  __ldg(org + f[k].y2 * pitch + f[k].x1) - __ldg(org + f[k].y1 * pitch + f[k].x2);
-    d = __dadd_rn(d, static_cast<double>(__fmul_rn(__int2float_rn(s), f[k].w)));
-  }
+  for (int k = 0; k < 4; ++k)
+    if (k < n) d = __dadd_rn(d, static_cast<double>(__fmul_rn(__int2float_rn(box[k]), w[k])));
   return __double2float_rn(d);
 }
-
-__global__ void __launch_bounds__(256)
-surf_det_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc,
-                int64_t det_frame_stride, float* __restrict__ det) {
-  const int l = blockIdx.y, b = blockIdx.z;
-  const SurfLayer& L = oc.layer[l];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= oc.rows * oc.cols) return;
-  const int r = idx / oc.cols, c = idx - r * oc.cols;
-  const int i = r - L.margin, j = c - L.margin;
-  float v = 0.0f;  // the filter does not fit here
-  if (i >= 0 && i < L.ni && j >= 0 && j < L.nj) {
-    const int pitch = W + 1;
-    const int32_t* org = sum + static_cast<int64_t>(b) * (H + 1) * pitch + static_cast<int64_t>(i) * oc.step * pitch +
-                         j * oc.step;
-    const float dx = haar<3>(org, pitch, L.dx);
-    const float dy = haar<3>(org, pitch, L.dy);
-    const float dxy = haar<4>(org, pitch, L.dxy);
-    v = __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
+__device__ __forceinline__ float det_at(const int32_t* __restrict__ org, int pitch, const SurfLayer& L) {
+  int box[4];
+  float w[4];
+  {  // Dxx: rows y1 / y2 of box 0, columns x1_0, x2_0 (= x1_1), x2_1 (= x1_2), x2_2
+    const int32_t* t = org + L.dx[0].y1 * pitch;
+    const int32_t* u = org + L.dx[0].y2 * pitch;
+    const int xs[4] = {L.dx[0].x1, L.dx[0].x2, L.dx[1].x2, L.dx[2].x2};
+    int top[4], bot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      top[q] = __ldg(t + xs[q]);
+      bot[q] = __ldg(u + xs[q]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      box[k] = (bot[k + 1] - bot[k]) - (top[k + 1] - top[k]);
+      w[k] = L.dx[k].w;
+    }
   }
-  det[static_cast<int64_t>(b) * det_frame_stride + oc.det_off + static_cast<int64_t>(l) * oc.rows * oc.cols + idx] = v;
+  const float dx = haar_acc(box, w, 3);
+  {  // Dyy: columns x1 / x2 of box 0, rows y1_0, y2_0, y2_1, y2_2
+    const int ys[4] = {L.dy[0].y1, L.dy[0].y2, L.dy[1].y2, L.dy[2].y2};
+    int lft[4], rgt[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      lft[q] = __ldg(org + ys[q] * pitch + L.dy[0].x1);
+      rgt[q] = __ldg(org + ys[q] * pitch + L.dy[0].x2);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      box[k] = (rgt[k + 1] - rgt[k]) - (lft[k + 1] - lft[k]);
+      w[k] = L.dy[k].w;
+    }
+  }
+  const float dy = haar_acc(box, w, 3);
+  {  // Dxy: corners on the grid {x1_0, x2_0, x1_1, x2_1} x {y1_0, y2_0, y1_2, y2_2}
+    const int xs[4] = {L.dxy[0].x1, L.dxy[0].x2, L.dxy[1].x1, L.dxy[1].x2};
+    const int ys[4] = {L.dxy[0].y1, L.dxy[0].y2, L.dxy[2].y1, L.dxy[2].y2};
+    int g[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g[r][c] = __ldg(org + ys[r] * pitch + xs[c]);
+    box[0] = (g[1][1] - g[1][0]) - (g[0][1] - g[0][0]);
+    box[1] = (g[1][3] - g[1][2]) - (g[0][3] - g[0][2]);
+    box[2] = (g[3][1] - g[3][0]) - (g[2][1] - g[2][0]);
+    box[3] = (g[3][3] - g[3][2]) - (g[2][3] - g[2][2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = L.dxy[k].w;
+  }
+  const float dxy = haar_acc(box, w, 4);
+  return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
 
 // ---------------------------------------------------------------- maxima
@@ -181,70 +214,92 @@ __device__ bool orientation_samplable(float x, float y, float size, int H, int W
   return false;
 }
 
+// One octave, fused: a CTA evaluates the determinant of all layers on a tile of kSurfTile x kSurfTile samples plus a
+// one-sample halo into shared memory (the layers never go to HBM), then finds the maxima of the middle layers there.
+constexpr int kSurfTile = 32;
+constexpr int kSurfHalo = kSurfTile + 2;
 __global__ void __launch_bounds__(256)
-surf_maxima_kernel(const float* __restrict__ det, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
-                   int64_t det_frame_stride, float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys,
-                   int* __restrict__ count) {
-  const int l = 1 + blockIdx.y, b = blockIdx.z;   // middle layers 1 .. n - 2
-  const SurfLayer& L = oc.layer[l];
-  const int size = L.size;
-  const int margin = (oc.layer[l + 1].size / 2) / oc.step + 1;
-  const int wr = oc.rows - 2 * margin, wc = oc.cols - 2 * margin;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wr <= 0 || wc <= 0 || idx >= wr * wc) return;
-  const int i = margin + idx / wc, j = margin + idx % wc;
-  const int64_t plane = static_cast<int64_t>(oc.rows) * oc.cols;
-  const float* d1 = det + static_cast<int64_t>(b) * det_frame_stride + oc.det_off + l * plane +
-                    static_cast<int64_t>(i) * oc.cols + j;
-  const float val0 = d1[0];
-  if (!(val0 > thr)) return;
-  float N9[3][9];
+surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
+                   float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ count) {
+  extern __shared__ float s_det[];   // [oc.n][kSurfHalo][kSurfHalo]
+  const int b = blockIdx.z;
+  const int tiles_x = (oc.cols + kSurfTile - 1) / kSurfTile;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int i0 = ty * kSurfTile - 1, j0 = tx * kSurfTile - 1;   // sample coordinates of the halo's corner
+  const int pitch = W + 1;
+  const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
+  constexpr int kCells = kSurfHalo * kSurfHalo;
+  for (int e = threadIdx.x; e < oc.n * kCells; e += blockDim.x) {
+    const int l = e / kCells, rc = e - l * kCells;
+    const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
+    const SurfLayer& L = oc.layer[l];
+    const int i = i0 + r - L.margin, j = j0 + c - L.margin;    // filter origin in samples
+    float v = 0.0f;                                            // the filter does not fit here
+    if (i >= 0 && i < L.ni && j >= 0 && j < L.nj)
+      v = det_at(frame + static_cast<int64_t>(i) * oc.step * pitch + j * oc.step, pitch, L);
+    s_det[e] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (oc.n - 2) * kSurfTile * kSurfTile; e += blockDim.x) {
+    const int l = 1 + e / (kSurfTile * kSurfTile);             // middle layers 1 .. n - 2
+    const int rc = e % (kSurfTile * kSurfTile);
+    const int r = 1 + rc / kSurfTile, c = 1 + rc % kSurfTile;
+    const int i = i0 + r, j = j0 + c;
+    const SurfLayer& L = oc.layer[l];
+    const int size = L.size;
+    const int margin = (oc.layer[l + 1].size / 2) / oc.step + 1;
+    if (i < margin || i >= oc.rows - margin || j < margin || j >= oc.cols - margin) continue;
+    const float* d1 = s_det + l * kCells + r * kSurfHalo + c;
+    const float val0 = d1[0];
+    if (!(val0 > thr)) continue;
+    float N9[3][9];
 #pragma unroll
-  for (int dl = 0; dl < 3; ++dl)
+    for (int dl = 0; dl < 3; ++dl)
 #pragma unroll
-    for (int di = 0; di < 3; ++di)
+      for (int di = 0; di < 3; ++di)
 #pragma unroll
-      for (int dj = 0; dj < 3; ++dj)
-        N9[dl][di * 3 + dj] = d1[(dl - 1) * plane + (di - 1) * oc.cols + (dj - 1)];
-  bool is_max = true;
-#pragma unroll
-  for (int dl = 0; dl < 3; ++dl)
-#pragma unroll
-    for (int q = 0; q < 9; ++q)
-      if (!(dl == 1 && q == 4)) is_max = is_max && (val0 > N9[dl][q]);
-  if (!is_max) return;
-  const int sum_i = oc.step * (i - (size / 2) / oc.step);
-  const int sum_j = oc.step * (j - (size / 2) / oc.step);
-  const float cy = __fadd_rn(static_cast<float>(sum_i), __fmul_rn(static_cast<float>(size - 1), 0.5f));
-  const float cx = __fadd_rn(static_cast<float>(sum_j), __fmul_rn(static_cast<float>(size - 1), 0.5f));
-  const int ds = size - oc.layer[l - 1].size;
-  // negative first derivatives and the Hessian of the 3x3x3 neighbourhood (float32, as Vec3f / Matx33f)
-  const float bx = __fdiv_rn(-__fsub_rn(N9[1][5], N9[1][3]), 2.0f);
-  const float by = __fdiv_rn(-__fsub_rn(N9[1][7], N9[1][1]), 2.0f);
-  const float bs = __fdiv_rn(-__fsub_rn(N9[2][4], N9[0][4]), 2.0f);
-  const float axx = __fadd_rn(__fsub_rn(N9[1][3], __fmul_rn(2.0f, N9[1][4])), N9[1][5]);
-  const float ayy = __fadd_rn(__fsub_rn(N9[1][1], __fmul_rn(2.0f, N9[1][4])), N9[1][7]);
-  const float ass = __fadd_rn(__fsub_rn(N9[0][4], __fmul_rn(2.0f, N9[1][4])), N9[2][4]);
-  const float axy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[1][8], N9[1][6]), N9[1][2]), N9[1][0]), 4.0f);
-  const float axs = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][5], N9[2][3]), N9[0][5]), N9[0][3]), 4.0f);
-  const float ays = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][7], N9[2][1]), N9[0][7]), N9[0][1]), 4.0f);
-  double M[3][4] = {{axx, axy, axs, bx}, {axy, ayy, ays, by}, {axs, ays, ass, bs}};
-  double xd[3];
-  if (!solve3(M, xd)) return;
-  const float x0 = __double2float_rn(xd[0]), x1 = __double2float_rn(xd[1]), x2 = __double2float_rn(xd[2]);
-  if (!((x0 != 0.0f || x1 != 0.0f || x2 != 0.0f) && fabsf(x0) <= 1.0f && fabsf(x1) <= 1.0f && fabsf(x2) <= 1.0f)) return;
-  const float px = __fadd_rn(cx, __fmul_rn(x0, static_cast<float>(oc.step)));
-  const float py = __fadd_rn(cy, __fmul_rn(x1, static_cast<float>(oc.step)));
-  const float ksize = rintf(__fadd_rn(static_cast<float>(size), __fmul_rn(x2, static_cast<float>(ds))));
-  if (!orientation_samplable(px, py, ksize, H, W)) return;
-  const int slot = atomicAdd(count + b, 1);
-  if (slot >= kSurfCap) return;
-  // order: response descending, then detection order (octave, layer, row, column) ascending
-  const uint32_t order = (static_cast<uint32_t>(octave) << 29) | (static_cast<uint32_t>(l) << 26) |
-                         (static_cast<uint32_t>(i) << 13) | static_cast<uint32_t>(j);
-  cand[static_cast<int64_t>(b) * kSurfCap + slot] = make_float4(px, py, ksize, val0);
-  keys[static_cast<int64_t>(b) * kSurfCap + slot] =
-      (static_cast<unsigned long long>(__float_as_uint(val0)) << 32) | static_cast<unsigned long long>(~order);
+        for (int dj = 0; dj < 3; ++dj)
+          N9[dl][di * 3 + dj] = d1[(dl - 1) * kCells + (di - 1) * kSurfHalo + (dj - 1)];
+    bool is_max = true;
+  #pragma unroll
+    for (int dl = 0; dl < 3; ++dl)
+  #pragma unroll
+      for (int q = 0; q < 9; ++q)
+        if (!(dl == 1 && q == 4)) is_max = is_max && (val0 > N9[dl][q]);
+    if (!is_max) continue;
+    const int sum_i = oc.step * (i - (size / 2) / oc.step);
+    const int sum_j = oc.step * (j - (size / 2) / oc.step);
+    const float cy = __fadd_rn(static_cast<float>(sum_i), __fmul_rn(static_cast<float>(size - 1), 0.5f));
+    const float cx = __fadd_rn(static_cast<float>(sum_j), __fmul_rn(static_cast<float>(size - 1), 0.5f));
+    const int ds = size - oc.layer[l - 1].size;
+    // negative first derivatives and the Hessian of the 3x3x3 neighbourhood (float32, as Vec3f / Matx33f)
+    const float bx = __fdiv_rn(-__fsub_rn(N9[1][5], N9[1][3]), 2.0f);
+    const float by = __fdiv_rn(-__fsub_rn(N9[1][7], N9[1][1]), 2.0f);
+    const float bs = __fdiv_rn(-__fsub_rn(N9[2][4], N9[0][4]), 2.0f);
+    const float axx = __fadd_rn(__fsub_rn(N9[1][3], __fmul_rn(2.0f, N9[1][4])), N9[1][5]);
+    const float ayy = __fadd_rn(__fsub_rn(N9[1][1], __fmul_rn(2.0f, N9[1][4])), N9[1][7]);
+    const float ass = __fadd_rn(__fsub_rn(N9[0][4], __fmul_rn(2.0f, N9[1][4])), N9[2][4]);
+    const float axy = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[1][8], N9[1][6]), N9[1][2]), N9[1][0]), 4.0f);
+    const float axs = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][5], N9[2][3]), N9[0][5]), N9[0][3]), 4.0f);
+    const float ays = __fdiv_rn(__fadd_rn(__fsub_rn(__fsub_rn(N9[2][7], N9[2][1]), N9[0][7]), N9[0][1]), 4.0f);
+    double M[3][4] = {{axx, axy, axs, bx}, {axy, ayy, ays, by}, {axs, ays, ass, bs}};
+    double xd[3];
+    if (!solve3(M, xd)) continue;
+    const float x0 = __double2float_rn(xd[0]), x1 = __double2float_rn(xd[1]), x2 = __double2float_rn(xd[2]);
+    if (!((x0 != 0.0f || x1 != 0.0f || x2 != 0.0f) && fabsf(x0) <= 1.0f && fabsf(x1) <= 1.0f && fabsf(x2) <= 1.0f)) continue;
+    const float px = __fadd_rn(cx, __fmul_rn(x0, static_cast<float>(oc.step)));
+    const float py = __fadd_rn(cy, __fmul_rn(x1, static_cast<float>(oc.step)));
+    const float ksize = rintf(__fadd_rn(static_cast<float>(size), __fmul_rn(x2, static_cast<float>(ds))));
+    if (!orientation_samplable(px, py, ksize, H, W)) continue;
+    const int slot = atomicAdd(count + b, 1);
+    if (slot >= kSurfCap) continue;
+    // order: response descending, then detection order (octave, layer, row, column) ascending
+    const uint32_t order = (static_cast<uint32_t>(octave) << 29) | (static_cast<uint32_t>(l) << 26) |
+                           (static_cast<uint32_t>(i) << 13) | static_cast<uint32_t>(j);
+    cand[static_cast<int64_t>(b) * kSurfCap + slot] = make_float4(px, py, ksize, val0);
+    keys[static_cast<int64_t>(b) * kSurfCap + slot] =
+        (static_cast<unsigned long long>(__float_as_uint(val0)) << 32) | static_cast<unsigned long long>(~order);
+  }
 }
 
 // ---------------------------------------------------------------- n best per frame
@@ -328,8 +383,8 @@ static void resize_pattern(const int (*src)[5], int n, int size, SurfBox* dst) {
 struct SurfPlan {
   int n_octaves;
   SurfOctave oc[kSurfMaxOctaves];
-  int64_t det_floats_per_frame;
-  size_t off_sum, off_det, off_cand, off_keys, off_count, total;
+  bool structure_ok;
+  size_t off_sum, off_cand, off_keys, off_count, total;
 };
 static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
   static const int dx_s[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
@@ -337,15 +392,13 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
   static const int dxy_s[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
   SurfPlan p{};
   p.n_octaves = n_octaves;
-  int64_t off = 0;
+  p.structure_ok = true;
   for (int o = 0; o < n_octaves; ++o) {
     SurfOctave& oc = p.oc[o];
     oc.step = 1 << o;
     oc.rows = H / oc.step;
     oc.cols = W / oc.step;
     oc.n = n_layers + 2;
-    oc.det_off = off;
-    off += static_cast<int64_t>(oc.n) * oc.rows * oc.cols;
     for (int l = 0; l < oc.n; ++l) {
       SurfLayer& L = oc.layer[l];
       L.size = (9 + 6 * l) << o;
@@ -356,9 +409,17 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
       resize_pattern(dx_s, 3, L.size, L.dx);
       resize_pattern(dy_s, 3, L.size, L.dy);
       resize_pattern(dxy_s, 4, L.size, L.dxy);
+      // the shared-corner evaluation of det_at() relies on this (it follows from scaling equal coordinates equally)
+      for (int k = 0; k < 3; ++k) {
+        p.structure_ok = p.structure_ok && L.dx[k].y1 == L.dx[0].y1 && L.dx[k].y2 == L.dx[0].y2 &&
+                         L.dy[k].x1 == L.dy[0].x1 && L.dy[k].x2 == L.dy[0].x2 &&
+                         (k == 0 || (L.dx[k].x1 == L.dx[k - 1].x2 && L.dy[k].y1 == L.dy[k - 1].y2));
+      }
+      p.structure_ok = p.structure_ok && L.dxy[2].x1 == L.dxy[0].x1 && L.dxy[2].x2 == L.dxy[0].x2 &&
+                       L.dxy[3].x1 == L.dxy[1].x1 && L.dxy[3].x2 == L.dxy[1].x2 && L.dxy[1].y1 == L.dxy[0].y1 &&
+                       L.dxy[1].y2 == L.dxy[0].y2 && L.dxy[3].y1 == L.dxy[2].y1 && L.dxy[3].y2 == L.dxy[2].y2;
     }
   }
-  p.det_floats_per_frame = off;
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
@@ -366,7 +427,6 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
     return at;
   };
   p.off_sum = take(sizeof(int32_t) * static_cast<size_t>(B) * (H + 1) * (W + 1));
-  p.off_det = take(sizeof(float) * static_cast<size_t>(B) * off);
   p.off_cand = take(sizeof(float4) * static_cast<size_t>(B) * kSurfCap);
   p.off_keys = take(sizeof(unsigned long long) * static_cast<size_t>(B) * kSurfCap);
   p.off_count = take(sizeof(int) * static_cast<size_t>(B));
@@ -399,12 +459,12 @@ extern "C" int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, floa
   DLC_CHECK_ARG(img_dev && xy_dev && found_dev && ws_dev);
   DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0);
   const SurfPlan p = surf_plan(B, H, W, n_octaves, n_layers);
+  if (!p.structure_ok) return fail(DLC_EUNSUPPORTED, "dlc_surf_detect: unexpected box-filter layout");
   if (ws_bytes < p.total)
     return fail(DLC_ENOMEM, "dlc_surf_detect: workspace of %zu bytes needed, %zu given", p.total, ws_bytes);
   cudaStream_t s = as_stream(stream);
   char* ws = static_cast<char*>(ws_dev);
   int32_t* sum = reinterpret_cast<int32_t*>(ws + p.off_sum);
-  float* det = reinterpret_cast<float*>(ws + p.off_det);
   float4* cand = reinterpret_cast<float4*>(ws + p.off_cand);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + p.off_keys);
   int* count = reinterpret_cast<int*>(ws + p.off_count);
@@ -415,9 +475,9 @@ extern "C" int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, floa
     const SurfOctave& oc = p.oc[o];
     const int cells = oc.rows * oc.cols;
     if (cells == 0) continue;
-    surf_det_kernel<<<dim3(ceil_div(cells, 256), oc.n, B), 256, 0, s>>>(sum, H, W, oc, p.det_floats_per_frame, det);
-    surf_maxima_kernel<<<dim3(ceil_div(cells, 256), n_layers, B), 256, 0, s>>>(det, H, W, oc, o, p.det_floats_per_frame,
-                                                                             hessian_threshold, cand, keys, count);
+    const int tiles = ceil_div(oc.rows, kSurfTile) * ceil_div(oc.cols, kSurfTile);
+    surf_octave_kernel<<<dim3(tiles, 1, B), 256, sizeof(float) * oc.n * kSurfHalo * kSurfHalo, s>>>(
+        sum, H, W, oc, o, hessian_threshold, cand, keys, count);
   }
   surf_top_kernel<<<B, 256, 0, s>>>(cand, keys, count, H, W, top_n, xy_dev, info_dev, found_dev);
   DLC_CUDA(cudaGetLastError());

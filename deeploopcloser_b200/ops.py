@@ -100,7 +100,7 @@ _ws_surf = Workspace()
 def surf_detect(img, top_n=30, hessian_threshold=100.0, n_octaves=4, n_layers=3, chunk=64):
     """img uint8 [B,H,W] (CUDA) -> (xy float32 [B,top_n,2], info float32 [B,top_n,2] = (size, response),
     found int32 [B]): the top_n fast-Hessian keypoints of every frame, best response first (see dlc_surf_detect).
-    Frames are processed `chunk` at a time to bound the workspace (~10 MB per 640x480 frame)."""
+    Frames are processed `chunk` at a time to bound the workspace (~1.7 MB per 640x480 frame)."""
     _check_cuda(img)
     assert img.dtype == torch.uint8 and img.dim() == 3
     B, H, W = img.shape
