@@ -36,6 +36,10 @@ struct SurfBox {
 struct SurfLayer {
   int size, ni, nj, margin;
   SurfBox dx[3], dy[3], dxy[4];
+  // integral-image offsets (y * pitch + x) of the shared box corners, filled by surf_plan:
+  int off_dx[8];    // [top | bottom][x1_0, x2_0, x2_1, x2_2]
+  int off_dy[8];    // [left | right][y1_0, y2_0, y2_1, y2_2]
+  int off_dxy[16];  // [y1_0, y2_0, y1_2, y2_2][x1_0, x2_0, x1_1, x2_1]
 };
 struct SurfOctave {
   int step, rows, cols, n;            // n layers of rows x cols samples
@@ -106,18 +110,15 @@ __device__ __forceinline__ float haar_acc(const int (&box)[4], const float (&w)[
     if (k < n) d = __dadd_rn(d, static_cast<double>(__fmul_rn(__int2float_rn(box[k]), w[k])));
   return __double2float_rn(d);
 }
-__device__ __forceinline__ float det_at(const int32_t* __restrict__ org, int pitch, const SurfLayer& L) {
+__device__ __forceinline__ float det_at(const int32_t* __restrict__ org, const SurfLayer& L) {
   int box[4];
   float w[4];
-  {  // Dxx: rows y1 / y2 of box 0, columns x1_0, x2_0 (= x1_1), x2_1 (= x1_2), x2_2
-    const int32_t* t = org + L.dx[0].y1 * pitch;
-    const int32_t* u = org + L.dx[0].y2 * pitch;
-    const int xs[4] = {L.dx[0].x1, L.dx[0].x2, L.dx[1].x2, L.dx[2].x2};
+  {
     int top[4], bot[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      top[q] = __ldg(t + xs[q]);
-      bot[q] = __ldg(u + xs[q]);
+      top[q] = __ldg(org + L.off_dx[q]);
+      bot[q] = __ldg(org + L.off_dx[4 + q]);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -126,13 +127,12 @@ __device__ __forceinline__ float det_at(const int32_t* __restrict__ org, int pit
     }
   }
   const float dx = haar_acc(box, w, 3);
-  {  // Dyy: columns x1 / x2 of box 0, rows y1_0, y2_0, y2_1, y2_2
-    const int ys[4] = {L.dy[0].y1, L.dy[0].y2, L.dy[1].y2, L.dy[2].y2};
+  {
     int lft[4], rgt[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      lft[q] = __ldg(org + ys[q] * pitch + L.dy[0].x1);
-      rgt[q] = __ldg(org + ys[q] * pitch + L.dy[0].x2);
+      lft[q] = __ldg(org + L.off_dy[q]);
+      rgt[q] = __ldg(org + L.off_dy[4 + q]);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -141,14 +141,12 @@ __device__ __forceinline__ float det_at(const int32_t* __restrict__ org, int pit
     }
   }
   const float dy = haar_acc(box, w, 3);
-  {  // Dxy: corners on the grid {x1_0, x2_0, x1_1, x2_1} x {y1_0, y2_0, y1_2, y2_2}
-    const int xs[4] = {L.dxy[0].x1, L.dxy[0].x2, L.dxy[1].x1, L.dxy[1].x2};
-    const int ys[4] = {L.dxy[0].y1, L.dxy[0].y2, L.dxy[2].y1, L.dxy[2].y2};
+  {
     int g[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) g[r][c] = __ldg(org + ys[r] * pitch + xs[c]);
+      for (int c = 0; c < 4; ++c) g[r][c] = __ldg(org + L.off_dxy[r * 4 + c]);
     box[0] = (g[1][1] - g[1][0]) - (g[0][1] - g[0][0]);
     box[1] = (g[1][3] - g[1][2]) - (g[0][3] - g[0][2]);
     box[2] = (g[3][1] - g[3][0]) - (g[2][1] - g[2][0]);
@@ -229,15 +227,16 @@ surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_c
   const int pitch = W + 1;
   const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
   constexpr int kCells = kSurfHalo * kSurfHalo;
-  for (int e = threadIdx.x; e < oc.n * kCells; e += blockDim.x) {
-    const int l = e / kCells, rc = e - l * kCells;
-    const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
+  // layer outermost: the layer's offsets and weights are warp-uniform (they come from the parameter bank)
+  for (int l = 0; l < oc.n; ++l) {
     const SurfLayer& L = oc.layer[l];
-    const int i = i0 + r - L.margin, j = j0 + c - L.margin;    // filter origin in samples
-    float v = 0.0f;                                            // the filter does not fit here
-    if (i >= 0 && i < L.ni && j >= 0 && j < L.nj)
-      v = det_at(frame + static_cast<int64_t>(i) * oc.step * pitch + j * oc.step, pitch, L);
-    s_det[e] = v;
+    for (int rc = threadIdx.x; rc < kCells; rc += blockDim.x) {
+      const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
+      const int i = i0 + r - L.margin, j = j0 + c - L.margin;  // filter origin in samples
+      float v = 0.0f;                                          // the filter does not fit here
+      if (i >= 0 && i < L.ni && j >= 0 && j < L.nj) v = det_at(frame + (i * pitch + j) * oc.step, L);
+      s_det[l * kCells + rc] = v;
+    }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < (oc.n - 2) * kSurfTile * kSurfTile; e += blockDim.x) {
@@ -409,6 +408,20 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
       resize_pattern(dx_s, 3, L.size, L.dx);
       resize_pattern(dy_s, 3, L.size, L.dy);
       resize_pattern(dxy_s, 4, L.size, L.dxy);
+      {
+        const int pitch = W + 1;
+        const int xs[4] = {L.dx[0].x1, L.dx[0].x2, L.dx[1].x2, L.dx[2].x2};
+        const int ys[4] = {L.dy[0].y1, L.dy[0].y2, L.dy[1].y2, L.dy[2].y2};
+        const int gx[4] = {L.dxy[0].x1, L.dxy[0].x2, L.dxy[1].x1, L.dxy[1].x2};
+        const int gy[4] = {L.dxy[0].y1, L.dxy[0].y2, L.dxy[2].y1, L.dxy[2].y2};
+        for (int q = 0; q < 4; ++q) {
+          L.off_dx[q] = L.dx[0].y1 * pitch + xs[q];
+          L.off_dx[4 + q] = L.dx[0].y2 * pitch + xs[q];
+          L.off_dy[q] = ys[q] * pitch + L.dy[0].x1;
+          L.off_dy[4 + q] = ys[q] * pitch + L.dy[0].x2;
+          for (int c = 0; c < 4; ++c) L.off_dxy[q * 4 + c] = gy[q] * pitch + gx[c];
+        }
+      }
       // the shared-corner evaluation of det_at() relies on this (it follows from scaling equal coordinates equally)
       for (int k = 0; k < 3; ++k) {
         p.structure_ok = p.structure_ok && L.dx[k].y1 == L.dx[0].y1 && L.dx[k].y2 == L.dx[0].y2 &&

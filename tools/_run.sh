@@ -1,3 +1,2 @@
 timeout 900 python -m pytest tests -x -q -m gpu -k "surf" > gpurun_out/pytest_surf.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_surf.log
 timeout 600 python tools/bench_surf.py > gpurun_out/bench_surf.log 2>&1; cat gpurun_out/bench_surf.log | tail -5
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_surf.csv python tools/bench_surf.py > /dev/null 2>&1; echo "ncu exit $?"
