@@ -26,8 +26,19 @@ class LoopClosurePipeline:
         for l, (w, b) in enumerate(zip(weights, biases)):
             self.encoder.set_layer(l, w, b)
 
-    def encode(self, frames, xy):
-        """frames uint8 [B,H,W] (CUDA), xy float32 [B,P,2] (CUDA) -> float32 [B*P, D] descriptors."""
+    def detect(self, frames, n=30, **detector_args):
+        """frames uint8 [B,H,W] (CUDA) -> float32 [B,n,2] keypoint centres (x, y), best response first: the
+        fast-Hessian detector in front of the patch gather (get_top_n_key_points, CvInputParser.py:36-46). Frames
+        with fewer than n keypoints are padded with the image centre (the reference would hand the encoder fewer
+        than 30 patches and fail)."""
+        xy, _, _ = ops.surf_detect(frames, top_n=n, **detector_args)
+        return xy
+
+    def encode(self, frames, xy=None):
+        """frames uint8 [B,H,W] (CUDA), xy float32 [B,P,2] (CUDA; None: detect P = 30 keypoints per frame on the
+        device) -> float32 [B*P, D] descriptors."""
+        if xy is None:
+            xy = self.detect(frames, 30)
         if self.raw_pixels:
             hi, lo = ops.patch_gather_u8(frames, xy, self.patch, self.swap_xy_quirk), None
         else:
@@ -40,7 +51,7 @@ class LoopClosurePipeline:
         cand = ops.topk_rows(S, min(k, max(n_frames - 1, 1)), largest=True, exclude_band=exclude_band)
         return S, cand
 
-    def run(self, frames, xy, k=10, exclude_band=0):
+    def run(self, frames, xy=None, k=10, exclude_band=0):
         desc = self.encode(frames, xy)
         S, cand = self.match(desc, frames.shape[0], k, exclude_band)
         return {"descriptors": desc, "similarity": S, "candidates": cand}

@@ -38,13 +38,13 @@ class StreamingLoopCloser:
     def world(self):
         return self.db.world
 
-    def frame_descriptors(self, frames, xy):
-        desc = self.pipe.encode(frames, xy)                       # [b*P, D]
+    def frame_descriptors(self, frames, xy=None):
+        desc = self.pipe.encode(frames, xy)                       # [b*P, D]; xy None: keypoints detected on the device
         return ops.mean_pool_rows(desc, self.rows_per_frame)      # [b, D]
 
-    def step(self, frames_local, xy_local):
-        """frames_local uint8 [b, H, W], xy_local float32 [b, P, 2]: this rank's slice of the batch (same b on every
-        rank). Returns (scores [B, k], global indices [B, k]) for the whole batch, identical on every rank, matched
+    def step(self, frames_local, xy_local=None):
+        """frames_local uint8 [b, H, W], xy_local float32 [b, P, 2] (None: the fast-Hessian detector finds the 30
+        keypoints of every frame on the device): this rank's slice of the batch (same b on every rank). Returns (scores [B, k], global indices [B, k]) for the whole batch, identical on every rank, matched
         against the database as it was BEFORE this batch is inserted."""
         q_local = self.frame_descriptors(frames_local, xy_local)
         if self.world > 1:

@@ -237,3 +237,36 @@ def test_create_matrix_scripts(cuda, tmp_path):
     assert D.shape == (5, 5) and np.all(np.diag(D) == 0)
     png = cv2.imread(str(tmp_path / "d.png"), cv2.IMREAD_GRAYSCALE)
     assert np.array_equal(png, o_img.imwrite_u8(o_img.distance_image_f64(D)))
+
+
+def test_pipeline_detects_keypoints_when_none_given(cuda):
+    """LoopClosurePipeline.run(frames) with no keypoints: fast-Hessian detector -> patch gather -> encoder -> score
+    matrix, all on the device; equals the same pipeline fed the oracle detector's keypoints."""
+    import torch
+
+    from deeploopcloser_b200.pipeline import LoopClosurePipeline
+    from oracle import surf
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[0:120, 0:160].astype(np.float64)
+    frames = []
+    for _ in range(5):
+        img = np.full((120, 160), 100.0)
+        for _ in range(60):
+            s = rng.uniform(2.6, 7.0)
+            img += rng.choice([-1, 1]) * rng.uniform(30, 120) * np.exp(
+                -((xx - rng.uniform(0, 160)) ** 2 + (yy - rng.uniform(0, 120)) ** 2) / (2 * s * s))
+        frames.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+    frames = np.stack(frames)
+    dims = [1681, 128, 64]
+    ws, bs = o_sda.make_weights(dims, seed=1, scale="xavier")
+    pipe = LoopClosurePipeline(dims)
+    pipe.set_weights(ws, bs)
+    f_d = torch.from_numpy(frames).cuda()
+    got = pipe.run(f_d, k=3)
+    xy_ref = []
+    for f in frames:
+        kp = surf.top_n(surf.detect(f), 30)
+        assert len(kp) == 30                       # enough structure in the synthetic frames
+        xy_ref.append(kp[:, :2].astype(np.float32))
+    want = pipe.run(f_d, torch.from_numpy(np.stack(xy_ref)).cuda(), k=3)
+    assert torch.equal(got["descriptors"], want["descriptors"]) and torch.equal(got["similarity"], want["similarity"])

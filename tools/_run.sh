@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "surf" > gpurun_out/pytest_surf.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_surf.log
-timeout 600 python tools/bench_surf.py > gpurun_out/bench_surf.log 2>&1; cat gpurun_out/bench_surf.log | tail -5
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest.log
+timeout 300 python tools/bench_streaming.py --db-rows 1000000 --batch 256 --steps 5 > gpurun_out/stream1.log 2>&1; grep '^{' gpurun_out/stream1.log | tail -1
+timeout 300 python tools/bench_streaming.py --db-rows 1000000 --batch 256 --steps 5 --detect > gpurun_out/stream1d.log 2>&1; grep '^{' gpurun_out/stream1d.log | tail -1

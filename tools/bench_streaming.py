@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--detect", action="store_true", help="find the 30 keypoints per frame on the device (fast-Hessian "
+                    "detector) instead of feeding seeded keypoints; frames are then a smooth synthetic texture")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -44,6 +46,11 @@ def main():
     frames = torch.randint(0, 256, (b_local, args.height, args.width), dtype=torch.uint8, device="cuda", generator=g)
     xy = torch.stack([torch.rand((b_local, 30), device="cuda", generator=g) * args.width,
                       torch.rand((b_local, 30), device="cuda", generator=g) * args.height], -1).contiguous()
+    if args.detect:
+        base = torch.rand((b_local, 1, args.height // 8 + 2, args.width // 8 + 2), device="cuda", generator=g) * 255
+        frames = torch.nn.functional.interpolate(base, size=(args.height, args.width), mode="bicubic")[:, 0]
+        frames = frames.clamp(0, 255).round().to(torch.uint8).contiguous()
+        xy = None
     for _ in range(args.warmup):
         s, i = sl.step(frames, xy)
     torch.cuda.synchronize()
@@ -62,7 +69,8 @@ def main():
     own = int(((i[:, 0] - sl.db.row_offset) >= shard).sum()) if world == 1 else None
     if rank == 0:
         print(json.dumps({"bench": "streaming", "n_gpus": world, "db_rows": args.db_rows, "batch": args.batch,
-                          "frame": [args.height, args.width], "ms_per_batch": float(ms.item()),
+                          "frame": [args.height, args.width], "keypoints": "detected on the device" if args.detect else "seeded",
+                          "ms_per_batch": float(ms.item()),
                           "frames_per_s": args.batch / float(ms.item()) * 1e3,
                           "top1_is_previously_inserted_copy": own, "db_rows_after": len(sl.db.local) * world}))
     if world > 1:
