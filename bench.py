@@ -335,7 +335,26 @@ def run_ours(args):
                         "%dx that on the tensor pipe (in gram-only timing mode both gated kernels are launched, the "
                         "unselected one returns immediately); ms_with_refinement_pass adds gram_refine_fix_kernel, the "
                         "exact re-evaluation of the frame pairs the one-product kernel deferred" % (args.sim_precision, products)}
+        # stage split (each stage timed alone; informational)
+        def t_stage(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        if args.split_pixel_input:
+            stage_ms["patch_gather"] = t_stage(lambda: ops.patch_gather(frames_d, xy_d, PATCH, True,
+                                                                        need_lo=args.precision == "fp16x2"))
+        else:
+            stage_ms["patch_gather"] = t_stage(lambda: ops.patch_gather_u8(frames_d, xy_d, PATCH, True))
+        stage_ms["encode_total"] = t_stage(lambda: pipe.encode(frames_d, xy_d))
+        stage_ms["similarity_total"] = t_stage(lambda: ops.sdav_similarity(dview, precision=args.sim_precision))
         stage_ms["gram_kernel"] = gram_ms
+        stage_ms["gram_plus_refinement_pass"] = gram_total_ms
         enc_only = max(stage_ms["encode_total"] - stage_ms["patch_gather"], 1e-6)
         stage_ms["encode_tflops_algorithmic"] = N_FRAMES * ENC_FLOP_PER_FRAME / (enc_only * 1e-3) / 1e12
         if world == 1 and not args.no_cpu_baseline:
