@@ -36,10 +36,11 @@ struct SurfBox {
 struct SurfLayer {
   int size, ni, nj, margin;
   SurfBox dx[3], dy[3], dxy[4];
-  // integral-image offsets (y * pitch + x) of the shared box corners, filled by surf_plan:
-  int off_dx[8];    // [top | bottom][x1_0, x2_0, x2_1, x2_2]
-  int off_dy[8];    // [left | right][y1_0, y2_0, y2_1, y2_2]
-  int off_dxy[16];  // [y1_0, y2_0, y1_2, y2_2][x1_0, x2_0, x1_1, x2_1]
+  // integral-image BYTE offsets (4 * (y * pitch + x)) of the shared box corners, filled by surf_plan; 64-bit so that
+  // a lookup address is one 64-bit add of the sample's pointer and a parameter-bank operand
+  int64_t off_dx[8];    // [top | bottom][x1_0, x2_0, x2_1, x2_2]
+  int64_t off_dy[8];    // [left | right][y1_0, y2_0, y2_1, y2_2]
+  int64_t off_dxy[16];  // [y1_0, y2_0, y1_2, y2_2][x1_0, x2_0, x1_1, x2_1]
 };
 struct SurfOctave {
   int step, rows, cols, n;            // n layers of rows x cols samples
@@ -110,15 +111,16 @@ __device__ __forceinline__ float haar_acc(const int (&box)[4], const float (&w)[
     if (k < n) d = __dadd_rn(d, static_cast<double>(__fmul_rn(__int2float_rn(box[k]), w[k])));
   return __double2float_rn(d);
 }
-__device__ __forceinline__ float det_at(const int32_t* __restrict__ org, const SurfLayer& L) {
+__device__ __forceinline__ float det_at(const char* __restrict__ org, const SurfLayer& L) {
+#define SURF_AT(off) __ldg(reinterpret_cast<const int32_t*>(org + (off)))
   int box[4];
   float w[4];
   {
     int top[4], bot[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      top[q] = __ldg(org + L.off_dx[q]);
-      bot[q] = __ldg(org + L.off_dx[4 + q]);
+      top[q] = SURF_AT(L.off_dx[q]);
+      bot[q] = SURF_AT(L.off_dx[4 + q]);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -131,8 +133,8 @@ __device__ __forceinline__ float det_at(const int32_t* __restrict__ org, const S
     int lft[4], rgt[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      lft[q] = __ldg(org + L.off_dy[q]);
-      rgt[q] = __ldg(org + L.off_dy[4 + q]);
+      lft[q] = SURF_AT(L.off_dy[q]);
+      rgt[q] = SURF_AT(L.off_dy[4 + q]);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -146,7 +148,7 @@ __device__ __forceinline__ float det_at(const int32_t* __restrict__ org, const S
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) g[r][c] = __ldg(org + L.off_dxy[r * 4 + c]);
+      for (int c = 0; c < 4; ++c) g[r][c] = SURF_AT(L.off_dxy[r * 4 + c]);
     box[0] = (g[1][1] - g[1][0]) - (g[0][1] - g[0][0]);
     box[1] = (g[1][3] - g[1][2]) - (g[0][3] - g[0][2]);
     box[2] = (g[3][1] - g[3][0]) - (g[2][1] - g[2][0]);
@@ -155,6 +157,7 @@ __device__ __forceinline__ float det_at(const int32_t* __restrict__ org, const S
     for (int k = 0; k < 4; ++k) w[k] = L.dxy[k].w;
   }
   const float dxy = haar_acc(box, w, 4);
+#undef SURF_AT
   return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
 }
 
@@ -227,15 +230,19 @@ surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_c
   const int pitch = W + 1;
   const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
   constexpr int kCells = kSurfHalo * kSurfHalo;
-  // layer outermost: the layer's offsets and weights are warp-uniform (they come from the parameter bank)
-  for (int l = 0; l < oc.n; ++l) {
-    const SurfLayer& L = oc.layer[l];
-    for (int rc = threadIdx.x; rc < kCells; rc += blockDim.x) {
-      const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
-      const int i = i0 + r - L.margin, j = j0 + c - L.margin;  // filter origin in samples
-      float v = 0.0f;                                          // the filter does not fit here
-      if (i >= 0 && i < L.ni && j >= 0 && j < L.nj) v = det_at(frame + (i * pitch + j) * oc.step, L);
-      s_det[l * kCells + rc] = v;
+  // layer outermost and unrolled: the layer's offsets and weights are then direct parameter-bank operands
+#pragma unroll
+  for (int l = 0; l < kSurfMaxLayers; ++l) {
+    if (l < oc.n) {
+      const SurfLayer& L = oc.layer[l];
+      for (int rc = threadIdx.x; rc < kCells; rc += blockDim.x) {
+        const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
+        const int i = i0 + r - L.margin, j = j0 + c - L.margin;  // filter origin in samples
+        float v = 0.0f;                                          // the filter does not fit here
+        if (i >= 0 && i < L.ni && j >= 0 && j < L.nj)
+          v = det_at(reinterpret_cast<const char*>(frame + (i * pitch + j) * oc.step), L);
+        s_det[l * kCells + rc] = v;
+      }
     }
   }
   __syncthreads();
@@ -415,11 +422,11 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
         const int gx[4] = {L.dxy[0].x1, L.dxy[0].x2, L.dxy[1].x1, L.dxy[1].x2};
         const int gy[4] = {L.dxy[0].y1, L.dxy[0].y2, L.dxy[2].y1, L.dxy[2].y2};
         for (int q = 0; q < 4; ++q) {
-          L.off_dx[q] = L.dx[0].y1 * pitch + xs[q];
-          L.off_dx[4 + q] = L.dx[0].y2 * pitch + xs[q];
-          L.off_dy[q] = ys[q] * pitch + L.dy[0].x1;
-          L.off_dy[4 + q] = ys[q] * pitch + L.dy[0].x2;
-          for (int c = 0; c < 4; ++c) L.off_dxy[q * 4 + c] = gy[q] * pitch + gx[c];
+          L.off_dx[q] = 4ll * (L.dx[0].y1 * pitch + xs[q]);
+          L.off_dx[4 + q] = 4ll * (L.dx[0].y2 * pitch + xs[q]);
+          L.off_dy[q] = 4ll * (ys[q] * pitch + L.dy[0].x1);
+          L.off_dy[4 + q] = 4ll * (ys[q] * pitch + L.dy[0].x2);
+          for (int c = 0; c < 4; ++c) L.off_dxy[q * 4 + c] = 4ll * (gy[q] * pitch + gx[c]);
         }
       }
       // the shared-corner evaluation of det_at() relies on this (it follows from scaling equal coordinates equally)

@@ -1,3 +1,2 @@
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "exit $?"; tail -1 gpurun_out/bench_default.log > gpurun_out/r1_bench_1gpu_v4.json; python -c "import json; d=json.load(open('gpurun_out/r1_bench_1gpu_v4.json')); print(round(d['value']), round(d['ms_per_step'],3), d['e2e'], d['clocks'], {k:v for k,v in d['roofline'].items() if k not in ('note','precision_probe')}, d['cpu_baseline']['value'], d['gpu_launches'], d['stages_ms'])"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | cut -c1-300
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()"
+timeout 900 python -m pytest tests -x -q -m gpu -k "surf or detects" > gpurun_out/pytest_surf.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_surf.log
+timeout 600 python tools/bench_surf.py > gpurun_out/bench_surf.log 2>&1; cat gpurun_out/bench_surf.log | tail -5
