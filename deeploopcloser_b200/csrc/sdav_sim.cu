@@ -94,7 +94,9 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   const int64_t r = static_cast<int64_t>(f) * P + k;          // source row / N-side plane row
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
+  const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
+#pragma unroll 2
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     float x[8];
 #pragma unroll
@@ -113,13 +115,25 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
     }
     __align__(16) __half hh[8];
     __align__(16) __half ll[8];
+    double wv[8];
+    if (valid && wvec && c0 + 8 <= D) {   // four 16-byte loads of the weights instead of eight 8-byte ones
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 t = *reinterpret_cast<const double2*>(w + c0 + 2 * j);
+        wv[2 * j] = t.x;
+        wv[2 * j + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = (valid && c0 + j < D) ? w[c0 + j] : 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       split_f32(x[j], hh[j], ll[j]);
       if (valid && c0 + j < D) {
         const double xd = static_cast<double>(x[j]);
         n2 += xd * xd;
-        pr += xd * w[c0 + j];
+        pr += xd * wv[j];
       }
     }
     const int64_t oa = static_cast<int64_t>(warp) * ld + c0;

@@ -213,9 +213,11 @@ def sdav_weights(desc, mu=0.5, sigma=0.2):
     return w
 
 
-def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="fp16x2",
+def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="auto",
                     full_asymmetric=False, out=None):
-    """desc float32 [N,P,D] -> float32 [N,N] score matrix (reference order: i<j mirrored, diagonal -1)."""
+    """desc float32 [N,P,D] -> float32 [N,N] score matrix (reference order: i<j mirrored, diagonal -1).
+    precision: "auto" (default: one fp16 product + exact second pass over the ambiguous rows when a device-side probe
+    expects few of them, else three products), "fp16r" (always the former), "fp16x2" (always three products), "fp16"."""
     _check_cuda(desc, weights)
     N, P, D = desc.shape
     if out is None:
@@ -226,7 +228,7 @@ def sdav_similarity(desc, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, prec
     return out
 
 
-def sdav_similarity_part(desc, part, n_parts, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="fp16x2",
+def sdav_similarity_part(desc, part, n_parts, mu=0.5, sigma=0.2, a=10.0, b=-10.0, weights=None, precision="auto",
                          out=None):
     """The entries of the [N,N] score matrix owned by `part` of `n_parts` (other entries zero): sum over parts = the
     full matrix of sdav_similarity."""

@@ -6,7 +6,7 @@ import numpy as np
 
 
 class SimilarityCalculator:
-    def __init__(self, dataset, mu=0.5, sigma=0.2, a=10, b=-10, precision="fp16x2"):
+    def __init__(self, dataset, mu=0.5, sigma=0.2, a=10, b=-10, precision="auto"):
         self.mu = mu
         self.sigma = sigma
         self.a = a
