@@ -151,6 +151,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
 }  // namespace dlc
 
 using namespace dlc;
+extern int g_probe_side_stream;  // sdav_sim.cu
 
 extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 * 64; }
 
@@ -181,6 +182,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 2 && value >= 32) {
     g_promote_k = value;
+    return DLC_OK;
+  }
+  if (key == 9) {  // 0: the similarity precision probe runs on the caller's stream instead of its side stream
+    g_probe_side_stream = value ? 1 : 0;
     return DLC_OK;
   }
   if (key == 8) {  // capacity of the deferred-refinement list of the SDAV score kernel (-1: default, 0: refine in place)

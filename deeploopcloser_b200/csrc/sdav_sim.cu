@@ -912,6 +912,31 @@ static int run_gram_pair(const SimWorkspace& L, char* ws, GramParams p, cudaStre
 
 using namespace dlc;
 
+// Side stream of the precision probe: rep_mask + gram_probe read only the descriptors, so they run next to the
+// dataset-mean / prep_rows chain (which they do not depend on) and join before the probe is finalised - 0.12 ms of
+// latency-bound kernels off the critical path. One stream + two events per host thread and device, created lazily;
+// the fork / join is plain event ordering, so the call stays capturable and makes no host synchronisation.
+int g_probe_side_stream = 1;  // dlc_debug_set key 9 (0: everything on the caller's stream)
+struct ProbeSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ProbeSide* probe_side() {
+  thread_local ProbeSide side[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  ProbeSide& p = side[dev];
+  if (!p.stream) {
+    if (cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p.join, cudaEventDisableTiming) != cudaSuccess) {
+      p.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &p;
+}
+
 // Developer switch (dlc_debug_set key 1): launch only the Gram/score kernel, reusing the operand planes, statistics
 // and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
 static int g_gram_only = 0;
@@ -988,7 +1013,30 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
   uint32_t* rep = reinterpret_cast<uint32_t*>(ws + L.off_rep);
   static thread_local std::vector<int2> tiles, pair_tiles;
+  const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
+  ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
+  float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
+  ProbeSide* side = nullptr;
   if (!g_gram_only) {
+  // 0. precision probe, part one (classes of bit-identical rows, single-product error on sampled rows): reads only the
+  //    descriptors - forked onto the side stream so that it overlaps steps 1 and 2
+  if (probe) {
+    DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
+    side = g_probe_side_stream ? probe_side() : nullptr;
+    cudaStream_t ps = s;
+    if (side) {
+      DLC_CUDA(cudaEventRecord(side->fork, s));
+      DLC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      ps = side->stream;
+    }
+    rep_mask_kernel<<<N, 1024, 0, ps>>>(desc_dev, N, P, D, rep);
+    if (N >= 2) {
+      gram_probe_kernel<<<kProbeSamples, 1024, 0, ps>>>(desc_dev, N, P, D, rep, acc, gaps);
+    } else {
+      DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, ps));  // large gaps: nothing to refine
+    }
+    if (side) DLC_CUDA(cudaEventRecord(side->join, side->stream));
+  }
   // 1. dataset mean -> distinctive weights w
   if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
     w = const_cast<double*>(w_dev);
@@ -1001,27 +1049,18 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   //    the residual planes are written later and only if the probe picks the three-product kernel.
   {
     const bool sep = L.col_stride != kFrameRows;
-    const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
     const bool lo_now = precision == DLC_PREC_FP16X2;
-    ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
-    if (probe) DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
     prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
         desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi),
         lo_now ? reinterpret_cast<__half*>(ws + L.off_lo) : nullptr,
         sep ? reinterpret_cast<__half*>(ws + L.off_bhi) : nullptr,
         sep && lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw,
         probe ? &acc->nmax_bits : nullptr);
-    // 3. precision probe: classes of bit-identical rows, then the single-product error on sampled rows -> margin and
-    //    the device-side choice between the two Gram kernels
+    // 3. precision probe, part two (needs the largest row norm of step 2): margin and the device-side choice between
+    //    the two Gram kernels
     if (probe) {
       GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
-      float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
-      rep_mask_kernel<<<N, 1024, 0, s>>>(desc_dev, N, P, D, rep);
-      if (N >= 2) {
-        gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_dev, N, P, D, rep, acc, gaps);
-      } else {
-        DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
-      }
+      if (side) DLC_CUDA(cudaStreamWaitEvent(s, side->join, 0));
       gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, g_max_flag_frac,
                                                    precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
       if (precision == DLC_PREC_AUTO)  // fp16r never runs the three-product kernel
