@@ -282,7 +282,9 @@ def _check_topk(scores, idx, ref_scores, k, smaller, scale=None):
 
 @pytest.mark.parametrize("metric", ["cos", "dot", "l2"])
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
-@pytest.mark.parametrize("B,N,D,k", [(5, 1000, 128, 10), (130, 5000, 2500, 10), (300, 70000, 256, 32), (1, 37, 64, 5)])
+# B = 130 / 256 / 512: an even number of 128-query tiles -> the CTA-pair kernel (two lists per query and CTA group)
+@pytest.mark.parametrize("B,N,D,k", [(5, 1000, 128, 10), (130, 5000, 2500, 10), (300, 70000, 256, 32), (1, 37, 64, 5),
+                                     (256, 9000, 192, 32), (512, 40000, 128, 10)])
 def test_match_topk(cuda, metric, dtype, B, N, D, k):
     from deeploopcloser_b200.matcher import KeyframeDatabase
     rng = np.random.default_rng(B + N)

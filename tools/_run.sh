@@ -1,3 +1,2 @@
-timeout 300 python tools/ab_probe_side.py > gpurun_out/ab_probe_side.log 2>&1; tail -3 gpurun_out/ab_probe_side.log
-timeout 900 python -m pytest tests -x -q -m gpu -k "simil or sdav or fullsize or pipeline or stream" > gpurun_out/pytest_sim.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_sim.log
-timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_nocpu.log 2>&1; tail -1 gpurun_out/bench_nocpu.log | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), d['e2e']['ms_per_step'], d['clocks']['sm_mhz'], d['stages_ms'])"
+timeout 900 python -m pytest tests -x -q -m gpu -k "match or stream or fullsize or sharded or db" > gpurun_out/pytest_match.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest_match.log
+timeout 600 python tools/bench_matcher.py --rows 1000000 --dim 4096 --batches 32,256,512,1024,4096 > gpurun_out/matcher_pair.log 2>&1; grep '^{' gpurun_out/matcher_pair.log | cut -c1-330
