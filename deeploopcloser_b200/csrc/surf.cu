@@ -258,6 +258,15 @@ surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_c
     const float* d1 = s_det + l * kCells + r * kSurfHalo + c;
     const float val0 = d1[0];
     if (!(val0 > thr)) continue;
+    // strict maximum of the 3x3x3 neighbourhood: the 8 neighbours of the own layer first (a random sample fails
+    // there 8 times out of 9), the other two layers and the interpolation stencil only for the survivors
+    bool is_max = true;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di)
+#pragma unroll
+      for (int dj = -1; dj <= 1; ++dj)
+        if (di != 0 || dj != 0) is_max = is_max && (val0 > d1[di * kSurfHalo + dj]);
+    if (!is_max) continue;
     float N9[3][9];
 #pragma unroll
     for (int dl = 0; dl < 3; ++dl)
@@ -266,12 +275,8 @@ surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_c
 #pragma unroll
         for (int dj = 0; dj < 3; ++dj)
           N9[dl][di * 3 + dj] = d1[(dl - 1) * kCells + (di - 1) * kSurfHalo + (dj - 1)];
-    bool is_max = true;
-  #pragma unroll
-    for (int dl = 0; dl < 3; ++dl)
-  #pragma unroll
-      for (int q = 0; q < 9; ++q)
-        if (!(dl == 1 && q == 4)) is_max = is_max && (val0 > N9[dl][q]);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) is_max = is_max && (val0 > N9[0][q]) && (val0 > N9[2][q]);
     if (!is_max) continue;
     const int sum_i = oc.step * (i - (size / 2) / oc.step);
     const int sum_j = oc.step * (j - (size / 2) / oc.step);
