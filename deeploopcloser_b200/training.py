@@ -185,6 +185,11 @@ class DaeStackTrainer:
         self.last_grads = {"dW": {l: dW for l, dW, _ in grads}, "db": {l: db for l, _, db in grads}, "dbd": dbd}
         return loss
 
+    def graphed_step(self, x, top, keep_masks, add_masks=None, mask_rows=None, da_mode=False):
+        """The same step captured once in a CUDA graph (see GraphedStep): for the fit loops, which repeat one step
+        shape `epochs` times per batch and are launch-bound at the reference's batch of 10 frames."""
+        return GraphedStep(self, x, top, keep_masks, add_masks, mask_rows, da_mode)
+
     # ---- mask generators (device-side draws; the reference's are unseeded NumPy / TensorFlow shuffles)
     def sdav_masks(self, top, level, generator=None):
         """One [P, in_l] masking-noise mask per layer l <= top with exactly round(P * in_l * level) zeros
@@ -208,3 +213,50 @@ class DaeStackTrainer:
         coin = torch.rand(n, device=self.device, generator=generator) < 0.5
         om = ((zm == 0) & coin).to(torch.float32)
         return zm.reshape(rows, self.dims[0]), om.reshape(rows, self.dims[0])
+
+
+class GraphedStep:
+    """One `DaeStackTrainer.step` (fixed batch shape, loss layer and mask layout) captured in a CUDA graph.
+    At the reference's batch (10 frames x 30 patches) a step is ~25-60 short kernels plus as many allocator calls:
+    launch-bound. The graph replays them with one launch; inputs are copied into the captured buffers. Same kernels,
+    same order, same arithmetic as the eager step (tests/test_gpu_training.py compares them bit for bit).
+
+        g = trainer.graphed_step(x, top, masks)        # captures; performs NO update
+        loss = g(x, masks)                             # one SGD step; `loss` is overwritten by the next call"""
+
+    def __init__(self, trainer, x, top, keep_masks, add_masks=None, mask_rows=None, da_mode=False):
+        self.trainer = trainer
+        self.x = x.to(torch.float32).contiguous().clone()
+        self.keep = None if keep_masks is None else [None if m is None else m.clone() for m in keep_masks]
+        self.add = None if add_masks is None else [None if m is None else m.clone() for m in add_masks]
+        args = dict(mask_rows=mask_rows, da_mode=da_mode)
+        # warm-up on a side stream without touching the weights: first-launch attributes, allocator sizing
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                trainer.step(self.x, top, self.keep, self.add, apply_update=False, **args)
+        torch.cuda.current_stream().wait_stream(side)
+        step0 = trainer.global_step
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = trainer.step(self.x, top, self.keep, self.add, apply_update=True, **args)
+        trainer.global_step = step0          # capturing executes nothing
+
+    @staticmethod
+    def _copy_masks(dst, src):
+        if dst is None:
+            return
+        for d, m in zip(dst, src):
+            if d is not None:
+                d.copy_(m)
+
+    def __call__(self, x, keep_masks=None, add_masks=None):
+        self.x.copy_(x.reshape(self.x.shape))
+        if keep_masks is not None:
+            self._copy_masks(self.keep, keep_masks)
+        if add_masks is not None:
+            self._copy_masks(self.add, add_masks)
+        self.graph.replay()
+        self.trainer.global_step += 1
+        return self.loss

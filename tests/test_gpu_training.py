@@ -118,3 +118,31 @@ def test_sdav_and_da_fit_api(cuda, tmp_path):
     l0 = sda._layers[0]
     first_loss = l0.fit_dataset(list(frames[:4]))           # continues from the trained weights, same fixed masks
     assert first_loss < 1e9 and l0.global_step == 2 * 4 + 4
+
+
+@pytest.mark.parametrize("dims,top", [((70, 96, 40), 1), ((300, 130, 64, 33), 2)])
+def test_graphed_step_equals_eager(cuda, dims, top):
+    """DaeStackTrainer.graphed_step: the SGD step replayed as a CUDA graph gives the same losses (to the last bits of
+    their atomically summed float64) and bit-identical weights as the eager step over several steps with fresh masks;
+    capturing performs no update."""
+    from deeploopcloser_b200.training import DaeStackTrainer
+    B, P = 4, 5
+    rng, x, Ws, bs, bds = _setup(dims, B, P, 11, 0.3)
+    xd = torch.from_numpy(x).float().cuda()
+    a, b = DaeStackTrainer(dims, patches=P), DaeStackTrainer(dims, patches=P)
+    a.set_weights(Ws, bs, bds)
+    b.set_weights(Ws, bs, bds)
+    mask_sets = [[torch.from_numpy(o_train.sdav_mask(P, d, 0.3, rng)).float().cuda() for d in dims[:top + 1]]
+                 for _ in range(3)]
+    g = b.graphed_step(xd, top, mask_sets[0])
+    assert b.global_step == 0
+    for w0, w1 in zip(a.get_weights()[0], b.get_weights()[0]):
+        assert np.array_equal(w0, w1)                      # nothing moved during warm-up / capture
+    for masks in mask_sets:
+        la = float(a.step(xd, top, masks).item())
+        lb = float(g(xd, masks).item())
+        assert abs(la - lb) <= 1e-13 * abs(la)          # the loss is summed with float64 atomics: last-bit order effects
+    assert a.global_step == b.global_step == 3
+    for wa, wb in zip(a.get_weights(), b.get_weights()):
+        for u, v in zip(wa, wb):
+            assert np.array_equal(u, v)

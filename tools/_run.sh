@@ -1,3 +1,1 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest.log 2>&1; echo "exit $?"; tail -3 gpurun_out/pytest.log
-timeout 900 python bench.py > gpurun_out/bench_default.log 2>&1; echo "exit $?"; tail -1 gpurun_out/bench_default.log > gpurun_out/r1_bench_1gpu_v5.json; python -c "import json; d=json.load(open('gpurun_out/r1_bench_1gpu_v5.json')); print(round(d['value']), round(d['ms_per_step'],3), d['e2e']['ms_per_step'], d['clocks'], d['roofline']['ms_per_launch'], d['roofline']['frac'], d['cpu_baseline']['value'], d['gpu_launches'], d['stages_ms'])"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_v9.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu exit $?"
+timeout 900 python -m pytest tests/test_gpu_training.py tests/test_gpu_api.py -x -q -m gpu > gpurun_out/pytest_train.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_train.log

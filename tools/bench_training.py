@@ -40,6 +40,16 @@ for top in [int(v) for v in args.layers.split(",")]:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    g = tr.graphed_step(xd, top, masks)
+    for _ in range(3):
+        g(xd, masks)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        g(xd, masks)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / reps
     # forward + decoder + 2 gradient GEMMs at the top, forward + input-gradient below, weight gradients everywhere
     R = B * P
     flop = 0
@@ -49,7 +59,7 @@ for top in [int(v) for v in args.layers.split(",")]:
         flop += 2 * R * kn * (2 if l == top else 1)     # weight gradient (two contractions at the top)
     flop += 2 * R * dims[top] * dims[top + 1] * 2        # decoder forward, gradient into the hidden layer
     flop -= 2 * R * dims[0] * dims[1] if top > 0 else 0  # layer 0 has no input gradient
-    out = {"bench": "train_step", "loss_layer": top, "batch_frames": B, "rows": R, "gpu_ms_per_step": ms,
+    out = {"bench": "train_step", "loss_layer": top, "batch_frames": B, "rows": R, "gpu_ms_per_step": ms, "gpu_ms_per_step_cuda_graph": ms_graph,
            "algorithmic_gflop_per_step": flop / 1e9, "gpu_tflops": flop / ms / 1e9}
     if args.cpu:
         from oracle import train as o_train
