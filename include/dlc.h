@@ -59,10 +59,18 @@ extern "C" {
 
 const char* dlc_last_error(void);
 int dlc_version(void);
-/* Developer switch (key 0: K-block of the 3-product kernel, 32 or 64). Not part of the drop-in surface. */
+/* Developer switches for A/B measurements and tests; not part of the drop-in surface, defaults in brackets.
+ *   0: K block of the 3-product kernel, 32 or 64 [32]         1: (see dlc_sdav_debug_gram_only)
+ *   2: K elements accumulated in TMEM before promotion [256]   3: kernel experiment flags [0]
+ *   4: M tiles per L2 super-block of the SDAV tile order [32]  5: plane outputs through staged TMA stores [1]
+ *   6: CTA-pair kernels: 0 never, 1 when the problem fills the GPU, 2 whenever the shape allows [1]
+ *   7: SDAV Gram kernels on CTA pairs [1]
+ *   8: capacity of the deferred-refinement list of the SDAV score kernel; 0 = refine inside the epilogue [-1: default]
+ *   9: SDAV precision probe on its side stream [1] */
 int dlc_debug_set(int key, int value);
-/* Developer switch: when on, dlc_sdav_similarity launches only its Gram/score kernel and reuses the workspace
- * contents of the previous full call (used by bench.py to time that kernel alone). */
+/* Timing aid: 1 = dlc_sdav_similarity launches only the Gram / score kernels (+ refinement pass) on the operand
+ * planes, statistics and tile list a previous full call left in the workspace; 2 = without the refinement pass
+ * (results incomplete); 0 = normal. */
 int dlc_sdav_debug_gram_only(int on);
 /* 0 when the current CUDA device can run this library (compute capability 10.x), DLC_EUNSUPPORTED otherwise. */
 int dlc_device_check(void);
