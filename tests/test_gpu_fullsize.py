@@ -180,3 +180,32 @@ def test_config5_streaming_batch_256(cuda):
     s1, i1 = sl.step(frames, xy)
     assert torch.equal(i1[:, 0].cpu(), torch.arange(256))
     assert bool((s1[:, 0] > 0.999).all()) and len(sl.db.local) == 512
+
+
+def test_fullsize_keypoint_detector(cuda):
+    """Detector at the sizes of configs 2 and 5 (1063 frames 192x240; 64 frames 480x640): invariants over the whole
+    batch (in bounds, responses sorted, at least 30 keypoints on textured frames, idempotence, batch == frame by
+    frame) and sampled frames against the oracle bit for bit."""
+    from deeploopcloser_b200 import ops
+    from oracle import surf
+    for B, H, W, sample in ((1063, 192, 240, (0, 531, 1062)), (64, 480, 640, (7,))):
+        g = torch.Generator(device="cuda")
+        g.manual_seed(B)
+        base = torch.rand((B, 1, H // 8 + 2, W // 8 + 2), device="cuda", generator=g) * 255
+        frames = torch.nn.functional.interpolate(base, size=(H, W), mode="bicubic")[:, 0].clamp(0, 255).round()
+        frames = frames.to(torch.uint8).contiguous()
+        xy, info, found = ops.surf_detect(frames, top_n=30)
+        xy2, info2, found2 = ops.surf_detect(frames, top_n=30, chunk=17)        # other chunking, same result
+        assert torch.equal(xy, xy2) and torch.equal(info, info2) and torch.equal(found, found2)
+        assert int(found.min()) >= 30 and int(found.max()) <= ops.SURF_CANDIDATE_CAP
+        assert bool((xy[..., 0] >= 0).all()) and bool((xy[..., 0] <= W - 1).all())
+        assert bool((xy[..., 1] >= 0).all()) and bool((xy[..., 1] <= H - 1).all())
+        resp = info[..., 1]
+        assert bool((resp[:, :-1] >= resp[:, 1:]).all()) and bool((resp > 100.0).all())
+        f_np = frames.cpu().numpy()
+        for b in sample:
+            kp = surf.detect(f_np[b])
+            ref = surf.top_n(kp, 30)
+            assert int(found[b]) == len(kp)
+            assert np.array_equal(xy[b].cpu().numpy(), ref[:, :2].astype(np.float32))
+            assert np.array_equal(info[b].cpu().numpy(), ref[:, 2:4].astype(np.float32))
