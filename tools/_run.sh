@@ -1,1 +1,1 @@
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:prep_rows|gram_refine_fix|gram_probe_kernel|rep_mask|gemm_pair_kernel|colsum|patch_gather|topk|weights_kernel' --launch-skip 16 -c 16 -o gpurun_out/prof_step_r1v8 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
+timeout 300 python tools/ab_layer_bk.py > gpurun_out/ab_layer_bk.log 2>&1; tail -9 gpurun_out/ab_layer_bk.log
