@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DLC_LIB_PATH") or os.path.join(_HERE, "libdlc.so")  # env override: developer A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
-PREC_FP16, PREC_FP16X2, PREC_BF16, PREC_AUTO, PREC_FP16_REFINED = 0, 1, 2, 3, 4
+PREC_FP16, PREC_FP16X2, PREC_BF16, PREC_AUTO, PREC_FP16_REFINED, PREC_FP16X2_A16 = 0, 1, 2, 3, 4, 5
 F32, F64, F16, BF16, U8, I32 = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 METRIC_COS, METRIC_DOT, METRIC_L2 = 0, 1, 2
@@ -51,6 +51,9 @@ PROTOTYPES = {
     "dlc_sda_set_layer": (_i, [_p, _i, _p, _p]),
     "dlc_sda_workspace_bytes": (_sz, [_p, _i]),
     "dlc_sda_encode": (_i, [_p, _p, _p, _i, _p, _p, _sz, _p]),
+    "dlc_sda_probe": (_i, [_p, _p, _p, _i, _p, _sz, _p]),
+    "dlc_sda_chosen_precision": (_i, [_p]),
+    "dlc_sda_probe_stats": (_i, [_p, _p]),
     "dlc_sdav_similarity_workspace_bytes": (_sz, [_i, _i, _i]),
     "dlc_sdav_similarity": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _p, _p, _sz, _p]),
     "dlc_sdav_similarity_part": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
@@ -88,7 +91,7 @@ PROTOTYPES = {
     "dlc_maxpool_planes": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "dlc_cnnvtl_quantise": (_i, [C.POINTER(_p), C.POINTER(_i64), _i, _i, _p, _i, _p, _p, _p]),
 }
-_CHECKED = {n for n, (r, _) in PROTOTYPES.items() if r is _i and n not in ("dlc_version", "dlc_sm_count", "dlc_plane_ld")}
+_CHECKED = {n for n, (r, _) in PROTOTYPES.items() if r is _i and n not in ("dlc_version", "dlc_sm_count", "dlc_plane_ld", "dlc_sda_chosen_precision")}
 
 _lib = None
 

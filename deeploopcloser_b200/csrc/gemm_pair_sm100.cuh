@@ -246,13 +246,14 @@ template <class Policy>
 inline cudaError_t launch_gemm_pair(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
                                     const CUtensorMap& b1, const typename Policy::Params& p, int clusters,
                                     cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    static_assert(smem_bytes<Policy>() <= kSmemLimit, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(smem_bytes<Policy>() <= kSmemLimit, "exceeds the 227 KB per-CTA shared memory limit");
+  static std::atomic<bool> attr_set[kMaxDevices] = {};  // per device, see launch_gemm
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes<Policy>());
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   gemm_pair_kernel<Policy><<<2 * clusters, kGemmThreadsPromote, smem_bytes<Policy>(), stream>>>(a0, a1, b0, b1, p);
   return cudaGetLastError();

@@ -13,6 +13,7 @@
 // What happens to an accumulator tile is decided by the Policy's Epilogue (bias+sigmoid+re-split, argmin/score,
 // running top-k, ...), which reads TMEM directly - accumulators never visit HBM.
 #pragma once
+#include <atomic>
 #include <type_traits>
 #include <utility>
 
@@ -478,6 +479,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // Host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -557,26 +565,28 @@ inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
                                const CUtensorMap& b1, const typename Policy::Params& p, int grid,
                                cudaStream_t stream) {
   using Cfg = typename Policy::Cfg;
-  static bool attr_set = false;
-  if (!attr_set) {
-    static_assert(smem_bytes<Policy>() <= kSmemLimit, "exceeds the 227 KB per-CTA shared memory limit");
-    static_assert(policy_scratch<Policy>::value % 1024 == 0, "epilogue scratch must be a multiple of 1024 bytes");
+  static_assert(smem_bytes<Policy>() <= kSmemLimit, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(policy_scratch<Policy>::value % 1024 == 0, "epilogue scratch must be a multiple of 1024 bytes");
+  // the opt-in shared-memory size is a per-device function attribute: remember it per device, not per process
+  static std::atomic<bool> attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes<Policy>());
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   gemm_tc_kernel<Policy><<<grid, gemm_threads<Policy>(), smem_bytes<Policy>(), stream>>>(a0, a1, b0, b1, p);
   return cudaGetLastError();
 }
 
-inline int sm_count() {
-  static int n = 0;
+inline int sm_count() {  // of the CURRENT device (cached per device)
+  static std::atomic<int> cache[kMaxDevices] = {};
+  const int dev = current_device();
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

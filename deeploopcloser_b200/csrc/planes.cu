@@ -100,7 +100,7 @@ template <class Policy>
 static cudaError_t launch_gemm_pair_if(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
                                        const CUtensorMap& b1, const BiasActParams& p, int clusters,
                                        cudaStream_t stream) {
-  if constexpr (Policy::Cfg::NPROD == 3) return launch_gemm_pair<Policy>(a0, a1, b0, b1, p, clusters, stream);
+  if constexpr (!policy_im2col_a<Policy>::value) return launch_gemm_pair<Policy>(a0, a1, b0, b1, p, clusters, stream);
   else return cudaErrorInvalidValue;
 }
 
@@ -135,10 +135,14 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   // CTA pairs (cta_group::2) for large 3-product contractions: each CTA stages half of the B tile, see
   // gemm_pair_sm100.cuh. Needs an even split of n_tile into UMMA-legal halves and enough tiles to fill the GPU.
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  if (split && g_cta_pair && p.n_tile % 32 == 0 && (pair_tiles >= sm_count() / 2 || g_cta_pair == 2)) {
+  // One-product contractions run on pairs too: a single CTA needs (128 + n_tile) x BK operand bytes per MMA step,
+  // more than L2 -> SM sustains at the tensor peak (what the one-product Gram kernel showed).
+  if (!policy_im2col_a<Policy>::value && g_cta_pair && p.n_tile % 32 == 0 &&
+      (pair_tiles >= sm_count() / 2 || g_cta_pair == 2)) {
     if (!make_tmap_k_major(&tb0, b_hi, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile / 2) ||
-        !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile / 2))
+        (split && !make_tmap_k_major(&tb1, b_lo, p.ab_fmt, ld, n_pad, ld, BK, p.n_tile / 2)))
       return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (pair B)");
+    if (!split) tb1 = tb0;
     e = launch_gemm_pair_if<Policy>(ta0, ta1, tb0, tb1, p, std::min(pair_tiles, sm_count() / 2), stream);
   } else {
     const int grid = total < sm_count() ? total : sm_count();

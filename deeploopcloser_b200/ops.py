@@ -10,7 +10,8 @@ from . import _lib
 from ._cuda import Workspace, ptr, stream_ptr
 
 PRECISIONS = {"fp16": _lib.PREC_FP16, "fp16x2": _lib.PREC_FP16X2, "bf16": _lib.PREC_BF16, "auto": _lib.PREC_AUTO,
-              "fp16r": _lib.PREC_FP16_REFINED}
+              "fp16r": _lib.PREC_FP16_REFINED, "fp16x2a16": _lib.PREC_FP16X2_A16}
+PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
 METRICS = {"cos": _lib.METRIC_COS, "cosine": _lib.METRIC_COS, "dot": _lib.METRIC_DOT, "l2": _lib.METRIC_L2}
 _DT = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
@@ -184,9 +185,30 @@ class SdaEncoder:
         _lib.call("dlc_sda_encode", self._h, ptr(x_hi), ptr(x_lo), rows, ptr(out), ws, ws_bytes, stream_ptr())
         return out
 
+    def probe_planes(self, x_hi, x_lo, rows):
+        """precision="auto": choose the arithmetic now from a sample of this input (synchronises; see dlc_sda_probe).
+        encode_planes does it implicitly on its first call after set_layer."""
+        ws, ws_bytes = self._ws.get(_lib.call("dlc_sda_workspace_bytes", self._h, rows))
+        _lib.call("dlc_sda_probe", self._h, ptr(x_hi), ptr(x_lo), rows, ws, ws_bytes, stream_ptr())
+        return self.chosen_precision()
+
+    def chosen_precision(self):
+        """Name of the arithmetic encode uses ("fp16" = one tensor product, "fp16x2a16" = two, "fp16x2" = three);
+        "unprobed" for an auto encoder before its first encode."""
+        return PRECISION_NAMES.get(int(_lib.call("dlc_sda_chosen_precision", self._h)), "unprobed")
+
+    def probe_stats(self):
+        """(one-product, two-product) max relative descriptor error against three products on the probe sample."""
+        out = (C.c_double * 2)()
+        _lib.call("dlc_sda_probe_stats", self._h, C.cast(out, C.c_void_p))
+        return float(out[0]), float(out[1])
+
+    def needs_lo_input(self):
+        return precision_code(self.precision) in (_lib.PREC_FP16X2, _lib.PREC_AUTO) and not self.input_u8
+
     def encode(self, x):
         """x [rows, in] f32/f64 CUDA -> float32 [rows, out]."""
-        split = precision_code(self.precision) == _lib.PREC_FP16X2
+        split = precision_code(self.precision) in (_lib.PREC_FP16X2, _lib.PREC_AUTO)
         hi, lo = split_planes(x, need_lo=split)
         return self.encode_planes(hi, lo, x.shape[0])
 

@@ -9,6 +9,9 @@ class LoopClosurePipeline:
     def __init__(self, dims=(1681, 2500, 2500, 2500, 2500, 2500), precision="fp16x2", patch=41, swap_xy_quirk=True,
                  mu=0.5, sigma=0.2, a=10.0, b=-10.0, sim_precision="auto", raw_pixels=True):
         self.dims = list(dims)
+        # encoder arithmetic: "fp16x2" (three tensor products: holds 1e-3 on the reference's N(0,1) initialisation),
+        # "fp16" (one), "fp16x2a16" (two) or "auto" (the cheapest of them that stays inside the descriptor tolerance
+        # on a sample of the first batch - one product for trained-like weights, see dlc_sda_probe)
         self.precision = precision
         # "auto" (default): a device-side probe picks one fp16 product + exact refinement of the ambiguous rows when
         # few rows need it (< 1.2 %; bit-identical duplicate patches never do), else the three-product kernel.
@@ -42,7 +45,7 @@ class LoopClosurePipeline:
         if self.raw_pixels:
             hi, lo = ops.patch_gather_u8(frames, xy, self.patch, self.swap_xy_quirk), None
         else:
-            hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=self.precision == "fp16x2")
+            hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=self.encoder.needs_lo_input())
         return self.encoder.encode_planes(hi, lo, hi.shape[0])
 
     def match(self, desc, n_frames, k=10, exclude_band=0):

@@ -39,6 +39,14 @@ extern "C" {
 #define DLC_PREC_FP16_REFINED 4 /* one fp16 product; rows whose nearest-neighbour choice is ambiguous under the   */
                                 /* fp16 rounding error are re-evaluated exactly (float64-accumulated distances)   */
 
+/* dlc_sda_* only: */
+#define DLC_PREC_FP16X2_A16 5   /* two products: weights split hi/lo, activations rounded to fp16 between layers    */
+/* DLC_PREC_AUTO on dlc_sda_create: the handle keeps split weights and picks the cheapest of FP16 (1 product),
+ * FP16X2_A16 (2) and FP16X2 (3) whose sampled descriptors stay within 3e-4 of the three-product forward on the
+ * handle's OWN weights and the caller's own input (dlc_sda_probe; run implicitly by the first dlc_sda_encode). The
+ * reference restores trained checkpoints when it has them (SDAV.py:232-240) - well-scaled weights pass with one
+ * product - and otherwise draws N(0,1) weights (:189-217), whose saturating pre-activations need all three. */
+
 /* dtypes for untyped buffers */
 #define DLC_F32 0
 #define DLC_F64 1
@@ -150,6 +158,7 @@ int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, float hessian_t
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct dlc_sda dlc_sda;
 /* dims has n_layers+1 entries (1681,2500,2500,2500,2500,2500 for SDAV; in,hidden for one DA). */
+/* precision: DLC_PREC_FP16, DLC_PREC_FP16X2_A16, DLC_PREC_FP16X2 or DLC_PREC_AUTO. */
 int dlc_sda_create(dlc_sda** h, int n_layers, const int* dims, int precision);
 int dlc_sda_destroy(dlc_sda* h);
 /* Raw-pixel input mode (call before dlc_sda_set_layer(h, 0, ...); changing it un-sets layer 0): the x planes given to
@@ -161,6 +170,18 @@ int dlc_sda_set_input_u8(dlc_sda* h, int on);
 int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const double* b_host);
 /* bytes of scratch needed to encode `rows` patch rows */
 size_t dlc_sda_workspace_bytes(const dlc_sda* h, int rows);
+/* DLC_PREC_AUTO handles: choose the arithmetic now, from up to 512 sampled rows of this input (four blocks of 128
+ * rows spread over the batch) run through all layers in the three modes. Allocates and frees ~25 MB of device scratch
+ * and SYNCHRONISES the stream (it reads two error figures back): an initialisation step, not part of the hot path.
+ * dlc_sda_set_layer invalidates the choice. No-op (DLC_OK) on handles created with a fixed precision. */
+int dlc_sda_probe(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int rows, void* ws_dev, size_t ws_bytes,
+                  void* stream);
+/* The arithmetic dlc_sda_encode uses: DLC_PREC_FP16, DLC_PREC_FP16X2_A16 or DLC_PREC_FP16X2 (the creation-time
+ * precision, or the probe's choice); -1 for an AUTO handle that has not been probed yet. */
+int dlc_sda_chosen_precision(const dlc_sda* h);
+/* out_host[2] = max over the sample of |d - d3| / max(1, |d3|) for the one-product and the two-product forward
+ * against the three-product one (the figures the choice was made on; zeros before a probe). */
+int dlc_sda_probe_stats(const dlc_sda* h, double* out_host);
 /* x planes [rows, dlc_plane_ld(dims[0])] (from dlc_patch_gather or dlc_split_planes); out_dev float32
  * [rows, dims[n_layers]] dense (the reference's flat [B*30, 2500] result, SDAV.py:163). */
 int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int rows, float* out_dev, void* ws_dev,

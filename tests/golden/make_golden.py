@@ -138,8 +138,58 @@ def golden_images():
     np.savez_compressed(os.path.join(HERE, "images.npz"), **out)
 
 
+def golden_config1():
+    """SURVEY 8(d) config 1, the parity config: the 20 real frames of datasets/test read like CvInputParser.py:32
+    (cv2.imread GRAYSCALE), seeded keypoints (np.random.default_rng(0), x in U[0,240), y in U[0,192), 30 per frame),
+    the reference's OWN patch function (CvInputParser.py:100-123, 27), the float64 oracle encoder (the reference's
+    TensorFlow graph cannot run here) with SDA weights seed 1 (N(0,1), the reference's initialisation) and seed 2
+    (Xavier-scaled), and the reference's OWN SimilarityCalculator on those descriptors for every ordered pair i != j.
+    Stored: the frames, keypoints, a digest of the reference's patch array, and per weight set the 20 x 20 scores,
+    the matched patch index of every row and the gap to the runner-up (for the tie report)."""
+    import hashlib
+
+    import cv2
+    from src.sdav.input.CvInputParser import get_vectorized_patches_from_key_points
+    from src.sdav.similarity.SimilarityCalculator import SimilarityCalculator
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import sda as o_sda
+    from oracle import similarity as o_sim
+    names = sorted(f for f in os.listdir(os.path.join(REF, "datasets/test")) if f.endswith(".ppm"))
+    assert len(names) == 20
+    frames = np.stack([cv2.imread(os.path.join(REF, "datasets/test", f), cv2.IMREAD_GRAYSCALE) for f in names])
+    n, h, w = frames.shape
+    rng = np.random.default_rng(0)
+    xy = np.stack([rng.uniform(0, w, (n, 30)), rng.uniform(0, h, (n, 30))], -1).astype(np.float32)
+    x = np.stack([get_vectorized_patches_from_key_points(frames[i], [FakeKeyPoint(px, py) for px, py in xy[i]], 41)
+                  / 255.0 for i in range(n)])                                     # [20, 30, 1681] float64
+    out = {"frames": frames, "xy": xy, "names": np.array(names),
+           "patches_sha256": np.array(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())}
+    dims = [1681, 2500, 2500, 2500, 2500, 2500]
+    for tag, seed, scale in (("normal", 1, "normal"), ("xavier", 2, "xavier")):
+        ws, bs = o_sda.make_weights(dims, seed=seed, scale=scale)
+        desc = o_sda.sda_forward(x, ws, bs).reshape(n, 30, -1)
+        calc = SimilarityCalculator(desc)
+        S = np.full((n, n), -1.0)
+        idx = np.zeros((n, n, 30), dtype=np.int8)
+        gap = np.zeros((n, n, 30))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(n):
+                for j in range(n):
+                    if i == j:
+                        continue
+                    S[i, j] = calc.similarity_score(desc[i], desc[j])             # the reference class, unmodified
+                    idx[i, j] = o_sim.match_indices(desc[i], desc[j])
+                    gap[i, j] = o_sim.nn_margin(desc[i], desc[j])
+        out["S_" + tag] = S
+        out["idx_" + tag] = idx
+        out["gap_" + tag] = gap
+        out["desc_digest_" + tag] = np.array([desc.sum(), np.abs(desc).max(), desc[3, 7, 11], desc[19, 29, 2499]])
+    np.savez_compressed(os.path.join(HERE, "config1_frames.npz"), **out)
+
+
 if __name__ == "__main__":
-    golden_patches(); golden_similarity(); golden_hamming(); golden_misc(); golden_images()
+    golden_patches(); golden_similarity(); golden_hamming(); golden_misc(); golden_images(); golden_config1()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

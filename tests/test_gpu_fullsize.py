@@ -83,17 +83,21 @@ def test_config2_auto_mode_agrees_with_three_products(config2):
     ii, jj = np.nonzero(np.triu(rel > TOL, 1))
     print("auto vs three products: refine kernel used = %s, flagged rows %d, frame pairs differing by more than 1e-3: "
           "%d of %d" % (bool(stats["use_refine"]), int(stats["flagged_rows"]), len(ii), 1063 * 1062 // 2))
-    # The two arithmetics may part only where a row has two near-equidistant candidates (squared-distance gap ~1e-4
-    # on ~1e3, below the three-product kernel's resolution): rare, and there the refined mode must be the one that
-    # agrees with the float64 oracle (these are the north star's "ties within the tolerance").
-    assert len(ii) <= 0.001 * (1063 * 1062 // 2)
+    # The two arithmetics part only where a row has two near-equidistant candidates (squared-distance gap ~1e-4 on
+    # ~1e3, below the three-product kernel's resolution). EVERY such pair is checked against the float64 oracle on the
+    # same descriptors: the refined mode must be the one that agrees (the whole matrix is checked against the oracle by
+    # tools/check_config2_full.py -> profiles/r2_config2_full_parity.json).
     d = desc.cpu().numpy().astype(np.float64)
     w = o_sim.distinctive_weights(d)
+    x2_wrong = 0
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        for i, j in list(zip(ii, jj))[:25]:
+        for i, j in zip(ii, jj):
             want = o_sim.similarity_score(d[i], d[j], w)
             assert abs(Sa[i, j] - want) <= TOL * max(1.0, abs(want)), (i, j, want, Sa[i, j], S3[i, j])
+            x2_wrong += abs(S3[i, j] - want) > TOL * max(1.0, abs(want))
+    print("  all %d differing pairs: auto agrees with the float64 oracle; the three-product kernel is the one off on %d"
+          % (len(ii), x2_wrong))
     assert np.array_equal(Sa, Sa.T) and np.all(np.diag(Sa) == -1.0)
 
 

@@ -196,3 +196,73 @@ def test_surf_oracle_recovers_synthetic_blobs():
     # layer geometry: filter sizes of SURF_create() defaults
     assert surf.layer_sizes() == [[9, 15, 21, 27, 33], [18, 30, 42, 54, 66], [36, 60, 84, 108, 132],
                                   [72, 120, 168, 216, 264]]
+
+
+# ---------------------------------------------------------------------------------------------- config 1 (parity config)
+def _config1_oracle(g, tag):
+    """pixels -> patches -> float64 encoder for one weight set of the config-1 fixture."""
+    seed, scale = {"normal": (1, "normal"), "xavier": (2, "xavier")}[tag]
+    ws, bs = o_sda.make_weights([1681, 2500, 2500, 2500, 2500, 2500], seed=seed, scale=scale)
+    x = np.stack([o_patch.extract_patches(g["frames"][i], g["xy"][i]) for i in range(len(g["frames"]))])
+    return x, ws, bs, o_sda.sda_forward(x, ws, bs).reshape(len(x), 30, -1)
+
+
+def test_config1_fixture_pins_the_oracle_end_to_end(golden_dir):
+    """The 20 real datasets/test frames: oracle patches == the reference's own patch function (digest), and the oracle
+    scores / matches on the oracle descriptors == the reference's own SimilarityCalculator (tests/golden/make_golden.py
+    ::golden_config1), for every ordered pair, for N(0,1) and Xavier-scaled weights."""
+    import hashlib
+    g = np.load(golden_dir + "/config1_frames.npz")
+    assert g["frames"].shape == (20, 192, 240) and g["frames"].dtype == np.uint8
+    for tag in ("normal", "xavier"):
+        x, ws, bs, desc = _config1_oracle(g, tag)
+        assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest() == str(g["patches_sha256"])
+        dig = np.array([desc.sum(), np.abs(desc).max(), desc[3, 7, 11], desc[19, 29, 2499]])
+        assert np.allclose(dig, g["desc_digest_" + tag], rtol=1e-12, atol=0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S, det = o_sim.similarity_matrix(desc, full_asymmetric=True, return_details=True)
+        ref = g["S_" + tag]
+        m = ~np.eye(20, dtype=bool)
+        assert np.max(np.abs(S[m] - ref[m]) / np.maximum(1, np.abs(ref[m]))) < 1e-12
+        for (i, j), (idx, _) in det.items():
+            assert np.array_equal(idx, g["idx_" + tag][i, j])
+
+
+def test_parity_report_classes(golden_dir):
+    """The from-pixels report itself (tests/parity_report.py), driven on the CPU: a float32 evaluation of the encoder
+    stands in for the device (its descriptor error is of the order the device's is), scores are the float64 scores of
+    those descriptors. Everything must be explained; a corrupted score and a wrong match must not be."""
+    import parity_report as pr   # tests/ is on sys.path (rootdir conftest)
+    g = np.load(golden_dir + "/config1_frames.npz")
+    x, ws, bs, desc = _config1_oracle(g, "normal")
+    h = x.reshape(-1, x.shape[-1]).astype(np.float32)
+    for w, b in zip(ws, bs):
+        h = (1.0 / (1.0 + np.exp(-(h @ w.astype(np.float32) + b.astype(np.float32))))).astype(np.float32)
+    dev = h.reshape(desc.shape).astype(np.float64)
+    n = 8                                                   # sub-sequence: keeps the CPU suite short
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S_dev = o_sim.similarity_matrix(dev[:n], full_asymmetric=True)
+        S_ref = o_sim.similarity_matrix(desc[:n], full_asymmetric=True)
+    rep = pr.report(S_dev, dev[:n], desc[:n])
+    assert rep["pairs"] == n * (n - 1) and rep["unexplained"] == 0, rep
+    assert rep["ok"] + rep["tie"] + rep["conditioning"] == rep["pairs"]
+    assert rep["descriptor_max_rel_err"] < 1e-3
+    # fixtures as the oracle side give the same classes
+    rep2 = pr.report(S_dev, dev[:n], desc[:n], S_ref=S_ref)
+    assert {k: rep2[k] for k in ("ok", "tie", "conditioning")} == {k: rep[k] for k in ("ok", "tie", "conditioning")}
+    # a wrong score (2 % off) is caught ...
+    bad = S_dev.copy()
+    bad[1, 2] *= 1.02
+    assert pr.report(bad, dev[:n], desc[:n])["unexplained"] == 1
+    # ... and a device that matched a non-nearest patch in one row of one pair is, too
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        w_dev = o_sim.distinctive_weights(dev[:n])
+        _, idx, _ = o_sim.similarity_score(dev[2], dev[5], w_dev, return_details=True)
+        idx[4] = (idx[4] + 7) % 30
+        wrong = S_dev.copy()
+        wrong[2, 5] = np.sum(10.0 - 10.0 * np.log(np.abs((dev[2] - dev[5][idx]) @ w_dev)))
+    rep3 = pr.report(wrong, dev[:n], desc[:n])
+    assert rep3["unexplained"] == 1 and rep3["unexplained_detail"][0][0] == (2, 5)
