@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """Headline benchmark: loop-query frames/sec (encode + match) on BASELINE.json's config[1] workload:
 SDA descriptors + loop detection over an outdoor_kennedylong-shaped sequence (1063 frames, 240x192, 30 keypoints per
-frame) on 1 x B200. One step = one pass of the whole hot path over the sequence:
+frame) on B200. One step = one pass of the whole hot path over the sequence:
 
     patch gather -> 5 x (GEMM + bias + sigmoid) -> SDAV score matrix (Gram + argmin + score, i<j) -> per-row top-10
 
-`value`  : frames/s with the frames and keypoints already resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same through the public pipeline with HOST (pinned) frames/keypoints copied in and the candidate lists
-           copied out inside the timed region.
-N > 1    : every rank processes its own sequence (weak scaling; the path has no exchange step at this workload).
---impl reference : the reference's CPU path for the same step, timed on the host cores as a bounded sample. The
-           reference needs TensorFlow 1.x (not installable here) so this runs the float64 oracle port (oracle/), the
-           only place outside tests/smoke where oracle/ is executed.
+`value`   : frames/s with the frames and keypoints already resident in HBM (CUDA events, max over ranks).
+`e2e`     : the same through the public pipeline with HOST (pinned) frames/keypoints copied in and the candidate lists
+            copied out inside the timed region.
+`roofline`: the kernel with the largest share of the step (the encoder layer kernel), algorithmic FLOPs per launch over
+            its average launch time; `roofline_sim` is the score-matrix kernel alone, with its second pass, and with
+            the preparation kernels.
+`arms`    : the same step with trained-like (Xavier-scaled) weights next to the reference's N(0,1) initialisation
+            (SDAV.py:189-217 vs :232-240): the encoder's precision probe then needs one tensor product, not three.
+`other_configs` (N = 1): short runs of BASELINE configs 3, 4 and 5 (`--config 3|4|5` runs one of them as the headline).
+N > 1     : STRONG scaling - the ONE sequence is split over the ranks (frames dealt in blocks, descriptors exchanged
+            with NCCL all-gather, every rank evaluates its tile rows of the score matrix, scores all-reduced); plus
+            BASELINE config 4 (1 M x 4096 database row-sharded 1 M / N per rank, NCCL merge of the top-k lists).
+--impl reference : the reference's CPU path, timed on the host cores on a fixed sub-workload run to completion
+            (96 frames encoded + all 4560 frame pairs scored, dataset mean hoisted and un-hoisted). The reference needs
+            TensorFlow 1.x (not installable here) so this runs the float64 oracle port (oracle/), the only place outside
+            tests/smoke where oracle/ is executed.
 """
 import argparse
 import json
@@ -29,9 +38,12 @@ sys.path.insert(0, ROOT)
 N_FRAMES, H, W, P, PATCH = 1063, 192, 240, 30, 41
 DIMS = [1681, 2500, 2500, 2500, 2500, 2500]
 K_CAND = 10
+METRIC = "loop-query frames/sec (encode+match)"
 WORKLOAD = "SDA descriptors + loop detection, outdoor_kennedylong-shaped sequence (1063 frames 240x192, 30 kp/frame)"
 ENC_FLOP_PER_FRAME = 30 * 2 * (1681 * 2500 + 4 * 2500 * 2500)          # 1.75215 GFLOP
 GRAM_FLOP = 2.0 * 30 * 30 * 2500 * (N_FRAMES * (N_FRAMES - 1) / 2)       # i<j pairs, 2*30*30*2500 each = 2.54 TFLOP
+WEIGHT_NOTES = {"normal": "N(0,1) init (reference default, no checkpoint shipped)",
+                "xavier": "Xavier-scaled N(0, 1/fan_in), biases 0.1 N(0,1) (trained-like; no trained checkpoint exists)"}
 
 
 def synthetic_inputs(seed):
@@ -49,6 +61,14 @@ def reference_weights():
     return ws, bs
 
 
+def xavier_weights():
+    """Trained-like magnitudes (what restoring a checkpoint, SDAV.py:232-240, would give): sigma = 1/sqrt(fan_in)."""
+    rng = np.random.default_rng(2)
+    ws = [rng.standard_normal((k, n)) / np.sqrt(k) for k, n in zip(DIMS[:-1], DIMS[1:])]
+    bs = [0.1 * rng.standard_normal(n) for n in DIMS[1:]]
+    return ws, bs
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -57,6 +77,18 @@ def peaks():
         return {"tflops_sustained": p["bf16_tflops_sustained"], "tflops_burst": p["bf16_tflops"],
                 "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
     return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def kernel_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of one kernel, from the round's `ncu --set full`
+    capture (profiles/r2_traffic.json, written by tools/ncu_summary.py from the .ncu-rep); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(name)
+    return None if not e else float(e["dram_bytes_read"] + e["dram_bytes_write"])
 
 
 class ClockSampler(threading.Thread):
@@ -128,28 +160,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "how": self.how}
 
 
-# ---------------------------------------------------------------------------------------------- CPU baseline
+# ---------------------------------------------------------------------------------------------- CPU reference arm
 _PAIR_STATE = {}
 
 
-def _score_pairs(args):
-    """Worker: score `n` random frame pairs with the literal per-pair algorithm (dataset mean hoisted)."""
+def _score_pair_rows(args):
+    """Worker: score frame i against every j > i of the sub-sequence; hoisted = dataset weights computed once,
+    un-hoisted = recomputed for every pair like the literal reference (SimilarityCalculator.py:13-14)."""
     from oracle import similarity as o_sim
-    seed, n = args
+    i, hoisted = args
     desc, w = _PAIR_STATE["desc"], _PAIR_STATE["w"]
-    rng = np.random.default_rng(seed)
-    t0 = time.perf_counter()
     with np.errstate(all="ignore"):
-        for _ in range(n):
-            i, j = rng.choice(len(desc), 2, replace=False)
-            o_sim.similarity_score(desc[i], desc[j], w)
-    return time.perf_counter() - t0
+        for j in range(i + 1, len(desc)):
+            o_sim.similarity_score(desc[i], desc[j], w if hoisted else o_sim.distinctive_weights(desc))
+    return len(desc) - i - 1
 
 
-def cpu_step_sample(n_enc_frames=48, n_pairs=1200, seed=0):
-    """Bounded sample of the reference CPU path (float64 oracle port) on all host cores: encode n_enc_frames frames
-    (OpenBLAS threads) and score n_pairs frame pairs (one process per core); returns frames/s for the full 1063-frame
-    step extrapolated from the two per-unit costs. Must run in a process that has not initialised CUDA (it forks)."""
+def cpu_step_measured(n_frames=96, seed=0, unhoisted=True):
+    """One step of the reference CPU path (float64 oracle port) on a FIXED sub-workload run to completion on all host
+    cores: the first n_frames frames encoded (OpenBLAS threads) and ALL n_frames (n_frames - 1) / 2 frame pairs scored
+    (one process per core), with the dataset mean hoisted out of the pair loop and - the literal reference - recomputed
+    per pair. Returns measured times and the extrapolation to the 1063-frame step. Must run in a process that has not
+    initialised CUDA (it forks)."""
     import multiprocessing as mp
 
     from oracle import patches as o_patch
@@ -159,93 +191,110 @@ def cpu_step_sample(n_enc_frames=48, n_pairs=1200, seed=0):
     frames, xy = synthetic_inputs(seed)
     ws, bs = reference_weights()
     t0 = time.perf_counter()
-    x = np.concatenate([o_patch.extract_patches(frames[i], xy[i], PATCH) for i in range(n_enc_frames)])
-    desc = o_sda.sda_forward(x, ws, bs).reshape(n_enc_frames, P, -1)
-    t_enc = (time.perf_counter() - t0) / n_enc_frames
+    x = np.concatenate([o_patch.extract_patches(frames[i], xy[i], PATCH) for i in range(n_frames)])
+    desc = o_sda.sda_forward(x, ws, bs).reshape(n_frames, P, -1)
+    t_enc = time.perf_counter() - t0
     _PAIR_STATE["desc"] = desc
-    _PAIR_STATE["w"] = o_sim.distinctive_weights(desc)  # dataset mean hoisted (the literal reference recomputes it per pair)
-    per = max(n_pairs // cores, 1)
-    t0 = time.perf_counter()
+    _PAIR_STATE["w"] = o_sim.distinctive_weights(desc)
+    n_pairs = n_frames * (n_frames - 1) // 2
+    times = {}
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_score_pairs, [(100 + c, per) for c in range(cores)])
-    t_pair = (time.perf_counter() - t0) / (per * cores)   # wall time per pair with all cores busy
-    pairs_per_frame = (N_FRAMES - 1) / 2.0
-    fps = 1.0 / (t_enc + pairs_per_frame * t_pair)
-    sample = ("oracle port, float64, %d cores: %d frames encoded (%.1f ms/frame, OpenBLAS) + %d frame pairs scored "
-              "(%.3f ms/pair wall, one process per core), extrapolated to the 1063-frame step (%.0f pairs/frame)" %
-              (cores, n_enc_frames, t_enc * 1e3, per * cores, t_pair * 1e3, pairs_per_frame))
-    return fps, sample, cores
+        for label, hoisted in (("hoisted", True),) + ((("unhoisted", False),) if unhoisted else ()):
+            t0 = time.perf_counter()
+            done = sum(pool.imap_unordered(_score_pair_rows, [(i, hoisted) for i in range(n_frames - 1)], chunksize=2))
+            times[label] = time.perf_counter() - t0
+            assert done == n_pairs
+    full_pairs = N_FRAMES * (N_FRAMES - 1) // 2
+    scale = N_FRAMES / n_frames
+    t_full_h = t_enc * scale + times["hoisted"] * full_pairs / n_pairs
+    out = {"frames": n_frames, "pairs": n_pairs, "cores": cores, "encode_s": t_enc, "pairs_hoisted_s": times["hoisted"],
+           "measured_step_s": t_enc + times["hoisted"], "extrapolated_full_step_s": t_full_h}
+    if unhoisted:
+        # per pair the literal path adds one dataset mean, whose cost grows with the dataset (x scale)
+        t_mean = (times["unhoisted"] - times["hoisted"]) / n_pairs
+        out["pairs_unhoisted_s"] = times["unhoisted"]
+        out["extrapolated_full_step_unhoisted_s"] = t_full_h + full_pairs * t_mean * scale
+    return out
+
+
+def reference_sample_text(m):
+    s = ("oracle port, float64, %d cores, sub-workload run to completion: %d frames encoded in %.2f s (OpenBLAS) + all "
+         "%d frame pairs scored in %.2f s (dataset mean hoisted, one process per core) = %.2f s measured; extrapolated "
+         "to the 1063-frame step (x%.2f frames, x%.1f pairs): %.1f s" % (
+             m["cores"], m["frames"], m["encode_s"], m["pairs"], m["pairs_hoisted_s"], m["measured_step_s"],
+             N_FRAMES / m["frames"], (N_FRAMES * (N_FRAMES - 1) // 2) / m["pairs"], m["extrapolated_full_step_s"]))
+    if "pairs_unhoisted_s" in m:
+        s += ("; literal reference (mean recomputed per pair, SimilarityCalculator.py:13): %.2f s for the same pairs, "
+              "%.0f s extrapolated" % (m["pairs_unhoisted_s"], m["extrapolated_full_step_unhoisted_s"]))
+    return s
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    vals = []
-    sample = ""
-    for _ in range(args.warmup + args.steps):
-        fps, sample, cores = cpu_step_sample(*args.cpu_sample)
-        vals.append(fps)
-    vals = vals[args.warmup:] or vals
-    v = float(np.mean(vals))
-    line = {"metric": "loop-query frames/sec (encode+match)", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N_FRAMES / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "weights": "N(0,1) init (reference default, no checkpoint shipped)"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+    ms, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = cpu_step_measured(args.cpu_frames, unhoisted=(it == args.warmup + args.steps - 1))
+        if it >= args.warmup:
+            ms.append(last)
+    full_s = float(np.mean([m["extrapolated_full_step_s"] for m in ms]))
+    meas_s = float(np.mean([m["measured_step_s"] for m in ms]))
+    v = N_FRAMES / full_s
+    line = {"metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * meas_s, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "weights": WEIGHT_NOTES["normal"]},
+            "measured": {"what": "sub-workload of the step, run to completion every step: %d frames encoded + all %d "
+                                 "pairs scored (mean hoisted)" % (last["frames"], last["pairs"]),
+                         "ms_per_step": 1e3 * meas_s, "frames_per_s_of_the_sub_workload": last["frames"] / meas_s},
+            "extrapolated": {"what": "the 1063-frame step: encode time x 1063/%d, pair time x 564453/%d; `value` = "
+                                     "1063 / this" % (last["frames"], last["pairs"]),
+                             "ms_per_full_step": 1e3 * full_s,
+                             "ms_per_full_step_literal_unhoisted": 1e3 * last.get("extrapolated_full_step_unhoisted_s", 0.0)},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": last["cores"], "kind": "port",
+                             "sample": reference_sample_text(last)},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------- B200 path
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one bench run: ranks, barrier, timed loop."""
 
-    from deeploopcloser_b200 import _cuda, _lib, ops
-    from deeploopcloser_b200.pipeline import LoopClosurePipeline
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        from deeploopcloser_b200 import _cuda
+        _cuda.require_cuda()
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    _cuda.require_cuda()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return float(ms)
+        t = self.torch.tensor([ms], device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    frames_h, xy_h = synthetic_inputs(100 + rank)
-    ws, bs = reference_weights()
-    pipe = LoopClosurePipeline(DIMS, precision=args.precision, sim_precision=args.sim_precision,
-                               raw_pixels=not args.split_pixel_input)
-    pipe.set_weights(ws, bs)
-    frames_pin = torch.from_numpy(frames_h).pin_memory()
-    xy_pin = torch.from_numpy(xy_h).pin_memory()
-    frames_d = frames_pin.cuda()
-    xy_d = xy_pin.cuda()
-    out_s_pin = torch.empty((N_FRAMES, K_CAND), dtype=torch.float32).pin_memory()
-    out_i_pin = torch.empty((N_FRAMES, K_CAND), dtype=torch.int64).pin_memory()
-
-    def step_device():
-        return pipe.run(frames_d, xy_d, k=K_CAND, exclude_band=0)
-
-    def e2e_steps(n):
-        """n sequences through the public streaming call: host (pinned) frames + keypoints in, candidate lists out;
-        every step's H2D and D2H copies are issued inside the timed region (upload of step i+1 overlaps step i)."""
-        outs = pipe.run_host_stream([(frames_pin, xy_pin)] * n, k=K_CAND, exclude_band=0)
-        out_s_pin.copy_(outs[-1][0])
-        out_i_pin.copy_(outs[-1][1])
-
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(self, fn, steps, warmup, sampler=None):
+        """W untimed steps, barrier + synchronize, EXACTLY `steps` timed steps between CUDA events on the launch
+        stream, barrier + synchronize, max over ranks -> ms per step."""
+        torch = self.torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         if sampler:
             sampler.start()          # clocks are sampled during the timed region only
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,144 +302,346 @@ def run_ours(args):
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        self.barrier()
         if sampler:
             sampler.stop_flag.set()
             sampler.join()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total = timed(step_device, args.steps, args.warmup, sampler)
-    ms_step = ms_total / args.steps
-    value = world * N_FRAMES / (ms_step * 1e-3)
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
-    e2e_steps(max(args.warmup, 1))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_steps(args.steps)
-    e1.record()
-    barrier()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms_t.item()) / args.steps
-    e2e_value = world * N_FRAMES / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (Gram + argmin + score), timed alone with CUDA events on the launch stream
-    roof = None
-    cpu_base = None
-    stage_ms = {}
-    if rank == 0:
-        pk = peaks()
+def make_pipeline(ctx, weights, args):
+    from deeploopcloser_b200.pipeline import LoopClosurePipeline, ShardedSequencePipeline
+    ws, bs = reference_weights() if weights == "normal" else xavier_weights()
+    cls = ShardedSequencePipeline if ctx.world > 1 else LoopClosurePipeline
+    pipe = cls(DIMS, precision=args.precision, sim_precision=args.sim_precision, raw_pixels=not args.split_pixel_input)
+    pipe.set_weights(ws, bs)
+    return pipe
+
+
+def step_launches(sim_precision):
+    """Kernel launches of one step on one rank: patch gather, one kernel per layer, the similarity call (dataset
+    mean x2, row preparation, Gram; with a precision probe also rep_mask, probe, finalize, [auto: gated residual
+    planes], the second refinement pass and the gated three-product twin), per-row top-k."""
+    return 1 + len(DIMS) - 1 + {"auto": 10, "fp16r": 9}.get(sim_precision, 4) + 1
+
+
+def run_config2(ctx, args):
+    torch = ctx.torch
+    from deeploopcloser_b200 import _lib, ops
+    world, rank = ctx.world, ctx.rank
+    # strong scaling: every rank holds the same sequence (seed 100) and processes its share of it
+    frames_h, xy_h = synthetic_inputs(100)
+    frames_pin = torch.from_numpy(frames_h).pin_memory()
+    xy_pin = torch.from_numpy(xy_h).pin_memory()
+    frames_d, xy_d = frames_pin.cuda(), xy_pin.cuda()
+    out_s_pin = torch.empty((N_FRAMES, K_CAND), dtype=torch.float32).pin_memory()
+    out_i_pin = torch.empty((N_FRAMES, K_CAND), dtype=torch.int64).pin_memory()
+    pk = peaks()
+
+    def measure_arm(weights, sampler=None, detail=False):
+        pipe = make_pipeline(ctx, weights, args)
+
+        def step_device():
+            return pipe.run(frames_d, xy_d, k=K_CAND, exclude_band=0)
+
+        def e2e_steps(n):
+            """n sequences through the public streaming call: host (pinned) frames + keypoints in, candidate lists
+            out; every step's H2D and D2H copies are issued inside the timed region."""
+            outs = pipe.run_host_stream([(frames_pin, xy_pin)] * n, k=K_CAND, exclude_band=0)
+            out_s_pin.copy_(outs[-1][0])
+            out_i_pin.copy_(outs[-1][1])
+
+        ms_step = ctx.timed(step_device, args.steps, args.warmup, sampler)
+        e2e_steps(max(args.warmup, 1))
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps(args.steps)
+        e1.record()
+        ctx.barrier()
+        ms_e2e = ctx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        h2d, d2h = pipe.host_bytes_per_step(frames_pin, xy_pin, K_CAND)
+        arm = {"weights": WEIGHT_NOTES[weights], "value": N_FRAMES / (ms_step * 1e-3), "ms_per_step": ms_step,
+               "e2e": {"value": N_FRAMES / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+               "encoder_precision": pipe.encoder.chosen_precision(),
+               "encoder_probe_err_1prod_2prod_vs_3prod": list(pipe.encoder.probe_stats())}
+        if rank == 0 and detail:
+            arm.update(single_gpu_detail(pipe, weights))
+        return arm, pipe
+
+    def t_loop(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def single_gpu_detail(pipe, weights):
+        """Stage split + rooflines of this rank's kernels (each stage timed alone with CUDA events on the launch
+        stream; informational - `value` is the whole step)."""
+        reps = max(args.steps, 5)
+        enc = pipe.encoder
+        if args.split_pixel_input:
+            gather = lambda: ops.patch_gather(frames_d, xy_d, PATCH, True, need_lo=enc.needs_lo_input())  # noqa: E731
+        else:
+            gather = lambda: (ops.patch_gather_u8(frames_d, xy_d, PATCH, True), None)  # noqa: E731
+        hi, lo = gather()
+        rows = hi.shape[0]
+        products = {"fp16": [1] * 5, "fp16x2a16": [2] * 5, "fp16x2": [3] * 5}[enc.chosen_precision()]
+        if not args.split_pixel_input and products[0] == 3:
+            products[0] = 2                       # exact 8-bit pixel plane: no residual product in layer 0
+        exec_mult = (products[0] * 1681 * 2500 + sum(products[1:]) * 2500 * 2500) / (1681 * 2500 + 4 * 2500 * 2500)
+        st = {"patch_gather": t_loop(gather, reps)}
+        st["encoder_layers"] = t_loop(lambda: enc.encode_planes(hi, lo, rows), reps)
         desc = pipe.encode(frames_d, xy_d)
         dview = desc.view(N_FRAMES, P, -1)
-        ops.sdav_similarity(dview, precision=args.sim_precision)  # fills the workspace (planes, stats, tile list)
+        sim = lambda: pipe.similarity(desc, N_FRAMES)  # noqa: E731
+        sim()
         torch.cuda.synchronize()
-        sim_stats = ops.sdav_similarity_stats(N_FRAMES, P, DIMS[-1]) if args.sim_precision in ("auto", "fp16r") else None
-        products = 3 if (args.sim_precision == "fp16x2" or (sim_stats and not sim_stats["use_refine"])) else 1
+        probe = args.sim_precision in ("auto", "fp16r")
+        sim_stats = ops.sdav_similarity_stats(N_FRAMES, P, DIMS[-1]) if probe else None
+        sim_products = 3 if (args.sim_precision == "fp16x2" or (sim_stats and not sim_stats["use_refine"])) else 1
+
         def time_gram(mode):
             _lib.call("dlc_sdav_debug_gram_only", mode)
             try:
-                reps = max(args.steps, 3)
-                ops.sdav_similarity(dview, precision=args.sim_precision)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    ops.sdav_similarity(dview, precision=args.sim_precision)
-                e1.record()
-                torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / reps
+                return t_loop(sim, reps)
             finally:
                 _lib.call("dlc_sdav_debug_gram_only", 0)
 
-        # mode 1: the Gram kernel and (one-product mode) the second pass that re-evaluates the deferred pairs;
-        # mode 2: the Gram kernel alone - the dominant kernel, what `roofline` describes
-        gram_total_ms = time_gram(1)
-        gram_ms = time_gram(2) if products == 1 else gram_total_ms
-        ops.sdav_similarity(dview, precision=args.sim_precision)   # leave a complete result behind
-        achieved = GRAM_FLOP / (gram_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_gram_traffic.json")
-        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture per kernel
-            with open(tpath) as f:
-                tj = json.load(f)
-            tj = tj.get("GramRefinePolicy" if products == 1 else "GramPolicy<32,3>")
-            if tj:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        # the kernel is timed alone (back-to-back launches of itself): the burst bf16 figure is the denominator
-        roof = {"kernel": "gemm_pair_kernel<%s> (SDAV Gram + argmin + score)" % (
-                    "GramRefinePolicy" if products == 1 else "GramPolicy<32,3>"), "bound": "tensor",
-                "achieved": achieved, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tflops_burst"], "traffic": traffic,
-                "peak_source": pk["source"] + ", burst bf16 (kernel timed alone); sustained figure %.1f" % pk["tflops_sustained"],
-                "frac_of_sustained_peak": achieved / pk["tflops_sustained"],
-                "ms_per_launch": gram_ms, "algorithmic_flop_per_launch": GRAM_FLOP,
-                "ms_with_refinement_pass": gram_total_ms,
-                "precision_probe": sim_stats,
-                "note": "algorithmic FLOPs of the i<j pairs (2*30*30*2500 each); similarity precision mode %s issues "
-                        "%dx that on the tensor pipe (in gram-only timing mode both gated kernels are launched, the "
-                        "unselected one returns immediately); ms_with_refinement_pass adds gram_refine_fix_kernel, the "
-                        "exact re-evaluation of the frame pairs the one-product kernel deferred" % (args.sim_precision, products)}
-        # stage split (each stage timed alone; informational)
-        def t_stage(fn, reps=3):
-            fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-        if args.split_pixel_input:
-            stage_ms["patch_gather"] = t_stage(lambda: ops.patch_gather(frames_d, xy_d, PATCH, True,
-                                                                        need_lo=args.precision == "fp16x2"))
-        else:
-            stage_ms["patch_gather"] = t_stage(lambda: ops.patch_gather_u8(frames_d, xy_d, PATCH, True))
-        stage_ms["encode_total"] = t_stage(lambda: pipe.encode(frames_d, xy_d))
-        stage_ms["similarity_total"] = t_stage(lambda: ops.sdav_similarity(dview, precision=args.sim_precision))
-        stage_ms["gram_kernel"] = gram_ms
-        stage_ms["gram_plus_refinement_pass"] = gram_total_ms
-        enc_only = max(stage_ms["encode_total"] - stage_ms["patch_gather"], 1e-6)
-        stage_ms["encode_tflops_algorithmic"] = N_FRAMES * ENC_FLOP_PER_FRAME / (enc_only * 1e-3) / 1e12
-        if world == 1 and not args.no_cpu_baseline:
-            # timed in a fresh process (it forks one worker per core, which a CUDA-initialised process must not do)
-            try:
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                      "--warmup", "0", "--cpu-sample", "96,16000"], capture_output=True, text=True,
-                                     timeout=600).stdout
-                cpu_base = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])["cpu_baseline"]
-            except Exception as e:  # noqa: BLE001
-                cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-                            "sample": "failed: %r" % (e,)}
+        # mode 1: Gram kernel + (one-product mode) the second pass over the deferred pairs; mode 2: Gram kernel alone
+        gram_total = time_gram(1)
+        gram = time_gram(2) if sim_products == 1 else gram_total
+        st["similarity_total"] = t_loop(sim, reps)
+        st["gram_kernel"] = gram
+        st["gram_plus_refinement_pass"] = gram_total
+        st["similarity_preparation"] = st["similarity_total"] - gram_total
+        st["topk"] = t_loop(lambda: ops.topk_rows(pipe.last_similarity, K_CAND, largest=True, exclude_band=0), reps)
+        enc_flop = N_FRAMES * ENC_FLOP_PER_FRAME
+        layer_ms = st["encoder_layers"] / (len(DIMS) - 1)
+        ach = enc_flop / (len(DIMS) - 1) / (layer_ms * 1e-3) / 1e12
+        kname = "gemm_pair_kernel<BiasActPolicy<%s>>" % ("64,1" if products[-1] == 1 else "32,3")
+        roof = {"kernel": kname + " (the five encoder layers; largest share of the step)", "bound": "tensor",
+                "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
+                "traffic": kernel_traffic(kname),
+                "peak_source": pk["source"] + ", sustained bf16 (five launches per step inside a long loop); burst %.1f"
+                               % pk["tflops_burst"],
+                "ms_per_launch": layer_ms, "launches_per_step": len(DIMS) - 1,
+                "algorithmic_flop_per_launch": enc_flop / (len(DIMS) - 1),
+                "tensor_products_per_layer": products, "executed_over_algorithmic_flop": exec_mult,
+                "frac_executed": ach * exec_mult / pk["tflops_sustained"],
+                "note": "algorithmic FLOPs 2*M*K*N of the layers as the reference computes them; the arithmetic mode "
+                        "the precision probe chose issues `tensor_products_per_layer` fp16 products per algorithmic "
+                        "one (three are needed for 1e-3 parity on N(0,1) weights, SURVEY 7), so `frac` is capped at "
+                        "1/executed_over_algorithmic_flop and `frac_executed` is the tensor-pipe view"}
+        gname = "GramRefinePolicy" if sim_products == 1 else "GramPolicy<32,3>"
+        g_ach = GRAM_FLOP / (gram * 1e-3) / 1e12
+        roof_sim = {"kernel": "gemm_pair_kernel<%s> (SDAV Gram + argmin + score)" % gname, "bound": "tensor",
+                    "achieved": g_ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": g_ach / pk["tflops_burst"],
+                    "frac_of_sustained_peak": g_ach / pk["tflops_sustained"],
+                    "traffic": kernel_traffic("gemm_pair_kernel<%s>" % gname), "ms_per_launch": gram,
+                    "algorithmic_flop_per_launch": GRAM_FLOP, "tensor_products": sim_products,
+                    "with_refinement_pass": {"ms": gram_total,
+                                             "frac_of_burst": GRAM_FLOP / (gram_total * 1e-3) / 1e12 / pk["tflops_burst"],
+                                             "frac_of_sustained": GRAM_FLOP / (gram_total * 1e-3) / 1e12 / pk["tflops_sustained"]},
+                    "with_preparation_and_refinement": {
+                        "ms": st["similarity_total"],
+                        "frac_of_sustained": GRAM_FLOP / (st["similarity_total"] * 1e-3) / 1e12 / pk["tflops_sustained"]},
+                    "precision_probe": sim_stats,
+                    "peak_source": pk["source"] + ", burst bf16 for the kernel timed alone (back-to-back launches of "
+                                   "itself), sustained for the figures that include the other passes",
+                    "note": "algorithmic FLOPs of the i<j pairs (2*30*30*2500 each). The descriptors of the %s arm are "
+                            "%s: saturated operands draw less power, so the clock under this kernel is higher than "
+                            "under the cuBLAS run that set the peak" % (
+                                weights, "89 % saturated 0/1 values" if weights == "normal" else "dense mid-range values")}
+        return {"stages_ms": st, "roofline": roof, "roofline_sim": roof_sim,
+                "step_tflops_algorithmic": (enc_flop + GRAM_FLOP) / 1e12}
 
-    if rank == 0:
-        # gather, 5 layers, similarity (colsum, weights, prep_rows, gram; with a precision probe also rep_mask, probe,
-        # finalize, [auto: gated lo_planes], the second refinement pass and the gated three-product twin), top-k
-        launches_per_step = 1 + len(DIMS) - 1 + {"auto": 10, "fp16r": 9}.get(args.sim_precision, 4) + 1
-        line = {"metric": "loop-query frames/sec (encode+match)", "value": value, "unit": "frames/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f16 hi/lo split operands, f32 accumulate" if
-                args.precision == "fp16x2" else "f16 operands, f32 accumulate", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "precision": args.precision, "sim_precision": args.sim_precision,
-                           "weights": "N(0,1) init (reference default, no checkpoint shipped)",
-                           "layer0_input": "pixel/255 hi/lo planes (3 products)" if args.split_pixel_input else "exact 8-bit pixel plane, 1/255 folded into layer 0 (2 products)",
-                           "k": K_CAND, "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the 126 MB L2; no explicit flush",
-                           "multi_gpu": "independent sequence per rank, no collective"},
-                "e2e": {"value": e2e_value, "unit": "frames/s",
-                        "h2d_bytes_per_step": int(frames_pin.numel() + xy_pin.numel() * 4),
-                        "d2h_bytes_per_step": int(out_s_pin.numel() * 4 + out_i_pin.numel() * 8),
-                        "ms_per_step": ms_e2e},
-                "gpu_launches": launches_per_step * args.steps,
-                "clocks": sampler.summary() if sampler else None,
-                "roofline": roof, "cpu_baseline": cpu_base, "stages_ms": stage_ms}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    main_arm, pipe = measure_arm(args.weights, sampler, detail=(world == 1))
+    other = "xavier" if args.weights == "normal" else "normal"
+    arms = {args.weights: main_arm}
+    del pipe
+    if not args.one_arm:
+        arms[other], _ = measure_arm(other, None, detail=(world == 1))
+
+    extra = {}
+    if world > 1 and not args.headline_only:
+        extra["config4_sharded"] = bench_config4(ctx, args, batches=(32, 256, 1024))
+    if world == 1 and not args.headline_only:
+        extra["other_configs"] = {"config3": bench_config3(ctx, args), "config4": bench_config4(ctx, args, (32, 1024)),
+                                  "config5": bench_config5(ctx, args)}
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # timed in a fresh process (it forks one worker per core, which a CUDA-initialised process must not do)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0"], capture_output=True, text=True, timeout=900).stdout
+            cpu_base = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])["cpu_baseline"]
+        except Exception as e:  # noqa: BLE001
+            cpu_base = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": "failed: %r" % (e,)}
+    if rank != 0:
+        return
+    m = main_arm
+    prod = {"fp16": "f16 operands", "fp16x2a16": "f16 activations x f16 hi/lo split weights",
+            "fp16x2": "f16 hi/lo split operands"}.get(m["encoder_precision"], m["encoder_precision"])
+    line = {"metric": METRIC, "value": m["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": prod + ", f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "precision": args.precision, "encoder_precision_chosen": m["encoder_precision"],
+                       "sim_precision": args.sim_precision, "weights": m["weights"],
+                       "layer0_input": "pixel/255 hi/lo planes" if args.split_pixel_input else
+                                       "exact 8-bit pixel plane, 1/255 folded into layer 0",
+                       "k": K_CAND, "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the "
+                                          "126 MB L2; no explicit flush",
+                       "multi_gpu": "single GPU" if world == 1 else
+                                    "ONE sequence split over %d ranks (strong scaling): frames dealt in blocks, NCCL "
+                                    "all-gather of the descriptor planes and row statistics, every rank evaluates its "
+                                    "interleaved tile rows of the score matrix, NCCL all-reduce of the scores" % world},
+            "e2e": m["e2e"], "gpu_launches": step_launches(args.sim_precision) * args.steps,
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": m.get("roofline"), "roofline_sim": m.get("roofline_sim"), "cpu_baseline": cpu_base,
+            "stages_ms": m.get("stages_ms"),
+            "arms": {k: {kk: vv for kk, vv in v.items()} for k, v in arms.items() if k != args.weights}}
+    line.update(extra)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- configs 3 / 4 / 5
+def bench_config3(ctx, args, reps=5):
+    """BASELINE config 3: cnn_vtl descriptors of 1063 frames 192x240x3 + exact Hamming matrix + cosine top-10."""
+    torch = ctx.torch
+    from deeploopcloser_b200 import ops
+    from deeploopcloser_b200.cnn_vtl import CnnVtl
+    N = N_FRAMES
+    net = CnnVtl(input_shape=[N, H, W, 3], weights="synthetic", seed=3, precision="fp16x2")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    x = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, device="cuda", generator=g)
+    state = {}
+
+    def step():
+        d = torch.cat([net._forward_chunk(x[s:s + net.DEVICE_CHUNK]) for s in range(0, N, net.DEVICE_CHUNK)])
+        state["D"] = ops.hamming_matrix(d)
+        state["cand"] = net.cosine_candidates(d, k=K_CAND)
+        state["d"] = d
+
+    def head_only():
+        for s in range(0, N, net.DEVICE_CHUNK):
+            net._forward_chunk(x[s:s + net.DEVICE_CHUNK])
+
+    ms = ctx.timed(step, reps, 3)
+    ms_head = ctx.timed(head_only, reps, 1)
+    tf = 1.748e9 * N / ms_head / 1e9
+    ok = bool((state["cand"][1][:, 0] != torch.arange(N, device="cuda")).all())
+    return {"workload": "cnn_vtl descriptors (conv head, fp16x2) + Hamming matrix + cosine top-10, 1063 frames 192x240x3",
+            "frames_per_s": N / ms * 1e3, "ms_per_step": ms, "conv_head_ms": ms_head,
+            "conv_head_algorithmic_tflops": tf, "conv_head_frac_of_sustained_tensor_peak": tf / peaks()["tflops_sustained"],
+            "descriptor_len": int(state["d"].shape[1]), "self_excluded_from_candidates": ok}
+
+
+def bench_config4(ctx, args, batches=(32, 256, 1024), rows=1_000_000, dim=4096, reps=5):
+    """BASELINE config 4: synthetic 1 M x 4096 database (L2-normalised N(0,1) rows, fp16), batched top-10 queries with
+    planted near-duplicates; at N > 1 the database is row-sharded rows / N per rank (strong scaling) and the per-shard
+    lists are merged over NCCL."""
+    torch = ctx.torch
+    from deeploopcloser_b200.matcher import ShardedKeyframeDatabase
+    world, rank = ctx.world, ctx.rank
+    shard = rows // world
+    db = ShardedKeyframeDatabase(dim, shard, "cos", "fp16")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5 + rank)
+    keep = None
+    for s in range(0, shard, 65536):
+        chunk = torch.randn((min(65536, shard - s), dim), device="cuda", generator=g)
+        if s == 0:
+            keep = chunk[:128].clone()
+        db.append_local(chunk)
+    pk = peaks()
+    out = []
+    for B in batches:
+        gq = torch.Generator(device="cuda")
+        gq.manual_seed(6)
+        q = torch.randn((B, dim), device="cuda", generator=gq)
+        nplant = min(max(B // 10, 1), 128)
+        src = keep[:nplant].clone()
+        if world > 1:
+            ctx.dist.broadcast(src, 0)          # planted near-duplicates of rank 0's first rows, same queries everywhere
+        q[:nplant] = src + 0.05 * torch.randn((nplant, dim), device="cuda", generator=gq)
+        res = {}
+
+        def step():
+            res["s"], res["i"] = db.topk(q, K_CAND)
+
+        ms = ctx.timed(step, reps, 3)
+        flop, byts = 2.0 * B * dim * rows, float(rows) * dim * 2
+        out.append({"B": B, "ms": ms, "queries_per_s": B / ms * 1e3, "tflops": flop / ms / 1e9,
+                    "frac_of_sustained_tensor_peak_x_gpus": flop / ms / 1e9 / pk["tflops_sustained"] / world,
+                    "db_gbs": byts / ms / 1e6, "frac_of_hbm_peak_x_gpus": byts / ms / 1e6 / pk["hbm_gbs"] / world,
+                    "planted_top1_ok": bool((res["i"][:nplant, 0].cpu() == torch.arange(nplant)).all())})
+    del db
+    torch.cuda.empty_cache()
+    return {"workload": "1M x 4096 fp16 cosine database, top-10, row-sharded %d rows per rank%s" % (
+        shard, "" if world == 1 else ", NCCL all-gather + merge of the [B,k] lists"), "n_gpus": world, "batches": out}
+
+
+def bench_config5(ctx, args, db_rows=1_000_000, batch=256, reps=3):
+    """BASELINE config 5 shape on the available GPUs: 640x480 frames at batch 256 through SDA encode + incremental
+    match against a keyframe database (1 M rows per GPU here; the 10 M-row / 8-GPU run is tools/bench_streaming.py)."""
+    torch = ctx.torch
+    from deeploopcloser_b200.streaming import StreamingLoopCloser
+    world, rank = ctx.world, ctx.rank
+    b_local = batch // world
+    shard = db_rows // world
+    sl = StreamingLoopCloser(shard + (reps + 4) * b_local, DIMS, precision=args.precision)
+    sl.set_weights(*reference_weights())
+    g = torch.Generator(device="cuda")
+    g.manual_seed(50 + rank)
+    for s in range(0, shard, 65536):
+        sl.db.append_local(torch.rand((min(65536, shard - s), DIMS[-1]), device="cuda", generator=g))
+    frames = torch.randint(0, 256, (b_local, 480, 640), dtype=torch.uint8, device="cuda", generator=g)
+    xy = torch.stack([torch.rand((b_local, P), device="cuda", generator=g) * 640,
+                      torch.rand((b_local, P), device="cuda", generator=g) * 480], -1).contiguous()
+    ms = ctx.timed(lambda: sl.step(frames, xy), reps, 3)
+    del sl
+    torch.cuda.empty_cache()
+    return {"workload": "streaming: 640x480 frames, batch %d, SDA encode + top-10 against a %d-row database + insertion"
+                        % (batch, db_rows), "n_gpus": world, "ms_per_batch": ms, "frames_per_s": batch / ms * 1e3}
+
+
+def run_other_config(ctx, args):
+    fn = {3: bench_config3, 4: bench_config4, 5: bench_config5}[args.config]
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
+    if sampler:
+        sampler.start()
+    r = fn(ctx, args)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    if ctx.rank != 0:
+        return
+    if args.config == 4:
+        best = max(r["batches"], key=lambda b: b["queries_per_s"])
+        value, ms = best["queries_per_s"], best["ms"]
+    elif args.config == 3:
+        value, ms = r["frames_per_s"], r["ms_per_step"]
+    else:
+        value, ms = r["frames_per_s"], r["ms_per_batch"]
+    print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": ctx.world, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+                      "config": {"workload": r["workload"], "baseline_config": args.config},
+                      "clocks": sampler.summary() if sampler else None, "detail": r}))
 
 
 def main():
@@ -399,19 +650,31 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"], help="encoder arithmetic")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (1-based) to run as "
+                    "the headline; 2 = the config the metric is quoted on")
+    ap.add_argument("--weights", default="normal", choices=["normal", "xavier"],
+                    help="headline arm: the reference's N(0,1) initialisation, or trained-like Xavier-scaled weights")
+    ap.add_argument("--one-arm", action="store_true", help="skip the other weights arm")
+    ap.add_argument("--headline-only", action="store_true", help="skip the config 3/4/5 side measurements")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp16x2", "fp16x2a16", "fp16"],
+                    help="encoder arithmetic (auto: a probe on the weights picks the cheapest that holds 1e-3)")
     ap.add_argument("--sim-precision", default="auto", choices=["auto", "fp16r", "fp16x2", "fp16"],
                     help="SDAV score-matrix arithmetic")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-pixel-input", action="store_true",
-                    help="A/B: feed layer 0 pixel/255 as hi/lo planes (3 products) instead of exact pixel values (2)")
-    ap.add_argument("--cpu-sample", default="48,4800", type=lambda v: tuple(int(t) for t in v.split(",")),
-                    help="reference arm: frames encoded, frame pairs scored per step")
+                    help="A/B: feed layer 0 pixel/255 as hi/lo planes instead of exact pixel values")
+    ap.add_argument("--cpu-frames", default=96, type=int, help="reference arm: frames of the sub-workload")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+        return run_reference(args)
+    ctx = Ctx()
+    try:
+        if args.config == 2:
+            run_config2(ctx, args)
+        else:
+            run_other_config(ctx, args)
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

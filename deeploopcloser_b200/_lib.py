@@ -81,7 +81,7 @@ PROTOTYPES = {
     "dlc_cnnvtl_workspace_bytes": (_sz, [_p, _i]),
     "dlc_cnnvtl_forward": (_i, [_p, _p, _i, _i, _p, C.POINTER(_p), _p, _sz, _p]),
     "dlc_train_corrupt": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p]),
-    "dlc_train_xent_grad": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
+    "dlc_train_xent_grad": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "dlc_train_hidden_grad": (_i, [_p, _p, _p, _i, _i, _i, _f, _d, _d, _p, _p, _p, _p, _i, _p, _p]),
     "dlc_train_colsum": (_i, [_p, _i, _i, _p, _p]),
     "dlc_train_transpose_planes": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _p]),

@@ -214,6 +214,33 @@ class CnnVtl:
                 hi, lo = planes
         return ops.cnnvtl_quantise(segments, n, st["keep"])
 
+    def cosine_candidates(self, desc, k=10, db_dtype="fp16"):
+        """Loop candidates of BASELINE config 3 ("cnn_vtl descriptors + cosine top-k matching"): the int8 descriptors
+        of a sequence (CUDA tensor or ndarray [N, M], as transform returns them) de-quantised to float, every frame
+        matched against all the others by cosine similarity on the tensor cores (KeyframeDatabase, fused top-k) ->
+        (scores float32 [N, k], indices int64 [N, k]), best first, the frame itself excluded. New capability: the
+        reference only fills the dense Hamming matrix (create_distance_matrix.py:27-36)."""
+        import torch
+
+        from .matcher import KeyframeDatabase
+        d = desc if isinstance(desc, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(desc))
+        d = d.cuda().to(torch.float32).contiguous()
+        n = d.shape[0]
+        k = min(k, max(n - 1, 1))
+        db = getattr(self, "_cos_db", None)
+        if db is None or db.capacity < n or db.dim != d.shape[1] or db.dtype != db_dtype:
+            db = self._cos_db = KeyframeDatabase(d.shape[1], max(n, 1024), "cos", db_dtype)
+        db.clear()
+        db.append(d)
+        s, i = db.topk(d, k + 1)
+        # drop the frame itself (cosine 1 with its own stored row; a bit-identical other frame may sort before it)
+        self_col = (i == torch.arange(n, device=i.device)[:, None])
+        has_self = self_col.any(1, keepdim=True)
+        self_col = torch.where(has_self, self_col, torch.nn.functional.one_hot(
+            torch.full((n,), k, device=i.device), k + 1).bool())     # not listed: drop the last entry
+        keep = ~self_col
+        return s[keep].view(n, k), i[keep].view(n, k)
+
     # images per device pass of transform(): bounds the workspace (~7 MB per 192x240 image); the reference feeds
     # all N images to one session.run and never uses `batch_size` in transform (cnn_vtl.py:130-133)
     DEVICE_CHUNK = 256

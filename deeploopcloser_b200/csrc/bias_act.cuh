@@ -42,7 +42,7 @@ struct BiasActParams {
 };
 
 // Tensor maps of the plane outputs for the epilogue's staged TMA stores: box = 32 columns x 32 rows, SWIZZLE_64B.
-extern int g_tma_store;  // planes.cu
+extern std::atomic<int> g_tma_store;  // planes.cu
 inline bool attach_plane_store_maps(BiasActParams& p) {
   p.use_tma_store = 0;
   if (!p.out_hi || !g_tma_store) return true;

@@ -20,7 +20,7 @@
 
 namespace dlc {
 
-extern int g_promote_k;  // planes.cu: K elements accumulated in TMEM before promotion to fp32 registers
+extern std::atomic<int> g_promote_k;  // planes.cu: K elements accumulated in TMEM before promotion to fp32 registers
 
 // x planes [N*H*W, ld_in] -> im2col planes [N*OH*OW, ld]; column = (kh*KW + kw)*C + c; 8 columns per thread.
 __global__ void __launch_bounds__(256)
@@ -634,7 +634,7 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   if (!ok) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed for conv%d", l + 1);
   p.k_blocks = g.k_ld / BK;
   // a short K range (conv1: 576) is accumulated in one TMEM pass, which also enables the alternate-tile epilogue
-  p.kc = g.k_ld <= 1024 ? p.k_blocks : std::max(1, g_promote_k / BK);
+  p.kc = g.k_ld <= 1024 ? p.k_blocks : std::max(1, g_promote_k.load() / BK);
   if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();

@@ -113,11 +113,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t lbar = mapa_shared(&full[stage], 0);
             if (leader) mbar_arrive_expect_tx(&full[stage], tx_pair);
             uint8_t* st = smem + stage * stage_bytes;
-            tma_load_2d_pair(st, &tmA0, lbar, kb * BK, m0, Policy::kHintA);
-            if (kPl == 2 && !a_lo_zero) tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
             uint8_t* sb = st + a_planes * Cfg::kABytes;
-            tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
-            if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
+            if constexpr (policy_frame_maps<Policy>::value) {  // operands stored P rows per frame, see gemm_sm100.cuh
+              tma_load_3d_pair(st, &tmA0, lbar, kb * BK, 0, m0 >> 5, Policy::kHintA);
+              if (kPl == 2 && !a_lo_zero)
+                tma_load_3d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, 0, m0 >> 5, Policy::kHintA);
+              if (p.b_frame_map) {
+                tma_load_3d_pair(sb, &tmB0, lbar, kb * BK, 0, n0 >> 5, Policy::kHintB);
+                if (kPl == 2) tma_load_3d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, 0, n0 >> 5, Policy::kHintB);
+              } else {
+                tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
+                if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
+              }
+            } else {
+              tma_load_2d_pair(st, &tmA0, lbar, kb * BK, m0, Policy::kHintA);
+              if (kPl == 2 && !a_lo_zero) tma_load_2d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, m0, Policy::kHintA);
+              tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
+              if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
+            }
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;

@@ -119,6 +119,14 @@ struct policy_alt_tiles : std::false_type {};
 template <class P>
 struct policy_alt_tiles<P, std::enable_if_t<P::kAltTiles>> : std::true_type {};
 
+// Optional policy member `static constexpr bool kFrameMaps = true`: operands are stored at P <= 32 rows per frame and
+// read through 3-D tensor maps {K, P, frames} with 32-row boxes (rows P..31 arrive as zeros): the A tile is always
+// 4 frames x 32 rows; the B tile is frame-mapped when Params::b_frame_map != 0 (else a plain 2-D tile of n_tile rows).
+template <class P, class = void>
+struct policy_frame_maps : std::false_type {};
+template <class P>
+struct policy_frame_maps<P, std::enable_if_t<P::kFrameMaps>> : std::true_type {};
+
 // Optional policy member `static constexpr int kScratchBytes`: 1024-byte-aligned shared memory handed to the
 // epilogue (e.g. per-warp staging tiles for TMA stores); it is taken out of the operand ring.
 template <class P, class = void>
@@ -314,14 +322,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           }
-          if (!implicit_a) {
-            tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
-            if (Cfg::NPROD == 3 && !a_lo_zero)
-              tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
-          }
           uint8_t* sb = st + a_planes * Cfg::kABytes;
-          tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
-          if (Cfg::NPROD == 3) tma_load_2d(sb + b_plane_bytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
+          if constexpr (policy_frame_maps<Policy>::value) {
+            tma_load_3d(st, &tmA0, &full[stage], kb * BK, 0, m0 >> 5, Policy::kHintA);
+            if (Cfg::NPROD == 3 && !a_lo_zero)
+              tma_load_3d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, 0, m0 >> 5, Policy::kHintA);
+            if (p.b_frame_map) {
+              tma_load_3d(sb, &tmB0, &full[stage], kb * BK, 0, n0 >> 5, Policy::kHintB);
+              if (Cfg::NPROD == 3)
+                tma_load_3d(sb + b_plane_bytes, &tmB1, &full[stage], kb * BK, 0, n0 >> 5, Policy::kHintB);
+            } else {
+              tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
+              if (Cfg::NPROD == 3) tma_load_2d(sb + b_plane_bytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
+            }
+          } else {
+            if (!implicit_a) {
+              tma_load_2d(st, &tmA0, &full[stage], kb * BK, m0, Policy::kHintA);
+              if (Cfg::NPROD == 3 && !a_lo_zero)
+                tma_load_2d(st + Cfg::kABytes, &tmA1, &full[stage], kb * BK, m0, Policy::kHintA);
+            }
+            tma_load_2d(sb, &tmB0, &full[stage], kb * BK, n0, Policy::kHintB);
+            if (Cfg::NPROD == 3) tma_load_2d(sb + b_plane_bytes, &tmB1, &full[stage], kb * BK, n0, Policy::kHintB);
+          }
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -517,6 +539,23 @@ inline bool make_tmap_k_major(CUtensorMap* m, const void* base, int ab_fmt, uint
   CUtensorMapDataType dt = ab_fmt == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// Frame-grouped K-major planes [frames * rows_per_frame, ld] seen as {ld, rows_per_frame, frames}; box = bk columns x
+// 32 rows x box_frames frames. Rows rows_per_frame..31 of every frame (and frames beyond the last) read as zeros.
+inline bool make_tmap_frames(CUtensorMap* m, const void* base, uint64_t ld, int rows_per_frame, uint64_t frames, int bk,
+                             int box_frames) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {ld, static_cast<cuuint64_t>(rows_per_frame), frames};
+  cuuint64_t gstride[2] = {ld * 2, ld * 2 * static_cast<cuuint64_t>(rows_per_frame)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(bk), 32u, static_cast<cuuint32_t>(box_frames)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "bias_act.cuh"
 #include "gemm_pair_sm100.cuh"
@@ -81,20 +82,20 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
   }
 }
 
-static int g_split_bk = 32;  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
-int g_promote_k = 256;
+static std::atomic<int> g_split_bk{32};  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
+std::atomic<int> g_promote_k{256};
 // Valid K of the next dlc_gemm_planes call on this thread (0 = the whole ld). Callers that know their operands are zero
 // beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
 thread_local int g_gemm_k_valid = 0;
 // Scale of the accumulator before the bias of the next dlc_gemm_planes call on this thread (z = alpha * acc + bias;
 // reset to 1 by the call). The SDA encoder's first layer on raw 8-bit pixels uses 1/256 (see dlc_sda_set_input_u8).
 thread_local float g_gemm_alpha = 1.0f;
-int g_tma_store = 1;
-int g_cta_pair = 1;
-int g_gram_pair = 1;  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
-extern int g_sim_mgroup;  // sdav_sim.cu
-extern int g_refine_cap;  // sdav_sim.cu
-static int g_dbg_flags = 0;       // K elements accumulated inside the tensor core before promotion to fp32 registers
+std::atomic<int> g_tma_store{1};
+std::atomic<int> g_cta_pair{1};
+std::atomic<int> g_gram_pair{1};  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
+extern std::atomic<int> g_sim_mgroup;  // sdav_sim.cu
+extern std::atomic<int> g_refine_cap;  // sdav_sim.cu
+static std::atomic<int> g_dbg_flags{0};       // K elements accumulated inside the tensor core before promotion to fp32 registers
 
 template <class Policy>
 static cudaError_t launch_gemm_pair_if(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
@@ -127,7 +128,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   const int k_valid = (g_gemm_k_valid > 0 && g_gemm_k_valid <= ld) ? g_gemm_k_valid : ld;
   g_gemm_k_valid = 0;
   p.k_blocks = ceil_div(k_valid, BK);
-  p.kc = std::max(1, g_promote_k / BK);
+  p.kc = std::max(1, g_promote_k.load() / BK);
   p.dbg = g_dbg_flags;
   if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_gemm_planes: cuTensorMapEncodeTiled failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
@@ -155,7 +156,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
 }  // namespace dlc
 
 using namespace dlc;
-extern int g_probe_side_stream;  // sdav_sim.cu
+extern std::atomic<int> g_probe_side_stream;  // sdav_sim.cu
 
 extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 * 64; }
 

@@ -105,6 +105,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled load: (c0 = K coordinate, c1 = row inside the frame, c2 = frame). Used for operands stored at P rows per
+// frame and consumed at 32 rows per frame: the box is 32 rows tall, rows P..31 lie outside the tensor and arrive as
+// zeros, so the shared-memory image is the padded [frames x 32, K] tile without a padded copy in memory.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+
 // 4-D im2col-mode load from an NHWC tensor (dims C, W, H, N): `pixelsPerColumn` consecutive output pixels starting
 // at base pixel (w, h, n) - walking W, then H, then N inside the map's bounding box - each contributing
 // `channelsPerPixel` channels from c0 of the input pixel base + (off_w, off_h). Pixels outside the tensor read as
@@ -222,6 +234,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
       "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA

@@ -15,6 +15,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "gemm_pair_sm100.cuh"
@@ -25,7 +27,7 @@ namespace dlc {
 constexpr int kFrameRows = 32;                          // padded patch rows per frame
 constexpr int kFramesPerMTile = kTileM / kFrameRows;    // 4
 constexpr int kFramesPerNTile = kMaxTileN / kFrameRows; // 8
-int g_sim_mgroup = 32;                                  // M tiles per L2 super-block of the tile order (dlc_debug_set key 4)
+std::atomic<int> g_sim_mgroup{32};                                  // M tiles per L2 super-block of the tile order (dlc_debug_set key 4)
 
 // ---------------- column mean -> distinctive weights (deterministic two-stage reduction) ----------------
 constexpr int kColSumSlabs = 128;
@@ -40,110 +42,95 @@ __global__ void colsum_partial_kernel(const float* __restrict__ H, int64_t rows,
   part[static_cast<int64_t>(blockIdx.y) * D + col] = acc;
 }
 __global__ void weights_kernel(const double* __restrict__ part, int slabs, int64_t rows, int D, double mu, double sigma,
-                               double* __restrict__ w) {
+                               double* __restrict__ w, double* __restrict__ mean_out) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= D) return;
   double acc = 0.0;
   for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * D + col];
   const double mean = acc / static_cast<double>(rows);
   const double d = mean - mu;
-  w[col] = exp(-(d * d) / (2.0 * sigma * sigma));
+  if (w) w[col] = exp(-(d * d) / (2.0 * sigma * sigma));
+  if (mean_out) mean_out[col] = mean;
 }
-// per patch row: squared norm (float) and projection p = h . w (double); one warp per row, padded-row indexing
-__global__ void __launch_bounds__(256)
-rowstats_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
-                float* __restrict__ sqn, double* __restrict__ pw) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= N * kFrameRows) return;
-  const int f = warp / kFrameRows, k = warp % kFrameRows;
-  double n2 = 0.0, pr = 0.0;
-  if (k < P) {
-    const float* h = H + (static_cast<int64_t>(f) * P + k) * D;
-    for (int c = lane; c < D; c += 32) {
-      const double x = static_cast<double>(h[c]);
-      n2 += x * x;
-      pr += x * w[c];
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-    pr += __shfl_xor_sync(0xffffffffu, pr, off);
-  }
-  if (lane == 0) {
-    sqn[warp] = k < P ? static_cast<float>(n2) : INFINITY;
-    pw[warp] = pr;
-  }
-}
-
-// One pass over the descriptors for everything the Gram kernel needs per row: the M-side operand planes (frames
-// re-grouped P -> 32 rows, pad rows zero), the N-side planes (packed P rows per frame, when they are separate), the
-// squared norm and the projection p = h . w. One warp per PADDED row; replaces two split passes + rowstats_kernel
-// (three reads of the 0.3 GB descriptor array) with one.
+// One pass over the descriptors for everything the Gram kernel needs per row: the operand plane(s), the squared norm
+// and the projection p = h . w. One warp per PADDED row (frame f, k < 32); rows k >= P only get their statistics.
+//
+// CENTRING. The planes hold h - m (m = the dataset's column mean, already needed for the weights), not h: distances
+// are translation invariant, ||h2_j - h1_k||^2 = n'_k + n'_j - 2 G' with G' = (H - m)(H - m)^T, and the centred Gram
+// does not cancel. Without it a dataset whose descriptors nearly coincide (a trained-like, well-scaled encoder gives
+// row norms^2 ~ 7e2 but distances^2 ~ 1e-4) is unresolvable in ANY fp32 accumulator: n_k + n_j - 2G loses 1e-5
+// absolute, far above the 2e-7 gaps between candidates. On saturated N(0,1)-weight descriptors centring is neutral
+// (the fp16 rounding error of the distance, std ~4e-3, is unchanged). The planes are stored P rows per frame: both
+// sides of the Gram kernel read them (the M side through a 3-D tensor map whose 32-row boxes zero-fill rows P..31).
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
-                 __half* __restrict__ a_hi, __half* __restrict__ a_lo, __half* __restrict__ b_hi,
-                 __half* __restrict__ b_lo, int ld, float* __restrict__ sqn, double* __restrict__ pw,
-                 unsigned int* __restrict__ nmax_bits) {
+                 const double* __restrict__ mean, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int ld,
+                 float* __restrict__ sqn, double* __restrict__ pw, unsigned int* __restrict__ nmax_bits) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N * kFrameRows) return;
   const int f = warp / kFrameRows, k = warp % kFrameRows;
-  const bool valid = k < P;
-  const int64_t r = static_cast<int64_t>(f) * P + k;          // source row / N-side plane row
+  if (k >= P) {  // pad row: never wins an argmin, contributes no score
+    if (lane == 0) {
+      sqn[warp] = INFINITY;
+      pw[warp] = 0.0;
+    }
+    return;
+  }
+  const int64_t r = static_cast<int64_t>(f) * P + k;          // source row = plane row
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
-  const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+  const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
 #pragma unroll 2
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = 0.0f;
-    if (valid) {
-      if (vec && c0 + 8 <= D) {
-        const float4 u = *reinterpret_cast<const float4*>(h + c0);
-        const float4 v = *reinterpret_cast<const float4*>(h + c0 + 4);
-        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
-        x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-      } else {
+    if (vec && c0 + 8 <= D) {
+      const float4 u = *reinterpret_cast<const float4*>(h + c0);
+      const float4 v = *reinterpret_cast<const float4*>(h + c0 + 4);
+      x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+      x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c0 + j < D) x[j] = h[c0 + j];
-      }
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < D) x[j] = h[c0 + j];
     }
     __align__(16) __half hh[8];
     __align__(16) __half ll[8];
-    double wv[8];
-    if (valid && wvec && c0 + 8 <= D) {   // four 16-byte loads of the weights instead of eight 8-byte ones
+    double wv[8], mv[8];
+    if (wvec && c0 + 8 <= D) {   // 16-byte loads of the weights and the mean
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double2 t = *reinterpret_cast<const double2*>(w + c0 + 2 * j);
+        const double2 m2 = *reinterpret_cast<const double2*>(mean + c0 + 2 * j);
         wv[2 * j] = t.x;
         wv[2 * j + 1] = t.y;
+        mv[2 * j] = m2.x;
+        mv[2 * j + 1] = m2.y;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) wv[j] = (valid && c0 + j < D) ? w[c0 + j] : 0.0;
+      for (int j = 0; j < 8; ++j) {
+        wv[j] = c0 + j < D ? w[c0 + j] : 0.0;
+        mv[j] = c0 + j < D ? mean[c0 + j] : 0.0;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      split_f32(x[j], hh[j], ll[j]);
-      if (valid && c0 + j < D) {
+      float xc = 0.0f;
+      if (c0 + j < D) {
         const double xd = static_cast<double>(x[j]);
-        n2 += xd * xd;
-        pr += xd * wv[j];
+        xc = static_cast<float>(xd - mv[j]);
+        n2 = fma(static_cast<double>(xc), static_cast<double>(xc), n2);
+        pr = fma(xd, wv[j], pr);
       }
+      split_f32(xc, hh[j], ll[j]);
     }
-    const int64_t oa = static_cast<int64_t>(warp) * ld + c0;
-    *reinterpret_cast<uint4*>(a_hi + oa) = *reinterpret_cast<const uint4*>(hh);
-    if (a_lo) *reinterpret_cast<uint4*>(a_lo + oa) = *reinterpret_cast<const uint4*>(ll);
-    if (b_hi && valid) {
-      const int64_t ob = r * ld + c0;
-      *reinterpret_cast<uint4*>(b_hi + ob) = *reinterpret_cast<const uint4*>(hh);
-      if (b_lo) *reinterpret_cast<uint4*>(b_lo + ob) = *reinterpret_cast<const uint4*>(ll);
-    }
+    const int64_t ob = r * ld + c0;
+    *reinterpret_cast<uint4*>(b_hi + ob) = *reinterpret_cast<const uint4*>(hh);
+    if (b_lo) *reinterpret_cast<uint4*>(b_lo + ob) = *reinterpret_cast<const uint4*>(ll);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -151,43 +138,39 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
     pr += __shfl_xor_sync(0xffffffffu, pr, off);
   }
   if (lane == 0) {
-    sqn[warp] = valid ? static_cast<float>(n2) : INFINITY;
+    sqn[warp] = static_cast<float>(n2);
     pw[warp] = pr;
     // largest squared norm (the probe's margin scales an allowance with it); non-negative floats order like their
     // bit patterns, and the plain read first keeps all but a few rows off the atomic
-    if (nmax_bits && valid) {
+    if (nmax_bits) {
       const unsigned int bits = __float_as_uint(static_cast<float>(n2));
       if (bits > *reinterpret_cast<volatile unsigned int*>(nmax_bits)) atomicMax(nmax_bits, bits);
     }
   }
 }
 
-// Residual planes only (lo = fp16(x - fp16(x))), for the three-product kernel when the precision probe decided
-// against the one-product kernel: launched after the probe and skipped (device-side gate) otherwise, so the common
-// one-product path never writes the 0.3 GB of residual planes. Same indexing as prep_rows_kernel.
+// Residual planes only (lo = fp16(x - fp16(x)) of the centred values), for the three-product kernel when the
+// precision probe decided against the one-product kernel: launched after the probe and skipped (device-side gate)
+// otherwise, so the common one-product path never writes the residual planes. One warp per plane row.
 struct GramControl;
 __device__ __forceinline__ bool lo_planes_wanted(const GramControl* ctl);
 __global__ void __launch_bounds__(256)
-lo_planes_kernel(const float* __restrict__ H, int N, int P, int D, __half* __restrict__ a_lo,
+lo_planes_kernel(const float* __restrict__ H, int64_t rows, int D, const double* __restrict__ mean,
                  __half* __restrict__ b_lo, int ld, const GramControl* __restrict__ ctl) {
   if (!lo_planes_wanted(ctl)) return;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= N * kFrameRows) return;
-  const int f = warp / kFrameRows, k = warp % kFrameRows;
-  const bool valid = k < P;
-  const int64_t r = static_cast<int64_t>(f) * P + k;
+  if (r >= rows) return;
   const float* h = H + r * D;
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     __align__(16) __half ll[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = (valid && c0 + j < D) ? h[c0 + j] : 0.0f;
+      const float x = c0 + j < D ? static_cast<float>(static_cast<double>(h[c0 + j]) - mean[c0 + j]) : 0.0f;
       __half hh;
       split_f32(x, hh, ll[j]);
     }
-    *reinterpret_cast<uint4*>(a_lo + static_cast<int64_t>(warp) * ld + c0) = *reinterpret_cast<const uint4*>(ll);
-    if (b_lo && valid) *reinterpret_cast<uint4*>(b_lo + r * ld + c0) = *reinterpret_cast<const uint4*>(ll);
+    *reinterpret_cast<uint4*>(b_lo + r * ld + c0) = *reinterpret_cast<const uint4*>(ll);
   }
 }
 
@@ -238,7 +221,7 @@ rep_mask_kernel(const float* __restrict__ H, int N, int P, int D, uint32_t* __re
 }
 
 // ---------------- Gram + argmin + score epilogue ----------------
-extern int g_promote_k;  // planes.cu
+extern std::atomic<int> g_promote_k;  // planes.cu
 
 // Device-side precision decision written by the probe (see below); both Gram kernels are always launched and the
 // one that is not selected returns immediately, so the choice needs no host round trip.
@@ -281,8 +264,9 @@ struct GramParams {
   GramControl* ctl;   // NULL: always enabled
   int want_refine;    // this launch runs only when ctl->use_refine == want_refine
   const uint32_t* rep_mask;  // [N] bit c set = row c of the frame is the FIRST of its class of bit-identical rows
-  int col_stride;     // accumulator columns per frame on the N side: P when the B planes are packed P rows per
-                      // frame (even P < 32; n_tile = 8 P, no MMA work on pad rows), else 32
+  int col_stride;     // accumulator columns per frame on the N side: P when the N tile is read as 8 P plane rows (even
+                      // P < 32; no MMA work on pad rows), else 32
+  int b_frame_map;    // 1: the N side is read through the 3-D frame map (32-row boxes), 0: plain rows (col_stride = P)
   RefineEntry* work;  // deferred-refinement work list (NULL: refine inside the epilogue)
   int work_cap;       // entries the list holds; pairs beyond it are refined inside the epilogue
 };
@@ -375,6 +359,7 @@ template <int BK, int NPROD>
 struct GramPolicy {
   using Cfg = GemmCfg<BK, NPROD>;
   using Params = GramParams;
+  static constexpr bool kFrameMaps = true;  // planes stored P rows per frame, M side read in 32-row boxes
   static constexpr bool kPromote = NPROD == 3;
   static constexpr int kEpiWarps = 4;
   static constexpr uint64_t kHintA = kEvictNormal;
@@ -503,6 +488,7 @@ __device__ __forceinline__ int refine_rows(const GramParams& p, int fa, int fb, 
 struct GramRefinePolicy {
   using Cfg = GemmCfg<64, 1>;
   using Params = GramParams;
+  static constexpr bool kFrameMaps = true;
   static constexpr bool kPromote = false;
   static constexpr int kEpiWarps = 8;
   static constexpr uint64_t kHintA = kEvictNormal;
@@ -672,8 +658,8 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
 }
 // one CTA per sample: a random row k of frame fa against all P rows of a random other frame fb (warp j = row j)
 __global__ void __launch_bounds__(1024)
-gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const uint32_t* __restrict__ rep_mask,
-                  ProbeAccum* acc, float* gaps) {
+gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const double* __restrict__ mean,
+                  const uint32_t* __restrict__ rep_mask, ProbeAccum* acc, float* gaps) {
   __shared__ double s_e[32];
   __shared__ double s_d[32];
   const int sample = blockIdx.x;
@@ -696,21 +682,26 @@ gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const uin
     //        added in float64 (absolute error ~1e-5 on values ~1e3; it is compared with a margin ~1e-2).
     float err = 0.0f;
     double dist = 0.0;
-    auto term = [&](float x, float y) -> float {
+    // (x, y are the CENTRED values h - m the planes hold, see prep_rows_kernel)
+    auto term = [&](float xr, float yr, double m) -> float {
+      const float x = static_cast<float>(static_cast<double>(xr) - m), y = static_cast<float>(static_cast<double>(yr) - m);
       const float xh = __half2float(__float2half_rn(x)), yh = __half2float(__float2half_rn(y));
       err = fmaf(x - xh, y, fmaf(xh, y - yh, err));
       return y * (y - 2.0f * x);
     };
-    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(desc) & 15) == 0) {
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(desc) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0) {
       const float4* a4 = reinterpret_cast<const float4*>(a);
       const float4* b4 = reinterpret_cast<const float4*>(b);
+      const double2* m2 = reinterpret_cast<const double2*>(mean);
 #pragma unroll 4
       for (int c = lane; c < (D >> 2); c += 32) {
         const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
-        dist += static_cast<double>((term(x.x, y.x) + term(x.y, y.y)) + (term(x.z, y.z) + term(x.w, y.w)));
+        const double2 ma = __ldg(m2 + 2 * c), mb = __ldg(m2 + 2 * c + 1);
+        dist += static_cast<double>((term(x.x, y.x, ma.x) + term(x.y, y.y, ma.y)) +
+                                    (term(x.z, y.z, mb.x) + term(x.w, y.w, mb.y)));
       }
     } else {
-      for (int c = lane; c < D; c += 32) dist += static_cast<double>(term(a[c], b[c]));
+      for (int c = lane; c < D; c += 32) dist += static_cast<double>(term(a[c], b[c], mean[c]));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -791,7 +782,7 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
   // so the triangle's long and short rows are spread evenly; super-blocks of g_sim_mgroup M tiles for L2 locality.
   std::vector<int> owned;
   for (int q = part; q < m_pairs; q += n_parts) owned.push_back(q);
-  const size_t group = std::max(1, g_sim_mgroup / 2);
+  const size_t group = std::max(1, g_sim_mgroup.load() / 2);
   for (size_t g0 = 0; g0 < owned.size(); g0 += group) {
     const size_t g1 = std::min(g0 + group, owned.size());
     for (int nt = 0; nt < n_tiles; ++nt)
@@ -811,47 +802,102 @@ static void build_tile_list(int N, int full, int part, int n_parts, std::vector<
   }
 }
 
+// The work lists depend only on (N, full, part, n_parts, super-block size): they are built once per key and kept in
+// LIBRARY-OWNED device memory (a caller workspace could be overwritten between calls), so a call neither rebuilds the
+// list on the host nor copies it. A handful of keys per device is all a process uses (one per sequence length).
+struct TileListKey {
+  int dev, N, full, part, n_parts, mgroup;
+  bool operator==(const TileListKey& o) const {
+    return dev == o.dev && N == o.N && full == o.full && part == o.part && n_parts == o.n_parts && mgroup == o.mgroup;
+  }
+};
+struct TileListEntry {
+  TileListKey key;
+  int2* tiles = nullptr;
+  int2* pair_tiles = nullptr;
+  int num_tiles = 0, num_pair_tiles = 0;
+  uint64_t stamp = 0;
+};
+constexpr int kTileCacheSlots = 16;
+static std::mutex g_tile_mutex;
+static TileListEntry g_tile_cache[kTileCacheSlots];
+static uint64_t g_tile_stamp = 0;
+
+// Returns the cached device lists for the key (building + uploading them on a miss: synchronous, first call only).
+static int get_tile_lists(int N, int full, int part, int n_parts, TileListEntry* out) {
+  TileListKey key{current_device(), N, full ? 1 : 0, part, n_parts, g_sim_mgroup.load()};
+  std::lock_guard<std::mutex> lock(g_tile_mutex);
+  int victim = 0;
+  for (int i = 0; i < kTileCacheSlots; ++i) {
+    if (g_tile_cache[i].tiles && g_tile_cache[i].key == key) {
+      g_tile_cache[i].stamp = ++g_tile_stamp;
+      *out = g_tile_cache[i];
+      return DLC_OK;
+    }
+    if (g_tile_cache[i].stamp < g_tile_cache[victim].stamp) victim = i;
+  }
+  std::vector<int2> tiles, pair_tiles;
+  build_tile_list(N, full, part, n_parts, tiles, pair_tiles);
+  TileListEntry e;
+  e.key = key;
+  e.num_tiles = static_cast<int>(tiles.size());
+  e.num_pair_tiles = static_cast<int>(pair_tiles.size());
+  int2* mem = nullptr;
+  const size_t n_all = tiles.size() + pair_tiles.size();
+  DLC_CUDA(cudaMalloc(reinterpret_cast<void**>(&mem), sizeof(int2) * std::max<size_t>(n_all, 1)));
+  cudaError_t err = cudaSuccess;
+  if (!tiles.empty()) err = cudaMemcpy(mem, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && !pair_tiles.empty())
+    err = cudaMemcpy(mem + tiles.size(), pair_tiles.data(), sizeof(int2) * pair_tiles.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    cudaFree(mem);
+    return fail(DLC_ECUDA, "dlc_sdav_similarity: tile list upload failed: %s", cudaGetErrorString(err));
+  }
+  e.tiles = mem;
+  e.pair_tiles = mem + tiles.size();
+  e.stamp = ++g_tile_stamp;
+  // an evicted list may still be read by a kernel in flight on some stream: free it only after the device drained
+  if (g_tile_cache[victim].tiles) {
+    cudaDeviceSynchronize();
+    cudaFree(g_tile_cache[victim].tiles);
+  }
+  g_tile_cache[victim] = e;
+  *out = e;
+  return DLC_OK;
+}
+
 constexpr int64_t kMaxRefineEntries = 1 << 18;
-int g_refine_cap = -1;  // developer override of the list capacity (dlc_debug_set key 8; 0 = refine in the epilogue)
+std::atomic<int> g_refine_cap{-1};  // developer override of the list capacity (dlc_debug_set key 8; 0 = refine in the epilogue)
 struct SimWorkspace {
-  size_t off_hi, off_lo, off_bhi, off_blo, off_part, off_w, off_sqn, off_pw, off_tiles, off_ptiles, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
-  int ld, rows_pad, max_tiles;
-  int col_stride;  // 32, or P when the N-side planes are packed P rows per frame
-  int rows_b;      // rows of the N-side planes
+  size_t off_bhi, off_blo, off_part, off_w, off_mean, off_sqn, off_pw, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
+  int ld, rows_pad;
+  int col_stride;  // 32, or P when the N tile is read as 8 P plane rows
+  int rows_b;      // rows of the planes (N * P)
   int work_cap;    // entries of the deferred-refinement list
 };
 static SimWorkspace sim_layout(int N, int P, int D) {
   SimWorkspace w{};
   w.ld = dlc_plane_ld(D);
   w.rows_pad = N * kFrameRows;
-  w.max_tiles = ceil_div(N, kFramesPerMTile) * ceil_div(N, kFramesPerNTile);
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;
     o = align_up(o + bytes, 256);
     return at;
   };
-  const size_t plane = static_cast<size_t>(w.rows_pad) * w.ld * 2;
-  w.off_hi = take(plane);
-  w.off_lo = take(plane);
-  // N-side planes packed P rows per frame when that keeps UMMA's N = 8 P a multiple of 16 (even P): the MMA then
-  // does no work on the 32 - P pad rows of every frame column block. Otherwise the N side reads the M-side planes.
+  // ONE pair of planes, P rows per frame. The M side always reads them through the 3-D frame map (32-row boxes, rows
+  // P..31 zero-filled by TMA). The N side reads 8 P plain rows per tile when that keeps UMMA's N = 8 P a multiple of
+  // 16 (even P: no MMA work on the pad rows of every frame column block), else it uses the frame map as well.
   w.col_stride = (P < kFrameRows && (P & 1) == 0) ? P : kFrameRows;
-  w.rows_b = w.col_stride == kFrameRows ? w.rows_pad : N * P;
-  if (w.col_stride != kFrameRows) {
-    const size_t plane_b = static_cast<size_t>(w.rows_b) * w.ld * 2;
-    w.off_bhi = take(plane_b);
-    w.off_blo = take(plane_b);
-  } else {
-    w.off_bhi = w.off_hi;
-    w.off_blo = w.off_lo;
-  }
+  w.rows_b = N * P;
+  const size_t plane_b = static_cast<size_t>(w.rows_b) * w.ld * 2;
+  w.off_bhi = take(plane_b);
+  w.off_blo = take(plane_b);
   w.off_part = take(sizeof(double) * kColSumSlabs * D);
   w.off_w = take(sizeof(double) * D);
+  w.off_mean = take(sizeof(double) * D);
   w.off_sqn = take(sizeof(float) * w.rows_pad);
   w.off_pw = take(sizeof(double) * w.rows_pad);
-  w.off_tiles = take(sizeof(int2) * w.max_tiles);
-  w.off_ptiles = take(sizeof(int2) * w.max_tiles);
   w.off_rep = take(sizeof(uint32_t) * N);
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
@@ -861,25 +907,34 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.work_cap = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(N) * N, kMaxRefineEntries));
   w.off_work = take(sizeof(RefineEntry) * static_cast<size_t>(w.work_cap));
   w.total = o;
-  (void)P;
   return w;
+}
+
+// Tensor maps of one Gram launch: A = frame map (4 frames x 32 rows per tile); B = frame map of `b_box_frames` frames,
+// or plain rows (col_stride = P) of `b_rows` rows per load.
+static bool gram_maps(const SimWorkspace& L, char* ws, int N, int P, int BK, int n_tile, bool pair, CUtensorMap* ta0,
+                      CUtensorMap* ta1, CUtensorMap* tb0, CUtensorMap* tb1) {
+  const void* bhi = ws + L.off_bhi;
+  const void* blo = ws + L.off_blo;
+  if (!make_tmap_frames(ta0, bhi, L.ld, P, N, BK, kFramesPerMTile) ||
+      !make_tmap_frames(ta1, blo, L.ld, P, N, BK, kFramesPerMTile))
+    return false;
+  const int b_rows = pair ? n_tile / 2 : n_tile;
+  if (L.col_stride == kFrameRows)
+    return make_tmap_frames(tb0, bhi, L.ld, P, N, BK, b_rows / kFrameRows) &&
+           make_tmap_frames(tb1, blo, L.ld, P, N, BK, b_rows / kFrameRows);
+  return make_tmap_k_major(tb0, bhi, 0, L.ld, L.rows_b, L.ld, BK, b_rows) &&
+         make_tmap_k_major(tb1, blo, 0, L.ld, L.rows_b, L.ld, BK, b_rows);
 }
 
 template <class Policy>
 static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t stream) {
   constexpr int BK = Policy::Cfg::BK;
   CUtensorMap ta0, ta1, tb0, tb1;
-  const void* hi = ws + L.off_hi;
-  const void* lo = ws + L.off_lo;
-  const void* bhi = ws + L.off_bhi;
-  const void* blo = ws + L.off_blo;
-  if (!make_tmap_k_major(&ta0, hi, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb0, bhi, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile) ||
-      !make_tmap_k_major(&ta1, lo, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb1, blo, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile))
+  if (!gram_maps(L, ws, p.N, p.P, BK, p.n_tile, false, &ta0, &ta1, &tb0, &tb1))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = ceil_div(p.D, BK);  // K blocks that hold data: the planes are zero from D to ld
-  p.kc = std::max(1, g_promote_k / BK);
+  p.kc = std::max(1, g_promote_k.load() / BK);
   if (p.num_tiles == 0) return DLC_OK;  // a part that owns no tile (more parts than M tiles)
   const int grid = std::min(p.num_tiles, sm_count());
   cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
@@ -888,19 +943,16 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
 }
 
 // The same launch on CTA pairs (gemm_pair_sm100.cuh): each CTA stages half of the N tile.
-extern int g_cta_pair;   // planes.cu
-extern int g_gram_pair;  // planes.cu
+extern std::atomic<int> g_cta_pair;   // planes.cu
+extern std::atomic<int> g_gram_pair;  // planes.cu
 template <class Policy>
 static int run_gram_pair(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t stream) {
   constexpr int BK = Policy::Cfg::BK;
   CUtensorMap ta0, ta1, tb0, tb1;
-  if (!make_tmap_k_major(&ta0, ws + L.off_hi, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb0, ws + L.off_bhi, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile / 2) ||
-      !make_tmap_k_major(&ta1, ws + L.off_lo, 0, L.ld, L.rows_pad, L.ld, BK, kTileM) ||
-      !make_tmap_k_major(&tb1, ws + L.off_blo, 0, L.ld, L.rows_b, L.ld, BK, p.n_tile / 2))
+  if (!gram_maps(L, ws, p.N, p.P, BK, p.n_tile, true, &ta0, &ta1, &tb0, &tb1))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = ceil_div(p.D, BK);
-  p.kc = std::max(1, g_promote_k / BK);
+  p.kc = std::max(1, g_promote_k.load() / BK);
   if (p.num_pair_tiles == 0) return DLC_OK;  // a part that owns no tile
   const int clusters = std::min(p.num_pair_tiles, sm_count() / 2);
   cudaError_t e = launch_gemm_pair<Policy>(ta0, ta1, tb0, tb1, p, clusters, stream);
@@ -916,10 +968,10 @@ using namespace dlc;
 // dataset-mean / prep_rows chain (which they do not depend on) and join before the probe is finalised - 0.12 ms of
 // latency-bound kernels off the critical path. One stream + two events per host thread and device, created lazily;
 // the fork / join is plain event ordering, so the call stays capturable and makes no host synchronisation.
-int g_probe_side_stream = 1;  // dlc_debug_set key 9 (0: everything on the caller's stream)
+std::atomic<int> g_probe_side_stream{1};  // dlc_debug_set key 9 (0: everything on the caller's stream)
 struct ProbeSide {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, mean_ready = nullptr, join = nullptr;
 };
 static ProbeSide* probe_side() {
   thread_local ProbeSide side[64];
@@ -929,6 +981,7 @@ static ProbeSide* probe_side() {
   if (!p.stream) {
     if (cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p.mean_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&p.join, cudaEventDisableTiming) != cudaSuccess) {
       p.stream = nullptr;
       return nullptr;
@@ -939,7 +992,7 @@ static ProbeSide* probe_side() {
 
 // Developer switch (dlc_debug_set key 1): launch only the Gram/score kernel, reusing the operand planes, statistics
 // and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
-static int g_gram_only = 0;
+static std::atomic<int> g_gram_only{0};
 // AUTO uses the one-product + refinement kernel only when the probe expects at most this share of rows to need the
 // exact re-evaluation. Measured on B200 (1063 frames, 17 M row-vs-frame decisions): the refinement costs ~11 us per
 // 1000 flagged rows (each candidate streams 10 KB float32 rows from L2), i.e. ~0.2 ms per 0.1 % of flagged rows,
@@ -965,7 +1018,7 @@ extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, doub
   double* part = static_cast<double*>(ws_dev);
   const int64_t rows = static_cast<int64_t>(N) * P;
   colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
-  weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev);
+  weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev, nullptr);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
@@ -1009,54 +1062,58 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
 
   double* colsum_part = reinterpret_cast<double*>(ws + L.off_part);
   double* w = reinterpret_cast<double*>(ws + L.off_w);
+  double* mean = reinterpret_cast<double*>(ws + L.off_mean);
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
   uint32_t* rep = reinterpret_cast<uint32_t*>(ws + L.off_rep);
-  static thread_local std::vector<int2> tiles, pair_tiles;
   const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
   ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(ws + L.off_probe);
   float* gaps = reinterpret_cast<float*>(ws + L.off_gaps);
-  ProbeSide* side = nullptr;
-  if (!g_gram_only) {
-  // 0. precision probe, part one (classes of bit-identical rows, single-product error on sampled rows): reads only the
-  //    descriptors - forked onto the side stream so that it overlaps steps 1 and 2
-  if (probe) {
-    DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
-    side = g_probe_side_stream ? probe_side() : nullptr;
+  const int gram_only = g_gram_only.load();
+  TileListEntry lists;
+  if (int rc = get_tile_lists(N, full_asymmetric, part, n_parts, &lists)) return rc;
+  if (!gram_only) {
+    // 0. precision probe, part one (classes of bit-identical rows): reads only the descriptors - forked onto the side
+    //    stream so that it overlaps step 1
+    ProbeSide* side = nullptr;
     cudaStream_t ps = s;
-    if (side) {
-      DLC_CUDA(cudaEventRecord(side->fork, s));
-      DLC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-      ps = side->stream;
+    if (probe) {
+      DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
+      side = g_probe_side_stream.load() ? probe_side() : nullptr;
+      if (side) {
+        DLC_CUDA(cudaEventRecord(side->fork, s));
+        DLC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        ps = side->stream;
+      }
+      rep_mask_kernel<<<N, 1024, 0, ps>>>(desc_dev, N, P, D, rep);
     }
-    rep_mask_kernel<<<N, 1024, 0, ps>>>(desc_dev, N, P, D, rep);
-    if (N >= 2) {
-      gram_probe_kernel<<<kProbeSamples, 1024, 0, ps>>>(desc_dev, N, P, D, rep, acc, gaps);
-    } else {
-      DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, ps));  // large gaps: nothing to refine
-    }
-    if (side) DLC_CUDA(cudaEventRecord(side->join, side->stream));
-  }
-  // 1. dataset mean -> distinctive weights w
-  if (w_dev) {  // weights of another dataset (SimilarityCalculator.similarity_score on frames outside it)
-    w = const_cast<double*>(w_dev);
-  } else {
+    // 1. dataset mean -> centring vector of the planes and distinctive weights w (w_dev given: weights of another
+    //    dataset, SimilarityCalculator.similarity_score on frames outside it; the mean is still this dataset's)
     colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
-    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w);
-  }
-  // 2. one pass: operand planes (M side: frames padded P -> 32 rows; N side: packed P rows per frame when separate;
-  //    K padded with zeros), per-row squared norms and projections p = h . w. With a precision probe (auto / fp16r)
-  //    the residual planes are written later and only if the probe picks the three-product kernel.
-  {
-    const bool sep = L.col_stride != kFrameRows;
+    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w_dev ? nullptr : w,
+                                                     mean);
+    if (w_dev) w = const_cast<double*>(w_dev);
+    // 2. precision probe, part two (single-product error of the CENTRED values on sampled rows): next to step 3
+    if (probe) {
+      if (side) {
+        DLC_CUDA(cudaEventRecord(side->mean_ready, s));
+        DLC_CUDA(cudaStreamWaitEvent(side->stream, side->mean_ready, 0));
+      }
+      if (N >= 2) {
+        gram_probe_kernel<<<kProbeSamples, 1024, 0, ps>>>(desc_dev, N, P, D, mean, rep, acc, gaps);
+      } else {
+        DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, ps));  // large gaps: nothing to refine
+      }
+      if (side) DLC_CUDA(cudaEventRecord(side->join, side->stream));
+    }
+    // 3. one pass: centred operand planes (P rows per frame, K padded with zeros), per-row squared norms of the centred
+    //    rows and projections p = h . w. With a precision probe (auto / fp16r) the residual planes are written later and
+    //    only if the probe picks the three-product kernel.
     const bool lo_now = precision == DLC_PREC_FP16X2;
     prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
-        desc_dev, N, P, D, w, reinterpret_cast<__half*>(ws + L.off_hi),
-        lo_now ? reinterpret_cast<__half*>(ws + L.off_lo) : nullptr,
-        sep ? reinterpret_cast<__half*>(ws + L.off_bhi) : nullptr,
-        sep && lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw,
-        probe ? &acc->nmax_bits : nullptr);
-    // 3. precision probe, part two (needs the largest row norm of step 2): margin and the device-side choice between
+        desc_dev, N, P, D, w, mean, reinterpret_cast<__half*>(ws + L.off_bhi),
+        lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw, probe ? &acc->nmax_bits : nullptr);
+    // 4. precision probe, part three (needs the largest row norm of step 3): margin and the device-side choice between
     //    the two Gram kernels
     if (probe) {
       GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
@@ -1064,32 +1121,25 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
       gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, g_max_flag_frac,
                                                    precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
       if (precision == DLC_PREC_AUTO)  // fp16r never runs the three-product kernel
-        lo_planes_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
-            desc_dev, N, P, D, reinterpret_cast<__half*>(ws + L.off_lo),
-            sep ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, ctl);
+        lo_planes_kernel<<<static_cast<int>(ceil_div64(rows, 8)), 256, 0, s>>>(
+            desc_dev, rows, D, mean, reinterpret_cast<__half*>(ws + L.off_blo), L.ld, ctl);
     }
-  }
-  DLC_CUDA(cudaGetLastError());
-
-  // 4. tile work list (host-built, tiny) -> device
-  build_tile_list(N, full_asymmetric, part, n_parts, tiles, pair_tiles);
-  DLC_CUDA(cudaMemcpyAsync(ws + L.off_ptiles, pair_tiles.data(), sizeof(int2) * pair_tiles.size(),
-                           cudaMemcpyHostToDevice, s));
-  // a part of the matrix: entries other parts own stay zero, so the parts combine with a sum (all-reduce)
-  if (n_parts > 1) DLC_CUDA(cudaMemsetAsync(S_dev, 0, sizeof(float) * static_cast<size_t>(N) * N, s));
-  DLC_CUDA(cudaMemcpyAsync(ws + L.off_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, s));
-  }  // !g_gram_only
+    DLC_CUDA(cudaGetLastError());
+    // a part of the matrix: entries other parts own stay zero, so the parts combine with a sum (all-reduce)
+    if (n_parts > 1) DLC_CUDA(cudaMemsetAsync(S_dev, 0, sizeof(float) * static_cast<size_t>(N) * N, s));
+  }  // !gram_only
 
   // 5. Gram + argmin + score
   GramParams p{};
   p.rep_mask = rep;
   p.col_stride = L.col_stride;
+  p.b_frame_map = L.col_stride == kFrameRows ? 1 : 0;
   p.n_tile = kFramesPerNTile * L.col_stride;  // 256, or 240 for 30 patches per frame
   p.ab_fmt = 0;
-  p.tiles = reinterpret_cast<const int2*>(ws + L.off_tiles);
-  p.num_tiles = static_cast<int>(tiles.size());
-  p.pair_tiles = reinterpret_cast<const int2*>(ws + L.off_ptiles);
-  p.num_pair_tiles = static_cast<int>(pair_tiles.size());
+  p.tiles = lists.tiles;
+  p.num_tiles = lists.num_tiles;
+  p.pair_tiles = lists.pair_tiles;
+  p.num_pair_tiles = lists.num_pair_tiles;
   p.N = N;
   p.P = P;
   p.D = D;
@@ -1115,11 +1165,12 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
   p.ctl = ctl;
   p.want_refine = 1;
-  p.work_cap = g_refine_cap >= 0 ? std::min(g_refine_cap, L.work_cap) : L.work_cap;
+  const int cap = g_refine_cap.load();
+  p.work_cap = cap >= 0 ? std::min(cap, L.work_cap) : L.work_cap;
   p.work = p.work_cap > 0 ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
-  if (g_gram_only) DLC_CUDA(cudaMemsetAsync(&ctl->n_entries, 0, sizeof(unsigned int), s));  // else reset by the probe
+  if (gram_only) DLC_CUDA(cudaMemsetAsync(&ctl->n_entries, 0, sizeof(unsigned int), s));  // else reset by the probe
   if (int rc = pairs ? run_gram_pair<GramRefinePolicy>(L, ws, p, s) : run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
-  if (p.work && g_gram_only != 2) {
+  if (p.work && gram_only != 2) {
     gram_refine_fix_kernel<<<4 * sm_count(), kFixThreads, 0, s>>>(p);
     DLC_CUDA(cudaGetLastError());
   }

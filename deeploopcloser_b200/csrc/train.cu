@@ -75,12 +75,16 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 }
 
 // One block per row. cd = mean_rows( -sum_j L_j * log_softmax(y)_j )   (softmax_cross_entropy_with_logits_v2)
-//   dy_j = (softmax(y)_j * sum(L) - L_j) / R,  dzy = dy * y * (1 - y)  (y is a sigmoid output),
+//   dy_j = (softmax(y)_j - L_j) / R  - TensorFlow's REGISTERED gradient (the op's backprop output is softmax - labels,
+//          xent_op.h, scaled by the incoming gradient, nn_grad.py [TF1-doc]): what optimizer.minimize follows in the
+//          reference although the labels (patch rows) sum to hundreds, not one;
+//          exact != 0: the mathematical derivative (softmax(y)_j * sum(L) - L_j) / R instead;
+//   dzy = dy * y * (1 - y)  (y is a sigmoid output),
 //   dlabel_j = -log_softmax(y)_j / R  (the _v2 op back-propagates into its labels).
 __global__ void __launch_bounds__(256)
 xent_grad_kernel(const float* __restrict__ y, const float* __restrict__ labels, int R, int C,
                  float* __restrict__ dzy_f32, __half* __restrict__ hi, __half* __restrict__ lo, int ld,
-                 float* __restrict__ dlabel, double* __restrict__ loss) {
+                 float* __restrict__ dlabel, double* __restrict__ loss, int exact) {
   __shared__ double shd[8];
   __shared__ float shf[8];
   const int r = blockIdx.x;
@@ -107,7 +111,7 @@ xent_grad_kernel(const float* __restrict__ y, const float* __restrict__ labels, 
     if (c < C) {
       const double yv = yr[c];
       const double ls = yv - lse;
-      const double dy = (exp(ls) * sl - static_cast<double>(lr[c])) * inv_r;
+      const double dy = (exp(ls) * (exact ? sl : 1.0) - static_cast<double>(lr[c])) * inv_r;
       g = static_cast<float>(dy * yv * (1.0 - yv));
       if (dzy_f32) dzy_f32[static_cast<int64_t>(r) * C + c] = g;
       if (dlabel) dlabel[static_cast<int64_t>(r) * C + c] = static_cast<float>(-ls * inv_r);
@@ -274,14 +278,14 @@ extern "C" int dlc_train_corrupt(const float* x_dev, const float* keep_dev, cons
 
 extern "C" int dlc_train_xent_grad(const float* y_dev, const float* labels_dev, int R, int C, float* dzy_f32_dev,
                                    void* dzy_hi_dev, void* dzy_lo_dev, int ld, float* dlabel_dev, double* loss_dev,
-                                   void* stream) {
+                                   int exact_gradient, void* stream) {
   DLC_CHECK_ARG(y_dev && labels_dev && loss_dev);
   DLC_CHECK_ARG(R > 0 && C > 0);
   DLC_CHECK_ARG(!dzy_hi_dev || ld >= C);
   xent_grad_kernel<<<R, 256, 0, as_stream(stream)>>>(y_dev, labels_dev, R, C, dzy_f32_dev,
                                                      static_cast<__half*>(dzy_hi_dev),
                                                      static_cast<__half*>(dzy_lo_dev), dzy_hi_dev ? ld : C, dlabel_dev,
-                                                     loss_dev);
+                                                     loss_dev, exact_gradient);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }

@@ -130,12 +130,16 @@ class DA:
         trainer.set_weights([self._w0], [self._b0], [self._b1])
         trainer.global_step = int(getattr(self, "global_step", 0))
         rows = self.batch_size * self.input_shape[0]
-        if getattr(self, "_masks", None) is None:
+        # the masks are graph constants in the reference (drawn once per instance); here once per (seed, rows): a
+        # later call with another seed or batch size draws its own instead of silently reusing the first ones
+        mask_key = (seed, rows)
+        if getattr(self, "_masks", None) is None or getattr(self, "_masks_key", None) != mask_key:
             gen = None
             if seed is not None:
                 gen = torch.Generator(device="cuda")
                 gen.manual_seed(seed)
             self._masks = trainer.da_masks(rows, self.corruption_level, gen)
+            self._masks_key = mask_key
         zm, om = self._masks
         loss = None
         for batch_n, s in enumerate(range(0, len(frames), self.batch_size)):
@@ -145,10 +149,9 @@ class DA:
                                 "choose a batch size that is a factor of the dataset size.")
                 break
             xd = torch.from_numpy(np.ascontiguousarray(np.stack(batch), dtype=np.float32)).cuda()
-            graphed = None
             for step in range(self.epochs):
-                if self.epochs >= 4:   # launch-bound step: captured once per batch shape, replayed as a CUDA graph
-                    graphed = graphed or trainer.graphed_step(xd, 0, [zm], [om], mask_rows=rows, da_mode=True)
+                if self.epochs >= 4:   # launch-bound step: captured ONCE per step shape, replayed as a CUDA graph
+                    graphed = trainer.cached_graphed_step(xd, 0, [zm], [om], mask_rows=rows, da_mode=True)
                     loss = graphed(xd)
                 else:
                     loss = trainer.step(xd, 0, [zm], [om], mask_rows=rows, da_mode=True)

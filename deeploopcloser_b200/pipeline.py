@@ -48,11 +48,26 @@ class LoopClosurePipeline:
             hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=self.encoder.needs_lo_input())
         return self.encoder.encode_planes(hi, lo, hi.shape[0])
 
-    def match(self, desc, n_frames, k=10, exclude_band=0):
+    def similarity(self, desc, n_frames):
+        """float32 [n_frames*P, D] descriptors -> float32 [n_frames, n_frames] SDAV score matrix (i<j mirrored,
+        diagonal -1: create_similarity_matrix.py:31-38)."""
         P = desc.shape[0] // n_frames
-        S = ops.sdav_similarity(desc.view(n_frames, P, -1), precision=self.sim_precision, **self.sim_args)
+        self.last_similarity = ops.sdav_similarity(desc.view(n_frames, P, -1), precision=self.sim_precision,
+                                                   **self.sim_args)
+        return self.last_similarity
+
+    def match(self, desc, n_frames, k=10, exclude_band=0):
+        S = self.similarity(desc, n_frames)
         cand = ops.topk_rows(S, min(k, max(n_frames - 1, 1)), largest=True, exclude_band=exclude_band)
         return S, cand
+
+    @staticmethod
+    def host_bytes_per_step(frames_h, xy_h, k):
+        """(host->device, device->host) bytes one run_host_stream step moves: the frames and keypoints in, the
+        [N, k] candidate scores (float32) and indices (int64) out."""
+        n = frames_h.shape[0]
+        kk = min(k, max(n - 1, 1))
+        return int(frames_h.numel() * frames_h.element_size() + xy_h.numel() * xy_h.element_size()), int(n * kk * 12)
 
     def run(self, frames, xy=None, k=10, exclude_band=0):
         desc = self.encode(frames, xy)

@@ -46,7 +46,7 @@ class _Layer:
 
 class DaeStackTrainer:
     def __init__(self, dims, patches=30, sparse_level=0.05, sparse_penalty=1.0, consecutive_penalty=0.2,
-                 learning_rate=0.1, device="cuda"):
+                 learning_rate=0.1, device="cuda", exact_gradient=False):
         from . import _cuda
         _cuda.require_cuda()
         self.dims = [int(d) for d in dims]
@@ -55,6 +55,10 @@ class DaeStackTrainer:
         self.sparse_penalty = float(sparse_penalty)
         self.consecutive_penalty = float(consecutive_penalty)
         self.lr = float(learning_rate)
+        # False (reference-faithful): the cross-entropy term back-propagates TensorFlow's registered gradient
+        # (softmax - labels) / R, what optimizer.minimize follows in the reference; True: the mathematical derivative
+        # of the loss (they differ because patch rows do not sum to one, see dlc_train_xent_grad)
+        self.exact_gradient = bool(exact_gradient)
         self.device = torch.device(device)
         self.layers = [_Layer(k, n, self.device) for k, n in zip(self.dims[:-1], self.dims[1:])]
         self.loss = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -129,7 +133,7 @@ class DaeStackTrainer:
         dzy_h, dzy_l = self._planes(R, Lt.in_pad)
         dlabel = torch.empty_like(dzy) if label_grad else None
         _lib.call("dlc_train_xent_grad", ptr(y), ptr(labels), R, Lt.n_in, ptr(dzy), ptr(dzy_h), ptr(dzy_l), Lt.in_pad,
-                  ptr(dlabel), ptr(self.loss), st)
+                  ptr(dlabel), ptr(self.loss), int(self.exact_gradient), st)
         dbd = torch.empty(Lt.n_in, dtype=torch.float64, device=self.device)
         _lib.call("dlc_train_colsum", ptr(dzy), R, Lt.n_in, ptr(dbd), st)
         dh_rec, _ = self._gemm(dzy_h, dzy_l, Lt.wt_hi, Lt.wt_lo, R, Lt.n_hid, None, "none", False)   # dzy W
@@ -189,6 +193,16 @@ class DaeStackTrainer:
         """The same step captured once in a CUDA graph (see GraphedStep): for the fit loops, which repeat one step
         shape `epochs` times per batch and are launch-bound at the reference's batch of 10 frames."""
         return GraphedStep(self, x, top, keep_masks, add_masks, mask_rows, da_mode)
+
+    def cached_graphed_step(self, x, top, keep_masks, add_masks=None, mask_rows=None, da_mode=False):
+        """graphed_step, captured once per (batch shape, loss layer, mask layout) and reused across the batches of a
+        fit loop (a capture costs two warm-up steps, a graph and a private memory pool)."""
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        key = (tuple(x.shape), int(top), mask_rows, bool(da_mode), add_masks is not None)
+        g = cache.get(key)
+        if g is None:
+            g = cache[key] = self.graphed_step(x, top, keep_masks, add_masks, mask_rows, da_mode)
+        return g
 
     # ---- mask generators (device-side draws; the reference's are unseeded NumPy / TensorFlow shuffles)
     def sdav_masks(self, top, level, generator=None):

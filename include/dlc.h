@@ -323,10 +323,14 @@ int dlc_cnnvtl_quantise(const float* const* seg_ptrs_host, const int64_t* seg_si
 int dlc_train_corrupt(const float* x_dev, const float* keep_dev, const float* add_dev, int R, int C, int mask_rows,
                       float* out_f32_dev, void* out_hi_dev, void* out_lo_dev, int ld, void* stream);
 /* softmax_cross_entropy_with_logits_v2(labels, logits = y) averaged over the R rows (SDAV.py:172): adds the loss to
- * loss_dev[0]; dzy = d loss / d (decoder pre-activation) = dy * y * (1 - y) as float32 and/or planes; dlabel
- * (optional) = d loss / d labels. */
+ * loss_dev[0]; dzy = dy * y * (1 - y) (gradient at the decoder pre-activation) as float32 and/or planes; dlabel
+ * (optional) = d loss / d labels. exact_gradient = 0 (what the reference's optimizer.minimize follows): dy is
+ * TensorFlow's registered gradient (softmax(y) - labels) / R, which is not the derivative of the loss when a row's
+ * labels do not sum to one (they are patch rows here) [TF1-doc: xent_op.h, nn_grad.py]; != 0: the mathematical
+ * derivative (softmax(y) * sum(labels) - labels) / R. */
 int dlc_train_xent_grad(const float* y_dev, const float* labels_dev, int R, int C, float* dzy_f32_dev,
-                        void* dzy_hi_dev, void* dzy_lo_dev, int ld, float* dlabel_dev, double* loss_dev, void* stream);
+                        void* dzy_hi_dev, void* dzy_lo_dev, int ld, float* dlabel_dev, double* loss_dev,
+                        int exact_gradient, void* stream);
 /* dzh = (dh_rec + dh_up + cs_coef * sign(h - sparse_level) + cc_coef * d(sum_b ||h[b] - h[b+1]||_F)/dh) * h * (1 - h)
  * for h [B*P, C]; dh_rec / dh_up optional. cs_coef = sparse_penalty / count, cc_coef = consecutive_penalty / (B - 1)
  * (SDAV.py:174-183); the two loss terms are added to loss_dev[0]. norms_dev: B - 1 doubles of scratch. */

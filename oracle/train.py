@@ -72,12 +72,22 @@ def loss_terms(labels, y, h, B, P, sparse_level, cs_over_patches):
     return cd, cs, cc
 
 
-def loss_term_grads(labels, y, h, B, P, sparse_level, sparse_penalty, consecutive_penalty, cs_over_patches):
-    """d loss / d y, d loss / d labels, d loss / d h (the direct cs + cc part) for loss = cd + sp*cs + cp*cc."""
+def loss_term_grads(labels, y, h, B, P, sparse_level, sparse_penalty, consecutive_penalty, cs_over_patches,
+                    exact_gradient=False):
+    """d loss / d y, d loss / d labels, d loss / d h (the direct cs + cc part) for loss = cd + sp*cs + cp*cc.
+
+    d cd / d y: TensorFlow's `softmax_cross_entropy_with_logits_v2` (SDAV.py:172, DenoisingAutoencoderVariant.py:124)
+    does NOT differentiate its loss exactly when the labels of a row do not sum to one: the op emits
+    backprop = softmax(logits) - labels (tensorflow/core/kernels/xent_op.h) and the registered gradient only scales it
+    by the incoming gradient (python/ops/nn_grad.py: _SoftmaxCrossEntropyWithLogitsGrad) [TF1-doc]. The labels here are
+    image patches / activations that sum to hundreds per row, so `optimizer.minimize` in the reference follows
+    (softmax - labels) / R - the default here - not the mathematical derivative (softmax * sum(labels) - labels) / R
+    (`exact_gradient=True`; that one equals finite differences of the loss). The label gradient -log_softmax / R and
+    the loss value are the same in both."""
     R = B * P
     ls = log_softmax(y)
     sm = np.exp(ls)
-    dy = (sm * labels.sum(axis=1, keepdims=True) - labels) / R
+    dy = (sm * (labels.sum(axis=1, keepdims=True) if exact_gradient else 1.0) - labels) / R
     dlabels = -ls / R
     hid = h.shape[1]
     count = B * hid if cs_over_patches else R
@@ -118,7 +128,7 @@ def sdav_loss(x, Ws, bs, bds, layer_i, masks, sparse_level=0.05, sparse_penalty=
 
 
 def sdav_loss_and_grads(x, Ws, bs, bds, layer_i, masks, sparse_level=0.05, sparse_penalty=1.0,
-                        consecutive_penalty=0.2):
+                        consecutive_penalty=0.2, exact_gradient=False):
     """loss_i and its gradients: (loss, dW[0..i], db[0..i], dbd_i)."""
     B, P, _ = x.shape
     xs, hs, y = sdav_forward(x, Ws, bs, bds, layer_i, masks)
@@ -127,7 +137,7 @@ def sdav_loss_and_grads(x, Ws, bs, bds, layer_i, masks, sparse_level=0.05, spars
     cd, cs, cc = loss_terms(labels, y, hs[i], B, P, sparse_level, cs_over_patches=(i == 0))
     loss = cd + sparse_penalty * cs + consecutive_penalty * cc
     dy, dlabels, dh = loss_term_grads(labels, y, hs[i], B, P, sparse_level, sparse_penalty, consecutive_penalty,
-                                      cs_over_patches=(i == 0))
+                                      cs_over_patches=(i == 0), exact_gradient=exact_gradient)
     dzy = dy * y * (1 - y)
     dbd = dzy.sum(axis=0)
     dW = [None] * (i + 1)
@@ -170,13 +180,14 @@ def da_forward(x, w0, b0, b1, zeros_mask, ones_mask):
 
 
 def da_loss_and_grads(x, w0, b0, b1, zeros_mask, ones_mask, sparse_level=0.05, sparse_penalty=1.0,
-                      consecutive_penalty=0.2):
+                      consecutive_penalty=0.2, exact_gradient=False):
     B, P, _ = x.shape
     xc, h, y = da_forward(x, w0, b0, b1, zeros_mask, ones_mask)
     labels = x.reshape(B * P, -1)
     cd, cs, cc = loss_terms(labels, y, h, B, P, sparse_level, cs_over_patches=False)
     loss = cd + sparse_penalty * cs + consecutive_penalty * cc
-    dy, _, dh = loss_term_grads(labels, y, h, B, P, sparse_level, sparse_penalty, consecutive_penalty, False)
+    dy, _, dh = loss_term_grads(labels, y, h, B, P, sparse_level, sparse_penalty, consecutive_penalty, False,
+                                exact_gradient=exact_gradient)
     dzy = dy * y * (1 - y)
     dh = dh + dzy @ w0
     dzh = dh * h * (1 - h)

@@ -5,8 +5,10 @@ arguments:
 
     python -m src.sdav.create_similarity_matrix DATASET_DIR OUT.png [--checkpoint DIR] [--keypoints seeded|surf]
 
-`--keypoints seeded` (default when OpenCV's non-free SURF is absent) draws 30 uniform keypoints per frame from
-np.random.default_rng(seed)."""
+`--keypoints surf` (default) finds the 30 strongest fast-Hessian keypoints of every frame with the B200 detector
+(dlc_surf_detect - the reference calls cv2.xfeatures2d.SURF_create().detect, CvInputParser.py:36-46; OpenCV's non-free
+module is not needed and not used). `--keypoints seeded` is an explicit opt-in for tests: 30 uniform keypoints per
+frame from np.random.default_rng(seed)."""
 import argparse
 import glob
 import logging
@@ -20,7 +22,7 @@ def main(argv=None):
     ap.add_argument("dataset")
     ap.add_argument("out_png")
     ap.add_argument("--checkpoint", default=None, help="SDAV checkpoint directory (TensorFlow format); default: N(0,1) init")
-    ap.add_argument("--keypoints", default=None, choices=["seeded", "surf"])
+    ap.add_argument("--keypoints", default="surf", choices=["seeded", "surf"])
     ap.add_argument("--seed", type=int, default=0)
     args = ap.parse_args(argv)
     logging.getLogger().setLevel(logging.INFO)
@@ -35,9 +37,8 @@ def main(argv=None):
     if args.checkpoint:
         network.load_weights(args.checkpoint)
     files = sorted(glob.glob(os.path.join(args.dataset, "*")))
-    mode = args.keypoints or ("surf" if hasattr(cv2, "xfeatures2d") else "seeded")
-    key_points = None
-    if mode == "seeded":
+    key_points = None                # "surf": CvInputParser runs the device detector on every frame
+    if args.keypoints == "seeded":
         rng = np.random.default_rng(args.seed)
 
         def key_points(i, path):

@@ -95,6 +95,17 @@ def _rows(args):
     return i, out
 
 
+def _classify(pairs):
+    """Worker: class of each frame pair outside the tolerance (tests/parity_report.py)."""
+    import parity_report as pr
+    out = []
+    for i, j in pairs:
+        c, det = pr.classify_pair(_STATE["S_auto"][i, j], _STATE["dev"][i], _STATE["dev"][j], _STATE["ref"][i],
+                                  _STATE["ref"][j], _STATE["w_dev"], _STATE["w_ref"], tol=TOL, s_ref=None)
+        out.append((i, j, c, det if c == "unexplained" else None))
+    return out
+
+
 def oracle_matrix(which, pool, n):
     S = np.full((n, n), -1.0)
     order = sorted(range(n - 1), key=lambda i: i)            # long rows first: balanced tail
@@ -145,15 +156,22 @@ def main():
     desc_ref = o_sda.sda_forward(x, ws, bs).reshape(n, 30, -1)
     t_enc = time.perf_counter() - t0
     _STATE.update(dev=desc_dev, ref=desc_ref, w_dev=o_sim.distinctive_weights(desc_dev),
-                  w_ref=o_sim.distinctive_weights(desc_ref))
+                  w_ref=o_sim.distinctive_weights(desc_ref), S_auto=S_auto)
     cores = os.cpu_count() or 1
+    iu = np.triu_indices(n, 1)
+    n_pairs = len(iu[0])
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
         S_stage = oracle_matrix("dev", pool, n)
         S_ref = oracle_matrix("ref", pool, n)
-    t_scores = time.perf_counter() - t0
-    iu = np.triu_indices(n, 1)
-    n_pairs = len(iu[0])
+        t_scores = time.perf_counter() - t0
+        # from pixels: classes of every pair outside the tolerance (in the pool: ~6 ms of float64 work per pair)
+        with np.errstate(invalid="ignore"):
+            rel_px = np.abs(S_auto - S_ref) / np.maximum(1.0, np.abs(S_ref))
+        rel_px[~np.isfinite(S_ref) & ~np.isfinite(S_auto)] = 0.0
+        outside = [(int(i), int(j)) for i, j in zip(*iu) if not rel_px[i, j] <= TOL]
+        chunks = [outside[c:c + 64] for c in range(0, len(outside), 64)]
+        classified = [r for part in pool.imap_unordered(_classify, chunks) for r in part]
 
     # ---- stage: the matcher on its own descriptors
     with np.errstate(invalid="ignore"):
@@ -176,20 +194,14 @@ def main():
     x2_bad_total = int(np.sum(~(rel_x2[iu] <= TOL) & np.isfinite(S_stage[iu])))
 
     # ---- from pixels: classes of every pair outside the tolerance
-    with np.errstate(invalid="ignore"):
-        rel_px = np.abs(S_auto - S_ref) / np.maximum(1.0, np.abs(S_ref))
-    rel_px[~np.isfinite(S_ref) & ~np.isfinite(S_auto)] = 0.0
-    outside = [(int(i), int(j)) for i, j in zip(*iu) if not rel_px[i, j] <= TOL]
     counts = {"ok": n_pairs - len(outside), "tie": 0, "conditioning": 0, "unexplained": 0}
     cls = np.full((n, n), "ok", dtype=object)
     unexplained = []
-    for i, j in outside:
-        c, det = pr.classify_pair(S_auto[i, j], desc_dev[i], desc_dev[j], desc_ref[i], desc_ref[j], _STATE["w_dev"],
-                                  _STATE["w_ref"], tol=TOL, s_ref=None)
+    for i, j, c, det in classified:
         counts[c] += 1
         cls[i, j] = cls[j, i] = c
         if c == "unexplained":
-            unexplained.append({"pair": [i, j], **{k: v for k, v in det.items()}})
+            unexplained.append({"pair": [i, j], **det})
     ok_mask = np.ones(n_pairs, dtype=bool)
     ok_mask[[k for k, (i, j) in enumerate(zip(*iu)) if cls[i, j] != "ok"]] = False
     finite = np.isfinite(S_ref[iu]) & ok_mask

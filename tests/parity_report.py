@@ -132,28 +132,37 @@ def pair_classes(S_dev, desc_dev, desc_ref, S_ref, idx_ref=None, a=10.0, b=-10.0
 
 def candidate_report(idx_dev, S_ref, cls, k, tol=1e-3):
     """Loop-candidate lists (per-row top-k of the mirrored score matrix, frame itself excluded, best first, ties ->
-    lowest index) of the device against the oracle's. A position where the two lists name different frames is a
-    'tie within tolerance' when both pairs are class ok and their ORACLE scores differ by at most 2 tol (each device
-    score may be off by tol), 'moved' when one of the two pairs is a tie / conditioning pair (its score legitimately
-    moved), else unexplained."""
+    lowest index) of the device against the oracle's ranking. A row's device list is checked through its INVERSIONS:
+    pairs (d, o) with d listed by the device, o ranked strictly better than d by the oracle, and o NOT listed before
+    d by the device (o is missing from the list or comes later). Comparing position by position would blame every
+    entry behind one moved candidate. An inversion is a
+      tie within tolerance  when both frame pairs are class ok and the oracle scores differ by at most 2 tol (each
+                            device score may be off by tol),
+      moved pair            when (row, d) or (row, o) is a tie / conditioning pair (its score legitimately moved),
+      unexplained           otherwise."""
     S = np.array(S_ref, dtype=np.float64)
     n = len(S)
     np.fill_diagonal(S, -np.inf)
     want = np.argsort(-S, axis=1, kind="stable")[:, :k]
-    out = {"rows": n, "rows_identical": 0, "positions_tie_within_tol": 0, "positions_moved_pair": 0,
-           "positions_unexplained": 0}
+    out = {"rows": n, "rows_identical": 0, "rows_with_inversions": 0, "inversions_tie_within_tol": 0,
+           "inversions_moved_pair": 0, "positions_unexplained": 0}
     for r in range(n):
         if np.array_equal(idx_dev[r], want[r]):
             out["rows_identical"] += 1
             continue
+        out["rows_with_inversions"] += 1
+        listed_before = np.zeros(n, dtype=bool)
         for p in range(k):
-            d, o = int(idx_dev[r, p]), int(want[r, p])
-            if d == o:
+            d = int(idx_dev[r, p])
+            if d < 0:
                 continue
-            if cls[r, d] != "ok" or cls[r, o] != "ok":
-                out["positions_moved_pair"] += 1
-            elif abs(S[r, d] - S[r, o]) <= 2 * tol * max(1.0, abs(S[r, o])):
-                out["positions_tie_within_tol"] += 1
-            else:
-                out["positions_unexplained"] += 1
+            better = np.nonzero((S[r] > S[r, d]) & ~listed_before)[0]      # the oracle prefers these to d
+            for o in better:
+                if cls[r, d] != "ok" or cls[r, o] != "ok":
+                    out["inversions_moved_pair"] += 1
+                elif S[r, o] - S[r, d] <= 2 * tol * max(1.0, abs(S[r, o])):
+                    out["inversions_tie_within_tol"] += 1
+                else:
+                    out["positions_unexplained"] += 1
+            listed_before[d] = True
     return out

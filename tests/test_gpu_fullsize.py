@@ -139,6 +139,45 @@ def test_config3_cnnvtl_descriptors_and_hamming_matrix(cuda):
         assert D[i, j] == o_ham.distance(d[i], d[j])
 
 
+def test_config3_cosine_topk_on_cnnvtl_descriptors(cuda):
+    """Config 3's matcher as BASELINE states it: "cnn_vtl descriptors + cosine top-k matching". CnnVtl.transform ->
+    KeyframeDatabase("cos") (CnnVtl.cosine_candidates) on 400 frames against the float64 oracle on the stored
+    (L2-normalised, fp16-rounded) descriptors: indices identical except ties within the tolerance (reported), scores
+    within 1e-3, the frame itself never listed. Parity unpinned by construction (the reference has no such step,
+    create_distance_matrix.py:27-36 only fills the Hamming matrix)."""
+    from deeploopcloser_b200.cnn_vtl import CnnVtl
+    from oracle import matcher as o_match
+    N, H, W, k = 400, 192, 240, 10
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (N // 4, H, W, 3), dtype=np.uint8)
+    # revisits: every fourth of the sequence is the first quarter again plus pixel noise -> true loop closures
+    x = np.concatenate([np.clip(base.astype(np.int16) + rng.integers(-6 * r, 6 * r + 1, base.shape), 0, 255)
+                        .astype(np.uint8) for r in range(4)])
+    params = o_cnn.make_weights(3)
+    keep = o_cnn.make_keep_columns(o_cnn.layer_sizes((H, W)), seed=4)
+    net = CnnVtl(input_shape=[N, H, W, 3], weights=params, keep_cols=keep)
+    d = net.transform(x)
+    scores, idx = [t.cpu().numpy() for t in net.cosine_candidates(d, k=k)]
+    assert scores.shape == (N, k) and idx.shape == (N, k)
+    assert not np.any(idx == np.arange(N)[:, None])                    # the frame itself is excluded
+    f = torch.from_numpy(d.astype(np.float32))
+    stored = (f / f.norm(dim=1, keepdim=True).clamp_min(1e-30)).half().double().numpy()
+    ref = stored @ stored.T                                            # queries are rounded like the stored rows
+    np.fill_diagonal(ref, -np.inf)
+    rs, ri = o_match.topk(ref, k)
+    ties = 0
+    for r in range(N):
+        for t in range(k):
+            if idx[r, t] != ri[r, t]:
+                assert abs(ref[r, idx[r, t]] - rs[r, t]) <= 2 * TOL, (r, t, idx[r], ri[r])
+                ties += 1
+        assert np.all(np.abs(scores[r] - ref[r, idx[r]]) <= TOL)
+    revisit = np.mean([(r % (N // 4)) in (idx[r] % (N // 4)) for r in range(N)])
+    print("config 3 cosine top-%d on %d cnn_vtl descriptors: ties within tol %d, rows whose list holds a revisit of "
+          "the same place %.3f" % (k, N, ties, revisit))
+    assert revisit > 0.95
+
+
 def test_config4_matcher_full_size_properties(cuda):
     """Config 4 on one GPU: 1 M x 4096 database, 1024 queries, top-10. Planted near-duplicates come back first,
     lists are sorted, and the list over the whole database equals the merge of the lists over its two halves."""

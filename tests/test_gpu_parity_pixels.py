@@ -63,7 +63,7 @@ def test_config1_from_pixels(cuda, config1, tag, seed, scale, precision):
     cls = pr.pair_classes(S_sym, desc_dev, desc_ref, S_ref, idx_ref=g["idx_" + tag], tol=TOL)
     assert not np.any(cls == "unexplained")
     crep = pr.candidate_report(res[1][1].cpu().numpy(), S_ref, cls, K, TOL)
-    print("  candidate lists (top-%d of 20 rows): identical rows %d, positions differing by a tie within tolerance %d, "
+    print("  candidate lists (top-%d of 20 rows): identical rows %d, inversions by a tie within tolerance %d, "
           "by a pair whose score moved %d, unexplained %d" % (K, crep["rows_identical"],
-          crep["positions_tie_within_tol"], crep["positions_moved_pair"], crep["positions_unexplained"]))
+          crep["inversions_tie_within_tol"], crep["inversions_moved_pair"], crep["positions_unexplained"]))
     assert crep["positions_unexplained"] == 0

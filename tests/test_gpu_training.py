@@ -23,18 +23,21 @@ def _setup(dims, B, P, seed, scale):
     return rng, x, Ws, bs, bds
 
 
-@pytest.mark.parametrize("dims,B,P,top", [((70, 96, 40), 4, 5, 0), ((70, 96, 40), 4, 5, 1), ((300, 130, 64, 33), 3, 30, 2),
-                                          ((1681, 2500), 10, 30, 0)])
-def test_sdav_train_step_vs_oracle(cuda, dims, B, P, top):
+# exact = False: TensorFlow's registered cross-entropy gradient (softmax - labels), the reference-faithful default;
+# exact = True: the mathematical derivative of the loss (see dlc_train_xent_grad)
+@pytest.mark.parametrize("dims,B,P,top,exact", [((70, 96, 40), 4, 5, 0, False), ((70, 96, 40), 4, 5, 1, False),
+                                                ((70, 96, 40), 4, 5, 1, True), ((300, 130, 64, 33), 3, 30, 2, False),
+                                                ((300, 130, 64, 33), 3, 30, 2, True), ((1681, 2500), 10, 30, 0, False)])
+def test_sdav_train_step_vs_oracle(cuda, dims, B, P, top, exact):
     from deeploopcloser_b200.training import DaeStackTrainer
     rng, x, Ws, bs, bds = _setup(dims, B, P, 7 + top, 0.3 if dims[0] < 1000 else 0.05)
     masks = [o_train.sdav_mask(P, d, 0.3, rng) for d in dims[:top + 1]]
-    tr = DaeStackTrainer(dims, patches=P)
+    tr = DaeStackTrainer(dims, patches=P, exact_gradient=exact)
     tr.set_weights(Ws, bs, bds)
     xd = torch.from_numpy(x).float().cuda()
     md = [torch.from_numpy(m).float().cuda() for m in masks]
     loss = float(tr.step(xd, top, md).item())
-    want_loss, dW, db, dbd = o_train.sdav_loss_and_grads(x, Ws, bs, bds, top, masks)
+    want_loss, dW, db, dbd = o_train.sdav_loss_and_grads(x, Ws, bs, bds, top, masks, exact_gradient=exact)
     g = tr.last_grads
     print("loss %.9f vs %.9f" % (loss, want_loss))
     assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
@@ -44,7 +47,7 @@ def test_sdav_train_step_vs_oracle(cuda, dims, B, P, top):
         assert e_w <= 1e-4 and e_b <= 1e-4
     assert _nerr(g["dbd"].cpu().numpy(), dbd) <= 1e-4
     # the update itself: every layer <= top moved by lr * grad, the decoder bias only at `top`
-    _, W2, b2, bd2 = o_train.sdav_train_step(x, Ws, bs, bds, top, masks, lr=0.1)
+    _, W2, b2, bd2 = o_train.sdav_train_step(x, Ws, bs, bds, top, masks, lr=0.1, exact_gradient=exact)
     gW, gb, gbd = tr.get_weights()
     for l in range(len(dims) - 1):
         assert _nerr(gW[l], W2[l]) <= 1e-6 and _nerr(gb[l], b2[l]) <= 1e-5
@@ -73,7 +76,9 @@ def test_training_reduces_the_loss(cuda):
     from deeploopcloser_b200.training import DaeStackTrainer
     dims, B, P = (64, 48), 6, 4
     rng, x, Ws, bs, bds = _setup(dims, B, P, 11, 0.2)
-    tr = DaeStackTrainer(dims, patches=P, learning_rate=0.05)
+    # exact_gradient: descent on the loss itself (TensorFlow's registered cross-entropy gradient, the default, is not
+    # the derivative of this loss on un-normalised labels, so monotone decrease is only guaranteed for the exact one)
+    tr = DaeStackTrainer(dims, patches=P, learning_rate=0.05, exact_gradient=True)
     tr.set_weights(Ws, bs, bds)
     gen = torch.Generator(device="cuda")
     gen.manual_seed(0)
