@@ -59,6 +59,13 @@ PROTOTYPES = {
     "dlc_sdav_similarity_part": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_sdav_similarity_stats": (_i, [_i, _i, _i, _p, _p, _p]),
     "dlc_sdav_weights": (_i, [_p, _i, _i, _i, _d, _d, _p, _p, _sz, _p]),
+    "dlc_sdav_stage_stats_bytes": (_sz, [_i]),
+    "dlc_sdav_stage_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "dlc_sdav_stage_colsum": (_i, [_p, _i64, _i, _p, _p, _sz, _p]),
+    "dlc_sdav_stage_weights": (_i, [_p, _i, _i64, _i, _d, _d, _p, _p, _p]),
+    "dlc_sdav_stage_prepare": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "dlc_sdav_stage_gram": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _sz, _p]),
+    "dlc_sdav_stage_fix": (_i, [_p, _p, _i, _i, _i, _d, _d, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "dlc_mean_pool_rows": (_i, [_p, _i, _i, _i, _p, _p]),
     "dlc_db_create": (_i, [C.POINTER(_p), _i, _i64, _i, _i]),

@@ -912,10 +912,15 @@ static SimWorkspace sim_layout(int N, int P, int D) {
 
 // Tensor maps of one Gram launch: A = frame map (4 frames x 32 rows per tile); B = frame map of `b_box_frames` frames,
 // or plain rows (col_stride = P) of `b_rows` rows per load.
-static bool gram_maps(const SimWorkspace& L, char* ws, int N, int P, int BK, int n_tile, bool pair, CUtensorMap* ta0,
+struct GramPlanes {
+  const void* hi;   // [N * P, ld] fp16, centred
+  const void* lo;   // residual plane (three-product kernel only; may alias hi when unused)
+  int ld, col_stride;
+};
+static bool gram_maps(const GramPlanes& L, int N, int P, int BK, int n_tile, bool pair, CUtensorMap* ta0,
                       CUtensorMap* ta1, CUtensorMap* tb0, CUtensorMap* tb1) {
-  const void* bhi = ws + L.off_bhi;
-  const void* blo = ws + L.off_blo;
+  const void* bhi = L.hi;
+  const void* blo = L.lo ? L.lo : L.hi;
   if (!make_tmap_frames(ta0, bhi, L.ld, P, N, BK, kFramesPerMTile) ||
       !make_tmap_frames(ta1, blo, L.ld, P, N, BK, kFramesPerMTile))
     return false;
@@ -923,15 +928,16 @@ static bool gram_maps(const SimWorkspace& L, char* ws, int N, int P, int BK, int
   if (L.col_stride == kFrameRows)
     return make_tmap_frames(tb0, bhi, L.ld, P, N, BK, b_rows / kFrameRows) &&
            make_tmap_frames(tb1, blo, L.ld, P, N, BK, b_rows / kFrameRows);
-  return make_tmap_k_major(tb0, bhi, 0, L.ld, L.rows_b, L.ld, BK, b_rows) &&
-         make_tmap_k_major(tb1, blo, 0, L.ld, L.rows_b, L.ld, BK, b_rows);
+  const uint64_t rows_b = static_cast<uint64_t>(N) * P;
+  return make_tmap_k_major(tb0, bhi, 0, L.ld, rows_b, L.ld, BK, b_rows) &&
+         make_tmap_k_major(tb1, blo, 0, L.ld, rows_b, L.ld, BK, b_rows);
 }
 
 template <class Policy>
-static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t stream) {
+static int run_gram(const GramPlanes& L, GramParams p, cudaStream_t stream) {
   constexpr int BK = Policy::Cfg::BK;
   CUtensorMap ta0, ta1, tb0, tb1;
-  if (!gram_maps(L, ws, p.N, p.P, BK, p.n_tile, false, &ta0, &ta1, &tb0, &tb1))
+  if (!gram_maps(L, p.N, p.P, BK, p.n_tile, false, &ta0, &ta1, &tb0, &tb1))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = ceil_div(p.D, BK);  // K blocks that hold data: the planes are zero from D to ld
   p.kc = std::max(1, g_promote_k.load() / BK);
@@ -946,10 +952,10 @@ static int run_gram(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t 
 extern std::atomic<int> g_cta_pair;   // planes.cu
 extern std::atomic<int> g_gram_pair;  // planes.cu
 template <class Policy>
-static int run_gram_pair(const SimWorkspace& L, char* ws, GramParams p, cudaStream_t stream) {
+static int run_gram_pair(const GramPlanes& L, GramParams p, cudaStream_t stream) {
   constexpr int BK = Policy::Cfg::BK;
   CUtensorMap ta0, ta1, tb0, tb1;
-  if (!gram_maps(L, ws, p.N, p.P, BK, p.n_tile, true, &ta0, &ta1, &tb0, &tb1))
+  if (!gram_maps(L, p.N, p.P, BK, p.n_tile, true, &ta0, &ta1, &tb0, &tb1))
     return fail(DLC_ECUDA, "dlc_sdav_similarity: cuTensorMapEncodeTiled failed");
   p.k_blocks = ceil_div(p.D, BK);
   p.kc = std::max(1, g_promote_k.load() / BK);
@@ -1026,6 +1032,10 @@ extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, doub
 static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
                                 double b, const double* w_dev, int precision, int full_asymmetric, int part,
                                 int n_parts, float* S_dev, void* ws_dev, size_t ws_bytes, void* stream);
+static bool use_pairs(const GramParams& p) {
+  return g_cta_pair && g_gram_pair && p.n_tile >= 32 && p.n_tile % 16 == 0 && (p.n_tile / 2) % 8 == 0 &&
+         (p.num_pair_tiles >= sm_count() / 2 || g_cta_pair == 2);
+}
 
 extern "C" int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a,
                                    double b, const double* w_dev, int precision, int full_asymmetric,
@@ -1153,12 +1163,12 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.ctl = nullptr;
   p.want_refine = 0;
   // enough pair tiles to fill the GPU and an N tile that splits into two UMMA-legal halves: CTA pairs
-  const bool pairs = g_cta_pair && g_gram_pair && p.n_tile >= 32 && p.n_tile % 16 == 0 && (p.n_tile / 2) % 8 == 0 &&
-                     (p.num_pair_tiles >= sm_count() / 2 || g_cta_pair == 2);
+  const bool pairs = use_pairs(p);
+  const GramPlanes planes{ws + L.off_bhi, ws + L.off_blo, L.ld, L.col_stride};
   if (precision == DLC_PREC_FP16X2)
-    return pairs ? run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s) : run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+    return pairs ? run_gram_pair<GramPolicy<32, 3>>(planes, p, s) : run_gram<GramPolicy<32, 3>>(planes, p, s);
   if (precision == DLC_PREC_FP16)
-    return pairs ? run_gram_pair<GramPolicy<64, 1>>(L, ws, p, s) : run_gram<GramPolicy<64, 1>>(L, ws, p, s);
+    return pairs ? run_gram_pair<GramPolicy<64, 1>>(planes, p, s) : run_gram<GramPolicy<64, 1>>(planes, p, s);
 
   // DLC_PREC_AUTO / DLC_PREC_FP16_REFINED: probe the single-product error on the data, then launch both kernels; the
   // device-side control block lets exactly one of them run (no host round trip).
@@ -1169,14 +1179,302 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   p.work_cap = cap >= 0 ? std::min(cap, L.work_cap) : L.work_cap;
   p.work = p.work_cap > 0 ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
   if (gram_only) DLC_CUDA(cudaMemsetAsync(&ctl->n_entries, 0, sizeof(unsigned int), s));  // else reset by the probe
-  if (int rc = pairs ? run_gram_pair<GramRefinePolicy>(L, ws, p, s) : run_gram<GramRefinePolicy>(L, ws, p, s)) return rc;
+  if (int rc = pairs ? run_gram_pair<GramRefinePolicy>(planes, p, s) : run_gram<GramRefinePolicy>(planes, p, s)) return rc;
   if (p.work && gram_only != 2) {
     gram_refine_fix_kernel<<<4 * sm_count(), kFixThreads, 0, s>>>(p);
     DLC_CUDA(cudaGetLastError());
   }
   p.work = nullptr;
   p.want_refine = 0;
-  return pairs ? run_gram_pair<GramPolicy<32, 3>>(L, ws, p, s) : run_gram<GramPolicy<32, 3>>(L, ws, p, s);
+  return pairs ? run_gram_pair<GramPolicy<32, 3>>(planes, p, s) : run_gram<GramPolicy<32, 3>>(planes, p, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Staged form of the same computation, for ONE sequence whose frames are split over the GPUs of a box:
+// every stage works on rank-local rows and writes into this rank's slice of arrays that the host exchanges with
+// NCCL all-gathers between the stages (frames are dealt in contiguous blocks of `frames_per_part`, so the gathered
+// arrays are the flat global ones). Nothing is computed twice: the dataset mean, the row statistics, the operand
+// planes and the precision probe are all produced once, by the rank that encoded the frame.
+//   stage_colsum   local descriptors -> column sums [D]                       | all-gather [n_parts, D] doubles
+//   stage_weights  all column sums   -> mean [D], weights w [D]               | (identical on every rank)
+//   stage_prepare  local descriptors -> centred plane slice + stats block     | all-gather planes, all-gather stats
+//   stage_gram     planes + stats    -> this part's tile rows of S + the list of ambiguous pairs
+//   stage_fix      float32 descriptors of ALL frames -> exact scores of the listed pairs   (after their all-gather,
+//                  which the host overlaps with stage_gram)
+// ------------------------------------------------------------------------------------------------------------
+namespace dlc {
+struct StageStats {  // layout of one part's stats block
+  size_t off_sqn, off_pw, off_rep, off_probe, off_gaps, total;
+};
+static StageStats stage_stats_layout(int frames_per_part) {
+  StageStats t{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o = align_up(o + bytes, 16);
+    return at;
+  };
+  t.off_sqn = take(sizeof(float) * frames_per_part * kFrameRows);
+  t.off_pw = take(sizeof(double) * frames_per_part * kFrameRows);
+  t.off_rep = take(sizeof(uint32_t) * frames_per_part);
+  t.off_probe = take(sizeof(ProbeAccum));
+  t.off_gaps = take(sizeof(float) * kProbeSamples);
+  t.total = align_up(o, 256);
+  return t;
+}
+struct StageWorkspace {
+  size_t off_part, off_sqn, off_pw, off_rep, off_ctl, off_work, total;
+  int work_cap;
+};
+static StageWorkspace stage_layout(int N, int D, int n_parts) {
+  StageWorkspace w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  w.off_part = take(sizeof(double) * kColSumSlabs * D);
+  w.off_sqn = take(sizeof(float) * N * kFrameRows);
+  w.off_pw = take(sizeof(double) * N * kFrameRows);
+  w.off_rep = take(sizeof(uint32_t) * N);
+  w.off_ctl = take(sizeof(GramControl));
+  // one entry per frame pair this part can own (+ slack for the interleaving): the list never overflows, so the Gram
+  // kernel itself never reads the float32 descriptors - their exchange overlaps it
+  const int64_t pairs = (static_cast<int64_t>(N) * N / 2) / n_parts + 64LL * N + 1024;
+  w.work_cap = static_cast<int>(std::min<int64_t>(pairs, int64_t{1} << 22));
+  w.off_work = take(sizeof(RefineEntry) * static_cast<size_t>(w.work_cap));
+  w.total = o;
+  return w;
+}
+
+__global__ void colsum_reduce_kernel(const double* __restrict__ part, int slabs, int D, double* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  double acc = 0.0;
+  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * D + col];
+  out[col] = acc;
+}
+
+// stats blocks of all parts -> flat sqn [N*32], pw [N*32], rep [N] (frame g lives in block g / per at g % per)
+__global__ void stage_unpack_kernel(const uint8_t* __restrict__ blocks, size_t block_bytes, StageStats t, int per,
+                                    int N, float* __restrict__ sqn, double* __restrict__ pw,
+                                    uint32_t* __restrict__ rep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // padded row index
+  if (i >= N * kFrameRows) return;
+  const int g = i / kFrameRows, k = i % kFrameRows;
+  const uint8_t* b = blocks + static_cast<size_t>(g / per) * block_bytes;
+  const int l = g % per;
+  sqn[i] = reinterpret_cast<const float*>(b + t.off_sqn)[l * kFrameRows + k];
+  pw[i] = reinterpret_cast<const double*>(b + t.off_pw)[l * kFrameRows + k];
+  if (k == 0) rep[g] = reinterpret_cast<const uint32_t*>(b + t.off_rep)[l];
+}
+
+// probe blocks of all parts -> one control block (same rule as gram_probe_finalize_kernel, over all samples)
+__global__ void stage_probe_finalize_kernel(const uint8_t* __restrict__ blocks, size_t block_bytes, StageStats t,
+                                            int n_parts, GramControl* ctl) {
+  __shared__ int s_cnt, s_tot;
+  __shared__ float s_margin, s_rms;
+  if (threadIdx.x == 0) {
+    double sum_err2 = 0.0;
+    unsigned long long n_err = 0, max_row = 0;
+    unsigned int nmax = 0;
+    for (int r = 0; r < n_parts; ++r) {
+      const ProbeAccum* a = reinterpret_cast<const ProbeAccum*>(blocks + r * block_bytes + t.off_probe);
+      sum_err2 += a->sum_err2;
+      n_err += a->n_err;
+      max_row = a->max_row_bits > max_row ? a->max_row_bits : max_row;
+      nmax = a->nmax_bits > nmax ? a->nmax_bits : nmax;
+    }
+    const double rms = sqrt(sum_err2 / static_cast<double>(n_err > 0 ? n_err : 1));
+    const double rms_max = sqrt(__longlong_as_double(static_cast<long long>(max_row)));
+    s_margin = static_cast<float>(1.41421356 * fmax(8.0 * rms, 4.0 * rms_max)) + 4e-6f * __uint_as_float(nmax);
+    s_rms = static_cast<float>(rms);
+    s_cnt = 0;
+    s_tot = 0;
+  }
+  __syncthreads();
+  int cnt = 0, tot = 0;
+  for (int i = threadIdx.x; i < n_parts * kProbeSamples; i += blockDim.x) {
+    const float g = reinterpret_cast<const float*>(blocks + (i / kProbeSamples) * block_bytes + t.off_gaps)[i % kProbeSamples];
+    if (g < 1e30f) {   // parts with fewer than two frames sample nothing (their gaps are a large sentinel)
+      ++tot;
+      cnt += g < s_margin ? 1 : 0;
+    }
+  }
+  atomicAdd(&s_cnt, cnt);
+  atomicAdd(&s_tot, tot);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctl->margin = s_margin;
+    ctl->sigma = s_rms;
+    ctl->flagged_frac = s_tot ? static_cast<float>(s_cnt) / s_tot : 0.0f;
+    ctl->use_refine = 1;
+    ctl->flagged_rows = 0;
+    ctl->refined_cands = 0;
+    ctl->n_entries = 0;
+  }
+}
+}  // namespace dlc
+
+extern "C" size_t dlc_sdav_stage_stats_bytes(int frames_per_part) {
+  return frames_per_part > 0 ? stage_stats_layout(frames_per_part).total : 0;
+}
+extern "C" size_t dlc_sdav_stage_workspace_bytes(int N, int P, int D, int n_parts) {
+  if (N <= 0 || P <= 0 || D <= 0 || n_parts <= 0) return 0;
+  return stage_layout(N, D, n_parts).total;
+}
+
+extern "C" int dlc_sdav_stage_colsum(const float* desc_local_dev, int64_t rows_local, int D, double* colsum_dev,
+                                     void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(colsum_dev && ws_dev && D >= 1 && rows_local >= 0);
+  DLC_CHECK_ARG(desc_local_dev || rows_local == 0);
+  if (ws_bytes < sizeof(double) * kColSumSlabs * D)
+    return fail(DLC_ENOMEM, "dlc_sdav_stage_colsum: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * D);
+  cudaStream_t s = as_stream(stream);
+  double* part = static_cast<double*>(ws_dev);
+  colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_local_dev, rows_local, D, part);
+  colsum_reduce_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, D, colsum_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+extern "C" int dlc_sdav_stage_weights(const double* colsums_dev, int n_parts, int64_t rows_total, int D, double mu,
+                                      double sigma, double* w_dev, double* mean_dev, void* stream) {
+  DLC_CHECK_ARG(colsums_dev && w_dev && mean_dev);
+  DLC_CHECK_ARG(n_parts >= 1 && rows_total >= 1 && D >= 1 && sigma != 0.0);
+  weights_kernel<<<ceil_div(D, 128), 128, 0, as_stream(stream)>>>(colsums_dev, n_parts, rows_total, D, mu, sigma, w_dev,
+                                                                  mean_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+extern "C" int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, int frames_per_part, int P, int D,
+                                      const double* w_dev, const double* mean_dev, int precision,
+                                      void* plane_hi_local_dev, void* plane_lo_local_dev, void* stats_local_dev,
+                                      void* stream) {
+  DLC_CHECK_ARG(stats_local_dev && w_dev && mean_dev);
+  DLC_CHECK_ARG(n_local >= 0 && n_local <= frames_per_part && P >= 1 && P <= kFrameRows && D >= 1);
+  DLC_CHECK_ARG(n_local == 0 || (desc_local_dev && plane_hi_local_dev));
+  DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || plane_lo_local_dev || n_local == 0);
+  cudaStream_t s = as_stream(stream);
+  const StageStats t = stage_stats_layout(frames_per_part);
+  uint8_t* st = static_cast<uint8_t*>(stats_local_dev);
+  DLC_CUDA(cudaMemsetAsync(st, 0, t.total, s));
+  float* gaps = reinterpret_cast<float*>(st + t.off_gaps);
+  DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // "nothing sampled" sentinel (3.4e38)
+  if (n_local == 0) return DLC_OK;
+  const int ld = dlc_plane_ld(D);
+  ProbeAccum* acc = reinterpret_cast<ProbeAccum*>(st + t.off_probe);
+  uint32_t* rep = reinterpret_cast<uint32_t*>(st + t.off_rep);
+  const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
+  prep_rows_kernel<<<ceil_div(n_local * kFrameRows, 8), 256, 0, s>>>(
+      desc_local_dev, n_local, P, D, w_dev, mean_dev, static_cast<__half*>(plane_hi_local_dev),
+      precision == DLC_PREC_FP16X2 ? static_cast<__half*>(plane_lo_local_dev) : nullptr, ld,
+      reinterpret_cast<float*>(st + t.off_sqn), reinterpret_cast<double*>(st + t.off_pw),
+      probe ? &acc->nmax_bits : nullptr);
+  if (probe) {
+    rep_mask_kernel<<<n_local, 1024, 0, s>>>(desc_local_dev, n_local, P, D, rep);
+    if (n_local >= 2)
+      gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_local_dev, n_local, P, D, mean_dev, rep, acc, gaps);
+  }
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
+
+static int stage_params(const void* plane_hi_all_dev, const void* plane_lo_all_dev, const float* desc_all_dev, int N,
+                        int P, int D, double a, double b, int precision, int full_asymmetric, int part, int n_parts,
+                        float* S_dev, char* ws, const StageWorkspace& L, GramParams* out, GramPlanes* planes) {
+  TileListEntry lists;
+  if (int rc = get_tile_lists(N, full_asymmetric, part, n_parts, &lists)) return rc;
+  const int col_stride = (P < kFrameRows && (P & 1) == 0) ? P : kFrameRows;
+  GramParams p{};
+  p.rep_mask = reinterpret_cast<const uint32_t*>(ws + L.off_rep);
+  p.col_stride = col_stride;
+  p.b_frame_map = col_stride == kFrameRows ? 1 : 0;
+  p.n_tile = kFramesPerNTile * col_stride;
+  p.ab_fmt = 0;
+  p.tiles = lists.tiles;
+  p.num_tiles = lists.num_tiles;
+  p.pair_tiles = lists.pair_tiles;
+  p.num_pair_tiles = lists.num_pair_tiles;
+  p.N = N;
+  p.P = P;
+  p.D = D;
+  p.desc = desc_all_dev;
+  p.sqn = reinterpret_cast<const float*>(ws + L.off_sqn);
+  p.pw = reinterpret_cast<const double*>(ws + L.off_pw);
+  p.a = static_cast<float>(a);
+  p.b = static_cast<float>(b);
+  p.full = full_asymmetric ? 1 : 0;
+  p.S = S_dev;
+  const bool refine = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
+  p.ctl = refine ? reinterpret_cast<GramControl*>(ws + L.off_ctl) : nullptr;
+  p.want_refine = refine ? 1 : 0;
+  p.work = refine ? reinterpret_cast<RefineEntry*>(ws + L.off_work) : nullptr;
+  p.work_cap = refine ? L.work_cap : 0;
+  *out = p;
+  *planes = GramPlanes{plane_hi_all_dev, plane_lo_all_dev, dlc_plane_ld(D), col_stride};
+  return DLC_OK;
+}
+
+extern "C" int dlc_sdav_stage_gram(const void* plane_hi_all_dev, const void* plane_lo_all_dev,
+                                   const void* stats_all_dev, int n_parts, int frames_per_part, int N, int P, int D,
+                                   double a, double b, int precision, int full_asymmetric, int part, float* S_dev,
+                                   void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(plane_hi_all_dev && stats_all_dev && S_dev && ws_dev);
+  DLC_CHECK_ARG(N >= 1 && P >= 1 && P <= kFrameRows && D >= 1);
+  DLC_CHECK_ARG(n_parts >= 1 && part >= 0 && part < n_parts && frames_per_part >= 1 &&
+                static_cast<int64_t>(frames_per_part) * n_parts >= N);
+  DLC_CHECK_ARG(precision == DLC_PREC_FP16 || precision == DLC_PREC_FP16X2 || precision == DLC_PREC_AUTO ||
+                precision == DLC_PREC_FP16_REFINED);
+  DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || plane_lo_all_dev);
+  DLC_CHECK_ARG((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0);
+  const StageWorkspace L = stage_layout(N, D, n_parts);
+  if (ws_bytes < L.total)
+    return fail(DLC_ENOMEM, "dlc_sdav_stage_gram: workspace of %zu bytes needed, %zu given", L.total, ws_bytes);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(ws_dev);
+  const StageStats t = stage_stats_layout(frames_per_part);
+  const uint8_t* blocks = static_cast<const uint8_t*>(stats_all_dev);
+  stage_unpack_kernel<<<ceil_div(N * kFrameRows, 256), 256, 0, s>>>(
+      blocks, t.total, t, frames_per_part, N, reinterpret_cast<float*>(ws + L.off_sqn),
+      reinterpret_cast<double*>(ws + L.off_pw), reinterpret_cast<uint32_t*>(ws + L.off_rep));
+  GramParams p;
+  GramPlanes planes;
+  if (int rc = stage_params(plane_hi_all_dev, plane_lo_all_dev, nullptr, N, P, D, a, b, precision, full_asymmetric,
+                            part, n_parts, S_dev, ws, L, &p, &planes))
+    return rc;
+  if (p.ctl) stage_probe_finalize_kernel<<<1, 256, 0, s>>>(blocks, t.total, t, n_parts, p.ctl);
+  DLC_CUDA(cudaGetLastError());
+  if (n_parts > 1) DLC_CUDA(cudaMemsetAsync(S_dev, 0, sizeof(float) * static_cast<size_t>(N) * N, s));
+  const bool pairs = use_pairs(p);
+  if (precision == DLC_PREC_FP16X2)
+    return pairs ? run_gram_pair<GramPolicy<32, 3>>(planes, p, s) : run_gram<GramPolicy<32, 3>>(planes, p, s);
+  if (precision == DLC_PREC_FP16)
+    return pairs ? run_gram_pair<GramPolicy<64, 1>>(planes, p, s) : run_gram<GramPolicy<64, 1>>(planes, p, s);
+  // one product + deferred exact refinement (AUTO is treated as FP16_REFINED here: choosing the three-product kernel
+  // on the device would need the residual planes of every rank, i.e. a second exchange decided without the host)
+  return pairs ? run_gram_pair<GramRefinePolicy>(planes, p, s) : run_gram<GramRefinePolicy>(planes, p, s);
+}
+
+extern "C" int dlc_sdav_stage_fix(const void* plane_hi_all_dev, const float* desc_all_dev, int N, int P, int D, double a,
+                                  double b, int precision, int full_asymmetric, int part, int n_parts, float* S_dev,
+                                  void* ws_dev, size_t ws_bytes, void* stream) {
+  DLC_CHECK_ARG(desc_all_dev && S_dev && ws_dev && plane_hi_all_dev);
+  DLC_CHECK_ARG(N >= 1 && P >= 1 && P <= kFrameRows && D >= 1 && n_parts >= 1 && part >= 0 && part < n_parts);
+  if (!(precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED)) return DLC_OK;  // nothing was deferred
+  const StageWorkspace L = stage_layout(N, D, n_parts);
+  if (ws_bytes < L.total)
+    return fail(DLC_ENOMEM, "dlc_sdav_stage_fix: workspace of %zu bytes needed, %zu given", L.total, ws_bytes);
+  GramParams p;
+  GramPlanes planes;
+  if (int rc = stage_params(plane_hi_all_dev, nullptr, desc_all_dev, N, P, D, a, b, precision, full_asymmetric, part,
+                            n_parts, S_dev, static_cast<char*>(ws_dev), L, &p, &planes))
+    return rc;
+  gram_refine_fix_kernel<<<4 * sm_count(), kFixThreads, 0, as_stream(stream)>>>(p);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
 }
 
 // Diagnostics of the last AUTO / FP16_REFINED call that used this workspace: out_host[0..5] = use_refine, margin,

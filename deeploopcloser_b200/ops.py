@@ -274,6 +274,61 @@ def sdav_similarity_stats(N, P, D):
     return dict(zip(keys, list(out)))
 
 
+# ---- staged form for a sequence split over several GPUs (see dlc_sdav_stage_* in include/dlc.h)
+plane_ld = _lib.plane_ld
+_ws_stage = Workspace()
+
+
+def sdav_stage_stats_bytes(frames_per_part):
+    return int(_lib.call("dlc_sdav_stage_stats_bytes", int(frames_per_part)))
+
+
+def _stage_ws(N, P, D, n_parts):
+    return _ws_stage.get(max(_lib.call("dlc_sdav_stage_workspace_bytes", N, P, D, n_parts), 128 * D * 8))
+
+
+def sdav_stage_colsum(desc_local, out):
+    """desc_local float32 [rows, D] (this rank's descriptor rows) -> out float64 [D] column sums."""
+    _check_cuda(desc_local, out)
+    rows, D = desc_local.shape
+    ws, ws_bytes = _ws_stage.get(128 * D * 8)
+    _lib.call("dlc_sdav_stage_colsum", ptr(desc_local), rows, D, ptr(out), ws, ws_bytes, stream_ptr())
+
+
+def sdav_stage_weights(colsums, rows_total, w, mean, mu=0.5, sigma=0.2):
+    """colsums float64 [n_parts, D] (all-gathered) -> w, mean float64 [D]."""
+    _check_cuda(colsums, w, mean)
+    _lib.call("dlc_sdav_stage_weights", ptr(colsums), colsums.shape[0], int(rows_total), colsums.shape[1], float(mu),
+              float(sigma), ptr(w), ptr(mean), stream_ptr())
+
+
+def sdav_stage_prepare(desc_local, n_local, frames_per_part, P, w, mean, precision, plane_local, plane_lo_local,
+                       stats_local):
+    """This rank's block: desc_local float32 [frames_per_part*P, D] (first n_local frames valid) -> centred fp16
+    plane slice [frames_per_part*P, ld] (+ residual plane for fp16x2) and the stats block (uint8)."""
+    _check_cuda(desc_local, w, mean, plane_local, plane_lo_local, stats_local)
+    D = desc_local.shape[1]
+    _lib.call("dlc_sdav_stage_prepare", ptr(desc_local), int(n_local), int(frames_per_part), int(P), D, ptr(w), ptr(mean),
+              precision_code(precision), ptr(plane_local), ptr(plane_lo_local), ptr(stats_local), stream_ptr())
+
+
+def sdav_stage_gram(plane_all, plane_lo_all, stats_all, n_parts, frames_per_part, N, P, D, precision, part, S,
+                    a=10.0, b=-10.0, full_asymmetric=False):
+    _check_cuda(plane_all, plane_lo_all, stats_all, S)
+    ws, ws_bytes = _stage_ws(N, P, D, n_parts)
+    _lib.call("dlc_sdav_stage_gram", ptr(plane_all), ptr(plane_lo_all), ptr(stats_all), int(n_parts),
+              int(frames_per_part), int(N), int(P), int(D), float(a), float(b), precision_code(precision),
+              int(bool(full_asymmetric)), int(part), ptr(S), ws, ws_bytes, stream_ptr())
+
+
+def sdav_stage_fix(plane_all, desc_all, N, P, D, precision, part, n_parts, S, a=10.0, b=-10.0, full_asymmetric=False):
+    _check_cuda(plane_all, desc_all, S)
+    ws, ws_bytes = _stage_ws(N, P, D, n_parts)
+    _lib.call("dlc_sdav_stage_fix", ptr(plane_all), ptr(desc_all), int(N), int(P), int(D), float(a), float(b),
+              precision_code(precision), int(bool(full_asymmetric)), int(part), int(n_parts), ptr(S), ws, ws_bytes,
+              stream_ptr())
+
+
 def topk_rows(scores, k, largest=True, exclude_band=-1, cand_idx=None):
     """Per-row top-k of a dense [rows, cols] float32 matrix -> (scores [rows,k] f32, idx [rows,k] i64)."""
     _check_cuda(scores, cand_idx)

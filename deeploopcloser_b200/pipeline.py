@@ -80,6 +80,10 @@ class LoopClosurePipeline:
         buffer owned by the pipeline: valid until the next call).
         The upload of batch i+1 runs on a copy stream while batch i computes (double-buffered device inputs), the
         candidate lists come back with asynchronous D2H copies; one synchronisation at the end."""
+        return self._host_stream([(f, x, f.shape[0]) for f, x in batches], k, exclude_band,
+                                 lambda f, x, n: self.run(f, x, k, exclude_band))
+
+    def _host_stream(self, batches, k, exclude_band, run):
         batches = list(batches)
         if not batches:
             return []
@@ -89,7 +93,7 @@ class LoopClosurePipeline:
 
         def upload(i):
             slot = i & 1
-            f_h, x_h = batches[i]
+            f_h, x_h, _ = batches[i]
             if consumed[slot] is not None:
                 copy.wait_event(consumed[slot])      # the compute stream is done reading this slot
             with torch.cuda.stream(copy):
@@ -111,7 +115,7 @@ class LoopClosurePipeline:
                 upload(i + 1)
             compute.wait_event(ready[slot])
             f_d, x_d = bufs[slot]
-            r = self.run(f_d, x_d, k, exclude_band)
+            r = run(f_d, x_d, batches[i][2])
             ev = torch.cuda.Event()
             ev.record(compute)
             consumed[slot] = ev
@@ -132,12 +136,21 @@ class LoopClosurePipeline:
 
 
 class ShardedSequencePipeline(LoopClosurePipeline):
-    """ONE sequence over the GPUs of a box (strong scaling of BASELINE config 2): one process per GPU
-    (torch.distributed, NCCL). Frames are dealt in contiguous blocks: every rank gathers + encodes its block, the
-    descriptors are all-gathered (every rank needs all of them for the score matrix), every rank evaluates its
-    interleaved tile rows of the SDAV score matrix (`dlc_sdav_similarity_part`), the parts are summed with an
-    all-reduce, and the candidate lists are selected on every rank (identical everywhere). Two exchange steps:
-    N*30*D*4 bytes of descriptors and N*N*4 bytes of scores; everything else is rank-local."""
+    """ONE sequence over the GPUs of a box (strong scaling of BASELINE config 2): one process per
+    GPU (torch.distributed, NCCL). Frames are dealt in contiguous blocks of `per = ceil(N / world)`; every rank gathers
+    and encodes ITS block, and the score matrix is evaluated through the staged C ABI (dlc_sdav_stage_*) so that no
+    work is replicated:
+
+      encode block -> [fp32 descriptors: all-gather, in the background on a second communicator]
+                   -> column sums -> all-gather (world x D doubles) -> mean, weights
+                   -> centred fp16 operand planes + row statistics + precision probe of the block
+                   -> all-gather planes (N x P x ld x 2 bytes) and stats blocks
+                   -> Gram + argmin + score of this rank's interleaved tile rows (one tensor product; ambiguous pairs
+                      are listed) -> wait for the descriptors -> exact second pass over the listed pairs
+                   -> all-reduce (sum) of the N x N scores -> loop candidates on every rank.
+
+    The exchanged operand is the fp16 plane (half the bytes of the descriptors); only the second pass needs the
+    float32 descriptors, whose all-gather overlaps everything up to it."""
 
     def __init__(self, *args, group=None, **kwargs):
         super().__init__(*args, **kwargs)
@@ -146,31 +159,132 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._bg_group = None       # second communicator: the descriptor all-gather runs next to the other collectives
+        self._buf_key = None
 
     @staticmethod
     def frame_block(n_frames, rank, world):
-        """(start, end, per): frames [start, end) belong to `rank`; `per` = block length used for the gather."""
+        """(start, end, per): frames [start, end) belong to `rank`; `per` = block length used for the gathers."""
         per = -(-n_frames // world)
         start = min(rank * per, n_frames)
         return start, min(start + per, n_frames), per
 
+    # ---- device stages (overridden by CPU stand-ins in tests/test_distributed_cpu.py)
+    def _alloc(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device="cuda")
+
+    def _buffers(self, n, P):
+        D = self.dims[-1]
+        key = (n, P, D, self.world)
+        if self._buf_key != key:
+            per = -(-n // self.world)
+            ld = ops.plane_ld(D)
+            rows = self.world * per * P
+            self._b = {
+                "desc": self._alloc((rows, D), torch.float32),
+                "plane": self._alloc((rows, ld), torch.float16),
+                "plane_lo": self._alloc((rows, ld), torch.float16) if self.sim_precision == "fp16x2" else None,
+                "stats": self._alloc((self.world, ops.sdav_stage_stats_bytes(per)), torch.uint8),
+                "colsums": self._alloc((self.world, D), torch.float64),
+                "w": self._alloc((D,), torch.float64), "mean": self._alloc((D,), torch.float64),
+                "S": self._alloc((n, n), torch.float32),
+            }
+            self._buf_key = key
+        return self._b
+
+    def _encode_into(self, frames, xy, out):
+        if xy is None:
+            xy = self.detect(frames, 30)
+        if self.raw_pixels:
+            hi, lo = ops.patch_gather_u8(frames, xy, self.patch, self.swap_xy_quirk), None
+        else:
+            hi, lo = ops.patch_gather(frames, xy, self.patch, self.swap_xy_quirk, need_lo=self.encoder.needs_lo_input())
+        self.encoder.encode_planes(hi, lo, hi.shape[0], out=out)
+
+    def _stage_colsum(self, desc_local, out):
+        ops.sdav_stage_colsum(desc_local, out)
+
+    def _stage_weights(self, colsums, rows_total, w, mean):
+        ops.sdav_stage_weights(colsums, rows_total, w, mean, self.sim_args.get("mu", 0.5), self.sim_args.get("sigma", 0.2))
+
+    def _stage_prepare(self, desc_local, n_local, per, P, w, mean, plane_local, plane_lo_local, stats_local):
+        ops.sdav_stage_prepare(desc_local, n_local, per, P, w, mean, self.sim_precision, plane_local, plane_lo_local,
+                               stats_local)
+
+    def _stage_gram(self, b, per, n, P):
+        ops.sdav_stage_gram(b["plane"], b["plane_lo"], b["stats"], self.world, per, n, P, self.dims[-1], self.sim_precision,
+                            self.rank, b["S"], a=self.sim_args.get("a", 10.0), b=self.sim_args.get("b", -10.0))
+
+    def _stage_fix(self, b, n, P):
+        ops.sdav_stage_fix(b["plane"], b["desc"], n, P, self.dims[-1], self.sim_precision, self.rank, self.world, b["S"],
+                           a=self.sim_args.get("a", 10.0), b=self.sim_args.get("b", -10.0))
+
+    def _all_gather(self, full, rank_slice, group, async_op=False):
+        return self.dist.all_gather_into_tensor(full, rank_slice, group=group, async_op=async_op)
+
     def run(self, frames, xy, k=10, exclude_band=0):
-        """frames uint8 [N,H,W] and xy float32 [N,P,2]: the WHOLE sequence, resident on every rank."""
-        n, P = frames.shape[0], xy.shape[1]
+        """frames uint8 [N,H,W] and xy float32 [N,P,2]: the WHOLE sequence, resident on every rank (each rank reads
+        only its block)."""
+        n = frames.shape[0]
+        start, end, _ = self.frame_block(n, self.rank, self.world)
+        return self.run_block(frames[start:end], None if xy is None else xy[start:end], n, k, exclude_band)
+
+    def run_block(self, frames_local, xy_local, n, k=10, exclude_band=0, P=None):
+        """frames_local / xy_local: this rank's block of the N-frame sequence (frame_block(N, rank, world))."""
+        P = P or (xy_local.shape[1] if xy_local is not None else 30)
         D = self.dims[-1]
         start, end, per = self.frame_block(n, self.rank, self.world)
-        local = torch.zeros((per * P, D), dtype=torch.float32, device=frames.device)
-        if end > start:
-            local[:(end - start) * P] = self.encode(frames[start:end], xy[start:end])
+        n_local = end - start
+        assert frames_local.shape[0] == n_local, "expected this rank's block of %d frames" % n_local
+        b = self._buffers(n, P)
+        lo_r, hi_r = self.rank * per * P, (self.rank + 1) * per * P
+        desc_local = b["desc"][lo_r:hi_r]
+        if n_local < per:
+            desc_local[n_local * P:].zero_()          # padded tail of the last block(s): gathered but never read
+        if n_local:
+            self._encode_into(frames_local, xy_local, desc_local[:n_local * P])
+        work = None
         if self.world > 1:
-            gathered = torch.empty((self.world * per * P, D), dtype=torch.float32, device=frames.device)
-            self.dist.all_gather_into_tensor(gathered, local, group=self.group)
-            desc = gathered[:n * P]
-        else:
-            desc = local[:n * P]
-        S = ops.sdav_similarity_part(desc.view(n, P, D), self.rank, self.world, precision=self.sim_precision,
-                                     **self.sim_args)
+            if self._bg_group is None:
+                self._bg_group = self.dist.new_group(list(range(self.world))) if self.group is None else self.group
+            # float32 descriptors of all frames: only the second pass reads them -> gathered in the background
+            work = self._all_gather(b["desc"], desc_local, self._bg_group, async_op=True)
+        # dataset mean / weights
+        self._stage_colsum(desc_local[:n_local * P], b["colsums"][self.rank])
+        if self.world > 1:
+            self._all_gather(b["colsums"].view(-1), b["colsums"][self.rank], self.group)
+        self._stage_weights(b["colsums"], n * P, b["w"], b["mean"])
+        # centred planes + statistics + probe of this block, then their exchange
+        plane_lo_local = None if b["plane_lo"] is None else b["plane_lo"][lo_r:hi_r]
+        self._stage_prepare(desc_local, n_local, per, P, b["w"], b["mean"], b["plane"][lo_r:hi_r], plane_lo_local,
+                            b["stats"][self.rank])
+        if self.world > 1:
+            self._all_gather(b["plane"].view(-1), b["plane"][lo_r:hi_r].view(-1), self.group)
+            if plane_lo_local is not None:
+                self._all_gather(b["plane_lo"].view(-1), plane_lo_local.view(-1), self.group)
+            self._all_gather(b["stats"].view(-1), b["stats"][self.rank], self.group)
+        self._stage_gram(b, per, n, P)
+        if work is not None:
+            work.wait()                                # the compute stream waits for the descriptor gather
+        self._stage_fix(b, n, P)
+        S = b["S"]
         if self.world > 1:
             self.dist.all_reduce(S, group=self.group)
+        self.last_similarity = S
         cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
-        return {"descriptors": desc, "similarity": S, "candidates": cand}
+        return {"descriptors": b["desc"][:n * P], "similarity": S, "candidates": cand}
+
+    def run_host_stream(self, batches, k=10, exclude_band=0):
+        """Stream of HOST sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] (pinned, the same on every rank):
+        each rank uploads only ITS block of every sequence; see LoopClosurePipeline.run_host_stream."""
+        mine = []
+        for f_h, x_h in batches:
+            start, end, _ = self.frame_block(f_h.shape[0], self.rank, self.world)
+            mine.append((f_h[start:end], x_h[start:end], f_h.shape[0]))
+        return self._host_stream(mine, k, exclude_band, lambda f, x, n: self.run_block(f, x, n, k, exclude_band))
+
+    def host_bytes_per_step(self, frames_h, xy_h, k):
+        n = frames_h.shape[0]
+        start, end, _ = self.frame_block(n, self.rank, self.world)
+        per_frame = frames_h[0].numel() * frames_h.element_size() + xy_h[0].numel() * xy_h.element_size()
+        return int((end - start) * per_frame), int(n * min(k, max(n - 1, 1)) * 12)

@@ -207,6 +207,39 @@ int dlc_sdav_similarity(const float* desc_dev, int N, int P, int D, double mu, d
 int dlc_sdav_similarity_part(const float* desc_dev, int N, int P, int D, double mu, double sigma, double a, double b,
                              const double* w_dev, int precision, int full_asymmetric, int part, int n_parts,
                              float* S_dev, void* ws_dev, size_t ws_bytes, void* stream);
+/* ---- The same computation in stages, for ONE sequence whose frames are split over the GPUs of a box (SURVEY 8e row 3;
+ * workload: the one N x N matrix of src/sdav/create_similarity_matrix.py:31-38). Frames are dealt to the parts (ranks) in
+ * contiguous blocks of frames_per_part = ceil(N / n_parts); every stage works on the part's own rows and writes into the
+ * part's slice of arrays that the HOST exchanges between stages (NCCL all-gather; gathered slices form the flat global
+ * arrays). No work is replicated: mean, row statistics, operand planes and the precision probe are produced once, by
+ * the part that holds the frame.
+ *   1. dlc_sdav_stage_colsum   local desc -> colsum [D] float64            -> all-gather: colsums [n_parts, D]
+ *   2. dlc_sdav_stage_weights  colsums -> mean [D], w [D]                  (same result on every part)
+ *   3. dlc_sdav_stage_prepare  local desc -> centred fp16 plane slice [frames_per_part * P, dlc_plane_ld(D)] (+ the
+ *                              residual plane for DLC_PREC_FP16X2) and a stats block (dlc_sdav_stage_stats_bytes)
+ *                                                                          -> all-gather planes, all-gather stats
+ *   4. dlc_sdav_stage_gram     planes + stats of all parts -> this part's entries of S (others zero: combine with a
+ *                              sum / all-reduce) + the list of frame pairs with ambiguous rows (in ws_dev)
+ *   5. dlc_sdav_stage_fix      float32 descriptors of ALL frames [N, P, D] -> exact scores of the listed pairs. Only
+ *                              this stage reads them, so their all-gather can overlap stage 4.
+ * precision: DLC_PREC_FP16, DLC_PREC_FP16X2, DLC_PREC_FP16_REFINED; DLC_PREC_AUTO means DLC_PREC_FP16_REFINED here.
+ * Stages 4 and 5 share ws_dev (dlc_sdav_stage_workspace_bytes, 256-byte aligned). */
+size_t dlc_sdav_stage_stats_bytes(int frames_per_part);
+size_t dlc_sdav_stage_workspace_bytes(int N, int P, int D, int n_parts);
+int dlc_sdav_stage_colsum(const float* desc_local_dev, int64_t rows_local, int D, double* colsum_dev, void* ws_dev,
+                          size_t ws_bytes, void* stream);
+int dlc_sdav_stage_weights(const double* colsums_dev, int n_parts, int64_t rows_total, int D, double mu, double sigma,
+                           double* w_dev, double* mean_dev, void* stream);
+int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, int frames_per_part, int P, int D,
+                           const double* w_dev, const double* mean_dev, int precision, void* plane_hi_local_dev,
+                           void* plane_lo_local_dev, void* stats_local_dev, void* stream);
+int dlc_sdav_stage_gram(const void* plane_hi_all_dev, const void* plane_lo_all_dev, const void* stats_all_dev,
+                        int n_parts, int frames_per_part, int N, int P, int D, double a, double b, int precision,
+                        int full_asymmetric, int part, float* S_dev, void* ws_dev, size_t ws_bytes, void* stream);
+int dlc_sdav_stage_fix(const void* plane_hi_all_dev, const float* desc_all_dev, int N, int P, int D, double a, double b,
+                       int precision, int full_asymmetric, int part, int n_parts, float* S_dev, void* ws_dev,
+                       size_t ws_bytes, void* stream);
+
 /* Diagnostics of the last AUTO / FP16_REFINED call on this workspace: out_host[6] = {use_refine, margin, sigma,
  * estimated flagged fraction, flagged rows, refined candidates}. Synchronises the stream. */
 int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream);

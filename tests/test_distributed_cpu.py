@@ -61,9 +61,10 @@ def test_sharded_exchange_world2_gloo():
 
 
 def _seq_worker(rank, world, port, q):
-    """ShardedSequencePipeline.run with the three GPU stages replaced by oracle stand-ins: the host logic under test
-    is the frame blocks, the descriptor all-gather (with the padded last block), the parts-sum all-reduce and that
-    every rank ends with the same matrix."""
+    """ShardedSequencePipeline.run_block with the device stages replaced by CPU stand-ins: the host logic under test is
+    the frame blocks (padded last block), the in-place all-gathers of descriptors / column sums / planes / stats
+    blocks, the background gather on the second communicator being complete before the second pass, the parts-sum
+    all-reduce, and that every rank ends with the same matrix."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -74,36 +75,65 @@ def _seq_worker(rank, world, port, q):
         n, P, D = 7, 3, 5                                  # 7 frames over 2 ranks: blocks of 4 and 3 (+1 pad)
         rng = np.random.default_rng(3)
         table = rng.uniform(0, 1, (n, P, D)).astype(np.float32)   # "descriptor" of frame f = table[f]
-        pipe = ShardedSequencePipeline.__new__(ShardedSequencePipeline)
+        seen = {}
+
+        class Pipe(ShardedSequencePipeline):
+            def _alloc(self, shape, dtype):
+                return torch.zeros(shape, dtype=dtype)
+
+            def _encode_into(self, frames, xy, out):
+                out.copy_(torch.from_numpy(table[frames.numpy()[:, 0, 0]].reshape(-1, D)))
+
+            def _stage_colsum(self, desc_local, out):
+                out.copy_(desc_local.double().sum(0))
+
+            def _stage_weights(self, colsums, rows_total, w, mean):
+                mean.copy_(colsums.sum(0) / rows_total)
+                w.copy_(torch.exp(-(mean - 0.5) ** 2 / (2 * 0.2 ** 2)))
+
+            def _stage_prepare(self, desc_local, n_local, per, P_, w, mean, plane_local, plane_lo_local, stats_local):
+                plane_local.zero_()
+                plane_local[:n_local * P_, :D] = (desc_local[:n_local * P_].double() - mean).half()
+                stats_local.fill_(self.rank + 1)
+
+            def _stage_gram(self, b, per, n_, P_):
+                # every rank sees every rank's centred planes and stats block
+                want = torch.from_numpy(table.reshape(-1, D)).double() - b["mean"]
+                assert torch.allclose(b["plane"][:n_ * P_, :D].double(), want, atol=2e-3)
+                assert [int(b["stats"][r, 0]) for r in range(self.world)] == [r + 1 for r in range(self.world)]
+                w_ref = o_sim.distinctive_weights(table.astype(np.float64))
+                assert np.allclose(b["w"].numpy(), w_ref, rtol=1e-12)
+                S = o_sim.similarity_matrix(table.astype(np.float64))
+                own = np.zeros_like(S)
+                for i, j in zip(*np.triu_indices(n_, 1)):
+                    if i % self.world == self.rank:
+                        own[i, j] = own[j, i] = S[i, j]
+                if self.rank == 0:
+                    np.fill_diagonal(own, -1.0)
+                b["S"].copy_(torch.from_numpy(own.astype(np.float32)))
+
+            def _stage_fix(self, b, n_, P_):
+                # the background all-gather of the float32 descriptors has completed when the second pass starts
+                seen["desc_complete"] = bool(np.array_equal(b["desc"][:n_ * P_].numpy(), table.reshape(-1, D)))
+
+        pipe = Pipe.__new__(Pipe)
         pipe.dims, pipe.dist, pipe.group, pipe.rank, pipe.world = [1, D], dist, None, rank, world
-        pipe.sim_precision, pipe.sim_args = "fp16x2", {}
-        pipe.encode = lambda frames, xy: torch.from_numpy(table[frames.numpy()[:, 0, 0]].reshape(-1, D))
-
-        def fake_part(desc, part, n_parts, **kw):          # rows part, part + n_parts, ... of the oracle matrix
-            S = o_sim.similarity_matrix(desc.numpy().astype(np.float64))
-            own = np.zeros_like(S)
-            iu = np.triu_indices(n, 1)
-            for i, j in zip(*iu):
-                if i % n_parts == part:
-                    own[i, j] = own[j, i] = S[i, j]
-            if part == 0:
-                np.fill_diagonal(own, -1.0)
-            return torch.from_numpy(own.astype(np.float32))
-
-        def fake_topk(S, k, largest=True, exclude_band=-1):
-            return torch.topk(S, k, dim=1)
-
-        ops.sdav_similarity_part, ops.topk_rows = fake_part, fake_topk
+        pipe.sim_precision, pipe.sim_args, pipe._bg_group, pipe._buf_key = "fp16r", {}, None, None
+        ops.topk_rows = lambda S, k, largest=True, exclude_band=-1: torch.topk(S, k, dim=1)
         frames = torch.arange(n).reshape(n, 1, 1).repeat(1, 2, 2)          # frame id stored in its pixels
         xy = torch.zeros((n, P, 2))
-        res = pipe.run(frames, xy, k=2)
+        for _ in range(2):                                                   # second call reuses the buffers
+            res = pipe.run(frames, xy, k=2)
         want = o_sim.similarity_matrix(table.astype(np.float64))
         assert np.allclose(res["similarity"].numpy(), want, rtol=1e-5, atol=1e-5)
         assert np.array_equal(res["descriptors"].numpy(), table.reshape(-1, D))
+        assert seen["desc_complete"]
+        start, end, per = Pipe.frame_block(n, rank, world)
+        assert (start, end, per) == ((0, 4, 4) if rank == 0 else (4, 7, 4))
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
-        q.put((rank, traceback.format_exc()[-600:] or repr(e)))
+        q.put((rank, traceback.format_exc()[-900:] or repr(e)))
     finally:
         dist.destroy_process_group()
 
