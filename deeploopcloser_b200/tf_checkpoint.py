@@ -151,12 +151,20 @@ def _encode_entry(dtype_code, shape, offset, size, crc):
 
 
 # ------------------------------------------------------------------------------------------------ SSTable (.index)
-def _read_block(buf, offset, size):
-    """One table block -> list of (key, value). Trailer: 1 byte compression type + 4 bytes masked crc32c."""
+def _read_block(buf, offset, size, verify_crc=True):
+    """One table block -> list of (key, value). Trailer: 1 byte compression type + 4 bytes masked crc32c of the block
+    contents and the type byte (table_format.md); keys are prefix-compressed against their predecessor (`shared`
+    bytes) except at restart points."""
+    if offset + size + 5 > len(buf):
+        raise ValueError("table block [%d, +%d) runs past the end of the file" % (offset, size))
     ctype = buf[offset + size]
     if ctype != 0:
         raise ValueError("compressed table block (type %d): only uncompressed checkpoint indices are supported" % ctype)
     block = buf[offset:offset + size]
+    if verify_crc:
+        stored = struct.unpack_from("<I", buf, offset + size + 1)[0]
+        if masked_crc32c(bytes(block) + b"\x00") != stored:
+            raise ValueError("table block at offset %d: crc32c mismatch (corrupt checkpoint index)" % offset)
     n_restarts = struct.unpack_from("<I", block, len(block) - 4)[0]
     end = len(block) - 4 - 4 * n_restarts
     pos, key, out = 0, b"", []
@@ -191,12 +199,24 @@ def _read_table(path):
     return entries
 
 
-def _build_block(items):
-    """Uncompressed block with a restart point at every entry (no prefix sharing), plus its 5-byte trailer."""
+def _build_block(items, restart_interval=16):
+    """Uncompressed block as LevelDB's BlockBuilder (and therefore TensorFlow's checkpoint index) lays it out: every
+    key drops the prefix it shares with its predecessor, a restart point (full key) every `restart_interval` entries,
+    then the restart offsets, their count, and the 5-byte trailer. restart_interval = 1 gives no prefix sharing."""
     body, restarts = bytearray(), []
+    last, counter = b"", 0
     for k, v in items:
-        restarts.append(len(body))
-        body += _put_varint(0) + _put_varint(len(k)) + _put_varint(len(v)) + k + v
+        shared = 0
+        if counter < restart_interval and restarts:
+            n = min(len(last), len(k))
+            while shared < n and last[shared] == k[shared]:
+                shared += 1
+        else:
+            restarts.append(len(body))
+            counter = 0
+        body += _put_varint(shared) + _put_varint(len(k) - shared) + _put_varint(len(v)) + k[shared:] + v
+        last = k
+        counter += 1
     if not restarts:
         restarts = [0]
     for r in restarts:
@@ -206,18 +226,32 @@ def _build_block(items):
     return bytes(body), trailer
 
 
-def _write_table(path, items):
+def _write_table(path, items, block_size=4096, restart_interval=16):
+    """Sorted (key, value) items -> table file: data blocks of about `block_size` bytes (prefix-compressed keys, restart
+    interval 16 - LevelDB's defaults, which TensorFlow's table builder keeps), an empty metaindex block, the index
+    block (one entry per data block: its last key -> block handle; restart interval 1 as in LevelDB) and the footer."""
     items = sorted(items)
     out = bytearray()
-    data, tr = _build_block(items)
-    data_handle = _put_varint(0) + _put_varint(len(data))
-    out += data + tr
+    index_items = []
+    cur, cur_bytes = [], 0
+    chunks = []
+    for k, v in items:
+        cur.append((k, v))
+        cur_bytes += len(k) + len(v) + 3
+        if cur_bytes >= block_size:
+            chunks.append(cur)
+            cur, cur_bytes = [], 0
+    if cur or not chunks:
+        chunks.append(cur)
+    for chunk in chunks:
+        data, tr = _build_block(chunk, restart_interval)
+        index_items.append((chunk[-1][0] if chunk else b"", _put_varint(len(out)) + _put_varint(len(data))))
+        out += data + tr
     meta_off = len(out)
     meta, tr = _build_block([])
     out += meta + tr
     index_off = len(out)
-    last_key = items[-1][0] if items else b""
-    index, tr = _build_block([(last_key, data_handle)])
+    index, tr = _build_block(index_items, 1)
     out += index + tr
     footer = _put_varint(meta_off) + _put_varint(len(meta)) + _put_varint(index_off) + _put_varint(len(index))
     footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", _TABLE_MAGIC)
@@ -285,8 +319,9 @@ def load_checkpoint(prefix, verify_crc=True):
     return out
 
 
-def save_checkpoint(prefix, tensors, update_state=True):
-    """Write {name: ndarray} as a single-shard V2 checkpoint at `prefix` (+ the `checkpoint` state file)."""
+def save_checkpoint(prefix, tensors, update_state=True, block_size=4096, restart_interval=16):
+    """Write {name: ndarray} as a single-shard V2 checkpoint at `prefix` (+ the `checkpoint` state file). The index
+    is laid out like TensorFlow's (prefix-compressed keys, restart interval 16; see _write_table)."""
     os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
     items = []
     offset = 0
@@ -304,7 +339,7 @@ def save_checkpoint(prefix, tensors, update_state=True):
             items.append((name.encode(), _encode_entry(_DT_INV[np.dtype(dt)], a.shape, offset, len(raw), _fast_masked_crc(raw))))
             offset += len(raw)
     header = _field(1, 0, _put_varint(1)) + _field(2, 0, _put_varint(0)) + _field(3, 2, _put_varint(2) + _field(1, 0, _put_varint(1)))
-    _write_table(prefix + ".index", [(b"", header)] + items)
+    _write_table(prefix + ".index", [(b"", header)] + items, block_size, restart_interval)
     if update_state:
         directory = os.path.dirname(os.path.abspath(prefix))
         rel = os.path.basename(prefix)

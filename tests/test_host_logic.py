@@ -214,3 +214,98 @@ def test_tf_checkpoint_roundtrip_and_sdav_restore(tmp_path):
     assert os.path.basename(p2) == "checkpoint_file-12"
     again = tc.load_checkpoint(tc.latest_checkpoint(net.checkpoints_path))
     assert all(np.array_equal(again[k], tensors[k]) for k in tensors)
+
+
+def _crc32c_bitwise(data):
+    """CRC-32C written independently of the product (bit by bit, no table)."""
+    crc = 0xFFFFFFFF
+    for byte in data:
+        crc ^= byte
+        for _ in range(8):
+            crc = (crc >> 1) ^ (0x82F63B78 & -(crc & 1))
+    return crc ^ 0xFFFFFFFF
+
+
+def _hand_block(entries, restarts):
+    """Table block assembled by hand from (shared, unshared key bytes, value) triples and explicit restart offsets -
+    independent of the product's writer (table_format.md: varint32 shared | non_shared | value_length, key delta, value;
+    uint32 restarts[], uint32 num_restarts; trailer = type byte 0 + masked crc32c of block + type)."""
+    def varint(v):
+        out = bytearray()
+        while v >= 0x80:
+            out.append((v & 0x7F) | 0x80)
+            v >>= 7
+        out.append(v)
+        return bytes(out)
+    body = b"".join(varint(s) + varint(len(k)) + varint(len(v)) + k + v for s, k, v in entries)
+    body += b"".join(r.to_bytes(4, "little") for r in restarts) + len(restarts).to_bytes(4, "little")
+    c = _crc32c_bitwise(body + b"\x00")
+    masked = (((c >> 15) | (c << 17)) + 0xa282ead8) & 0xFFFFFFFF
+    return body, body + b"\x00" + masked.to_bytes(4, "little"), varint
+
+
+def test_tf_checkpoint_index_with_shared_prefixes_and_several_blocks(tmp_path):
+    """Real tf.train.Saver indices are LevelDB tables with prefix-compressed keys (restart interval 16) and may span
+    several data blocks. (1) An index assembled by hand from the table-format specification - shared-prefix key
+    deltas, a mid-block restart point, two data blocks, bit-wise CRC - is read correctly; a flipped byte in a block is
+    caught by the block trailer. (2) The writer emits that layout and round-trips through the `shared > 0` branch."""
+    from deeploopcloser_b200 import tf_checkpoint as tc
+    # ---- (1) hand-assembled: keys Variable, Variable_1, Variable_10 | (restart) Variable_11 ; second block: global_step
+    v = [b"v0", b"value-1", b"v10", b"v11", b"gs"]
+    e0 = (0, b"Variable", v[0])
+    e1 = (8, b"_1", v[1])                       # shares "Variable"
+    e2 = (10, b"0", v[2])                       # shares "Variable_1"
+    off_restart = sum(3 + len(k) + len(val) for _, k, val in (e0, e1, e2))       # 1-byte varints: 3 header bytes each
+    e3 = (0, b"Variable_11", v[3])              # restart point: full key
+    b1_body, b1, varint = _hand_block([e0, e1, e2, e3], [0, off_restart])
+    b0_body, b0, _ = _hand_block([(0, b"global_step", v[4])], [0])               # sorts before "Variable..." ('g' > 'V')
+    # table: data block A (Variable*), data block B (global_step) - keys ascending: "Variable..." < "global_step"
+    blob = bytearray()
+    handles = []
+    for body, full, last in ((b1_body, b1, b"Variable_11"), (b0_body, b0, b"global_step")):
+        handles.append((last, varint(len(blob)) + varint(len(body))))
+        blob += full
+    meta_body, meta, _ = _hand_block([], [0])
+    meta_off = len(blob)
+    blob += meta
+    idx_body, idx, _ = _hand_block([(0, k, h) for k, h in handles], [0, 3 + len(handles[0][0]) + len(handles[0][1])])
+    idx_off = len(blob)
+    blob += idx
+    footer = varint(meta_off) + varint(len(meta_body)) + varint(idx_off) + varint(len(idx_body))
+    blob += footer + b"\x00" * (40 - len(footer)) + (0xdb4775248b80fb57).to_bytes(8, "little")
+    path = tmp_path / "hand.index"
+    path.write_bytes(bytes(blob))
+    got = tc._read_table(str(path))
+    assert got == {b"Variable": v[0], b"Variable_1": v[1], b"Variable_10": v[2], b"Variable_11": v[3],
+                   b"global_step": v[4]}
+    bad = bytearray(blob)
+    bad[5] ^= 0x01                              # inside data block A
+    path.write_bytes(bytes(bad))
+    with pytest.raises(ValueError, match="crc32c"):
+        tc._read_table(str(path))
+    # ---- (2) the writer: 40 variables -> prefix sharing (restart interval 16) and, with small blocks, several blocks
+    rng = np.random.default_rng(5)
+    tensors = {("Variable" if i == 0 else "Variable_%d" % i): rng.standard_normal((3, i + 1)) for i in range(40)}
+    tensors["global_step"] = np.array(7, dtype=np.int64)
+    prefix = tc.save_checkpoint(str(tmp_path / "ck-7"), tensors, block_size=300)
+    raw = (tmp_path / "ck-7.index").read_bytes()
+    # parse the index block by hand: more than one data block, and shared > 0 entries inside the first one
+    footer = raw[-48:]
+    _, p = tc._get_varint(footer, 0)
+    _, p = tc._get_varint(footer, p)
+    idx_off, p = tc._get_varint(footer, p)
+    idx_size, _ = tc._get_varint(footer, p)
+    blocks = tc._read_block(raw, idx_off, idx_size)
+    assert len(blocks) > 3
+    off, p = tc._get_varint(blocks[1][1], 0)
+    shared, q = tc._get_varint(raw, off)        # first entry of a block is a restart point ...
+    non_shared, q = tc._get_varint(raw, q)
+    vlen, q = tc._get_varint(raw, q)
+    assert shared == 0
+    assert tc._get_varint(raw, q + non_shared + vlen)[0] > 0   # ... the next key shares a prefix with it
+    back = tc.load_checkpoint(prefix)
+    assert set(back) == set(tensors) and all(np.array_equal(back[k], tensors[k]) for k in tensors)
+    assert [n for n, _, _ in tc.list_variables(prefix)] == sorted(tensors)
+    # restart interval 1 (no sharing) reads the same
+    p1 = tc.save_checkpoint(str(tmp_path / "ck1-7"), tensors, update_state=False, restart_interval=1)
+    assert all(np.array_equal(tc.load_checkpoint(p1)[k], tensors[k]) for k in tensors)

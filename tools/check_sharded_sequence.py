@@ -1,5 +1,7 @@
 """Multi-GPU check + timing of ONE sequence split over the ranks (run under torchrun, one rank per GPU): the score
-matrix and candidate lists of ShardedSequencePipeline must equal the single-GPU pipeline's bit for bit on every rank.
+matrix and candidate lists of ShardedSequencePipeline against the single-GPU pipeline on every rank: descriptors
+bit-identical, candidate indices identical, scores within float32 rounding (the dataset mean is summed in another order
+across ranks, so the last bits of a score may differ; whether they are bit-identical is reported).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded_sequence.py"""
 import json
@@ -26,9 +28,10 @@ pipe = ShardedSequencePipeline(bench.DIMS)
 pipe.set_weights(ws, bs)
 got = pipe.run(f_d, x_d, k=bench.K_CAND)
 torch.cuda.synchronize()
-same = torch.tensor([int(torch.equal(got["similarity"], want["similarity"]) and
-                         torch.equal(got["candidates"][1], want["candidates"][1]) and
-                         torch.equal(got["descriptors"], want["descriptors"]))], device="cuda")
+rel = ((got["similarity"] - want["similarity"]).abs() / want["similarity"].abs().clamp_min(1.0)).max()
+same = torch.tensor([int(bool(rel <= 1e-5) and torch.equal(got["candidates"][1], want["candidates"][1]) and
+                         torch.equal(got["descriptors"], want["descriptors"])),
+                     int(torch.equal(got["similarity"], want["similarity"]))], device="cuda")
 dist.all_reduce(same, op=dist.ReduceOp.MIN)
 
 
@@ -53,7 +56,8 @@ t_one = timed(lambda: ref.run(f_d, x_d, k=bench.K_CAND))
 t_all = timed(lambda: pipe.run(f_d, x_d, k=bench.K_CAND))
 if rank == 0:
     print(json.dumps({"check": "sharded_sequence", "n_gpus": world, "frames": bench.N_FRAMES,
-                      "identical_to_single_gpu_on_all_ranks": bool(same.item()),
+                      "matches_single_gpu_on_all_ranks": bool(same[0].item()),
+                      "scores_bit_identical_on_all_ranks": bool(same[1].item()), "max_rel_score_diff": float(rel),
                       "single_gpu_ms": t_one, "sharded_ms": t_all, "speedup": t_one / t_all,
                       "frames_per_s": bench.N_FRAMES / t_all * 1e3}))
 dist.destroy_process_group()
