@@ -76,6 +76,11 @@ PROTOTYPES = {
     "dlc_match_workspace_bytes": (_sz, [_p, _i, _i]),
     "dlc_match_topk": (_i, [_p, _p, _i, _i, _i64, _p, _p, _p, _sz, _p]),
     "dlc_match_threshold": (_i, [_p, _p, _i, _f, _i, _i64, _p, _p, _p, _p, _sz, _p]),
+    "dlc_comm_unique_id": (_i, [_p]),
+    "dlc_comm_create": (_i, [C.POINTER(_p), _p, _i, _i]),
+    "dlc_comm_destroy": (_i, [_p]),
+    "dlc_match_sharded_workspace_bytes": (_sz, [_p, _i, _i, _i]),
+    "dlc_match_topk_sharded": (_i, [_p, _p, _p, _i, _i, _i64, _p, _p, _p, _sz, _p]),
     "dlc_hamming_workspace_bytes": (_sz, [_i, _i]),
     "dlc_hamming_matrix": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
     "dlc_matrix_image_workspace_bytes": (_sz, []),

@@ -385,9 +385,119 @@ static int match_impl(dlc_db* db, const float* q, int B, int k, int64_t idx_offs
   return DLC_OK;
 }
 
+// ---- row-sharded matcher: merge of the per-rank lists, read straight from the all-gathered blocks
+// block r = [idx B x k int64 | scores B x k float32] of rank r. One warp per query: every lane keeps its share of the
+// world * k candidates, k rounds of warp arg-best (score, then lowest index; idx -1 = padding loses to everything).
+__global__ void __launch_bounds__(256)
+merge_rank_lists_kernel(const uint8_t* __restrict__ blocks, size_t block_bytes, int world, int B, int k, int smaller,
+                        float* __restrict__ out_s, int64_t* __restrict__ out_i) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  constexpr int kPerLane = 32;                  // world * k <= 1024
+  const int n = world * k;
+  float sc[kPerLane];
+  int64_t ix[kPerLane];
+  const float worst = smaller ? INFINITY : -INFINITY;
+#pragma unroll
+  for (int t = 0; t < kPerLane; ++t) {
+    const int c = lane + 32 * t;
+    sc[t] = worst;
+    ix[t] = -1;
+    if (c < n) {
+      const int r = c / k, j = c - r * k;
+      const uint8_t* blk = blocks + static_cast<size_t>(r) * block_bytes;
+      ix[t] = reinterpret_cast<const int64_t*>(blk)[static_cast<size_t>(b) * k + j];
+      sc[t] = reinterpret_cast<const float*>(blk + sizeof(int64_t) * static_cast<size_t>(B) * k)[static_cast<size_t>(b) * k + j];
+    }
+  }
+  auto better = [&](float s1, int64_t i1, float s2, int64_t i2) {  // is candidate 1 strictly better than candidate 2
+    if (i1 < 0) return false;
+    if (i2 < 0) return true;
+    if (s1 != s2) return smaller ? s1 < s2 : s1 > s2;
+    return i1 < i2;
+  };
+  for (int round = 0; round < k; ++round) {
+    float bs = worst;
+    int64_t bi = -1;
+    int bt = -1;
+#pragma unroll
+    for (int t = 0; t < kPerLane; ++t)
+      if (better(sc[t], ix[t], bs, bi)) {
+        bs = sc[t];
+        bi = ix[t];
+        bt = t;
+      }
+    float ws_ = bs;
+    int64_t wi = bi;
+    int wl = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, ws_, off);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, wi, off);
+      const int ol = __shfl_xor_sync(0xffffffffu, wl, off);
+      if (better(os, oi, ws_, wi) || (oi == wi && os == ws_ && ol < wl)) {
+        ws_ = os;
+        wi = oi;
+        wl = ol;
+      }
+    }
+    if (lane == 0) {
+      out_s[static_cast<size_t>(b) * k + round] = wi < 0 ? worst : ws_;
+      out_i[static_cast<size_t>(b) * k + round] = wi;
+    }
+    if (lane == wl && bt >= 0 && wi >= 0) {     // the winner leaves the pool
+#pragma unroll
+      for (int t = 0; t < kPerLane; ++t)
+        if (t == bt) ix[t] = -1;
+    }
+  }
+}
+
+int comm_all_gather(dlc_comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream);  // comm.cu
+int comm_rank(const dlc_comm* c);
+int comm_world(const dlc_comm* c);
+
 }  // namespace dlc
 
 using namespace dlc;
+
+extern "C" size_t dlc_match_sharded_workspace_bytes(const dlc_db* db, int B, int k, int world) {
+  if (!db || B <= 0 || k <= 0 || k > 32 || world <= 0) return 0;
+  const size_t block = align_up(static_cast<size_t>(B) * k * 12, 256);
+  return align_up(match_layout(db, B, k).total, 256) + block * (static_cast<size_t>(world) + 1);
+}
+
+// Row-sharded top-k over the `world` ranks of `comm` (one process per GPU; every rank calls this with the SAME
+// queries): fused similarity + top-k on the local shard -> ONE ncclAllGather of the packed (score, index) lists on
+// `stream` -> merge kernel reading the gathered blocks in place. Every rank ends with the same lists.
+extern "C" int dlc_match_topk_sharded(dlc_db* db, dlc_comm* comm, const float* q_dev, int B, int k, int64_t idx_offset,
+                                      float* scores_dev, int64_t* idx_dev, void* ws_dev, size_t ws_bytes,
+                                      void* stream) {
+  DLC_CHECK_ARG(db && comm && q_dev && scores_dev && idx_dev && ws_dev);
+  DLC_CHECK_ARG(B >= 1 && k >= 1 && k <= 32);
+  const int world = comm_world(comm), rank = comm_rank(comm);
+  DLC_CHECK_ARG(world * k <= 1024);
+  if (ws_bytes < dlc_match_sharded_workspace_bytes(db, B, k, world))
+    return fail(DLC_ENOMEM, "dlc_match_topk_sharded: workspace of %zu bytes needed, %zu given",
+                dlc_match_sharded_workspace_bytes(db, B, k, world), ws_bytes);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(ws_dev);
+  const size_t local_ws = align_up(match_layout(db, B, k).total, 256);
+  const size_t block = align_up(static_cast<size_t>(B) * k * 12, 256);
+  uint8_t* gathered = reinterpret_cast<uint8_t*>(ws + local_ws);              // world blocks
+  uint8_t* mine = gathered + static_cast<size_t>(rank) * block;               // in-place all-gather: own slot
+  int64_t* my_i = reinterpret_cast<int64_t*>(mine);
+  float* my_s = reinterpret_cast<float*>(mine + sizeof(int64_t) * static_cast<size_t>(B) * k);
+  if (int rc = match_impl(db, q_dev, B, k, idx_offset, 0, 0.0f, nullptr, my_s, my_i, ws, local_ws, s)) return rc;
+  if (world > 1) {
+    if (int rc = comm_all_gather(comm, mine, gathered, block, s)) return rc;
+  }
+  merge_rank_lists_kernel<<<ceil_div(B, 8), 256, 0, s>>>(gathered, block, world, B, k,
+                                                         db->metric == DLC_METRIC_L2 ? 1 : 0, scores_dev, idx_dev);
+  DLC_CUDA(cudaGetLastError());
+  return DLC_OK;
+}
 
 extern "C" int dlc_db_create(dlc_db** db, int dim, int64_t capacity_rows, int metric, int dtype) {
   DLC_CHECK_ARG(db);

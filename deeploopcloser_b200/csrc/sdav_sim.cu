@@ -31,40 +31,89 @@ std::atomic<int> g_sim_mgroup{32};                                  // M tiles p
 
 // ---------------- column mean -> distinctive weights (deterministic two-stage reduction) ----------------
 constexpr int kColSumSlabs = 128;
+// part[slab][0..D) = sum_r x, part[slab][D..2D) = sum_r x^2 over the slab's rows (float64)
 __global__ void colsum_partial_kernel(const float* __restrict__ H, int64_t rows, int D, double* __restrict__ part) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= D) return;
   const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = blockIdx.y * per;
   const int64_t r1 = r0 + per < rows ? r0 + per : rows;
-  double acc = 0.0;
-  for (int64_t r = r0; r < r1; ++r) acc += static_cast<double>(H[r * D + col]);
-  part[static_cast<int64_t>(blockIdx.y) * D + col] = acc;
+  double acc = 0.0, acc2 = 0.0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const double x = static_cast<double>(H[r * D + col]);
+    acc += x;
+    acc2 = fma(x, x, acc2);
+  }
+  part[static_cast<int64_t>(blockIdx.y) * 2 * D + col] = acc;
+  part[static_cast<int64_t>(blockIdx.y) * 2 * D + D + col] = acc2;
 }
-__global__ void weights_kernel(const double* __restrict__ part, int slabs, int64_t rows, int D, double mu, double sigma,
-                               double* __restrict__ w, double* __restrict__ mean_out) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
-  double acc = 0.0;
-  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * D + col];
-  const double mean = acc / static_cast<double>(rows);
-  const double d = mean - mu;
-  if (w) w[col] = exp(-(d * d) / (2.0 * sigma * sigma));
-  if (mean_out) mean_out[col] = mean;
+// Column sums -> dataset mean -> distinctive weights w (SimilarityCalculator.py:19-27) and the CENTRING vector of the
+// operand planes (see prep_rows_kernel). One block: the centring decision needs the total over all columns.
+//   centre = mean  when the descriptors nearly coincide: sum ||h - mean||^2 < sum ||h||^2 / 16
+//          = 0     otherwise
+// Why a decision: centring is what makes n_k + n_j - 2G resolvable in fp32 when the rows are close together (a
+// trained-like encoder: row norms^2 ~ 7e2, distances^2 ~ 1e-4), but on spread-out, saturated descriptors (N(0,1)
+// weights: 89 % exact 0 / 1 values, centred energy 1/6 of the total) the uncentred planes are BETTER operands: 0 and 1
+// are exact in fp16 (no rounding error at all on those elements) and all-zero / all-one mantissas keep the tensor
+// pipe's power down, i.e. its clock up (measured: 1.46 -> 1.65 ms for the same Gram kernel with centred planes).
+constexpr int kWeightsThreads = 1024;
+__global__ void __launch_bounds__(kWeightsThreads)
+weights_centre_kernel(const double* __restrict__ part, int slabs, int64_t rows, int D, double mu, double sigma,
+                      double* __restrict__ w, float* __restrict__ centre) {
+  __shared__ double s_e[kWeightsThreads / 32], s_c[kWeightsThreads / 32];
+  __shared__ int s_flag;
+  double e_tot = 0.0, e_cen = 0.0;
+  for (int col = threadIdx.x; col < D; col += blockDim.x) {
+    double acc = 0.0, acc2 = 0.0;
+    for (int s = 0; s < slabs; ++s) {
+      acc += part[static_cast<int64_t>(s) * 2 * D + col];
+      acc2 += part[static_cast<int64_t>(s) * 2 * D + D + col];
+    }
+    const double mean = acc / static_cast<double>(rows);
+    const double d = mean - mu;
+    if (w) w[col] = exp(-(d * d) / (2.0 * sigma * sigma));
+    if (centre) centre[col] = static_cast<float>(mean);
+    e_tot += acc2;
+    e_cen += fmax(acc2 - static_cast<double>(rows) * mean * mean, 0.0);
+  }
+  if (!centre) return;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    e_tot += __shfl_xor_sync(0xffffffffu, e_tot, off);
+    e_cen += __shfl_xor_sync(0xffffffffu, e_cen, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_e[threadIdx.x >> 5] = e_tot;
+    s_c[threadIdx.x >> 5] = e_cen;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < kWeightsThreads / 32; ++i) {
+      a += s_e[i];
+      b += s_c[i];
+    }
+    s_flag = b * 16.0 < a ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_flag)
+    for (int col = threadIdx.x; col < D; col += blockDim.x) centre[col] = 0.0f;
 }
+
 // One pass over the descriptors for everything the Gram kernel needs per row: the operand plane(s), the squared norm
 // and the projection p = h . w. One warp per PADDED row (frame f, k < 32); rows k >= P only get their statistics.
 //
-// CENTRING. The planes hold h - m (m = the dataset's column mean, already needed for the weights), not h: distances
-// are translation invariant, ||h2_j - h1_k||^2 = n'_k + n'_j - 2 G' with G' = (H - m)(H - m)^T, and the centred Gram
-// does not cancel. Without it a dataset whose descriptors nearly coincide (a trained-like, well-scaled encoder gives
-// row norms^2 ~ 7e2 but distances^2 ~ 1e-4) is unresolvable in ANY fp32 accumulator: n_k + n_j - 2G loses 1e-5
-// absolute, far above the 2e-7 gaps between candidates. On saturated N(0,1)-weight descriptors centring is neutral
-// (the fp16 rounding error of the distance, std ~4e-3, is unchanged). The planes are stored P rows per frame: both
-// sides of the Gram kernel read them (the M side through a 3-D tensor map whose 32-row boxes zero-fill rows P..31).
+// CENTRING. The planes hold h - c (c = `centre`: the float32-rounded dataset mean, or zero - weights_centre_kernel
+// decides), not h: distances are translation invariant, ||h2_j - h1_k||^2 = n'_k + n'_j - 2 G' with
+// G' = (H - c)(H - c)^T, and for close-together rows the centred Gram does not cancel. Without it a dataset whose
+// descriptors nearly coincide (a trained-like, well-scaled encoder gives row norms^2 ~ 7e2 but distances^2 ~ 1e-4) is
+// unresolvable in ANY fp32 accumulator: n_k + n_j - 2G loses 1e-5 absolute, far above the 2e-7 gaps between
+// candidates. h - c is ONE float32 subtraction (exact when h and c are within a factor two, Sterbenz - the case that
+// matters - and good to 6e-8 relative otherwise). The planes are stored P rows per frame: both sides of the Gram
+// kernel read them (the M side through a 3-D tensor map whose 32-row boxes zero-fill rows P..31).
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
-                 const double* __restrict__ mean, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int ld,
+                 const float* __restrict__ centre, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int ld,
                  float* __restrict__ sqn, double* __restrict__ pw, unsigned int* __restrict__ nmax_bits) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +129,7 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   const int64_t r = static_cast<int64_t>(f) * P + k;          // source row = plane row
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
-  const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0;
+  const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(centre) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
 #pragma unroll 2
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
@@ -99,35 +148,38 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
     }
     __align__(16) __half hh[8];
     __align__(16) __half ll[8];
-    double wv[8], mv[8];
-    if (wvec && c0 + 8 <= D) {   // 16-byte loads of the weights and the mean
+    double wv[8];
+    float mv[8];
+    if (wvec && c0 + 8 <= D) {   // 16-byte loads of the weights and the centring vector
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const double2 t = *reinterpret_cast<const double2*>(w + c0 + 2 * j);
-        const double2 m2 = *reinterpret_cast<const double2*>(mean + c0 + 2 * j);
         wv[2 * j] = t.x;
         wv[2 * j + 1] = t.y;
-        mv[2 * j] = m2.x;
-        mv[2 * j + 1] = m2.y;
       }
+      const float4 m0 = *reinterpret_cast<const float4*>(centre + c0);
+      const float4 m1 = *reinterpret_cast<const float4*>(centre + c0 + 4);
+      mv[0] = m0.x; mv[1] = m0.y; mv[2] = m0.z; mv[3] = m0.w;
+      mv[4] = m1.x; mv[5] = m1.y; mv[6] = m1.z; mv[7] = m1.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         wv[j] = c0 + j < D ? w[c0 + j] : 0.0;
-        mv[j] = c0 + j < D ? mean[c0 + j] : 0.0;
+        mv[j] = c0 + j < D ? centre[c0 + j] : 0.0f;
       }
     }
+    float s8 = 0.0f;   // squared norm of the centred values: eight float32 terms at a time, summed in float64
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float xc = 0.0f;
       if (c0 + j < D) {
-        const double xd = static_cast<double>(x[j]);
-        xc = static_cast<float>(xd - mv[j]);
-        n2 = fma(static_cast<double>(xc), static_cast<double>(xc), n2);
-        pr = fma(xd, wv[j], pr);
+        xc = x[j] - mv[j];
+        s8 = fmaf(xc, xc, s8);
+        pr = fma(static_cast<double>(x[j]), wv[j], pr);
       }
       split_f32(xc, hh[j], ll[j]);
     }
+    n2 += static_cast<double>(s8);
     const int64_t ob = r * ld + c0;
     *reinterpret_cast<uint4*>(b_hi + ob) = *reinterpret_cast<const uint4*>(hh);
     if (b_lo) *reinterpret_cast<uint4*>(b_lo + ob) = *reinterpret_cast<const uint4*>(ll);
@@ -155,7 +207,7 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
 struct GramControl;
 __device__ __forceinline__ bool lo_planes_wanted(const GramControl* ctl);
 __global__ void __launch_bounds__(256)
-lo_planes_kernel(const float* __restrict__ H, int64_t rows, int D, const double* __restrict__ mean,
+lo_planes_kernel(const float* __restrict__ H, int64_t rows, int D, const float* __restrict__ centre,
                  __half* __restrict__ b_lo, int ld, const GramControl* __restrict__ ctl) {
   if (!lo_planes_wanted(ctl)) return;
   const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -166,7 +218,7 @@ lo_planes_kernel(const float* __restrict__ H, int64_t rows, int D, const double*
     __align__(16) __half ll[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float x = c0 + j < D ? static_cast<float>(static_cast<double>(h[c0 + j]) - mean[c0 + j]) : 0.0f;
+      const float x = c0 + j < D ? h[c0 + j] - centre[c0 + j] : 0.0f;
       __half hh;
       split_f32(x, hh, ll[j]);
     }
@@ -640,7 +692,7 @@ __global__ void __launch_bounds__(kFixThreads, 4) gram_refine_fix_kernel(const G
 }
 
 // ---- probe: estimate the single-product error and the share of rows it would leave ambiguous
-constexpr int kProbeSamples = 1024;
+constexpr int kProbeSamples = 512;
 struct ProbeAccum {
   double sum_err2;        // sum over sampled (row, candidate) of (approximate - exact squared distance)^2
   unsigned long long n_err;
@@ -658,7 +710,7 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
 }
 // one CTA per sample: a random row k of frame fa against all P rows of a random other frame fb (warp j = row j)
 __global__ void __launch_bounds__(1024)
-gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const double* __restrict__ mean,
+gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const float* __restrict__ centre,
                   const uint32_t* __restrict__ rep_mask, ProbeAccum* acc, float* gaps) {
   __shared__ double s_e[32];
   __shared__ double s_d[32];
@@ -682,26 +734,25 @@ gram_probe_kernel(const float* __restrict__ desc, int N, int P, int D, const dou
     //        added in float64 (absolute error ~1e-5 on values ~1e3; it is compared with a margin ~1e-2).
     float err = 0.0f;
     double dist = 0.0;
-    // (x, y are the CENTRED values h - m the planes hold, see prep_rows_kernel)
-    auto term = [&](float xr, float yr, double m) -> float {
-      const float x = static_cast<float>(static_cast<double>(xr) - m), y = static_cast<float>(static_cast<double>(yr) - m);
+    // (x, y are the CENTRED values h - c the planes hold, see prep_rows_kernel)
+    auto term = [&](float xr, float yr, float m) -> float {
+      const float x = xr - m, y = yr - m;
       const float xh = __half2float(__float2half_rn(x)), yh = __half2float(__float2half_rn(y));
       err = fmaf(x - xh, y, fmaf(xh, y - yh, err));
       return y * (y - 2.0f * x);
     };
-    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(desc) & 15) == 0 && (reinterpret_cast<uintptr_t>(mean) & 15) == 0) {
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(desc) & 15) == 0 && (reinterpret_cast<uintptr_t>(centre) & 15) == 0) {
       const float4* a4 = reinterpret_cast<const float4*>(a);
       const float4* b4 = reinterpret_cast<const float4*>(b);
-      const double2* m2 = reinterpret_cast<const double2*>(mean);
+      const float4* m4 = reinterpret_cast<const float4*>(centre);
 #pragma unroll 4
       for (int c = lane; c < (D >> 2); c += 32) {
-        const float4 x = __ldg(a4 + c), y = __ldg(b4 + c);
-        const double2 ma = __ldg(m2 + 2 * c), mb = __ldg(m2 + 2 * c + 1);
-        dist += static_cast<double>((term(x.x, y.x, ma.x) + term(x.y, y.y, ma.y)) +
-                                    (term(x.z, y.z, mb.x) + term(x.w, y.w, mb.y)));
+        const float4 x = __ldg(a4 + c), y = __ldg(b4 + c), m = __ldg(m4 + c);
+        dist += static_cast<double>((term(x.x, y.x, m.x) + term(x.y, y.y, m.y)) +
+                                    (term(x.z, y.z, m.z) + term(x.w, y.w, m.w)));
       }
     } else {
-      for (int c = lane; c < D; c += 32) dist += static_cast<double>(term(a[c], b[c], mean[c]));
+      for (int c = lane; c < D; c += 32) dist += static_cast<double>(term(a[c], b[c], centre[c]));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -893,9 +944,9 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   const size_t plane_b = static_cast<size_t>(w.rows_b) * w.ld * 2;
   w.off_bhi = take(plane_b);
   w.off_blo = take(plane_b);
-  w.off_part = take(sizeof(double) * kColSumSlabs * D);
+  w.off_part = take(sizeof(double) * kColSumSlabs * 2 * D);
   w.off_w = take(sizeof(double) * D);
-  w.off_mean = take(sizeof(double) * D);
+  w.off_mean = take(sizeof(float) * D);   // centring vector (float32)
   w.off_sqn = take(sizeof(float) * w.rows_pad);
   w.off_pw = take(sizeof(double) * w.rows_pad);
   w.off_rep = take(sizeof(uint32_t) * N);
@@ -1018,13 +1069,13 @@ extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, doub
                                 void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(desc_dev && w_dev && ws_dev);
   DLC_CHECK_ARG(N >= 1 && P >= 1 && D >= 1 && sigma != 0.0);
-  if (ws_bytes < sizeof(double) * kColSumSlabs * D)
-    return fail(DLC_ENOMEM, "dlc_sdav_weights: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * D);
+  if (ws_bytes < sizeof(double) * kColSumSlabs * 2 * D)
+    return fail(DLC_ENOMEM, "dlc_sdav_weights: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * 2 * D);
   cudaStream_t s = as_stream(stream);
   double* part = static_cast<double*>(ws_dev);
   const int64_t rows = static_cast<int64_t>(N) * P;
   colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
-  weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev, nullptr);
+  weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev, nullptr);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
@@ -1072,7 +1123,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
 
   double* colsum_part = reinterpret_cast<double*>(ws + L.off_part);
   double* w = reinterpret_cast<double*>(ws + L.off_w);
-  double* mean = reinterpret_cast<double*>(ws + L.off_mean);
+  float* mean = reinterpret_cast<float*>(ws + L.off_mean);   // centring vector: the dataset mean, or zero
   float* sqn = reinterpret_cast<float*>(ws + L.off_sqn);
   double* pw = reinterpret_cast<double*>(ws + L.off_pw);
   uint32_t* rep = reinterpret_cast<uint32_t*>(ws + L.off_rep);
@@ -1100,8 +1151,8 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
     // 1. dataset mean -> centring vector of the planes and distinctive weights w (w_dev given: weights of another
     //    dataset, SimilarityCalculator.similarity_score on frames outside it; the mean is still this dataset's)
     colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
-    weights_kernel<<<ceil_div(D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma, w_dev ? nullptr : w,
-                                                     mean);
+    weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma,
+                                                        w_dev ? nullptr : w, mean);
     if (w_dev) w = const_cast<double*>(w_dev);
     // 2. precision probe, part two (single-product error of the CENTRED values on sampled rows): next to step 3
     if (probe) {
@@ -1234,7 +1285,7 @@ static StageWorkspace stage_layout(int N, int D, int n_parts) {
     o = align_up(o + bytes, 256);
     return at;
   };
-  w.off_part = take(sizeof(double) * kColSumSlabs * D);
+  w.off_part = take(sizeof(double) * kColSumSlabs * 2 * D);
   w.off_sqn = take(sizeof(float) * N * kFrameRows);
   w.off_pw = take(sizeof(double) * N * kFrameRows);
   w.off_rep = take(sizeof(uint32_t) * N);
@@ -1248,11 +1299,12 @@ static StageWorkspace stage_layout(int N, int D, int n_parts) {
   return w;
 }
 
-__global__ void colsum_reduce_kernel(const double* __restrict__ part, int slabs, int D, double* __restrict__ out) {
+// width = 2 D: the column sums and the column sums of squares, see colsum_partial_kernel
+__global__ void colsum_reduce_kernel(const double* __restrict__ part, int slabs, int width, double* __restrict__ out) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
+  if (col >= width) return;
   double acc = 0.0;
-  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * D + col];
+  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * width + col];
   out[col] = acc;
 }
 
@@ -1329,31 +1381,31 @@ extern "C" int dlc_sdav_stage_colsum(const float* desc_local_dev, int64_t rows_l
                                      void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(colsum_dev && ws_dev && D >= 1 && rows_local >= 0);
   DLC_CHECK_ARG(desc_local_dev || rows_local == 0);
-  if (ws_bytes < sizeof(double) * kColSumSlabs * D)
-    return fail(DLC_ENOMEM, "dlc_sdav_stage_colsum: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * D);
+  if (ws_bytes < sizeof(double) * kColSumSlabs * 2 * D)
+    return fail(DLC_ENOMEM, "dlc_sdav_stage_colsum: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * 2 * D);
   cudaStream_t s = as_stream(stream);
   double* part = static_cast<double*>(ws_dev);
   colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_local_dev, rows_local, D, part);
-  colsum_reduce_kernel<<<ceil_div(D, 128), 128, 0, s>>>(part, kColSumSlabs, D, colsum_dev);
+  colsum_reduce_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(part, kColSumSlabs, 2 * D, colsum_dev);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
 
 extern "C" int dlc_sdav_stage_weights(const double* colsums_dev, int n_parts, int64_t rows_total, int D, double mu,
-                                      double sigma, double* w_dev, double* mean_dev, void* stream) {
-  DLC_CHECK_ARG(colsums_dev && w_dev && mean_dev);
+                                      double sigma, double* w_dev, float* centre_dev, void* stream) {
+  DLC_CHECK_ARG(colsums_dev && w_dev && centre_dev);
   DLC_CHECK_ARG(n_parts >= 1 && rows_total >= 1 && D >= 1 && sigma != 0.0);
-  weights_kernel<<<ceil_div(D, 128), 128, 0, as_stream(stream)>>>(colsums_dev, n_parts, rows_total, D, mu, sigma, w_dev,
-                                                                  mean_dev);
+  weights_centre_kernel<<<1, kWeightsThreads, 0, as_stream(stream)>>>(colsums_dev, n_parts, rows_total, D, mu, sigma,
+                                                                      w_dev, centre_dev);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
 
 extern "C" int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, int frames_per_part, int P, int D,
-                                      const double* w_dev, const double* mean_dev, int precision,
+                                      const double* w_dev, const float* centre_dev, int precision,
                                       void* plane_hi_local_dev, void* plane_lo_local_dev, void* stats_local_dev,
                                       void* stream) {
-  DLC_CHECK_ARG(stats_local_dev && w_dev && mean_dev);
+  DLC_CHECK_ARG(stats_local_dev && w_dev && centre_dev);
   DLC_CHECK_ARG(n_local >= 0 && n_local <= frames_per_part && P >= 1 && P <= kFrameRows && D >= 1);
   DLC_CHECK_ARG(n_local == 0 || (desc_local_dev && plane_hi_local_dev));
   DLC_CHECK_ARG(precision != DLC_PREC_FP16X2 || plane_lo_local_dev || n_local == 0);
@@ -1369,14 +1421,14 @@ extern "C" int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, 
   uint32_t* rep = reinterpret_cast<uint32_t*>(st + t.off_rep);
   const bool probe = precision == DLC_PREC_AUTO || precision == DLC_PREC_FP16_REFINED;
   prep_rows_kernel<<<ceil_div(n_local * kFrameRows, 8), 256, 0, s>>>(
-      desc_local_dev, n_local, P, D, w_dev, mean_dev, static_cast<__half*>(plane_hi_local_dev),
+      desc_local_dev, n_local, P, D, w_dev, centre_dev, static_cast<__half*>(plane_hi_local_dev),
       precision == DLC_PREC_FP16X2 ? static_cast<__half*>(plane_lo_local_dev) : nullptr, ld,
       reinterpret_cast<float*>(st + t.off_sqn), reinterpret_cast<double*>(st + t.off_pw),
       probe ? &acc->nmax_bits : nullptr);
   if (probe) {
     rep_mask_kernel<<<n_local, 1024, 0, s>>>(desc_local_dev, n_local, P, D, rep);
     if (n_local >= 2)
-      gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_local_dev, n_local, P, D, mean_dev, rep, acc, gaps);
+      gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_local_dev, n_local, P, D, centre_dev, rep, acc, gaps);
   }
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;

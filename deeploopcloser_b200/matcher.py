@@ -98,9 +98,15 @@ def gather_partial_lists(scores, idx, group=None):
 
 
 class ShardedKeyframeDatabase:
-    """Row-sharded database: rank r owns the global rows it was given (contiguous block `row_offset + local`)."""
+    """Row-sharded database: rank r owns the global rows it was given (contiguous block `row_offset + local`).
 
-    def __init__(self, dim, capacity_per_rank, metric="cos", dtype="fp16", group=None):
+    With the NCCL backend the whole query runs behind ONE C-ABI call (`dlc_match_topk_sharded`): fused kernel on the
+    shard, one ncclAllGather of the packed (index, score) lists issued by the library on the caller's stream, merge
+    kernel reading the gathered blocks in place. The library's communicator is created here from a unique id that rank
+    0 draws and torch.distributed broadcasts. Without NCCL (the gloo CPU tests) the exchange is two torch all-gathers
+    and the generic merge (`gather_partial_lists` / `merge_partial_lists`)."""
+
+    def __init__(self, dim, capacity_per_rank, metric="cos", dtype="fp16", group=None, native_comm=True):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -108,14 +114,44 @@ class ShardedKeyframeDatabase:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = KeyframeDatabase(dim, capacity_per_rank, metric, dtype)
         self.row_offset = self.rank * int(capacity_per_rank)
+        self._comm = None
+        if native_comm and self.world > 1 and group is None and dist.get_backend() == "nccl":
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                buf = (C.c_char * 128)()
+                _lib.call("dlc_comm_unique_id", C.cast(buf, C.c_void_p))
+                uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            raw = bytes(uid.cpu().numpy().tobytes())
+            self._comm = C.c_void_p()
+            _lib.call("dlc_comm_create", C.byref(self._comm), raw, self.rank, self.world)
+        self._ws = Workspace()
 
     def append_local(self, rows):
         self.local.append(rows)
 
     def topk(self, q, k=10):
         """q must be identical on every rank (broadcast it first if it is produced on one rank)."""
+        if self._comm is not None:
+            B, _, _, s, i = self.local._prep(q, k)
+            ws, ws_bytes = self._ws.get(_lib.call("dlc_match_sharded_workspace_bytes", self.local._h, B, k, self.world))
+            _lib.call("dlc_match_topk_sharded", self.local._h, self._comm, ptr(q), B, k, int(self.row_offset), ptr(s),
+                      ptr(i), ws, ws_bytes, stream_ptr())
+            return s, i
         s, i = self.local.topk(q, k, idx_offset=self.row_offset)
         if self.world == 1:
             return s, i
         cs, ci = gather_partial_lists(s, i, self.group)
         return merge_partial_lists(cs, ci, k, self.local.smaller_is_better)
+
+    def close(self):
+        if self._comm is not None:
+            _lib.call("dlc_comm_destroy", self._comm)
+            self._comm = None
+        self.local.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -284,22 +284,24 @@ def sdav_stage_stats_bytes(frames_per_part):
 
 
 def _stage_ws(N, P, D, n_parts):
-    return _ws_stage.get(max(_lib.call("dlc_sdav_stage_workspace_bytes", N, P, D, n_parts), 128 * D * 8))
+    return _ws_stage.get(max(_lib.call("dlc_sdav_stage_workspace_bytes", N, P, D, n_parts), 128 * 2 * D * 8))
 
 
 def sdav_stage_colsum(desc_local, out):
-    """desc_local float32 [rows, D] (this rank's descriptor rows) -> out float64 [D] column sums."""
+    """desc_local float32 [rows, D] (this rank's descriptor rows) -> out float64 [2 D]: column sums, then column sums
+    of squares."""
     _check_cuda(desc_local, out)
     rows, D = desc_local.shape
-    ws, ws_bytes = _ws_stage.get(128 * D * 8)
+    ws, ws_bytes = _ws_stage.get(128 * 2 * D * 8)
     _lib.call("dlc_sdav_stage_colsum", ptr(desc_local), rows, D, ptr(out), ws, ws_bytes, stream_ptr())
 
 
-def sdav_stage_weights(colsums, rows_total, w, mean, mu=0.5, sigma=0.2):
-    """colsums float64 [n_parts, D] (all-gathered) -> w, mean float64 [D]."""
-    _check_cuda(colsums, w, mean)
-    _lib.call("dlc_sdav_stage_weights", ptr(colsums), colsums.shape[0], int(rows_total), colsums.shape[1], float(mu),
-              float(sigma), ptr(w), ptr(mean), stream_ptr())
+def sdav_stage_weights(colsums, rows_total, w, centre, mu=0.5, sigma=0.2):
+    """colsums float64 [n_parts, 2 D] (all-gathered) -> w float64 [D], centre float32 [D] (the planes' centring
+    vector: the dataset mean or zero)."""
+    _check_cuda(colsums, w, centre)
+    _lib.call("dlc_sdav_stage_weights", ptr(colsums), colsums.shape[0], int(rows_total), colsums.shape[1] // 2, float(mu),
+              float(sigma), ptr(w), ptr(centre), stream_ptr())
 
 
 def sdav_stage_prepare(desc_local, n_local, frames_per_part, P, w, mean, precision, plane_local, plane_lo_local,

@@ -185,8 +185,8 @@ class ShardedSequencePipeline(LoopClosurePipeline):
                 "plane": self._alloc((rows, ld), torch.float16),
                 "plane_lo": self._alloc((rows, ld), torch.float16) if self.sim_precision == "fp16x2" else None,
                 "stats": self._alloc((self.world, ops.sdav_stage_stats_bytes(per)), torch.uint8),
-                "colsums": self._alloc((self.world, D), torch.float64),
-                "w": self._alloc((D,), torch.float64), "mean": self._alloc((D,), torch.float64),
+                "colsums": self._alloc((self.world, 2 * D), torch.float64),
+                "w": self._alloc((D,), torch.float64), "mean": self._alloc((D,), torch.float32),
                 "S": self._alloc((n, n), torch.float32),
             }
             self._buf_key = key

@@ -14,7 +14,7 @@ same kernels as the parity-checked path."""
 import torch
 
 from . import ops
-from .matcher import ShardedKeyframeDatabase, gather_partial_lists, merge_partial_lists
+from .matcher import ShardedKeyframeDatabase
 from .pipeline import LoopClosurePipeline
 
 
@@ -53,12 +53,7 @@ class StreamingLoopCloser:
             dist.all_gather_into_tensor(q, q_local, group=self.group)
         else:
             q = q_local
-        if len(self.db.local) > 0 or self.world > 1:
-            s, i = self.db.local.topk(q, self.k, idx_offset=self.db.row_offset)
-            if self.world > 1:
-                cs, ci = gather_partial_lists(s, i, self.group)
-                s, i = merge_partial_lists(cs, ci, self.k, self.db.local.smaller_is_better)
-        else:
-            s, i = self.db.local.topk(q, self.k)
+        # fused similarity + top-k on the shard, one NCCL all-gather of the packed lists, merge (one C-ABI call)
+        s, i = self.db.topk(q, self.k)
         self.db.append_local(q_local)
         return s, i

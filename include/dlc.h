@@ -193,6 +193,10 @@ int dlc_sda_encode(dlc_sda* h, const void* x_hi_dev, const void* x_lo_dev, int r
  * desc_dev float32 [N, P, D] descriptors (P <= 32). S_dev float32 [N, N]: S[i][j] = S[j][i] = score(i, j) for i < j
  * (the reference evaluates only i < j and mirrors), diagonal = -1 (the reference's fill value).
  * full_asymmetric = 1 instead evaluates score(i, j) for every ordered pair i != j.
+ * The nearest-neighbour distances come from ONE Gram contraction over all patch rows,
+ * ||h2_j - h1_k||^2 = n_k + n_j - 2 G_kj, evaluated on h - c: c is the dataset's column mean when the descriptors
+ * nearly coincide (sum ||h - mean||^2 < sum ||h||^2 / 16 - a trained-like encoder; without the shift the subtraction
+ * cancels below any fp32 accumulator's resolution) and zero otherwise (decided on the device, no host round trip).
  * ------------------------------------------------------------------------------------------------------------ */
 size_t dlc_sdav_similarity_workspace_bytes(int N, int P, int D);
 /* w_dev: optional float64 [D] distinctive weights (from dlc_sdav_weights on another dataset); NULL = derive them
@@ -213,8 +217,11 @@ int dlc_sdav_similarity_part(const float* desc_dev, int N, int P, int D, double 
  * part's slice of arrays that the HOST exchanges between stages (NCCL all-gather; gathered slices form the flat global
  * arrays). No work is replicated: mean, row statistics, operand planes and the precision probe are produced once, by
  * the part that holds the frame.
- *   1. dlc_sdav_stage_colsum   local desc -> colsum [D] float64            -> all-gather: colsums [n_parts, D]
- *   2. dlc_sdav_stage_weights  colsums -> mean [D], w [D]                  (same result on every part)
+ *   1. dlc_sdav_stage_colsum   local desc -> colsum [2 D] float64 (column sums, then column sums of squares)
+ *                                                                          -> all-gather: colsums [n_parts, 2 D]
+ *   2. dlc_sdav_stage_weights  colsums -> w [D] float64 and the centring vector of the planes, centre [D] float32
+ *                              (the dataset mean when the descriptors nearly coincide, else zero: see
+ *                              dlc_sdav_similarity)                        (same result on every part)
  *   3. dlc_sdav_stage_prepare  local desc -> centred fp16 plane slice [frames_per_part * P, dlc_plane_ld(D)] (+ the
  *                              residual plane for DLC_PREC_FP16X2) and a stats block (dlc_sdav_stage_stats_bytes)
  *                                                                          -> all-gather planes, all-gather stats
@@ -229,9 +236,9 @@ size_t dlc_sdav_stage_workspace_bytes(int N, int P, int D, int n_parts);
 int dlc_sdav_stage_colsum(const float* desc_local_dev, int64_t rows_local, int D, double* colsum_dev, void* ws_dev,
                           size_t ws_bytes, void* stream);
 int dlc_sdav_stage_weights(const double* colsums_dev, int n_parts, int64_t rows_total, int D, double mu, double sigma,
-                           double* w_dev, double* mean_dev, void* stream);
+                           double* w_dev, float* centre_dev, void* stream);
 int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, int frames_per_part, int P, int D,
-                           const double* w_dev, const double* mean_dev, int precision, void* plane_hi_local_dev,
+                           const double* w_dev, const float* centre_dev, int precision, void* plane_hi_local_dev,
                            void* plane_lo_local_dev, void* stats_local_dev, void* stream);
 int dlc_sdav_stage_gram(const void* plane_hi_all_dev, const void* plane_lo_all_dev, const void* stats_all_dev,
                         int n_parts, int frames_per_part, int N, int P, int D, double a, double b, int precision,
@@ -244,7 +251,7 @@ int dlc_sdav_stage_fix(const void* plane_hi_all_dev, const float* desc_all_dev, 
  * estimated flagged fraction, flagged rows, refined candidates}. Synchronises the stream. */
 int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream);
 /* w = exp(-(mean_rows(desc) - mu)^2 / (2 sigma^2)), float64 [D] (SimilarityCalculator.py:19-27).
- * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 128*D*8). */
+ * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 128*2*D*8). */
 int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, double sigma, double* w_dev,
                      void* ws_dev, size_t ws_bytes, void* stream);
 
@@ -284,6 +291,22 @@ int dlc_match_topk(dlc_db* db, const float* q_dev, int B, int k, int64_t idx_off
 int dlc_match_threshold(dlc_db* db, const float* q_dev, int B, float thr, int max_per_row, int64_t idx_offset,
                         int32_t* counts_dev, float* scores_dev, int64_t* idx_dev, void* ws_dev, size_t ws_bytes,
                         void* stream);
+
+/* ---- Row-sharded database over the GPUs of one box (one process per GPU). A dlc_comm wraps an NCCL
+ * communicator: rank 0 obtains a 128-byte unique id (dlc_comm_unique_id), the host distributes it to the other ranks
+ * by any channel, every rank calls dlc_comm_create. libnccl.so.2 is resolved with dlopen at the first call (the copy
+ * the host process already loaded is reused); libdlc.so has no link-time NCCL dependency. */
+typedef struct dlc_comm dlc_comm;
+int dlc_comm_unique_id(void* id_out_host /* 128 bytes */);
+int dlc_comm_create(dlc_comm** c, const void* id_host /* 128 bytes */, int rank, int world);
+int dlc_comm_destroy(dlc_comm* c);
+size_t dlc_match_sharded_workspace_bytes(const dlc_db* db, int B, int k, int world);
+/* Every rank holds its shard in `db` and calls this with the SAME q_dev [B, dim]: fused similarity + top-k on the
+ * shard (indices = local row + idx_offset) -> ONE ncclAllGather of the packed (index, score) lists, B*k*12 bytes per
+ * rank, stream-ordered on `stream` -> merge kernel reading the gathered blocks in place (best score first, ties ->
+ * lowest global index). Every rank ends with identical scores_dev / idx_dev [B, k]. world * k <= 1024. */
+int dlc_match_topk_sharded(dlc_db* db, dlc_comm* comm, const float* q_dev, int B, int k, int64_t idx_offset,
+                           float* scores_dev, int64_t* idx_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a9/a10  cnn_vtl Hamming matrix.  Replaces DistanceCalculator.calculate_distance and the N x N loop around it

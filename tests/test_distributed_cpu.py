@@ -85,20 +85,22 @@ def _seq_worker(rank, world, port, q):
                 out.copy_(torch.from_numpy(table[frames.numpy()[:, 0, 0]].reshape(-1, D)))
 
             def _stage_colsum(self, desc_local, out):
-                out.copy_(desc_local.double().sum(0))
+                out[:D].copy_(desc_local.double().sum(0))
+                out[D:].copy_((desc_local.double() ** 2).sum(0))
 
             def _stage_weights(self, colsums, rows_total, w, mean):
-                mean.copy_(colsums.sum(0) / rows_total)
-                w.copy_(torch.exp(-(mean - 0.5) ** 2 / (2 * 0.2 ** 2)))
+                m = colsums[:, :D].sum(0) / rows_total
+                mean.copy_(m.float())
+                w.copy_(torch.exp(-(m - 0.5) ** 2 / (2 * 0.2 ** 2)))
 
             def _stage_prepare(self, desc_local, n_local, per, P_, w, mean, plane_local, plane_lo_local, stats_local):
                 plane_local.zero_()
-                plane_local[:n_local * P_, :D] = (desc_local[:n_local * P_].double() - mean).half()
+                plane_local[:n_local * P_, :D] = (desc_local[:n_local * P_] - mean).half()
                 stats_local.fill_(self.rank + 1)
 
             def _stage_gram(self, b, per, n_, P_):
                 # every rank sees every rank's centred planes and stats block
-                want = torch.from_numpy(table.reshape(-1, D)).double() - b["mean"]
+                want = torch.from_numpy(table.reshape(-1, D)).double() - b["mean"].double()
                 assert torch.allclose(b["plane"][:n_ * P_, :D].double(), want, atol=2e-3)
                 assert [int(b["stats"][r, 0]) for r in range(self.world)] == [r + 1 for r in range(self.world)]
                 w_ref = o_sim.distinctive_weights(table.astype(np.float64))

@@ -36,9 +36,9 @@ def test_staged_parts_sum_to_the_matrix(cuda, n, P, D, parts, precision, saturat
     plane = torch.zeros((rows, ld), dtype=torch.float16, device="cuda")
     plane_lo = torch.zeros_like(plane) if precision == "fp16x2" else None
     stats = torch.zeros((parts, ops.sdav_stage_stats_bytes(per)), dtype=torch.uint8, device="cuda")
-    colsums = torch.zeros((parts, D), dtype=torch.float64, device="cuda")
+    colsums = torch.zeros((parts, 2 * D), dtype=torch.float64, device="cuda")
     w = torch.empty(D, dtype=torch.float64, device="cuda")
-    mean = torch.empty(D, dtype=torch.float64, device="cuda")
+    mean = torch.empty(D, dtype=torch.float32, device="cuda")             # centring vector (dataset mean or zero)
     blocks = [(min(r * per, n), min((r + 1) * per, n)) for r in range(parts)]
     for r, (s, e) in enumerate(blocks):                          # stage 1 on every "rank"
         ops.sdav_stage_colsum(desc_flat[s * P:e * P], colsums[r])
