@@ -373,8 +373,8 @@ static int match_impl(dlc_db* db, const float* q, int B, int k, int64_t idx_offs
   if (rc != DLC_OK) return rc;
   // merge the per-CTA partial lists; L2: reported score = |q|^2 - key = squared distance
   const int cols = L.slots * L.kmax;
-  rc = topk_rows_impl(p.part_scores, p.part_idx, B, cols, cols, k, /*largest=*/1, /*exclude_band=*/-1,
-                      l2 ? aux : nullptr, l2 ? -1.0f : 1.0f, scores, idx, s);
+  rc = merge_partials_impl(p.part_scores, p.part_idx, B, cols, cols, k, /*largest=*/1, l2 ? aux : nullptr,
+                           l2 ? -1.0f : 1.0f, scores, idx, s);
   if (rc != DLC_OK) return rc;
   if (l2 || use_thr) {
     // L2 padding convention (+inf) and threshold filtering of the listed entries

@@ -114,7 +114,8 @@ weights_centre_kernel(const double* __restrict__ part, int slabs, int64_t rows, 
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
                  const float* __restrict__ centre, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int ld,
-                 float* __restrict__ sqn, double* __restrict__ pw, unsigned int* __restrict__ nmax_bits) {
+                 float* __restrict__ sqn, double* __restrict__ pw, unsigned int* __restrict__ nmax_bits,
+                 unsigned long long* __restrict__ rowhash) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N * kFrameRows) return;
@@ -123,9 +124,11 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
     if (lane == 0) {
       sqn[warp] = INFINITY;
       pw[warp] = 0.0;
+      if (rowhash) rowhash[warp] = 0ull;
     }
     return;
   }
+  uint32_t h0 = 0x811c9dc5u, h1 = 0x9747b28cu;   // 64-bit content hash of the row's float32 bits (rep_from_hash_kernel)
   const int64_t r = static_cast<int64_t>(f) * P + k;          // source row = plane row
   const float* h = H + r * D;
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
@@ -173,6 +176,9 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
     for (int j = 0; j < 8; ++j) {
       float xc = 0.0f;
       if (c0 + j < D) {
+        const uint32_t bits = __float_as_uint(x[j]);
+        h0 = (h0 ^ bits) * 0x01000193u;
+        h1 = (h1 + bits) * 0x9E3779B1u + (h1 >> 15);
         xc = x[j] - mv[j];
         s8 = fmaf(xc, xc, s8);
         pr = fma(static_cast<double>(x[j]), wv[j], pr);
@@ -188,6 +194,17 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   for (int off = 16; off > 0; off >>= 1) {
     n2 += __shfl_xor_sync(0xffffffffu, n2, off);
     pr += __shfl_xor_sync(0xffffffffu, pr, off);
+  }
+  if (rowhash) {   // lanes combined position-dependently: identical rows -> identical hashes, always
+    h0 *= 2u * lane + 1u;
+    h1 ^= h1 >> 13;
+    h1 *= 2u * lane + 0x85ebca6bu;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      h0 += __shfl_xor_sync(0xffffffffu, h0, off);
+      h1 ^= __shfl_xor_sync(0xffffffffu, h1, off);
+    }
+    if (lane == 0) rowhash[warp] = (static_cast<unsigned long long>(h0) << 32) | h1;
   }
   if (lane == 0) {
     sqn[warp] = static_cast<float>(n2);
@@ -229,47 +246,47 @@ lo_planes_kernel(const float* __restrict__ H, int64_t rows, int D, const float* 
 // rep_mask[f]: bit c set iff patch row c of frame f is not bit-identical to an earlier row of the same frame.
 // Duplicate patches are common (keypoints near a corner are all shifted onto the same corner patch); their squared
 // distances to any row are bit-identical in every arithmetic, np.argmin keeps the first of them, and so does the
-// strict '<' scan of the kernels - they never need the exact re-evaluation. One CTA per frame, warp c = row c:
-// lane e < c compares the first elements of rows e and c, only rows with an equal prefix are compared in full.
-constexpr int kRepPrefix = 32;
-__global__ void __launch_bounds__(1024)
-rep_mask_kernel(const float* __restrict__ H, int N, int P, int D, uint32_t* __restrict__ rep_mask) {
-  __shared__ uint32_t s_rep;
-  const int f = blockIdx.x;
-  const int c = threadIdx.x >> 5;
+// strict '<' scan of the kernels - they never need the exact re-evaluation.
+// The mask comes from the row hashes prep_rows_kernel computed while it had the rows in registers (no second pass over
+// the descriptors): one warp per frame, lane c = row c. A hash match is only a FILTER - the two rows are then compared
+// in full by the whole warp, so the mask is exact (identical rows always hash alike; a 64-bit
+// collision between different rows is caught by the comparison).
+__global__ void __launch_bounds__(256)
+rep_from_hash_kernel(const float* __restrict__ H, int N, int P, int D, const unsigned long long* __restrict__ rowhash,
+                     uint32_t* __restrict__ rep_mask) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) s_rep = 0;
-  __syncthreads();
-  if (c < P) {
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + c) * D);
-    uint32_t diff = 1;
-    if (lane < c) {  // branch-free accumulation: the loads of the prefix are independent and issue back to back
-      const uint32_t* b = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + lane) * D);
-      const int n = D < kRepPrefix ? D : kRepPrefix;
-      diff = 0;
-      for (int i = 0; i < n; ++i) diff |= a[i] ^ b[i];
-    }
-    uint32_t cand = __ballot_sync(0xffffffffu, diff == 0);
+  if (f >= N) return;
+  const unsigned long long mine = rowhash[static_cast<int64_t>(f) * kFrameRows + lane];
+  int cand = -1;   // first earlier row with my hash
+  for (int e = 0; e < P; ++e) {
+    const unsigned long long he = __shfl_sync(0xffffffffu, mine, e);
+    if (cand < 0 && e < lane && lane < P && he == mine) cand = e;
+  }
+  uint32_t pending = __ballot_sync(0xffffffffu, cand >= 0);
+  uint32_t dup_mask = 0;
+  while (pending) {
+    const int c = __ffs(pending) - 1;
+    pending &= pending - 1;
+    int e = __shfl_sync(0xffffffffu, cand, c);
     bool dup = false;
-    while (cand && !dup) {
-      const int e = __ffs(cand) - 1;
-      cand &= cand - 1;
+    while (e >= 0 && !dup) {   // verify against the candidate; on a (never observed) collision try later rows
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + c) * D);
       const uint32_t* b = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + e) * D);
-      dup = true;
-      for (int base = 0; base < D && dup; base += 32 * 8) {  // 8 independent loads per lane, then one vote
-        uint32_t d = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = base + u * 32 + lane;
-          if (i < D) d |= a[i] ^ b[i];
-        }
-        dup = !__any_sync(0xffffffffu, d != 0);
+      uint32_t d = 0;
+      for (int i = lane; i < D; i += 32) d |= a[i] ^ b[i];
+      dup = !__any_sync(0xffffffffu, d != 0);
+      if (!dup) {
+        const unsigned long long hc = __shfl_sync(0xffffffffu, mine, c);
+        int nxt = -1;
+        for (int e2 = e + 1; e2 < c; ++e2)
+          if (nxt < 0 && __shfl_sync(0xffffffffu, mine, e2) == hc) nxt = e2;
+        e = nxt;
       }
     }
-    if (!dup && lane == 0) atomicOr(&s_rep, 1u << c);
+    if (dup) dup_mask |= 1u << c;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) rep_mask[f] = s_rep;
+  if (lane == 0) rep_mask[f] = ((P >= 32 ? 0xffffffffu : ((1u << P) - 1u)) & ~dup_mask);
 }
 
 // ---------------- Gram + argmin + score epilogue ----------------
@@ -920,7 +937,7 @@ static int get_tile_lists(int N, int full, int part, int n_parts, TileListEntry*
 constexpr int64_t kMaxRefineEntries = 1 << 18;
 std::atomic<int> g_refine_cap{-1};  // developer override of the list capacity (dlc_debug_set key 8; 0 = refine in the epilogue)
 struct SimWorkspace {
-  size_t off_bhi, off_blo, off_part, off_w, off_mean, off_sqn, off_pw, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
+  size_t off_bhi, off_blo, off_part, off_w, off_mean, off_sqn, off_pw, off_hash, off_rep, off_ctl, off_probe, off_gaps, off_work, total;
   int ld, rows_pad;
   int col_stride;  // 32, or P when the N tile is read as 8 P plane rows
   int rows_b;      // rows of the planes (N * P)
@@ -949,6 +966,7 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   w.off_mean = take(sizeof(float) * D);   // centring vector (float32)
   w.off_sqn = take(sizeof(float) * w.rows_pad);
   w.off_pw = take(sizeof(double) * w.rows_pad);
+  w.off_hash = take(sizeof(unsigned long long) * w.rows_pad);
   w.off_rep = take(sizeof(uint32_t) * N);
   w.off_ctl = take(sizeof(GramControl));
   w.off_probe = take(sizeof(ProbeAccum));
@@ -1021,31 +1039,7 @@ static int run_gram_pair(const GramPlanes& L, GramParams p, cudaStream_t stream)
 
 using namespace dlc;
 
-// Side stream of the precision probe: rep_mask + gram_probe read only the descriptors, so they run next to the
-// dataset-mean / prep_rows chain (which they do not depend on) and join before the probe is finalised - 0.12 ms of
-// latency-bound kernels off the critical path. One stream + two events per host thread and device, created lazily;
-// the fork / join is plain event ordering, so the call stays capturable and makes no host synchronisation.
-std::atomic<int> g_probe_side_stream{1};  // dlc_debug_set key 9 (0: everything on the caller's stream)
-struct ProbeSide {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, mean_ready = nullptr, join = nullptr;
-};
-static ProbeSide* probe_side() {
-  thread_local ProbeSide side[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  ProbeSide& p = side[dev];
-  if (!p.stream) {
-    if (cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p.mean_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p.join, cudaEventDisableTiming) != cudaSuccess) {
-      p.stream = nullptr;
-      return nullptr;
-    }
-  }
-  return &p;
-}
+std::atomic<int> g_probe_side_stream{1};  // dlc_debug_set key 9: kept for compatibility, no effect (the probe is serial)
 
 // Developer switch (dlc_debug_set key 1): launch only the Gram/score kernel, reusing the operand planes, statistics
 // and tile list a previous full call left in the workspace. Lets bench.py time that kernel alone with CUDA events.
@@ -1134,51 +1128,32 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   TileListEntry lists;
   if (int rc = get_tile_lists(N, full_asymmetric, part, n_parts, &lists)) return rc;
   if (!gram_only) {
-    // 0. precision probe, part one (classes of bit-identical rows): reads only the descriptors - forked onto the side
-    //    stream so that it overlaps step 1
-    ProbeSide* side = nullptr;
-    cudaStream_t ps = s;
-    if (probe) {
-      DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
-      side = g_probe_side_stream.load() ? probe_side() : nullptr;
-      if (side) {
-        DLC_CUDA(cudaEventRecord(side->fork, s));
-        DLC_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        ps = side->stream;
-      }
-      rep_mask_kernel<<<N, 1024, 0, ps>>>(desc_dev, N, P, D, rep);
-    }
-    // 1. dataset mean -> centring vector of the planes and distinctive weights w (w_dev given: weights of another
-    //    dataset, SimilarityCalculator.similarity_score on frames outside it; the mean is still this dataset's)
+    // 1. dataset mean -> distinctive weights w and the centring vector of the planes (w_dev given: weights of another
+    //    dataset, SimilarityCalculator.similarity_score on frames outside it; the centring is still this dataset's)
     colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
     weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma,
                                                         w_dev ? nullptr : w, mean);
     if (w_dev) w = const_cast<double*>(w_dev);
-    // 2. precision probe, part two (single-product error of the CENTRED values on sampled rows): next to step 3
-    if (probe) {
-      if (side) {
-        DLC_CUDA(cudaEventRecord(side->mean_ready, s));
-        DLC_CUDA(cudaStreamWaitEvent(side->stream, side->mean_ready, 0));
-      }
-      if (N >= 2) {
-        gram_probe_kernel<<<kProbeSamples, 1024, 0, ps>>>(desc_dev, N, P, D, mean, rep, acc, gaps);
-      } else {
-        DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, ps));  // large gaps: nothing to refine
-      }
-      if (side) DLC_CUDA(cudaEventRecord(side->join, side->stream));
-    }
-    // 3. one pass: centred operand planes (P rows per frame, K padded with zeros), per-row squared norms of the centred
-    //    rows and projections p = h . w. With a precision probe (auto / fp16r) the residual planes are written later and
-    //    only if the probe picks the three-product kernel.
+    // 2. one pass: centred operand planes (P rows per frame, K padded with zeros), per-row squared norms of the centred
+    //    rows, projections p = h . w and a content hash of every row. With a precision probe (auto / fp16r) the
+    //    residual planes are written later and only if the probe picks the three-product kernel.
     const bool lo_now = precision == DLC_PREC_FP16X2;
+    unsigned long long* rowhash = reinterpret_cast<unsigned long long*>(ws + L.off_hash);
+    if (probe) DLC_CUDA(cudaMemsetAsync(acc, 0, sizeof(ProbeAccum), s));
     prep_rows_kernel<<<ceil_div(N * kFrameRows, 8), 256, 0, s>>>(
         desc_dev, N, P, D, w, mean, reinterpret_cast<__half*>(ws + L.off_bhi),
-        lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw, probe ? &acc->nmax_bits : nullptr);
-    // 4. precision probe, part three (needs the largest row norm of step 3): margin and the device-side choice between
-    //    the two Gram kernels
+        lo_now ? reinterpret_cast<__half*>(ws + L.off_blo) : nullptr, L.ld, sqn, pw, probe ? &acc->nmax_bits : nullptr,
+        probe ? rowhash : nullptr);
+    // 3. precision probe: classes of bit-identical rows (from the hashes, verified), the single-product error of the
+    //    centred values on sampled rows, then the margin and the device-side choice between the two Gram kernels
     if (probe) {
       GramControl* ctl = reinterpret_cast<GramControl*>(ws + L.off_ctl);
-      if (side) DLC_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+      rep_from_hash_kernel<<<ceil_div(N, 8), 256, 0, s>>>(desc_dev, N, P, D, rowhash, rep);
+      if (N >= 2) {
+        gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_dev, N, P, D, mean, rep, acc, gaps);
+      } else {
+        DLC_CUDA(cudaMemsetAsync(gaps, 0x7f, sizeof(float) * kProbeSamples, s));  // large gaps: nothing to refine
+      }
       gram_probe_finalize_kernel<<<1, 256, 0, s>>>(acc, gaps, g_max_flag_frac,
                                                    precision == DLC_PREC_FP16_REFINED ? 1 : -1, ctl);
       if (precision == DLC_PREC_AUTO)  // fp16r never runs the three-product kernel
@@ -1255,7 +1230,7 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
 // ------------------------------------------------------------------------------------------------------------
 namespace dlc {
 struct StageStats {  // layout of one part's stats block
-  size_t off_sqn, off_pw, off_rep, off_probe, off_gaps, total;
+  size_t off_sqn, off_pw, off_rep, off_probe, off_gaps, off_hash, total;
 };
 static StageStats stage_stats_layout(int frames_per_part) {
   StageStats t{};
@@ -1270,6 +1245,7 @@ static StageStats stage_stats_layout(int frames_per_part) {
   t.off_rep = take(sizeof(uint32_t) * frames_per_part);
   t.off_probe = take(sizeof(ProbeAccum));
   t.off_gaps = take(sizeof(float) * kProbeSamples);
+  t.off_hash = take(sizeof(unsigned long long) * frames_per_part * kFrameRows);  // scratch of stage_prepare (exchanged, unused)
   t.total = align_up(o, 256);
   return t;
 }
@@ -1424,9 +1400,10 @@ extern "C" int dlc_sdav_stage_prepare(const float* desc_local_dev, int n_local, 
       desc_local_dev, n_local, P, D, w_dev, centre_dev, static_cast<__half*>(plane_hi_local_dev),
       precision == DLC_PREC_FP16X2 ? static_cast<__half*>(plane_lo_local_dev) : nullptr, ld,
       reinterpret_cast<float*>(st + t.off_sqn), reinterpret_cast<double*>(st + t.off_pw),
-      probe ? &acc->nmax_bits : nullptr);
+      probe ? &acc->nmax_bits : nullptr, probe ? reinterpret_cast<unsigned long long*>(st + t.off_hash) : nullptr);
   if (probe) {
-    rep_mask_kernel<<<n_local, 1024, 0, s>>>(desc_local_dev, n_local, P, D, rep);
+    rep_from_hash_kernel<<<ceil_div(n_local, 8), 256, 0, s>>>(
+        desc_local_dev, n_local, P, D, reinterpret_cast<const unsigned long long*>(st + t.off_hash), rep);
     if (n_local >= 2)
       gram_probe_kernel<<<kProbeSamples, 1024, 0, s>>>(desc_local_dev, n_local, P, D, centre_dev, rep, acc, gaps);
   }

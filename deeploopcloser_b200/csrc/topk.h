@@ -8,4 +8,8 @@ namespace dlc {
 int topk_rows_impl(const float* scores, const int64_t* cand_idx, int rows, int cols, int ld, int k, int largest,
                    int exclude_band, const float* row_add, float scale, float* out_scores, int64_t* out_idx,
                    cudaStream_t stream);
+// merge of per-CTA partial top-k lists (cand_idx required, unique non-negative indices, -1 = padding): one CTA per row,
+// candidates read once
+int merge_partials_impl(const float* scores, const int64_t* cand_idx, int rows, int cols, int ld, int k, int largest,
+                        const float* row_add, float scale, float* out_scores, int64_t* out_idx, cudaStream_t stream);
 }

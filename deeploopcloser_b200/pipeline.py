@@ -74,6 +74,12 @@ class LoopClosurePipeline:
         S, cand = self.match(desc, frames.shape[0], k, exclude_band)
         return {"descriptors": desc, "similarity": S, "candidates": cand}
 
+    def run_many(self, sequences, k=10, exclude_band=0):
+        """A stream of device-resident sequences [(frames, xy), ...] -> [(scores [N,k], idx [N,k]), ...]: on one GPU
+        simply run() after run() (the sharded pipeline overlaps the encoder of the next sequence with the exchange
+        stage of the current one)."""
+        return [self.run(f, x, k, exclude_band)["candidates"] for f, x in sequences]
+
     def run_host_stream(self, batches, k=10, exclude_band=0):
         """Process a stream of HOST batches [(frames uint8 [B,H,W], xy float32 [B,P,2]), ...] (pinned torch tensors)
         end to end and return the candidate lists [(scores [B,k], idx [B,k]), ...] in pinned host memory (views of a
@@ -182,6 +188,7 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             rows = self.world * per * P
             self._b = {
                 "desc": self._alloc((rows, D), torch.float32),
+                "desc_slots": None,
                 "plane": self._alloc((rows, ld), torch.float16),
                 "plane_lo": self._alloc((rows, ld), torch.float16) if self.sim_precision == "fp16x2" else None,
                 "stats": self._alloc((self.world, ops.sdav_stage_stats_bytes(per)), torch.uint8),
@@ -232,23 +239,35 @@ class ShardedSequencePipeline(LoopClosurePipeline):
     def run_block(self, frames_local, xy_local, n, k=10, exclude_band=0, P=None):
         """frames_local / xy_local: this rank's block of the N-frame sequence (frame_block(N, rank, world))."""
         P = P or (xy_local.shape[1] if xy_local is not None else 30)
-        D = self.dims[-1]
+        b = self._buffers(n, P)
+        self._encode_block(frames_local, xy_local, n, P, b["desc"])
+        return self._match_block(b, b["desc"], n, P, k, exclude_band)
+
+    def _encode_block(self, frames_local, xy_local, n, P, desc_all):
+        """Stage A (rank-local, no collective): patch gather + encoder of this rank's frames into its slice of the
+        float32 descriptor buffer."""
         start, end, per = self.frame_block(n, self.rank, self.world)
         n_local = end - start
         assert frames_local.shape[0] == n_local, "expected this rank's block of %d frames" % n_local
-        b = self._buffers(n, P)
         lo_r, hi_r = self.rank * per * P, (self.rank + 1) * per * P
-        desc_local = b["desc"][lo_r:hi_r]
+        desc_local = desc_all[lo_r:hi_r]
         if n_local < per:
             desc_local[n_local * P:].zero_()          # padded tail of the last block(s): gathered but never read
         if n_local:
             self._encode_into(frames_local, xy_local, desc_local[:n_local * P])
+
+    def _match_block(self, b, desc_all, n, P, k, exclude_band):
+        """Stage B: everything after the encoder (collectives + score matrix + candidates)."""
+        start, end, per = self.frame_block(n, self.rank, self.world)
+        n_local = end - start
+        lo_r, hi_r = self.rank * per * P, (self.rank + 1) * per * P
+        desc_local = desc_all[lo_r:hi_r]
         work = None
         if self.world > 1:
             if self._bg_group is None:
                 self._bg_group = self.dist.new_group(list(range(self.world))) if self.group is None else self.group
             # float32 descriptors of all frames: only the second pass reads them -> gathered in the background
-            work = self._all_gather(b["desc"], desc_local, self._bg_group, async_op=True)
+            work = self._all_gather(desc_all, desc_local, self._bg_group, async_op=True)
         # dataset mean / weights
         self._stage_colsum(desc_local[:n_local * P], b["colsums"][self.rank])
         if self.world > 1:
@@ -266,13 +285,57 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         self._stage_gram(b, per, n, P)
         if work is not None:
             work.wait()                                # the compute stream waits for the descriptor gather
-        self._stage_fix(b, n, P)
+        self._stage_fix(dict(b, desc=desc_all), n, P)
         S = b["S"]
         if self.world > 1:
             self.dist.all_reduce(S, group=self.group)
         self.last_similarity = S
         cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
-        return {"descriptors": b["desc"][:n * P], "similarity": S, "candidates": cand}
+        return {"descriptors": desc_all[:n * P], "similarity": S, "candidates": cand}
+
+    def run_many(self, sequences, k=10, exclude_band=0):
+        """A stream of sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] resident on the device (every rank
+        holds them; each reads its block) -> [(scores [N,k], idx [N,k]), ...]. Successive sequences are PIPELINED: the
+        encoder of sequence i+1 (rank-local, on its own stream, into the other descriptor slot) runs while sequence i
+        is in its exchange / score-matrix stage, so the GPU works through the NCCL waits that dominate a split
+        sequence. Per-sequence results are the same as run()."""
+        sequences = list(sequences)
+        if not sequences:
+            return []
+        main = torch.cuda.current_stream()
+        enc = self._enc_stream = getattr(self, "_enc_stream", None) or torch.cuda.Stream()
+        n0, P0 = sequences[0][0].shape[0], sequences[0][1].shape[1]
+        b = self._buffers(n0, P0)
+        if b["desc_slots"] is None:
+            b["desc_slots"] = [b["desc"], torch.empty_like(b["desc"])]
+        encoded, freed, outs = [None, None], [None, None], []
+        enc.wait_stream(main)
+
+        def encode(i):
+            f, x = sequences[i]
+            assert f.shape[0] == n0 and x.shape[1] == P0, "run_many expects sequences of one shape"
+            start, end, _ = self.frame_block(n0, self.rank, self.world)
+            slot = i & 1
+            if freed[slot] is not None:
+                enc.wait_event(freed[slot])           # sequence i-2 is done with this descriptor slot
+            with torch.cuda.stream(enc):
+                self._encode_block(f[start:end], x[start:end], n0, P0, b["desc_slots"][slot])
+                ev = torch.cuda.Event()
+                ev.record(enc)
+            encoded[slot] = ev
+
+        encode(0)
+        for i in range(len(sequences)):
+            slot = i & 1
+            if i + 1 < len(sequences):
+                encode(i + 1)
+            main.wait_event(encoded[slot])
+            r = self._match_block(b, b["desc_slots"][slot], n0, P0, k, exclude_band)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            freed[slot] = ev
+            outs.append(r["candidates"])
+        return outs
 
     def run_host_stream(self, batches, k=10, exclude_band=0):
         """Stream of HOST sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] (pinned, the same on every rank):

@@ -91,3 +91,30 @@ def test_sharded_pipeline_single_rank_equals_monolithic(cuda):
     sa, sb = ra["similarity"].cpu().numpy(), rb["similarity"].cpu().numpy()
     assert np.max(np.abs(sa - sb) / np.maximum(1.0, np.abs(sa))) <= 1e-5
     assert torch.equal(ra["candidates"][1], rb["candidates"][1])
+
+
+def test_run_many_pipelining_equals_run(cuda):
+    """run_many (the encoder of sequence i+1 on its own stream, into the other descriptor slot, under the score-matrix
+    stage of sequence i) returns exactly what run() returns for every sequence, also when the sequences differ."""
+    from deeploopcloser_b200.pipeline import ShardedSequencePipeline
+    from oracle import sda as o_sda
+    rng = np.random.default_rng(9)
+    n, H, W, P = 40, 96, 128, 30
+    dims = [1681, 320, 256]
+    seqs = []
+    for _ in range(4):
+        f = torch.from_numpy(rng.integers(0, 256, (n, H, W), dtype=np.uint8)).cuda()
+        x = torch.from_numpy(np.stack([rng.uniform(0, W, (n, P)), rng.uniform(0, H, (n, P))], -1).astype(np.float32)).cuda()
+        seqs.append((f, x))
+    ws, bs = o_sda.make_weights(dims, seed=1, scale="normal")
+    pipe = ShardedSequencePipeline(dims)
+    pipe.set_weights(ws, bs)
+    want = []
+    for f, x in seqs:
+        r = pipe.run(f, x, k=5)
+        want.append((r["candidates"][0].clone(), r["candidates"][1].clone()))
+    for _ in range(2):
+        got = pipe.run_many(seqs, k=5)
+        torch.cuda.synchronize()
+        for (ws_, wi), (gs, gi) in zip(want, got):
+            assert torch.equal(wi, gi) and torch.equal(ws_, gs)

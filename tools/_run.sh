@@ -1,6 +1,10 @@
 set -x
-TR8="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513"
-TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514"
-timeout 300 $TR8 tools/check_sharded_sequence.py > gpurun_out/r2_sharded_seq8.log 2>&1; grep '^{' gpurun_out/r2_sharded_seq8.log || tail -25 gpurun_out/r2_sharded_seq8.log
-NCCL_DEBUG=WARN timeout 400 $TR8 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench8.log 2>&1; echo "exit $?"; tail -1 gpurun_out/r2_bench8.log | cut -c1-600
-timeout 400 $TR4 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r2_bench4.log 2>&1; echo "exit $?"; tail -1 gpurun_out/r2_bench4.log | cut -c1-600
+KREG='regex:gemm_pair_kernel|gram_refine_fix_kernel|prep_rows_kernel|colsum_partial_kernel|gram_probe_kernel|patch_gather|topk_rows|weights_centre|rep_from_hash'
+for w in normal xavier; do
+python bench.py --steps 1 --warmup 1 --headline-only --one-arm --no-cpu-baseline --weights $w > gpurun_out/r2_plainfull_$w.log 2>&1 && \
+ncu --set full --clock-control none -k "$KREG" -c 15 -o /tmp/r2_prof_$w python bench.py --steps 1 --warmup 1 --headline-only --one-arm --no-cpu-baseline --weights $w > gpurun_out/r2_ncufull_$w.log 2>&1
+ncu -i /tmp/r2_prof_$w.ncu-rep --page raw --csv > gpurun_out/r2_ncu_raw_$w.csv 2>/dev/null
+ncu -i /tmp/r2_prof_$w.ncu-rep --page details > gpurun_out/r2_ncu_details_$w.txt 2>/dev/null
+done
+python bench.py --config 4 > gpurun_out/r2_bench_config4.json 2>gpurun_out/r2_bench_config4.err
+du -sh gpurun_out
