@@ -79,15 +79,16 @@ def peaks():
     return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def kernel_traffic(name):
+def kernel_traffic(name, arm):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of one kernel, from the round's `ncu --set full`
-    capture (profiles/r2_traffic.json, written by tools/ncu_summary.py from the .ncu-rep); None when not captured."""
+    capture of this weights arm (profiles/r2_traffic.json, written by tools/ncu_traffic.py from the capture's raw page);
+    None when not captured."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         t = json.load(f)
-    e = t.get(name)
+    e = t.get(name + "@" + arm) or t.get(name)
     return None if not e else float(e["dram_bytes_read"] + e["dram_bytes_write"])
 
 
@@ -455,7 +456,7 @@ def run_config2(ctx, args):
         kname = "gemm_pair_kernel<BiasActPolicy<%s>>" % ("64,1" if products[-1] == 1 else "32,3")
         roof = {"kernel": kname + " (the five encoder layers; largest share of the step)", "bound": "tensor",
                 "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
-                "traffic": kernel_traffic(kname),
+                "traffic": kernel_traffic(kname, weights),
                 "peak_source": pk["source"] + ", sustained bf16 (five launches per step inside a long loop); burst %.1f"
                                % pk["tflops_burst"],
                 "ms_per_launch": layer_ms, "launches_per_step": len(DIMS) - 1,
@@ -471,7 +472,7 @@ def run_config2(ctx, args):
         roof_sim = {"kernel": "gemm_pair_kernel<%s> (SDAV Gram + argmin + score)" % gname, "bound": "tensor",
                     "achieved": g_ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": g_ach / pk["tflops_burst"],
                     "frac_of_sustained_peak": g_ach / pk["tflops_sustained"],
-                    "traffic": kernel_traffic("gemm_pair_kernel<%s>" % gname), "ms_per_launch": gram,
+                    "traffic": kernel_traffic("gemm_pair_kernel<%s>" % gname, weights), "ms_per_launch": gram,
                     "algorithmic_flop_per_launch": GRAM_FLOP, "tensor_products": sim_products,
                     "with_refinement_pass": {"ms": gram_total,
                                              "frac_of_burst": GRAM_FLOP / (gram_total * 1e-3) / 1e12 / pk["tflops_burst"],

@@ -31,21 +31,48 @@ std::atomic<int> g_sim_mgroup{32};                                  // M tiles p
 
 // ---------------- column mean -> distinctive weights (deterministic two-stage reduction) ----------------
 constexpr int kColSumSlabs = 128;
-// part[slab][0..D) = sum_r x, part[slab][D..2D) = sum_r x^2 over the slab's rows (float64)
-__global__ void colsum_partial_kernel(const float* __restrict__ H, int64_t rows, int D, double* __restrict__ part) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
+// part[slab][0..D) = sum_r x, part[slab][D..2D) = sum_r x^2 over the slab's rows (float64). Block = 32 column lanes
+// x 8 row lanes: eight independent row streams per column keep enough loads in flight; the eight partial sums are
+// combined in a fixed order (deterministic).
+constexpr int kColSumRowLanes = 8;
+__global__ void __launch_bounds__(32 * kColSumRowLanes)
+colsum_partial_kernel(const float* __restrict__ H, int64_t rows, int D, double* __restrict__ part) {
+  __shared__ double s_a[kColSumRowLanes][33], s_b[kColSumRowLanes][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
   const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = blockIdx.y * per;
   const int64_t r1 = r0 + per < rows ? r0 + per : rows;
   double acc = 0.0, acc2 = 0.0;
-  for (int64_t r = r0; r < r1; ++r) {
-    const double x = static_cast<double>(H[r * D + col]);
-    acc += x;
-    acc2 = fma(x, x, acc2);
+  if (col < D) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += kColSumRowLanes) {
+      const double x = static_cast<double>(H[r * D + col]);
+      acc += x;
+      acc2 = fma(x, x, acc2);
+    }
   }
-  part[static_cast<int64_t>(blockIdx.y) * 2 * D + col] = acc;
-  part[static_cast<int64_t>(blockIdx.y) * 2 * D + D + col] = acc2;
+  s_a[ty][tx] = acc;
+  s_b[ty][tx] = acc2;
+  __syncthreads();
+  if (ty == 0 && col < D) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < kColSumRowLanes; ++i) {
+      a += s_a[i][tx];
+      b += s_b[i][tx];
+    }
+    part[static_cast<int64_t>(blockIdx.y) * 2 * D + col] = a;
+    part[static_cast<int64_t>(blockIdx.y) * 2 * D + D + col] = b;
+  }
+}
+// width = 2 D: the column sums and the column sums of squares of all slabs -> one row
+__global__ void colsum_reduce_kernel(const double* __restrict__ part, int slabs, int width, double* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= width) return;
+  double acc = 0.0;
+  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * width + col];
+  out[col] = acc;
 }
 // Column sums -> dataset mean -> distinctive weights w (SimilarityCalculator.py:19-27) and the CENTRING vector of the
 // operand planes (see prep_rows_kernel). One block: the centring decision needs the total over all columns.
@@ -274,7 +301,18 @@ rep_from_hash_kernel(const float* __restrict__ H, int N, int P, int D, const uns
       const uint32_t* a = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + c) * D);
       const uint32_t* b = reinterpret_cast<const uint32_t*>(H + (static_cast<int64_t>(f) * P + e) * D);
       uint32_t d = 0;
-      for (int i = lane; i < D; i += 32) d |= a[i] ^ b[i];
+      if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {   // 16-byte loads, no early exit: they pipeline
+        const uint4* a4 = reinterpret_cast<const uint4*>(a);
+        const uint4* b4 = reinterpret_cast<const uint4*>(b);
+#pragma unroll 10
+        for (int i = lane; i < (D >> 2); i += 32) {
+          const uint4 x = __ldg(a4 + i), y = __ldg(b4 + i);
+          d |= (x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w);
+        }
+      } else {
+#pragma unroll 8
+        for (int i = lane; i < D; i += 32) d |= __ldg(a + i) ^ __ldg(b + i);
+      }
       dup = !__any_sync(0xffffffffu, d != 0);
       if (!dup) {
         const unsigned long long hc = __shfl_sync(0xffffffffu, mine, c);
@@ -709,7 +747,7 @@ __global__ void __launch_bounds__(kFixThreads, 4) gram_refine_fix_kernel(const G
 }
 
 // ---- probe: estimate the single-product error and the share of rows it would leave ambiguous
-constexpr int kProbeSamples = 512;
+constexpr int kProbeSamples = 256;   // x (P - 1) ~ 7 k error samples: the margin rests on their rms (8 sigma), not on a tail
 struct ProbeAccum {
   double sum_err2;        // sum over sampled (row, candidate) of (approximate - exact squared distance)^2
   unsigned long long n_err;
@@ -961,7 +999,7 @@ static SimWorkspace sim_layout(int N, int P, int D) {
   const size_t plane_b = static_cast<size_t>(w.rows_b) * w.ld * 2;
   w.off_bhi = take(plane_b);
   w.off_blo = take(plane_b);
-  w.off_part = take(sizeof(double) * kColSumSlabs * 2 * D);
+  w.off_part = take(sizeof(double) * (kColSumSlabs + 1) * 2 * D);   // per-slab sums + their total
   w.off_w = take(sizeof(double) * D);
   w.off_mean = take(sizeof(float) * D);   // centring vector (float32)
   w.off_sqn = take(sizeof(float) * w.rows_pad);
@@ -1063,13 +1101,15 @@ extern "C" int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, doub
                                 void* ws_dev, size_t ws_bytes, void* stream) {
   DLC_CHECK_ARG(desc_dev && w_dev && ws_dev);
   DLC_CHECK_ARG(N >= 1 && P >= 1 && D >= 1 && sigma != 0.0);
-  if (ws_bytes < sizeof(double) * kColSumSlabs * 2 * D)
-    return fail(DLC_ENOMEM, "dlc_sdav_weights: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * 2 * D);
+  if (ws_bytes < sizeof(double) * (kColSumSlabs + 1) * 2 * D)
+    return fail(DLC_ENOMEM, "dlc_sdav_weights: workspace of %zu bytes needed", sizeof(double) * (kColSumSlabs + 1) * 2 * D);
   cudaStream_t s = as_stream(stream);
   double* part = static_cast<double*>(ws_dev);
   const int64_t rows = static_cast<int64_t>(N) * P;
-  colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, part);
-  weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(part, kColSumSlabs, rows, D, mu, sigma, w_dev, nullptr);
+  colsum_partial_kernel<<<dim3(ceil_div(D, 32), kColSumSlabs), 32 * kColSumRowLanes, 0, s>>>(desc_dev, rows, D, part);
+  double* total = part + static_cast<size_t>(kColSumSlabs) * 2 * D;
+  colsum_reduce_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(part, kColSumSlabs, 2 * D, total);
+  weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(total, 1, rows, D, mu, sigma, w_dev, nullptr);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;
 }
@@ -1130,9 +1170,11 @@ static int sdav_similarity_impl(const float* desc_dev, int N, int P, int D, doub
   if (!gram_only) {
     // 1. dataset mean -> distinctive weights w and the centring vector of the planes (w_dev given: weights of another
     //    dataset, SimilarityCalculator.similarity_score on frames outside it; the centring is still this dataset's)
-    colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_dev, rows, D, colsum_part);
-    weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(colsum_part, kColSumSlabs, rows, D, mu, sigma,
-                                                        w_dev ? nullptr : w, mean);
+    colsum_partial_kernel<<<dim3(ceil_div(D, 32), kColSumSlabs), 32 * kColSumRowLanes, 0, s>>>(desc_dev, rows, D, colsum_part);
+    // the slabs are summed by a wide kernel first: the single-block weights kernel reading all of them took 0.14 ms
+    double* colsum_total = colsum_part + static_cast<size_t>(kColSumSlabs) * 2 * D;
+    colsum_reduce_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(colsum_part, kColSumSlabs, 2 * D, colsum_total);
+    weights_centre_kernel<<<1, kWeightsThreads, 0, s>>>(colsum_total, 1, rows, D, mu, sigma, w_dev ? nullptr : w, mean);
     if (w_dev) w = const_cast<double*>(w_dev);
     // 2. one pass: centred operand planes (P rows per frame, K padded with zeros), per-row squared norms of the centred
     //    rows, projections p = h . w and a content hash of every row. With a precision probe (auto / fp16r) the
@@ -1275,15 +1317,6 @@ static StageWorkspace stage_layout(int N, int D, int n_parts) {
   return w;
 }
 
-// width = 2 D: the column sums and the column sums of squares, see colsum_partial_kernel
-__global__ void colsum_reduce_kernel(const double* __restrict__ part, int slabs, int width, double* __restrict__ out) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= width) return;
-  double acc = 0.0;
-  for (int s = 0; s < slabs; ++s) acc += part[static_cast<int64_t>(s) * width + col];
-  out[col] = acc;
-}
-
 // stats blocks of all parts -> flat sqn [N*32], pw [N*32], rep [N] (frame g lives in block g / per at g % per)
 __global__ void stage_unpack_kernel(const uint8_t* __restrict__ blocks, size_t block_bytes, StageStats t, int per,
                                     int N, float* __restrict__ sqn, double* __restrict__ pw,
@@ -1361,7 +1394,7 @@ extern "C" int dlc_sdav_stage_colsum(const float* desc_local_dev, int64_t rows_l
     return fail(DLC_ENOMEM, "dlc_sdav_stage_colsum: workspace of %zu bytes needed", sizeof(double) * kColSumSlabs * 2 * D);
   cudaStream_t s = as_stream(stream);
   double* part = static_cast<double*>(ws_dev);
-  colsum_partial_kernel<<<dim3(ceil_div(D, 128), kColSumSlabs), 128, 0, s>>>(desc_local_dev, rows_local, D, part);
+  colsum_partial_kernel<<<dim3(ceil_div(D, 32), kColSumSlabs), 32 * kColSumRowLanes, 0, s>>>(desc_local_dev, rows_local, D, part);
   colsum_reduce_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(part, kColSumSlabs, 2 * D, colsum_dev);
   DLC_CUDA(cudaGetLastError());
   return DLC_OK;

@@ -284,7 +284,7 @@ def sdav_stage_stats_bytes(frames_per_part):
 
 
 def _stage_ws(N, P, D, n_parts):
-    return _ws_stage.get(max(_lib.call("dlc_sdav_stage_workspace_bytes", N, P, D, n_parts), 128 * 2 * D * 8))
+    return _ws_stage.get(max(_lib.call("dlc_sdav_stage_workspace_bytes", N, P, D, n_parts), 129 * 2 * D * 8))
 
 
 def sdav_stage_colsum(desc_local, out):
@@ -292,7 +292,7 @@ def sdav_stage_colsum(desc_local, out):
     of squares."""
     _check_cuda(desc_local, out)
     rows, D = desc_local.shape
-    ws, ws_bytes = _ws_stage.get(128 * 2 * D * 8)
+    ws, ws_bytes = _ws_stage.get(129 * 2 * D * 8)
     _lib.call("dlc_sdav_stage_colsum", ptr(desc_local), rows, D, ptr(out), ws, ws_bytes, stream_ptr())
 
 

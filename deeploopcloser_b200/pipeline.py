@@ -1,8 +1,27 @@
 """The loop-closure hot path as one object: patch gather -> SDA encode -> SDAV score matrix -> loop candidates.
 This is what bench.py times and what smoke() exercises; every stage is a libdlc kernel launch on the current stream."""
+import contextlib
+import os
+
 import torch
 
 from . import ops
+
+# NVTX ranges around the stages of a step (tracing row of SURVEY 5): visible in an Nsight Systems / ncu --nvtx
+# timeline. Off unless DLC_NVTX=1 - range pushes are host calls on the launch path.
+_NVTX = os.environ.get("DLC_NVTX", "0") not in ("", "0")
+
+
+@contextlib.contextmanager
+def nvtx_range(name):
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        yield
 
 
 class LoopClosurePipeline:
@@ -70,8 +89,10 @@ class LoopClosurePipeline:
         return int(frames_h.numel() * frames_h.element_size() + xy_h.numel() * xy_h.element_size()), int(n * kk * 12)
 
     def run(self, frames, xy=None, k=10, exclude_band=0):
-        desc = self.encode(frames, xy)
-        S, cand = self.match(desc, frames.shape[0], k, exclude_band)
+        with nvtx_range("dlc.encode"):
+            desc = self.encode(frames, xy)
+        with nvtx_range("dlc.match"):
+            S, cand = self.match(desc, frames.shape[0], k, exclude_band)
         return {"descriptors": desc, "similarity": S, "candidates": cand}
 
     def run_many(self, sequences, k=10, exclude_band=0):
@@ -254,7 +275,8 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         if n_local < per:
             desc_local[n_local * P:].zero_()          # padded tail of the last block(s): gathered but never read
         if n_local:
-            self._encode_into(frames_local, xy_local, desc_local[:n_local * P])
+            with nvtx_range("dlc.encode_block"):
+                self._encode_into(frames_local, xy_local, desc_local[:n_local * P])
 
     def _match_block(self, b, desc_all, n, P, k, exclude_band):
         """Stage B: everything after the encoder (collectives + score matrix + candidates)."""
@@ -269,6 +291,8 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             # float32 descriptors of all frames: only the second pass reads them -> gathered in the background
             work = self._all_gather(desc_all, desc_local, self._bg_group, async_op=True)
         # dataset mean / weights
+        nvtx = nvtx_range("dlc.match_block")
+        nvtx.__enter__()
         self._stage_colsum(desc_local[:n_local * P], b["colsums"][self.rank])
         if self.world > 1:
             self._all_gather(b["colsums"].view(-1), b["colsums"][self.rank], self.group)
@@ -291,6 +315,7 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             self.dist.all_reduce(S, group=self.group)
         self.last_similarity = S
         cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
+        nvtx.__exit__(None, None, None)
         return {"descriptors": desc_all[:n * P], "similarity": S, "candidates": cand}
 
     def run_many(self, sequences, k=10, exclude_band=0):

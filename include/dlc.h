@@ -11,6 +11,12 @@
  *  - every launch goes on the cudaStream_t passed in (as void*; 0 = legacy default stream); no hidden syncs,
  *    no allocations on the hot path: scratch memory is caller-provided (`ws_dev`, size from *_workspace_bytes);
  *  - a handle is not thread-safe; distinct handles may be used from distinct threads; one process per GPU;
+ *  - ONE STREAM PER HANDLE / WORKSPACE: calls that share a handle (dlc_db_append then dlc_match_topk; dlc_sda_* on one
+ *    encoder) or a workspace buffer must be issued on the same stream, or the caller orders them with events - the
+ *    library records none. (dlc_db_append advances the row count on the host when the append kernel is ENQUEUED; a
+ *    match on another stream would read rows that kernel has not written yet.)
+ *  - dlc_debug_set / dlc_sdav_debug_gram_only are process-wide developer switches for A/B measurements (atomic
+ *    integers); they are not part of the drop-in surface and must not be flipped while other threads are in a call;
  *  - sm_100a only. There is no CPU fallback anywhere behind this ABI.
  */
 #ifndef DLC_H_
@@ -251,7 +257,7 @@ int dlc_sdav_stage_fix(const void* plane_hi_all_dev, const float* desc_all_dev, 
  * estimated flagged fraction, flagged rows, refined candidates}. Synchronises the stream. */
 int dlc_sdav_similarity_stats(int N, int P, int D, const void* ws_dev, double* out_host, void* stream);
 /* w = exp(-(mean_rows(desc) - mu)^2 / (2 sigma^2)), float64 [D] (SimilarityCalculator.py:19-27).
- * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 128*2*D*8). */
+ * ws_dev needs dlc_sdav_similarity_workspace_bytes(N, P, D) bytes (or at least 129*2*D*8). */
 int dlc_sdav_weights(const float* desc_dev, int N, int P, int D, double mu, double sigma, double* w_dev,
                      void* ws_dev, size_t ws_bytes, void* stream);
 

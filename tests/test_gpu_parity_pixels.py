@@ -45,11 +45,15 @@ def test_config1_from_pixels(cuda, config1, tag, seed, scale, precision):
     S_full = ops.sdav_similarity(desc.view(20, 30, -1), precision="auto", full_asymmetric=True).cpu().numpy()
     res = pipe.match(desc, 20, k=K, exclude_band=0)
     torch.cuda.synchronize()
+    sim_stats = ops.sdav_similarity_stats(20, 30, DIMS[-1])
     desc_dev = desc.cpu().numpy().reshape(20, 30, -1)
     # 1. descriptors
     err = pr.rel_err(desc_dev, desc_ref).max()
     print("\nconfig 1 [%s weights, encoder %s%s] descriptors vs float64 oracle from pixels: max rel err %.2e" % (
         tag, precision, (" -> " + pipe.encoder.chosen_precision()) if precision == "auto" else "", err))
+    print("  similarity `auto` on these real frames: %s, margin %.3g, flagged rows %d" % (
+        "one product + exact second pass" if sim_stats["use_refine"] else "three products", sim_stats["margin"],
+        int(sim_stats["flagged_rows"])))
     assert err <= TOL
     # 2. every ordered pair's score against the reference's SimilarityCalculator on the oracle descriptors
     rep = pr.report(S_full, desc_dev, desc_ref, S_ref=g["S_" + tag], idx_ref=g["idx_" + tag], tol=TOL)

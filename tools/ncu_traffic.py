@@ -2,7 +2,8 @@
 dram__bytes_read.sum / dram__bytes_write.sum, the duration, the tensor-pipe share and the SM clock (bench.py reads the
 bytes for `roofline.traffic`).
 
-    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ; python tools/ncu_traffic.py raw.csv [source note]"""
+    ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv ; python tools/ncu_traffic.py raw.csv [--suffix=@arm] [note]
+Entries are keyed by kernel name (+ suffix: the weights arm the capture was taken on)."""
 import collections
 import csv
 import json
@@ -27,7 +28,7 @@ def short_name(name):
     return re.sub(r"^(void )?(dlc::)?", "", re.sub(r"\(.*", "", name)).strip()
 
 
-def main(path, note=""):
+def main(path, note="", suffix=""):
     rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -39,12 +40,12 @@ def main(path, note=""):
 
     agg = collections.OrderedDict()
     for r in rows[2:]:
-        k = short_name(r[idx["Kernel Name"]])
+        k = short_name(r[idx["Kernel Name"]]) + suffix
         a = agg.setdefault(k, collections.defaultdict(list))
         for key, out in (("dram__bytes_read.sum", "dram_bytes_read"), ("dram__bytes_write.sum", "dram_bytes_write"),
                          ("gpu__time_duration.sum", "gpu_time_ms"),
                          ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_pct"),
-                         ("sm__cycles_elapsed.avg.per_second", "sm_clock_hz"),
+                         ("sm__cycles_elapsed.avg.per_second", "sm_clock_ghz"),
                          ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                          ("lts__t_sector_hit_rate.pct", "l2_hit_rate_pct")):
             v = val(r, key)
@@ -68,4 +69,8 @@ def main(path, note=""):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], " ".join(sys.argv[2:]))
+    args = sys.argv[2:]
+    sfx = ""
+    if args and args[0].startswith("--suffix="):
+        sfx = args.pop(0).split("=", 1)[1]
+    main(sys.argv[1], " ".join(args), sfx)
