@@ -1,3 +1,3 @@
 set -x
-python tools/check_config2_full.py --precision auto --out gpurun_out/r2_config2_full_parity.json > gpurun_out/r2_config2_full.log 2>&1
-tail -4 gpurun_out/r2_config2_full.log
+python -m pytest tests -x -q -m gpu 2>&1 | tail -6 > gpurun_out/r2_pytest_all.log; cat gpurun_out/r2_pytest_all.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
