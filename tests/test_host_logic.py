@@ -309,3 +309,31 @@ def test_tf_checkpoint_index_with_shared_prefixes_and_several_blocks(tmp_path):
     # restart interval 1 (no sharing) reads the same
     p1 = tc.save_checkpoint(str(tmp_path / "ck1-7"), tensors, update_state=False, restart_interval=1)
     assert all(np.array_equal(tc.load_checkpoint(p1)[k], tensors[k]) for k in tensors)
+
+
+def test_bench_reference_arm_is_a_measurement():
+    """bench.py --impl reference runs a fixed sub-workload to completion and reports measured and extrapolated figures
+    separately (both the hoisted and the literal, mean-per-pair variant of the pair loop)."""
+    import bench
+    m = bench.cpu_step_measured(n_frames=5, unhoisted=True)
+    assert m["frames"] == 5 and m["pairs"] == 10
+    assert m["measured_step_s"] == pytest.approx(m["encode_s"] + m["pairs_hoisted_s"])
+    assert m["extrapolated_full_step_s"] > m["measured_step_s"]
+    assert m["extrapolated_full_step_unhoisted_s"] >= m["extrapolated_full_step_s"]
+    text = bench.reference_sample_text(m)
+    assert "5 frames encoded" in text and "all 10 frame pairs" in text and "literal reference" in text
+
+
+def test_frame_blocks_cover_the_sequence():
+    """ShardedSequencePipeline.frame_block: contiguous blocks of ceil(N / world) frames, the last ones shorter or empty,
+    together exactly the sequence (the staged ABI relies on global frame g living in block g // per at g % per)."""
+    from deeploopcloser_b200.pipeline import ShardedSequencePipeline as S
+    for n, world in ((1063, 8), (1063, 3), (7, 2), (5, 8), (16, 4), (1, 1)):
+        seen = []
+        per0 = -(-n // world)
+        for r in range(world):
+            start, end, per = S.frame_block(n, r, world)
+            assert per == per0 and 0 <= end - start <= per
+            assert start == min(r * per, n)
+            seen += list(range(start, end))
+        assert seen == list(range(n))
