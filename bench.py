@@ -397,6 +397,8 @@ def run_config2(ctx, args):
                "encoder_probe_err_1prod_2prod_vs_3prod": list(pipe.encoder.probe_stats())}
         if rank == 0 and detail:
             arm.update(single_gpu_detail(pipe, weights))
+        elif rank == 0 and world > 1:
+            arm.update(sharded_detail(pipe, weights))
         return arm, pipe
 
     def t_loop(fn, reps):
@@ -409,6 +411,38 @@ def run_config2(ctx, args):
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
+
+    def sharded_detail(pipe, weights):
+        """N > 1, rank 0: roofline of the dominant kernel on THIS rank's share (the encoder layers over the rank's
+        block of frames, timed in a loop of their own)."""
+        reps = max(args.steps, 5)
+        enc = pipe.encoder
+        start, end, _ = pipe.frame_block(N_FRAMES, ctx.rank, world)
+        f_loc, x_loc = frames_d[start:end], xy_d[start:end]
+        if args.split_pixel_input:
+            hi, lo = ops.patch_gather(f_loc, x_loc, PATCH, True, need_lo=enc.needs_lo_input())
+        else:
+            hi, lo = ops.patch_gather_u8(f_loc, x_loc, PATCH, True), None
+        rows = hi.shape[0]
+        products = {"fp16": [1] * 5, "fp16x2a16": [2] * 5, "fp16x2": [3] * 5}[enc.chosen_precision()]
+        if not args.split_pixel_input and products[0] == 3:
+            products[0] = 2
+        exec_mult = (products[0] * 1681 * 2500 + sum(products[1:]) * 2500 * 2500) / (1681 * 2500 + 4 * 2500 * 2500)
+        ms = t_loop(lambda: enc.encode_planes(hi, lo, rows), reps)
+        flop = (end - start) * ENC_FLOP_PER_FRAME
+        layer_ms = ms / (len(DIMS) - 1)
+        ach = flop / (len(DIMS) - 1) / (layer_ms * 1e-3) / 1e12
+        kname = "gemm_pair_kernel<BiasActPolicy<%s>>" % ("64,1" if products[-1] == 1 else "32,3")
+        m_pairs = -(-(-(-rows // 128)) // 2)
+        return {"roofline": {
+            "kernel": kname + " (the five encoder layers over this rank's %d frames)" % (end - start), "bound": "tensor",
+            "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tflops_sustained"],
+            "traffic": None, "peak_source": pk["source"] + ", sustained bf16", "ms_per_launch": layer_ms,
+            "launches_per_step": len(DIMS) - 1, "algorithmic_flop_per_launch": flop / (len(DIMS) - 1),
+            "tensor_products_per_layer": products, "executed_over_algorithmic_flop": exec_mult,
+            "frac_executed": ach * exec_mult / pk["tflops_sustained"],
+            "note": "rank 0's share; %d pair-tiles per layer on %d CTA pairs = %.2f waves (the partial last wave is "
+                    "what a split sequence loses in the encoder)" % (m_pairs * 10, 74, m_pairs * 10 / 74.0)}}
 
     def single_gpu_detail(pipe, weights):
         """Stage split + rooflines of this rank's kernels (each stage timed alone with CUDA events on the launch

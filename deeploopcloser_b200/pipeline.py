@@ -324,7 +324,16 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         encoder of sequence i+1 (rank-local, on its own stream, into the other descriptor slot) runs while sequence i
         is in its exchange / score-matrix stage, so the GPU works through the NCCL waits that dominate a split
         sequence. Per-sequence results are the same as run()."""
-        sequences = list(sequences)
+        return self._pipelined(list(sequences), k, exclude_band, host=False)
+
+    def run_host_stream(self, batches, k=10, exclude_band=0):
+        """Stream of HOST sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] (pinned, the same on every rank):
+        each rank uploads only ITS block of every sequence (on the encoder stream, ahead of the encoder that reads
+        it), the steps are pipelined like run_many, and the candidate lists come back with asynchronous D2H copies
+        into pinned buffers owned by the pipeline (valid until the next call); one synchronisation at the end."""
+        return self._pipelined(list(batches), k, exclude_band, host=True)
+
+    def _pipelined(self, sequences, k, exclude_band, host):
         if not sequences:
             return []
         main = torch.cuda.current_stream()
@@ -335,16 +344,19 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             b["desc_slots"] = [b["desc"], torch.empty_like(b["desc"])]
         encoded, freed, outs = [None, None], [None, None], []
         enc.wait_stream(main)
+        start, end, _ = self.frame_block(n0, self.rank, self.world)
 
         def encode(i):
             f, x = sequences[i]
-            assert f.shape[0] == n0 and x.shape[1] == P0, "run_many expects sequences of one shape"
-            start, end, _ = self.frame_block(n0, self.rank, self.world)
+            assert f.shape[0] == n0 and x.shape[1] == P0, "a pipelined stream expects sequences of one shape"
             slot = i & 1
             if freed[slot] is not None:
                 enc.wait_event(freed[slot])           # sequence i-2 is done with this descriptor slot
             with torch.cuda.stream(enc):
-                self._encode_block(f[start:end], x[start:end], n0, P0, b["desc_slots"][slot])
+                f_loc, x_loc = f[start:end], x[start:end]
+                if host:                              # this rank's block only; stream-ordered ahead of its encoder
+                    f_loc, x_loc = f_loc.cuda(non_blocking=True), x_loc.cuda(non_blocking=True)
+                self._encode_block(f_loc, x_loc, n0, P0, b["desc_slots"][slot])
                 ev = torch.cuda.Event()
                 ev.record(enc)
             encoded[slot] = ev
@@ -359,17 +371,22 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             ev = torch.cuda.Event()
             ev.record(main)
             freed[slot] = ev
-            outs.append(r["candidates"])
+            if not host:
+                outs.append(r["candidates"])
+                continue
+            per = tuple(r["candidates"][0].shape)
+            pool = getattr(self, "_pinned_out", None)
+            if pool is None or tuple(pool[0].shape[1:]) != per or pool[0].shape[0] < len(sequences):
+                slots = max(64, len(sequences))
+                pool = self._pinned_out = (torch.empty((slots,) + per, dtype=torch.float32).pin_memory(),
+                                           torch.empty((slots,) + per, dtype=torch.int64).pin_memory())
+            s_h, i_h = pool[0][i], pool[1][i]
+            s_h.copy_(r["candidates"][0], non_blocking=True)
+            i_h.copy_(r["candidates"][1], non_blocking=True)
+            outs.append((s_h, i_h))
+        if host:
+            main.synchronize()
         return outs
-
-    def run_host_stream(self, batches, k=10, exclude_band=0):
-        """Stream of HOST sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] (pinned, the same on every rank):
-        each rank uploads only ITS block of every sequence; see LoopClosurePipeline.run_host_stream."""
-        mine = []
-        for f_h, x_h in batches:
-            start, end, _ = self.frame_block(f_h.shape[0], self.rank, self.world)
-            mine.append((f_h[start:end], x_h[start:end], f_h.shape[0]))
-        return self._host_stream(mine, k, exclude_band, lambda f, x, n: self.run_block(f, x, n, k, exclude_band))
 
     def host_bytes_per_step(self, frames_h, xy_h, k):
         n = frames_h.shape[0]

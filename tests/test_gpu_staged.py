@@ -118,3 +118,7 @@ def test_run_many_pipelining_equals_run(cuda):
         torch.cuda.synchronize()
         for (ws_, wi), (gs, gi) in zip(want, got):
             assert torch.equal(wi, gi) and torch.equal(ws_, gs)
+    # the same stream from pinned HOST memory: per-step upload on the encoder stream, results in pinned buffers
+    host = [(f.cpu().pin_memory(), x.cpu().pin_memory()) for f, x in seqs]
+    for (ws_, wi), (gs, gi) in zip(want, pipe.run_host_stream(host, k=5)):
+        assert not gs.is_cuda and torch.equal(wi.cpu(), gi) and torch.equal(ws_.cpu(), gs)
