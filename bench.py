@@ -340,6 +340,8 @@ def make_pipeline(ctx, weights, args):
     cls = ShardedSequencePipeline if ctx.world > 1 else LoopClosurePipeline
     pipe = cls(DIMS, precision=args.precision, sim_precision=args.sim_precision, raw_pixels=not args.split_pixel_input)
     pipe.set_weights(ws, bs)
+    if args.pipeline_stages and ctx.world > 1:
+        pipe.pipeline_stages = args.pipeline_stages
     return pipe
 
 
@@ -726,6 +728,8 @@ def main():
     ap.add_argument("--split-pixel-input", action="store_true",
                     help="A/B: feed layer 0 pixel/255 as hi/lo planes instead of exact pixel values")
     ap.add_argument("--cpu-frames", default=96, type=int, help="reference arm: frames of the sub-workload")
+    ap.add_argument("--pipeline-stages", type=int, default=0, choices=[0, 2, 3],
+                    help="N > 1: stages of the step pipeline (0 = the pipeline's default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -277,6 +277,7 @@ def sdav_similarity_stats(N, P, D):
 # ---- staged form for a sequence split over several GPUs (see dlc_sdav_stage_* in include/dlc.h)
 plane_ld = _lib.plane_ld
 _ws_stage = Workspace()
+_ws_colsum = Workspace()    # its own buffer: in a pipelined stream the column sums of step i+1 run next to step i's Gram
 
 
 def sdav_stage_stats_bytes(frames_per_part):
@@ -292,7 +293,7 @@ def sdav_stage_colsum(desc_local, out):
     of squares."""
     _check_cuda(desc_local, out)
     rows, D = desc_local.shape
-    ws, ws_bytes = _ws_stage.get(129 * 2 * D * 8)
+    ws, ws_bytes = _ws_colsum.get(129 * 2 * D * 8)
     _lib.call("dlc_sdav_stage_colsum", ptr(desc_local), rows, D, ptr(out), ws, ws_bytes, stream_ptr())
 
 

@@ -188,6 +188,10 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bg_group = None       # second communicator: the descriptor all-gather runs next to the other collectives
         self._buf_key = None
+        # pipelined streams (run_many / run_host_stream): 2 = the encoder of step i+1 on a side stream under the exchange
+        # + score stages of step i; 3 = encoder, exchange and score each on a stream of their own (steps i+2, i+1, i).
+        # Measured on 8 GPUs, see DESIGN.md 6.
+        self.pipeline_stages = 2
 
     @staticmethod
     def frame_block(n_frames, rank, world):
@@ -201,24 +205,32 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         return torch.empty(shape, dtype=dtype, device="cuda")
 
     def _buffers(self, n, P):
+        """Device buffers for an n-frame sequence: the score matrix and two SLOTS of everything that is exchanged
+        (descriptors, planes, stats blocks, column sums, weights, centring vector) - slot i & 1 belongs to step i of a
+        pipelined stream, so the exchange stage of step i+1 can run while step i is in its score-matrix stage. The second
+        slot is allocated on first use."""
         D = self.dims[-1]
         key = (n, P, D, self.world)
         if self._buf_key != key:
-            per = -(-n // self.world)
-            ld = ops.plane_ld(D)
-            rows = self.world * per * P
-            self._b = {
-                "desc": self._alloc((rows, D), torch.float32),
-                "desc_slots": None,
-                "plane": self._alloc((rows, ld), torch.float16),
-                "plane_lo": self._alloc((rows, ld), torch.float16) if self.sim_precision == "fp16x2" else None,
-                "stats": self._alloc((self.world, ops.sdav_stage_stats_bytes(per)), torch.uint8),
-                "colsums": self._alloc((self.world, 2 * D), torch.float64),
-                "w": self._alloc((D,), torch.float64), "mean": self._alloc((D,), torch.float32),
-                "S": self._alloc((n, n), torch.float32),
-            }
+            self._b = {"S": self._alloc((n, n), torch.float32), "slots": [self._slot(n, P), None]}
+            self._b.update(self._b["slots"][0])      # run_block / tests address slot 0 directly
             self._buf_key = key
         return self._b
+
+    def _slot(self, n, P):
+        D = self.dims[-1]
+        per = -(-n // self.world)
+        ld = ops.plane_ld(D)
+        rows = self.world * per * P
+        return {
+            "desc": self._alloc((rows, D), torch.float32),
+            "plane": self._alloc((rows, ld), torch.float16),
+            "plane_lo": self._alloc((rows, ld), torch.float16) if self.sim_precision == "fp16x2" else None,
+            "stats": self._alloc((self.world, ops.sdav_stage_stats_bytes(per)), torch.uint8),
+            "colsums": self._alloc((self.world, 2 * D), torch.float64),
+            "w": self._alloc((D,), torch.float64), "mean": self._alloc((D,), torch.float32),
+            "work": None,
+        }
 
     def _encode_into(self, frames, xy, out):
         if xy is None:
@@ -240,6 +252,7 @@ class ShardedSequencePipeline(LoopClosurePipeline):
                                stats_local)
 
     def _stage_gram(self, b, per, n, P):
+        """b: one slot + the score matrix "S"."""
         ops.sdav_stage_gram(b["plane"], b["plane_lo"], b["stats"], self.world, per, n, P, self.dims[-1], self.sim_precision,
                             self.rank, b["S"], a=self.sim_args.get("a", 10.0), b=self.sim_args.get("b", -10.0))
 
@@ -261,8 +274,10 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         """frames_local / xy_local: this rank's block of the N-frame sequence (frame_block(N, rank, world))."""
         P = P or (xy_local.shape[1] if xy_local is not None else 30)
         b = self._buffers(n, P)
-        self._encode_block(frames_local, xy_local, n, P, b["desc"])
-        return self._match_block(b, b["desc"], n, P, k, exclude_band)
+        slot = b["slots"][0]
+        self._encode_block(frames_local, xy_local, n, P, slot["desc"])
+        self._exchange_block(slot, n, P)
+        return self._score_block(b, slot, n, P, k, exclude_band)
 
     def _encode_block(self, frames_local, xy_local, n, P, desc_all):
         """Stage A (rank-local, no collective): patch gather + encoder of this rank's frames into its slice of the
@@ -278,45 +293,50 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             with nvtx_range("dlc.encode_block"):
                 self._encode_into(frames_local, xy_local, desc_local[:n_local * P])
 
-    def _match_block(self, b, desc_all, n, P, k, exclude_band):
-        """Stage B: everything after the encoder (collectives + score matrix + candidates)."""
+    def _exchange_block(self, slot, n, P):
+        """Stage B (the collectives): mean / weights, centred planes + statistics + probe of this rank's block, and
+        their all-gathers; the float32 descriptors start travelling in the background (second communicator)."""
         start, end, per = self.frame_block(n, self.rank, self.world)
         n_local = end - start
         lo_r, hi_r = self.rank * per * P, (self.rank + 1) * per * P
-        desc_local = desc_all[lo_r:hi_r]
-        work = None
-        if self.world > 1:
-            if self._bg_group is None:
-                self._bg_group = self.dist.new_group(list(range(self.world))) if self.group is None else self.group
-            # float32 descriptors of all frames: only the second pass reads them -> gathered in the background
-            work = self._all_gather(desc_all, desc_local, self._bg_group, async_op=True)
-        # dataset mean / weights
-        nvtx = nvtx_range("dlc.match_block")
-        nvtx.__enter__()
-        self._stage_colsum(desc_local[:n_local * P], b["colsums"][self.rank])
-        if self.world > 1:
-            self._all_gather(b["colsums"].view(-1), b["colsums"][self.rank], self.group)
-        self._stage_weights(b["colsums"], n * P, b["w"], b["mean"])
-        # centred planes + statistics + probe of this block, then their exchange
-        plane_lo_local = None if b["plane_lo"] is None else b["plane_lo"][lo_r:hi_r]
-        self._stage_prepare(desc_local, n_local, per, P, b["w"], b["mean"], b["plane"][lo_r:hi_r], plane_lo_local,
-                            b["stats"][self.rank])
-        if self.world > 1:
-            self._all_gather(b["plane"].view(-1), b["plane"][lo_r:hi_r].view(-1), self.group)
-            if plane_lo_local is not None:
-                self._all_gather(b["plane_lo"].view(-1), plane_lo_local.view(-1), self.group)
-            self._all_gather(b["stats"].view(-1), b["stats"][self.rank], self.group)
-        self._stage_gram(b, per, n, P)
-        if work is not None:
-            work.wait()                                # the compute stream waits for the descriptor gather
-        self._stage_fix(dict(b, desc=desc_all), n, P)
-        S = b["S"]
-        if self.world > 1:
-            self.dist.all_reduce(S, group=self.group)
-        self.last_similarity = S
-        cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
-        nvtx.__exit__(None, None, None)
-        return {"descriptors": desc_all[:n * P], "similarity": S, "candidates": cand}
+        desc_local = slot["desc"][lo_r:hi_r]
+        slot["work"] = None
+        with nvtx_range("dlc.exchange_block"):
+            if self.world > 1:
+                if self._bg_group is None:
+                    self._bg_group = self.dist.new_group(list(range(self.world))) if self.group is None else self.group
+                # float32 descriptors of all frames: only the second pass reads them -> gathered in the background
+                slot["work"] = self._all_gather(slot["desc"], desc_local, self._bg_group, async_op=True)
+            self._stage_colsum(desc_local[:n_local * P], slot["colsums"][self.rank])
+            if self.world > 1:
+                self._all_gather(slot["colsums"].view(-1), slot["colsums"][self.rank], self.group)
+            self._stage_weights(slot["colsums"], n * P, slot["w"], slot["mean"])
+            plane_lo_local = None if slot["plane_lo"] is None else slot["plane_lo"][lo_r:hi_r]
+            self._stage_prepare(desc_local, n_local, per, P, slot["w"], slot["mean"], slot["plane"][lo_r:hi_r],
+                                plane_lo_local, slot["stats"][self.rank])
+            if self.world > 1:
+                self._all_gather(slot["plane"].view(-1), slot["plane"][lo_r:hi_r].view(-1), self.group)
+                if plane_lo_local is not None:
+                    self._all_gather(slot["plane_lo"].view(-1), plane_lo_local.view(-1), self.group)
+                self._all_gather(slot["stats"].view(-1), slot["stats"][self.rank], self.group)
+
+    def _score_block(self, b, slot, n, P, k, exclude_band):
+        """Stage C: this rank's tile rows of the score matrix, the exact second pass (waits for the descriptor
+        gather), the all-reduce of the parts and the loop candidates."""
+        per = -(-n // self.world)
+        view = dict(slot, S=b["S"])
+        with nvtx_range("dlc.score_block"):
+            self._stage_gram(view, per, n, P)
+            if slot["work"] is not None:
+                slot["work"].wait()                    # the current stream waits for the descriptor gather
+                slot["work"] = None
+            self._stage_fix(view, n, P)
+            S = b["S"]
+            if self.world > 1:
+                self.dist.all_reduce(S, group=self.group)
+            self.last_similarity = S
+            cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
+        return {"descriptors": slot["desc"][:n * P], "similarity": S, "candidates": cand}
 
     def run_many(self, sequences, k=10, exclude_band=0):
         """A stream of sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] resident on the device (every rank
@@ -334,16 +354,22 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         return self._pipelined(list(batches), k, exclude_band, host=True)
 
     def _pipelined(self, sequences, k, exclude_band, host):
+        """Three stages per step: A = upload + encode (rank-local), B = exchange (collectives), C = score matrix +
+        candidates. A of step i+1 runs on a side stream, into slot (i+1) & 1, while B and C of step i run on the
+        caller's stream (pipeline_stages = 2) or B has a stream of its own as well (3). Collectives are issued in one
+        program order on every rank (C_i's all-reduce before B_{i+1}'s all-gathers), as NCCL requires."""
         if not sequences:
             return []
         main = torch.cuda.current_stream()
-        enc = self._enc_stream = getattr(self, "_enc_stream", None) or torch.cuda.Stream()
+        side = self._enc_stream = getattr(self, "_enc_stream", None) or torch.cuda.Stream()
+        xch = self._xch_stream = getattr(self, "_xch_stream", None) or torch.cuda.Stream()
         n0, P0 = sequences[0][0].shape[0], sequences[0][1].shape[1]
         b = self._buffers(n0, P0)
-        if b["desc_slots"] is None:
-            b["desc_slots"] = [b["desc"], torch.empty_like(b["desc"])]
-        encoded, freed, outs = [None, None], [None, None], []
-        enc.wait_stream(main)
+        if b["slots"][1] is None:
+            b["slots"][1] = self._slot(n0, P0)
+        encoded, exchanged, freed, outs = [None, None], [None, None], [None, None], []
+        side.wait_stream(main)
+        xch.wait_stream(main)
         start, end, _ = self.frame_block(n0, self.rank, self.world)
 
         def encode(i):
@@ -351,26 +377,44 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             assert f.shape[0] == n0 and x.shape[1] == P0, "a pipelined stream expects sequences of one shape"
             slot = i & 1
             if freed[slot] is not None:
-                enc.wait_event(freed[slot])           # sequence i-2 is done with this descriptor slot
-            with torch.cuda.stream(enc):
+                side.wait_event(freed[slot])          # step i-2 is done with this slot
+            with torch.cuda.stream(side):
                 f_loc, x_loc = f[start:end], x[start:end]
                 if host:                              # this rank's block only; stream-ordered ahead of its encoder
                     f_loc, x_loc = f_loc.cuda(non_blocking=True), x_loc.cuda(non_blocking=True)
-                self._encode_block(f_loc, x_loc, n0, P0, b["desc_slots"][slot])
+                self._encode_block(f_loc, x_loc, n0, P0, b["slots"][slot]["desc"])
                 ev = torch.cuda.Event()
-                ev.record(enc)
+                ev.record(side)
             encoded[slot] = ev
 
+        def exchange(i):
+            slot = i & 1
+            if getattr(self, "pipeline_stages", 2) < 3:      # two stages: the exchange stays on the caller's stream
+                main.wait_event(encoded[slot])
+                self._exchange_block(b["slots"][slot], n0, P0)
+                exchanged[slot] = None
+                return
+            xch.wait_event(encoded[slot])                    # three stages: the exchange has a stream of its own
+            with torch.cuda.stream(xch):
+                self._exchange_block(b["slots"][slot], n0, P0)
+                ev = torch.cuda.Event()
+                ev.record(xch)
+            exchanged[slot] = ev
+
         encode(0)
+        exchange(0)
         for i in range(len(sequences)):
             slot = i & 1
             if i + 1 < len(sequences):
                 encode(i + 1)
-            main.wait_event(encoded[slot])
-            r = self._match_block(b, b["desc_slots"][slot], n0, P0, k, exclude_band)
+            if exchanged[slot] is not None:
+                main.wait_event(exchanged[slot])
+            r = self._score_block(b, b["slots"][slot], n0, P0, k, exclude_band)
             ev = torch.cuda.Event()
             ev.record(main)
             freed[slot] = ev
+            if i + 1 < len(sequences):
+                exchange(i + 1)                       # issued after C_i: its all-gathers queue behind C_i's all-reduce
             if not host:
                 outs.append(r["candidates"])
                 continue

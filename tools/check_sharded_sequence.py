@@ -54,15 +54,23 @@ def timed(fn, reps=10):
 
 t_one = timed(lambda: ref.run(f_d, x_d, k=bench.K_CAND))
 t_all = timed(lambda: pipe.run(f_d, x_d, k=bench.K_CAND))
-many = pipe.run_many([(f_d, x_d)] * 3, k=bench.K_CAND)
-torch.cuda.synchronize()
-many_ok = all(torch.equal(m[1], want["candidates"][1]) for m in many)
-t_many = timed(lambda: pipe.run_many([(f_d, x_d)] * 10, k=bench.K_CAND), reps=2) / 10
+many_ok, t_many = True, {}
+for stages in (2, 3):                      # both depths of the step pipeline give run()'s lists
+    pipe.pipeline_stages = stages
+    many = pipe.run_many([(f_d, x_d)] * 5, k=bench.K_CAND)
+    torch.cuda.synchronize()
+    many_ok = many_ok and all(torch.equal(m[1], want["candidates"][1]) and torch.equal(m[0], want["candidates"][0])
+                              for m in many)
+    t_many[stages] = timed(lambda: pipe.run_many([(f_d, x_d)] * 10, k=bench.K_CAND), reps=2) / 10
+ok_t = torch.tensor([int(many_ok)], device="cuda")
+dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+many_ok = bool(ok_t.item())
 if rank == 0:
     print(json.dumps({"check": "sharded_sequence", "n_gpus": world, "frames": bench.N_FRAMES,
                       "matches_single_gpu_on_all_ranks": bool(same[0].item()),
                       "scores_bit_identical_on_all_ranks": bool(same[1].item()), "max_rel_score_diff": float(rel),
-                      "pipelined_run_many_matches": many_ok, "pipelined_ms_per_sequence": t_many,
+                      "pipelined_run_many_matches_on_all_ranks": many_ok, "pipelined_ms_per_sequence_2_stages": t_many[2],
+                      "pipelined_ms_per_sequence_3_stages": t_many[3],
                       "single_gpu_ms": t_one, "sharded_ms": t_all, "speedup": t_one / t_all,
                       "frames_per_s": bench.N_FRAMES / t_all * 1e3}))
 dist.destroy_process_group()
