@@ -122,3 +122,37 @@ def test_run_many_pipelining_equals_run(cuda):
     host = [(f.cpu().pin_memory(), x.cpu().pin_memory()) for f, x in seqs]
     for (ws_, wi), (gs, gi) in zip(want, pipe.run_host_stream(host, k=5)):
         assert not gs.is_cuda and torch.equal(wi.cpu(), gi) and torch.equal(ws_.cpu(), gs)
+
+
+@pytest.mark.parametrize("metric,B,k", [("cos", 70, 10), ("l2", 5, 32), ("dot", 300, 16)])
+def test_match_topk_sharded_world1_equals_local(cuda, metric, B, k):
+    """dlc_match_topk_sharded on a one-rank NCCL communicator created through the C ABI (dlc_comm_unique_id /
+    dlc_comm_create; libnccl resolved with dlopen): fused kernel -> packed list -> (no exchange at world 1) -> rank
+    merge kernel must reproduce dlc_match_topk on the same database, offsets included. The multi-rank exchange is
+    checked under torchrun by tools/check_sharded.py and on every bench.py --gpus N run (planted neighbours)."""
+    import ctypes as C
+
+    from deeploopcloser_b200 import _lib
+    from deeploopcloser_b200._cuda import Workspace, ptr, stream_ptr
+    from deeploopcloser_b200.matcher import KeyframeDatabase
+    rng = np.random.default_rng(B + k)
+    N, D = 5000, 192
+    scale = 1.0 if metric == "cos" else 0.25
+    db = KeyframeDatabase(D, N, metric, "fp16")
+    db.append(torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32) * scale).cuda())
+    q = torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32) * scale).cuda()
+    want_s, want_i = db.topk(q, k, idx_offset=1000)
+    uid = (C.c_char * 128)()
+    _lib.call("dlc_comm_unique_id", C.cast(uid, C.c_void_p))
+    comm = C.c_void_p()
+    _lib.call("dlc_comm_create", C.byref(comm), bytes(uid.raw), 0, 1)
+    try:
+        s = torch.empty((B, k), dtype=torch.float32, device="cuda")
+        i = torch.empty((B, k), dtype=torch.int64, device="cuda")
+        ws = Workspace()
+        w, wb = ws.get(_lib.call("dlc_match_sharded_workspace_bytes", db._h, B, k, 1))
+        _lib.call("dlc_match_topk_sharded", db._h, comm, ptr(q), B, k, 1000, ptr(s), ptr(i), w, wb, stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(i, want_i) and torch.equal(s, want_s)
+    finally:
+        _lib.call("dlc_comm_destroy", comm)
