@@ -46,6 +46,20 @@ WEIGHT_NOTES = {"normal": "N(0,1) init (reference default, no checkpoint shipped
                 "xavier": "Xavier-scaled N(0, 1/fan_in), biases 0.1 N(0,1) (trained-like; no trained checkpoint exists)"}
 
 
+def workload_config(weights, world):
+    """`config` of the JSON line: names the workload only, and is THE SAME dict in both arms (`--impl ours` and
+    `--impl reference`), so the driver can see that they measured the same thing. How our arm computes it (arithmetic
+    modes, input layout) is in `config_detail`."""
+    return {"workload": WORKLOAD, "weights": WEIGHT_NOTES[weights], "k": K_CAND,
+            "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the 126 MB L2; no explicit "
+                  "flush between steps",
+            "multi_gpu": "single GPU" if world == 1 else
+                         "strong scaling: ONE sequence split over %d ranks, frames dealt in blocks; NCCL all-gather of "
+                         "the fp16 descriptor planes, the row statistics and (in the background) the fp32 descriptors, "
+                         "every rank evaluates its interleaved tile rows of the score matrix, NCCL all-reduce (sum) of "
+                         "the scores" % world}
+
+
 def synthetic_inputs(seed):
     rng = np.random.default_rng(seed)
     frames = rng.integers(0, 256, (N_FRAMES, H, W), dtype=np.uint8)
@@ -246,7 +260,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * meas_s, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "weights": WEIGHT_NOTES["normal"]},
+            "config": workload_config("normal", int(os.environ.get("WORLD_SIZE", "1"))),
             "measured": {"what": "sub-workload of the step, run to completion every step: %d frames encoded + all %d "
                                  "pairs scored (mean hoisted)" % (last["frames"], last["pairs"]),
                          "ms_per_step": 1e3 * meas_s, "frames_per_s_of_the_sub_workload": last["frames"] / meas_s},
@@ -345,11 +359,17 @@ def make_pipeline(ctx, weights, args):
     return pipe
 
 
-def step_launches(sim_precision):
-    """Kernel launches of one step on one rank: patch gather, one kernel per layer, the similarity call (dataset
-    mean x2, row preparation, Gram; with a precision probe also rep_mask, probe, finalize, [auto: gated residual
-    planes], the second refinement pass and the gated three-product twin), per-row top-k."""
-    return 1 + len(DIMS) - 1 + {"auto": 10, "fp16r": 9}.get(sim_precision, 4) + 1
+def step_launches(sim_precision, world):
+    """OUR kernel launches of one step on one rank (NCCL's kernels are not counted): patch gather, one kernel per layer,
+    the similarity call - column sums, their reduction, weights / centring, row preparation, Gram; with a precision
+    probe also the duplicate-row mask, the probe, its finalisation, [auto: the gated residual planes], the second pass
+    and [auto, one GPU] the gated three-product twin; a split sequence adds the stats unpack - and the per-row top-k.
+    Checked against the ncu launch list (profiles/r2_launches_summary.txt)."""
+    if world > 1:
+        sim = {"auto": 10, "fp16r": 10}.get(sim_precision, 6)
+    else:
+        sim = {"auto": 11, "fp16r": 10}.get(sim_precision, 5)
+    return 1 + len(DIMS) - 1 + sim + 1
 
 
 def run_config2(ctx, args):
@@ -560,19 +580,16 @@ def run_config2(ctx, args):
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "ms_per_step_unpipelined": m["ms_per_step_unpipelined"],
             "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": prod + ", f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "precision": args.precision, "encoder_precision_chosen": m["encoder_precision"],
-                       "sim_precision": args.sim_precision, "weights": m["weights"],
-                       "layer0_input": "pixel/255 hi/lo planes" if args.split_pixel_input else
-                                       "exact 8-bit pixel plane, 1/255 folded into layer 0",
-                       "k": K_CAND, "l2": "per-step working set (~1.4 GB of operand planes and descriptors) exceeds the "
-                                          "126 MB L2; no explicit flush",
-                       "multi_gpu": "single GPU" if world == 1 else
-                                    "ONE sequence split over %d ranks (strong scaling): frames dealt in blocks, NCCL "
-                                    "all-gather of the descriptor planes and row statistics, every rank evaluates its "
-                                    "interleaved tile rows of the score matrix, NCCL all-reduce of the scores; successive "
-                                    "steps are pipelined (encoder of step i+1 under the exchange stage of step i); "
-                                    "ms_per_step_unpipelined = one step at a time" % world},
-            "e2e": m["e2e"], "gpu_launches": step_launches(args.sim_precision) * args.steps,
+            "config": workload_config(args.weights, world),
+            "config_detail": {"precision": args.precision, "encoder_precision_chosen": m["encoder_precision"],
+                              "sim_precision": args.sim_precision,
+                              "layer0_input": "pixel/255 hi/lo planes" if args.split_pixel_input else
+                                              "exact 8-bit pixel plane, 1/255 folded into layer 0",
+                              "pipelining": "none (one GPU: run() after run())" if world == 1 else
+                                            "successive steps pipelined: encoder of step i+1 on a side stream under the "
+                                            "exchange + score stages of step i; ms_per_step_unpipelined = one step at "
+                                            "a time"},
+            "e2e": m["e2e"], "gpu_launches": step_launches(args.sim_precision, world) * args.steps,
             "clocks": sampler.summary() if sampler else None,
             "roofline": m.get("roofline"), "roofline_sim": m.get("roofline_sim"), "cpu_baseline": cpu_base,
             "stages_ms": m.get("stages_ms"),
