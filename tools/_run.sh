@@ -1,4 +1,6 @@
 set -x
-python -m pytest tests/test_gpu_staged.py -x -q -m gpu -k "sharded_world1" 2>&1 | tail -4
-TR2="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515"
-timeout 200 $TR2 tools/check_sharded.py > gpurun_out/r2_check_sharded2.log 2>&1; echo "exit $?"; grep "^sharded" gpurun_out/r2_check_sharded2.log || tail -20 gpurun_out/r2_check_sharded2.log
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4 > gpurun_out/r2_pytest_final.log; cat gpurun_out/r2_pytest_final.log
+python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; tail -c 600 gpurun_out/r2_bench_final.json; tail -3 gpurun_out/r2_bench_final.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_final.json 2>&1; tail -c 400 gpurun_out/r2_bench_ref_final.json
+python bench.py --steps 2 --warmup 1 --headline-only --one-arm --no-cpu-baseline > gpurun_out/r2_plain_d.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches_d.csv python bench.py --steps 2 --warmup 1 --headline-only --one-arm --no-cpu-baseline > gpurun_out/r2_ncu_d.log 2>&1
