@@ -153,6 +153,10 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
   return DLC_OK;
 }
 
+// for translation units that do not include the GEMM headers (sda.cu)
+int device_sm_count() { return sm_count(); }
+bool gemm_pairs_enabled() { return g_cta_pair.load() != 0; }
+
 }  // namespace dlc
 
 using namespace dlc;

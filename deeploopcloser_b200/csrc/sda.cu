@@ -16,9 +16,10 @@ struct dlc_sda {
   std::vector<int> dims;     // n_layers + 1
   std::vector<int> ld;       // plane ld of each layer's input  (dlc_plane_ld(dims[l]))
   std::vector<int> n_pad;    // padded output width of each layer (= ld of the next layer's input)
-  std::vector<void*> w_hi;   // [n_pad[l], ld[l]] fp16 (or bf16)
+  std::vector<int> n_alloc;  // rows of the weight planes / bias entries (>= every width gemm_pad() may choose; zeros)
+  std::vector<void*> w_hi;   // [n_alloc[l], ld[l]] fp16 (or bf16)
   std::vector<void*> w_lo;
-  std::vector<float*> bias;  // [n_pad[l]]
+  std::vector<float*> bias;  // [n_alloc[l]]
   std::vector<bool> is_set;
   bool input_u8 = false;     // x planes hold raw pixel values 0..255 (dlc_sda_set_input_u8)
   int chosen = -1;           // DLC_PREC_AUTO: the probe's choice (-1 = not probed yet); else = precision
@@ -30,6 +31,8 @@ using namespace dlc;
 namespace dlc {
 extern thread_local int g_gemm_k_valid;  // planes.cu
 extern thread_local float g_gemm_alpha;  // planes.cu
+int device_sm_count();                   // planes.cu
+bool gemm_pairs_enabled();               // planes.cu
 }
 
 namespace {
@@ -42,6 +45,49 @@ int out_pad(int n) {
   // width <= 256 divides it with little waste: multiples of 256 when n > 256, else multiples of 64.
   if (n > 256) return (n + 255) / 256 * 256;
   return (n + 63) / 64 * 64;
+}
+
+// The accumulator width dlc_gemm_planes derives from a padded N (largest multiple of 32 <= 256 that divides it).
+int tile_of_pad(int n_pad) {
+  for (int cand = 256; cand >= 32; cand -= 32)
+    if (n_pad % cand == 0) return cand;
+  return 0;
+}
+// Relative cost of one layer on CTA pairs: tiles are dealt round-robin to sm/2 pairs, so the layer takes
+// ceil(tiles / pairs) tile times, and a tile time grows with its width (+ a fixed part: A tile, pipeline fill).
+int64_t pair_cost(int rows, int n_pad, int sms) {
+  const int tile = tile_of_pad(n_pad);
+  const int64_t tiles = static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (n_pad / tile);
+  const int pairs = std::max(1, sms / 2);
+  return (tiles + pairs - 1) / pairs * (tile + 16);
+}
+constexpr int kPadTiles[] = {256, 224, 192};  // accumulator widths tried per call (wide tiles only)
+// Padded GEMM width of a layer for this call's row count. With few rows per call (a block of a sequence split over
+// GPUs, a streaming batch) the default width leaves the last wave of tiles nearly empty - e.g. 3 990 rows x 2 500
+// columns: 160 tiles of 256 on 74 pairs = 3 waves for 2.16 waves of work; 192 tiles of 224 = 3 shorter waves.
+// The weight planes hold zeros beyond dims[l+1], so any width <= n_alloc gives the same values; the output planes keep
+// their width n_pad (columns beyond it are clipped by the store).
+int gemm_pad(const dlc_sda* h, int l, int rows) {
+  const int n = h->dims[l + 1], sms = device_sm_count();
+  int best = h->n_pad[l];
+  if (n <= 256 || !gemm_pairs_enabled() || (static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (best / tile_of_pad(best))) < sms / 2) return best;
+  int64_t best_cost = pair_cost(rows, best, sms);
+  for (int t : kPadTiles) {
+    const int cand = ceil_div(n, t) * t;
+    if (cand > h->n_alloc[l]) continue;
+    const int64_t c = pair_cost(rows, cand, sms);
+    if (c < best_cost) {
+      best_cost = c;
+      best = cand;
+    }
+  }
+  return best;
+}
+int alloc_pad(int n) {
+  int a = out_pad(n);
+  if (n > 256)
+    for (int t : kPadTiles) a = std::max(a, ceil_div(n, t) * t);
+  return a;
 }
 }  // namespace
 
@@ -59,19 +105,21 @@ extern "C" int dlc_sda_create(dlc_sda** h, int n_layers, const int* dims, int pr
   s->dims.assign(dims, dims + n_layers + 1);
   s->ld.resize(n_layers);
   s->n_pad.resize(n_layers);
+  s->n_alloc.resize(n_layers);
   s->w_hi.assign(n_layers, nullptr);
   s->w_lo.assign(n_layers, nullptr);
   s->bias.assign(n_layers, nullptr);
   s->is_set.assign(n_layers, false);
   for (int l = 0; l < n_layers; ++l) {
     s->n_pad[l] = out_pad(dims[l + 1]);
+    s->n_alloc[l] = alloc_pad(dims[l + 1]);
     s->ld[l] = l == 0 ? dlc_plane_ld(dims[0]) : s->n_pad[l - 1];
   }
   for (int l = 0; l < n_layers; ++l) {
-    const size_t plane = static_cast<size_t>(s->n_pad[l]) * s->ld[l] * 2;
+    const size_t plane = static_cast<size_t>(s->n_alloc[l]) * s->ld[l] * 2;
     cudaError_t e = cudaMalloc(&s->w_hi[l], plane);
     if (e == cudaSuccess && needs_lo(precision)) e = cudaMalloc(&s->w_lo[l], plane);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bias[l]), sizeof(float) * s->n_pad[l]);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->bias[l]), sizeof(float) * s->n_alloc[l]);
     if (e != cudaSuccess) {
       dlc_sda_destroy(s);
       return fail(DLC_ENOMEM, "dlc_sda_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -125,10 +173,10 @@ extern "C" int dlc_sda_set_layer(dlc_sda* h, int l, const double* w_host, const 
     if (h->precision == DLC_PREC_BF16)
       rc = fail(DLC_EUNSUPPORTED, "dlc_sda_set_layer: bf16 weight packing is not implemented for the encoder");
     else
-      rc = dlc_pack_weight_planes(w_dev, DLC_F64, k, n, h->n_pad[l], h->w_hi[l], h->w_lo[l], h->ld[l], nullptr);
+      rc = dlc_pack_weight_planes(w_dev, DLC_F64, k, n, h->n_alloc[l], h->w_hi[l], h->w_lo[l], h->ld[l], nullptr);
   }
   if (rc == DLC_OK) {
-    std::vector<float> b(h->n_pad[l], 0.0f);
+    std::vector<float> b(h->n_alloc[l], 0.0f);
     for (int i = 0; i < n; ++i) b[i] = static_cast<float>(b_host[i]);
     e = cudaMemcpy(h->bias[l], b.data(), sizeof(float) * b.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = fail(DLC_ECUDA, "dlc_sda_set_layer: bias copy failed: %s", cudaGetErrorString(e));
@@ -173,7 +221,7 @@ int run_chain(dlc_sda* h, int mode, const void* x_hi_dev, const void* x_lo_dev, 
     void* o_lo = last ? nullptr : buf_lo[l & 1];
     g_gemm_k_valid = h->dims[l];  // columns dims[l]..ld of both operands are zero padding
     if (l == 0 && h->input_u8) g_gemm_alpha = 1.0f / 256.0f;
-    int rc = dlc_gemm_planes(a_hi, a_lo, h->w_hi[l], h->w_lo[l], rows, h->dims[l + 1], h->n_pad[l], h->ld[l],
+    int rc = dlc_gemm_planes(a_hi, a_lo, h->w_hi[l], h->w_lo[l], rows, h->dims[l + 1], gemm_pad(h, l, rows), h->ld[l],
                              h->bias[l], DLC_ACT_SIGMOID, gemm_prec, last ? out_dev : nullptr, h->dims[l + 1], o_hi,
                              o_lo, h->n_pad[l], stream);
     if (rc != DLC_OK) return rc;

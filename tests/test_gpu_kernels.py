@@ -679,6 +679,31 @@ def test_encoder_raw_pixel_mode(cuda, dims, frames, pair_mode):
     assert errs[True] <= TOL and errs[True] <= 2.0 * errs[False] + 1e-6
 
 
+@pytest.mark.parametrize("precision", ["fp16x2", "fp16"])
+def test_encoder_wave_aware_width_gives_the_same_bits(cuda, precision):
+    """dlc_sda_encode picks the GEMM width per call from the row count (sda.cu gemm_pad: 3 990 rows = one rank's
+    block of config 2 split over 8 GPUs and 7 680 rows = a streaming batch of 256 frames use 224-wide accumulators,
+    the full sequence 256-wide ones). The tile shape must not change a single bit of a row's descriptor."""
+    from deeploopcloser_b200 import ops
+    dims = [1681, 2500, 2500, 2500]
+    ws, bs = o_sda.make_weights(dims, seed=2, scale="xavier")
+    rng = np.random.default_rng(5)
+    rows = 31890
+    x = torch.from_numpy(rng.integers(0, 256, (rows, 1728)).astype(np.float16))
+    x[:, 1681:] = 0
+    x = x.cuda()
+    enc = ops.SdaEncoder(dims, precision, input_u8=True)
+    for l, (w, b) in enumerate(zip(ws, bs)):
+        enc.set_layer(l, w, b)
+    full = enc.encode_planes(x, None, rows).clone()
+    for r in (3990, 7680, 12000):
+        part = enc.encode_planes(x[:r].contiguous(), None, r)
+        assert torch.equal(part, full[:r]), r
+    ref = o_sda.sda_forward(x[:60, :1681].double().cpu().numpy() / 255.0, ws, bs)
+    assert rel_err(full[:60].cpu().numpy(), ref) <= (TOL if precision == "fp16x2" else 5e-3)
+    enc.close()
+
+
 def test_encoder_raw_pixel_mode_needs_layer0_again(cuda):
     from deeploopcloser_b200 import _lib, ops
     enc = ops.SdaEncoder([1681, 64], "fp16x2")
