@@ -8,6 +8,10 @@
 #include "gemm_sm100.cuh"
 #include "util.h"
 
+#ifndef DLC_WIDE_STORE
+#define DLC_WIDE_STORE 1  // 0: every 32-column chunk leaves as its own 32 x 32 store (developer A/B build)
+#endif
+
 namespace dlc {
 
 // ------------------------------------------------------------------------------------------------
@@ -26,13 +30,17 @@ struct BiasActParams {
   void* out_hi;
   void* out_lo;
   int out_plane_ld;
-  // Plane outputs leave through TMA stores: each epilogue warp stages its 32 x 32 tile (64-byte rows, SWIZZLE_64B
-  // layout) in shared memory and one lane issues cp.async.bulk.tensor stores - full 64-byte row segments instead of
-  // 32 row-strided 16-byte stores per instruction (the LSU wavefronts of those were what the epilogue waited on).
-  // Rows beyond M are clipped by the tensor map.
+  // Plane outputs leave through TMA stores: each epilogue warp stages its 32 rows in shared memory and one lane issues
+  // cp.async.bulk.tensor stores. Two adjacent 32-column chunks of a tile are staged side by side (128-byte rows,
+  // SWIZZLE_128B) and leave as ONE 32 x 64 store per plane; a chunk without a partner (odd chunk count, edge of the
+  // plane) uses the 32 x 32 box (64-byte rows, SWIZZLE_64B). Halving the number of store operations matters: the
+  // stores share the SM's TMA unit with the operand loads (ncu A/B on the cnn_vtl conv2 layer: 1.54 ms with the
+  // 32-column stores, 1.31 ms with the store instructions removed). Rows beyond M are clipped by the tensor map.
   int use_tma_store;
-  alignas(64) CUtensorMap tm_out_hi;
+  alignas(64) CUtensorMap tm_out_hi;    // 32 x 32 box
   alignas(64) CUtensorMap tm_out_lo;
+  alignas(64) CUtensorMap tm_out_hi64;  // 32 rows x 64 columns
+  alignas(64) CUtensorMap tm_out_lo64;
   // cv_a_lo_zero: the A operand is exact in fp16, no residual plane (any BiasActPolicy)
   // ---- CONV only (cnn_vtl): implicit-GEMM A operand, see gemm_sm100.cuh (policy_im2col_a)
   int cv_implicit, cv_a_lo_zero, cv_ohw, cv_ow, cv_pad_t, cv_pad_l, cv_kw, cv_cblocks;
@@ -41,7 +49,8 @@ struct BiasActParams {
   int* mm;  // [images, 2]
 };
 
-// Tensor maps of the plane outputs for the epilogue's staged TMA stores: box = 32 columns x 32 rows, SWIZZLE_64B.
+// Tensor maps of the plane outputs for the epilogue's staged TMA stores: boxes of 32 rows x 32 columns (SWIZZLE_64B)
+// and 32 rows x 64 columns (SWIZZLE_128B).
 extern std::atomic<int> g_tma_store;  // planes.cu
 inline bool attach_plane_store_maps(BiasActParams& p) {
   p.use_tma_store = 0;
@@ -50,6 +59,11 @@ inline bool attach_plane_store_maps(BiasActParams& p) {
   p.tm_out_lo = p.tm_out_hi;
   if (p.out_lo && p.ab_fmt != 1 &&
       !make_tmap_k_major(&p.tm_out_lo, p.out_lo, p.ab_fmt, p.out_plane_ld, p.M, p.out_plane_ld, 32, 32))
+    return false;
+  if (!make_tmap_k_major(&p.tm_out_hi64, p.out_hi, p.ab_fmt, p.out_plane_ld, p.M, p.out_plane_ld, 64, 32)) return false;
+  p.tm_out_lo64 = p.tm_out_hi64;
+  if (p.out_lo && p.ab_fmt != 1 &&
+      !make_tmap_k_major(&p.tm_out_lo64, p.out_lo, p.ab_fmt, p.out_plane_ld, p.M, p.out_plane_ld, 64, 32))
     return false;
   p.use_tma_store = 1;
   return true;
@@ -76,7 +90,8 @@ struct BiasActPolicy {
   using Params = BiasActParams;
   static constexpr bool kIm2colA = CONV;
   static constexpr bool kAltTiles = CONV;
-  static constexpr int kScratchBytes = 8 * 4096;  // per epilogue warp: a hi and a lo staging tile of 32 x 64 bytes
+  static constexpr int kStageBytes = DLC_WIDE_STORE ? 8192 : 4096;  // per epilogue warp: a hi and a lo staging tile
+  static constexpr int kScratchBytes = 8 * kStageBytes;
   static constexpr bool kPromote = NPROD == 3;  // the high-precision mode also needs accurate accumulation
   static constexpr int kEpiWarps = 4;
   static __device__ __forceinline__ bool enabled(const Params&) { return true; }
@@ -113,10 +128,10 @@ struct BiasActPolicy {
   struct Epilogue {
     const Params& p;
     const int quarter, lane;
-    uint8_t* stage;  // this warp's staging tiles: hi at +0, lo at +2048
+    uint8_t* stage;  // this warp's staging tiles: hi at +0, lo at +kStageBytes / 2
     __device__ Epilogue(const Params& p_, int quarter_, int half_, int lane_, void* scratch)
         : p(p_), quarter(quarter_), lane(lane_),
-          stage(static_cast<uint8_t*>(scratch) + (half_ * 4 + quarter_) * 4096) {}
+          stage(static_cast<uint8_t*>(scratch) + (half_ * 4 + quarter_) * kStageBytes) {}
 
     int row;
     bool row_ok;
@@ -211,7 +226,7 @@ struct BiasActPolicy {
       }
       if (row_ok) {
         if (CONV) {
-          if (p.mm) {
+          if (p.mm && !(p.dbg & 8)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               t_lo = fminf(t_lo, h[j]);
@@ -249,11 +264,7 @@ struct BiasActPolicy {
               wh[j] = pack_bf2(a, b);
               wl[j] = 0u;
             } else {
-              __half h0, l0, h1, l1;
-              split_f32(a, h0, l0);
-              split_f32(b, h1, l1);
-              wh[j] = pack_h2(h0, h1);
-              wl[j] = pack_h2(l0, l1);
+              split_f32x2(a, b, wh[j], wl[j]);
             }
           }
           vh = make_uint4(wh[0], wh[1], wh[2], wh[3]);
@@ -274,25 +285,51 @@ struct BiasActPolicy {
           }
           return;
         }
-        // ---- staged TMA store (all 32 lanes take part; rows beyond M are clipped by the tensor map)
+        // ---- staged TMA store (all 32 lanes take part; rows beyond M are clipped by the tensor map).
+        // Contract with the kernels: the warp that handles an even chunk of a tile also handles the next odd one.
+        constexpr int kLo = kStageBytes / 2;
+        const bool odd = DLC_WIDE_STORE && (c & 1) != 0;
+        const bool partner = DLC_WIDE_STORE && !odd && (c + 1) * 32 < p.n_tile && col0 + 32 < p.out_plane_ld;
+        const bool wide = odd || partner;
+        if (!odd) {  // a new staging tile: the previous store of this warp has left the buffer
+          if (lane == 0 && store_pending && !(p.dbg & 4)) tma_store_wait_read();
+          __syncwarp();
+        }
         store_pending = true;
-        if (lane == 0) tma_store_wait_read();  // the previous tile of this warp has left the staging buffer
-        __syncwarp();
-        const int sw = (lane >> 1) & 3;         // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+        if (wide) {
+          const int sw = lane & 7;                // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+          const int q0 = odd ? 4 : 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 vh, vl;
-          pack8(q, vh, vl);
-          const int pos = (q ^ sw) * 16;
-          *reinterpret_cast<uint4*>(stage + lane * 64 + pos) = vh;
-          if (want_lo) *reinterpret_cast<uint4*>(stage + 2048 + lane * 64 + pos) = vl;
+          for (int q = 0; q < 4; ++q) {
+            uint4 vh, vl;
+            pack8(q, vh, vl);
+            const int pos = ((q0 + q) ^ sw) * 16;
+            *reinterpret_cast<uint4*>(stage + lane * 128 + pos) = vh;
+            if (want_lo) *reinterpret_cast<uint4*>(stage + kLo + lane * 128 + pos) = vl;
+          }
+          if (!odd) return;                       // the partner chunk completes the rows and issues the store
+        } else {
+          const int sw = (lane >> 1) & 3;         // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 vh, vl;
+            pack8(q, vh, vl);
+            const int pos = (q ^ sw) * 16;
+            *reinterpret_cast<uint4*>(stage + lane * 64 + pos) = vh;
+            if (want_lo) *reinterpret_cast<uint4*>(stage + kLo + lane * 64 + pos) = vl;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 4)) {
           const int row0 = row - lane;
-          tma_store_2d(&p.tm_out_hi, stage, col0, row0);
-          if (want_lo) tma_store_2d(&p.tm_out_lo, stage + 2048, col0, row0);
+          if (wide) {
+            tma_store_2d(&p.tm_out_hi64, stage, col0 - 32, row0);
+            if (want_lo) tma_store_2d(&p.tm_out_lo64, stage + kLo, col0 - 32, row0);
+          } else {
+            tma_store_2d(&p.tm_out_hi, stage, col0, row0);
+            if (want_lo) tma_store_2d(&p.tm_out_lo, stage + kLo, col0, row0);
+          }
           tma_store_commit();
         }
       }

@@ -16,11 +16,14 @@
 #include <vector>
 
 #include "bias_act.cuh"
+#include "gemm_pair_sm100.cuh"
 #include "util.h"
 
 namespace dlc {
 
 extern std::atomic<int> g_promote_k;  // planes.cu: K elements accumulated in TMEM before promotion to fp32 registers
+extern std::atomic<int> g_cta_pair;   // planes.cu: CTA-pair kernels (0 never, 1 when the GPU is filled, 2 always)
+int gemm_debug_flags();               // planes.cu
 
 // x planes [N*H*W, ld_in] -> im2col planes [N*OH*OW, ld]; column = (kh*KW + kw)*C + c; 8 columns per thread.
 __global__ void __launch_bounds__(256)
@@ -628,9 +631,19 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   if (ok && split && a_lo)
     ok = make_tmap_im2col_nhwc(&ta1, a_lo, 0, n, g.H, g.W, g.vcin, g.in_ld, g.vkh, g.vkw, g.pad_t, g.pad_l, g.pad_b,
                                g.pad_r, BK);
-  if (ok) ok = make_tmap_k_major(&tb0, h->w_hi[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
+  // CTA pairs (three-product policies): every conv layer is bound by L2 -> SM operand traffic on a single CTA
+  // (conv1: the whole 221 KB weight set per 128-pixel tile = 8.2 GB per 1063 frames at the ~12 TB/s the L2 delivers;
+  // ncu: tensor pipe 46 %); a pair stages each half of the weight tile once for 256 pixels.
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pair_mode = g_cta_pair.load();
+  // conv1 stays on the single-CTA kernel: its short K (576) makes it epilogue-bound, and there the alternate-tile
+  // epilogue (two warp groups, one tile each) beats the pair's column split (0.67 vs 0.71 ms per 1063 frames)
+  const bool pairs = split && pair_mode && p.n_tile % 32 == 0 &&
+                     ((pair_tiles >= sm_count() / 2 && g.k_ld > 1024) || pair_mode == 2);
+  const int b_rows = pairs ? p.n_tile / 2 : p.n_tile;
+  if (ok) ok = make_tmap_k_major(&tb0, h->w_hi[l], 0, g.k_ld, s.cout, g.k_ld, BK, b_rows);
   tb1 = tb0;
-  if (ok && split) ok = make_tmap_k_major(&tb1, h->w_lo[l], 0, g.k_ld, s.cout, g.k_ld, BK, p.n_tile);
+  if (ok && split) ok = make_tmap_k_major(&tb1, h->w_lo[l], 0, g.k_ld, s.cout, g.k_ld, BK, b_rows);
   if (!ok) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed for conv%d", l + 1);
   p.k_blocks = g.k_ld / BK;
   // a short K range (conv1: 576) is accumulated in one TMEM pass, which also enables the alternate-tile epilogue
@@ -638,7 +651,13 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   if (!attach_plane_store_maps(p)) return fail(DLC_ECUDA, "dlc_cnnvtl_forward: tensor map encoding failed (outputs)");
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  cudaError_t e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  cudaError_t e;
+  if constexpr (split) {
+    if (pairs) e = launch_gemm_pair<Policy>(ta0, ta1, tb0, tb1, p, std::min(pair_tiles, sm_count() / 2), stream);
+    else e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  } else {
+    e = launch_gemm<Policy>(ta0, ta1, tb0, tb1, p, grid, stream);
+  }
   if (e != cudaSuccess)
     return fail(DLC_ECUDA, "dlc_cnnvtl_forward: conv%d launch failed: %s", l + 1, cudaGetErrorString(e));
   return DLC_OK;
@@ -727,6 +746,7 @@ extern "C" int dlc_cnnvtl_forward(dlc_cnnvtl* h, const void* x_dev, int x_dtype,
     p.cv_kw = g.vkw;
     p.cv_cblocks = g.c_pad / g.bk;
     p.mm = out_dev ? mm : nullptr;
+    p.dbg = gemm_debug_flags();
     int rc;
     if (split && g.bk == 64) rc = run_conv<BiasActPolicy<64, 3, true>>(h, l, n, in_hi, in_lo, p, s);
     else if (split) rc = run_conv<BiasActPolicy<32, 3, true>>(h, l, n, in_hi, in_lo, p, s);

@@ -28,7 +28,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   static_assert(Cfg::NPROD == 3 ? Policy::kPromote : !Policy::kPromote,
                 "3-product policies use two-level accumulation, 1-product policies plain accumulation");
   constexpr int kPl = Cfg::kPlanes;
-  static_assert(!policy_im2col_a<Policy>::value, "implicit-GEMM operands are not supported by the pair kernel");
+  // implicit-GEMM (im2col) A operands: each CTA walks its own 128 output pixels. The column chunks are then split
+  // between the two epilogue warp groups at an even chunk near the middle (conv1: 3 chunks -> 2 + 1) instead of at
+  // chunk 4, so that narrow accumulators keep both groups busy; even, because the bias/activation epilogue stores
+  // chunk pairs.
+  constexpr bool kConv = policy_im2col_a<Policy>::value;
   constexpr int BK = Cfg::BK;
   constexpr int SMAX = Cfg::kMaxStages;
   constexpr int kEpiWarps = 8;
@@ -108,13 +112,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const TileCoord tc = Policy::tile_pair(p, cluster, nclusters, i);  // tc.mt = the pair's FIRST 128-row tile
           const int m0 = (tc.mt + static_cast<int>(rank)) * kTileM;
           const int n0 = tc.nt * n_tile + static_cast<int>(rank) * half_n;
+          // implicit-GEMM A operand: first output pixel of this CTA's rows -> base input pixel (w, h, image)
+          int cv_w = 0, cv_h = 0, cv_n = 0, cv_kh = 0, cv_kwi = 0, cv_cb = 0;
+          if constexpr (kConv) {
+            cv_n = m0 / p.cv_ohw;
+            const int rem = m0 - cv_n * p.cv_ohw;
+            const int oh = rem / p.cv_ow;
+            cv_h = oh - p.cv_pad_t;
+            cv_w = rem - oh * p.cv_ow - p.cv_pad_l;
+          }
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1u, 1);
             const uint32_t lbar = mapa_shared(&full[stage], 0);
             if (leader) mbar_arrive_expect_tx(&full[stage], tx_pair);
             uint8_t* st = smem + stage * stage_bytes;
             uint8_t* sb = st + a_planes * Cfg::kABytes;
-            if constexpr (policy_frame_maps<Policy>::value) {  // operands stored P rows per frame, see gemm_sm100.cuh
+            if constexpr (kConv) {
+              const uint16_t off_h = static_cast<uint16_t>(cv_kh), off_w = static_cast<uint16_t>(cv_kwi);
+              tma_load_im2col_4d_pair(st, &tmA0, lbar, cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
+              if (kPl == 2 && !a_lo_zero)
+                tma_load_im2col_4d_pair(st + Cfg::kABytes, &tmA1, lbar, cv_cb * BK, cv_w, cv_h, cv_n, off_w, off_h);
+              if (++cv_cb == p.cv_cblocks) {
+                cv_cb = 0;
+                if (++cv_kwi == p.cv_kw) {
+                  cv_kwi = 0;
+                  ++cv_kh;
+                }
+              }
+              tma_load_2d_pair(sb, &tmB0, lbar, kb * BK, n0, Policy::kHintB);
+              if (kPl == 2) tma_load_2d_pair(sb + b_plane_bytes, &tmB1, lbar, kb * BK, n0, Policy::kHintB);
+            } else if constexpr (policy_frame_maps<Policy>::value) {  // operands stored P rows per frame, see gemm_sm100.cuh
               tma_load_3d_pair(st, &tmA0, lbar, kb * BK, 0, m0 >> 5, Policy::kHintA);
               if (kPl == 2 && !a_lo_zero)
                 tma_load_3d_pair(st + Cfg::kABytes, &tmA1, lbar, kb * BK, 0, m0 >> 5, Policy::kHintA);
@@ -200,6 +227,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int cstride = policy_chunk_stride<Policy>::get(p);
     const int n_cchunks = n_tile / cstride;
     typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
+    // this warp group's chunks [c_first, c_first + c_count), at most 4
+    const int c_split = kConv ? min(n_cchunks, 2 * ((n_cchunks + 3) / 4)) : min(n_cchunks, 4);
+    const int c_first = half ? c_split : 0;
+    const int c_count = half ? n_cchunks - c_split : c_split;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int i = 0; i < my_tiles; ++i) {
@@ -210,11 +241,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         mbar_wait(&tfull[acc], acc_phase, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kMaxTileN) +
-                               (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(half * 4 * cstride);
+                               (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c_first * cstride);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          if (half * 4 + cc < n_cchunks) {
+          if (cc < c_count) {
             uint32_t v[32];
             tmem_ld_x32(taddr + cc * cstride, v);
             tmem_ld_wait();
@@ -235,10 +265,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       epi.begin_tile(tc);
       using Epi = typename Policy::Epilogue;
-      epi_slot_from_regs<Epi, 0>(epi, tc, sums, half, n_cchunks);
-      epi_slot_from_regs<Epi, 1>(epi, tc, sums, half, n_cchunks);
-      epi_slot_from_regs<Epi, 2>(epi, tc, sums, half, n_cchunks);
-      epi_slot_from_regs<Epi, 3>(epi, tc, sums, half, n_cchunks);
+      epi_slot_from_regs_at<Epi, 0>(epi, tc, sums, c_first, c_count);
+      epi_slot_from_regs_at<Epi, 1>(epi, tc, sums, c_first, c_count);
+      epi_slot_from_regs_at<Epi, 2>(epi, tc, sums, c_first, c_count);
+      epi_slot_from_regs_at<Epi, 3>(epi, tc, sums, c_first, c_count);
       epi.end_tile(tc);
       epi.post_tile(tc);
     }

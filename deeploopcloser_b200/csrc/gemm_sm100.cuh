@@ -198,6 +198,17 @@ __device__ __forceinline__ void epi_slot_from_regs(Epi& epi, TileCoord tc, const
     epi.template chunk<SLOT>(tc, c, v);
   }
 }
+// chunk c = first + SLOT for SLOT < count (the pair kernel's assignment)
+template <class Epi, int SLOT>
+__device__ __forceinline__ void epi_slot_from_regs_at(Epi& epi, TileCoord tc, const float (&sums)[128], int first,
+                                                      int count) {
+  if (SLOT < count) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = sums[SLOT * 32 + j];
+    epi.template chunk<SLOT>(tc, first + SLOT, v);
+  }
+}
 
 template <class Policy>
 __global__ void __launch_bounds__(gemm_threads<Policy>(), 1)
@@ -455,10 +466,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         epi.begin_tile(tc);
         using Epi = typename Policy::Epilogue;
-        epi_slot_from_regs<Epi, 0>(epi, tc, sums, col_half, n_cchunks);
-        epi_slot_from_regs<Epi, 1>(epi, tc, sums, col_half, n_cchunks);
-        epi_slot_from_regs<Epi, 2>(epi, tc, sums, col_half, n_cchunks);
-        epi_slot_from_regs<Epi, 3>(epi, tc, sums, col_half, n_cchunks);
+        bool rolled = false;
+        if constexpr (policy_alt_tiles<Policy>::value) rolled = alt_tiles;
+        if (rolled) {
+          // Narrow accumulator, short K (conv1): the MMA of a tile is brief and the epilogue is a latency chain of
+          // straight-line code that never repeats within a tile - ncu showed `no_instruction` among the top stalls.
+          // ONE copy of the chunk code, executed per chunk; the running sums rotate down by 32 registers.
+#pragma unroll 1
+          for (int cc = 0; cc < n_cchunks; ++cc) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sums[j];
+            epi.template chunk<0>(tc, cc, v);
+#pragma unroll
+            for (int j = 0; j < 96; ++j) sums[j] = sums[j + 32];
+          }
+        } else {
+          epi_slot_from_regs<Epi, 0>(epi, tc, sums, col_half, n_cchunks);
+          epi_slot_from_regs<Epi, 1>(epi, tc, sums, col_half, n_cchunks);
+          epi_slot_from_regs<Epi, 2>(epi, tc, sums, col_half, n_cchunks);
+          epi_slot_from_regs<Epi, 3>(epi, tc, sums, col_half, n_cchunks);
+        }
         epi.end_tile(tc);
         epi.post_tile(tc);
       } else {

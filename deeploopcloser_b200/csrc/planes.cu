@@ -156,6 +156,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
 // for translation units that do not include the GEMM headers (sda.cu)
 int device_sm_count() { return sm_count(); }
 bool gemm_pairs_enabled() { return g_cta_pair.load() != 0; }
+int gemm_debug_flags() { return g_dbg_flags.load(); }  // developer A/B switches of the epilogue (dlc_debug_set key 3)
 
 }  // namespace dlc
 

@@ -236,6 +236,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// im2col-mode load (see tma_load_im2col_4d) into THIS CTA's shared memory, completion counted on the pair leader's barrier
+__device__ __forceinline__ void tma_load_im2col_4d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar,
+                                                        int c0, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.cta_group::2"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
                                                  int c1, int c2, uint64_t hint) {
   asm volatile(
@@ -320,6 +329,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
+}
+// Two values at once with the packed conversion (cvt.rn.f16x2.f32: one instruction per pair instead of two F2F and a
+// byte permute); same bits as split_f32 on each value. hi2 / lo2 = {a in the low half, b in the high half}.
+__device__ __forceinline__ void split_f32x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ void split_f64(double x, __half& hi, __half& lo) {
   hi = __double2half(x);

@@ -1,5 +1,8 @@
-set -x
-timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "encoder or sda" 2>&1 | tail -5
-timeout 200 python tools/bench_overlap_1gpu.py --weights normal > gpurun_out/r2_overlap_normal.json 2> gpurun_out/r2_overlap_normal.err; cat gpurun_out/r2_overlap_normal.json; tail -3 gpurun_out/r2_overlap_normal.err
-timeout 200 python tools/bench_overlap_1gpu.py --weights xavier > gpurun_out/r2_overlap_xavier.json 2> gpurun_out/r2_overlap_xavier.err; cat gpurun_out/r2_overlap_xavier.json; tail -3 gpurun_out/r2_overlap_xavier.err
-timeout 200 python bench.py --config 5 --no-cpu-baseline > gpurun_out/r2_config5_wave.json 2> gpurun_out/r2_config5_wave.err; tail -c 700 gpurun_out/r2_config5_wave.json; tail -3 gpurun_out/r2_config5_wave.err
+for i in 1 2; do
+for L in "" "/root/repo/deeploopcloser_b200/libdlc_ab.so"; do
+echo "== lib=$L"
+DLC_LIB_PATH=$L timeout 300 python bench.py --headline-only --one-arm --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print(round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages_ms'].items()})"
+DLC_LIB_PATH=$L timeout 200 python tools/bench_cnnvtl.py 2>&1 | tail -1 | cut -c1-130
+done; done

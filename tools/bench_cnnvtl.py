@@ -18,6 +18,9 @@ from deeploopcloser_b200.cnn_vtl import CnnVtl  # noqa: E402
 N, H, W = 1063, 192, 240
 chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 1063
 precision = sys.argv[2] if len(sys.argv) > 2 else "fp16x2"
+if os.environ.get("DLC_CTA_PAIR"):            # A/B: 0 = single-CTA conv kernels, 1 = CTA pairs (default)
+    from deeploopcloser_b200 import _lib
+    _lib.call("dlc_debug_set", 6, int(os.environ["DLC_CTA_PAIR"]))
 net = CnnVtl(input_shape=[N, H, W, 3], weights="synthetic", seed=4, precision=precision)
 x = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, device="cuda")
 
