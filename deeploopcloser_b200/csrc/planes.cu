@@ -162,6 +162,9 @@ int gemm_debug_flags() { return g_dbg_flags.load(); }  // developer A/B switches
 
 using namespace dlc;
 extern std::atomic<int> g_probe_side_stream;  // sdav_sim.cu
+namespace dlc {
+extern std::atomic<int> g_surf_fast;  // surf.cu
+}
 
 extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 * 64; }
 
@@ -196,6 +199,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 9) {  // 0: the similarity precision probe runs on the caller's stream instead of its side stream
     g_probe_side_stream = value ? 1 : 0;
+    return DLC_OK;
+  }
+  if (key == 10) {  // 0: the keypoint detector always uses its generic octave kernel
+    g_surf_fast = value ? 1 : 0;
     return DLC_OK;
   }
   if (key == 8) {  // capacity of the deferred-refinement list of the SDAV score kernel (-1: default, 0: refine in place)

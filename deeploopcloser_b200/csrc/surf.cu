@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "util.h"
 
@@ -215,37 +216,14 @@ __device__ bool orientation_samplable(float x, float y, float size, int H, int W
   return false;
 }
 
-// One octave, fused: a CTA evaluates the determinant of all layers on a tile of kSurfTile x kSurfTile samples plus a
-// one-sample halo into shared memory (the layers never go to HBM), then finds the maxima of the middle layers there.
 constexpr int kSurfTile = 32;
 constexpr int kSurfHalo = kSurfTile + 2;
-__global__ void __launch_bounds__(256)
-surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
-                   float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ count) {
-  extern __shared__ float s_det[];   // [oc.n][kSurfHalo][kSurfHalo]
-  const int b = blockIdx.z;
-  const int tiles_x = (oc.cols + kSurfTile - 1) / kSurfTile;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int i0 = ty * kSurfTile - 1, j0 = tx * kSurfTile - 1;   // sample coordinates of the halo's corner
-  const int pitch = W + 1;
-  const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
+// Phase 2 of an octave kernel: the determinant layers of the tile (+ halo) are in shared memory; find the strict
+// 3x3x3 maxima of the middle layers, interpolate, test the orientation window, append to the frame's candidate list.
+__device__ __forceinline__ void surf_tile_maxima(const float* __restrict__ s_det, const SurfOctave& oc, int i0, int j0,
+                                                 int b, int octave, float thr, int H, int W, float4* __restrict__ cand,
+                                                 unsigned long long* __restrict__ keys, int* __restrict__ count) {
   constexpr int kCells = kSurfHalo * kSurfHalo;
-  // layer outermost and unrolled: the layer's offsets and weights are then direct parameter-bank operands
-#pragma unroll
-  for (int l = 0; l < kSurfMaxLayers; ++l) {
-    if (l < oc.n) {
-      const SurfLayer& L = oc.layer[l];
-      for (int rc = threadIdx.x; rc < kCells; rc += blockDim.x) {
-        const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
-        const int i = i0 + r - L.margin, j = j0 + c - L.margin;  // filter origin in samples
-        float v = 0.0f;                                          // the filter does not fit here
-        if (i >= 0 && i < L.ni && j >= 0 && j < L.nj)
-          v = det_at(reinterpret_cast<const char*>(frame + (i * pitch + j) * oc.step), L);
-        s_det[l * kCells + rc] = v;
-      }
-    }
-  }
-  __syncthreads();
   for (int e = threadIdx.x; e < (oc.n - 2) * kSurfTile * kSurfTile; e += blockDim.x) {
     const int l = 1 + e / (kSurfTile * kSurfTile);             // middle layers 1 .. n - 2
     const int rc = e % (kSurfTile * kSurfTile);
@@ -311,6 +289,193 @@ surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_c
     keys[static_cast<int64_t>(b) * kSurfCap + slot] =
         (static_cast<unsigned long long>(__float_as_uint(val0)) << 32) | static_cast<unsigned long long>(~order);
   }
+}
+
+// One octave, fused: a CTA evaluates the determinant of all layers on a tile of kSurfTile x kSurfTile samples plus a
+// one-sample halo into shared memory (the layers never go to HBM), then finds the maxima of the middle layers there.
+__global__ void __launch_bounds__(256)
+surf_octave_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
+                   float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys, int* __restrict__ count) {
+  extern __shared__ float s_det[];   // [oc.n][kSurfHalo][kSurfHalo]
+  const int b = blockIdx.z;
+  const int tiles_x = (oc.cols + kSurfTile - 1) / kSurfTile;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int i0 = ty * kSurfTile - 1, j0 = tx * kSurfTile - 1;   // sample coordinates of the halo's corner
+  const int pitch = W + 1;
+  const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
+  constexpr int kCells = kSurfHalo * kSurfHalo;
+  // layer outermost and unrolled: the layer's offsets and weights are then direct parameter-bank operands
+#pragma unroll
+  for (int l = 0; l < kSurfMaxLayers; ++l) {
+    if (l < oc.n) {
+      const SurfLayer& L = oc.layer[l];
+      for (int rc = threadIdx.x; rc < kCells; rc += blockDim.x) {
+        const int r = rc / kSurfHalo, c = rc - r * kSurfHalo;
+        const int i = i0 + r - L.margin, j = j0 + c - L.margin;  // filter origin in samples
+        float v = 0.0f;                                          // the filter does not fit here
+        if (i >= 0 && i < L.ni && j >= 0 && j < L.nj)
+          v = det_at(reinterpret_cast<const char*>(frame + (i * pitch + j) * oc.step), L);
+        s_det[l * kCells + rc] = v;
+      }
+    }
+  }
+  __syncthreads();
+  surf_tile_maxima(s_det, oc, i0, j0, b, octave, thr, H, W, cand, keys, count);
+}
+
+// ---------------------------------------------------------------- octaves 0 and 1 of the default pyramid
+// The generic kernel above is bound by instruction issue: every integral-image lookup costs a 64-bit address add (two
+// instructions) and a global load. With the default pyramid (3 layers per octave: filter sizes (9 + 6 l) << octave)
+// the box corners are compile-time constants, so this kernel first copies the integral-image region under the tile
+// (+ halo + filter extent) into shared memory and then reads every corner with ONE instruction (LDS [cell + imm]).
+// For step 2 the region is stored as 2 x 2 parity planes (pixel (y, x) -> plane (y & 1, x & 1), position (y >> 1,
+// x >> 1)): the 32 lanes of a warp are consecutive SAMPLES, i.e. every second pixel, and a box corner has a fixed
+// parity, so the lanes still read consecutive words. Box sums stay exact int32 and the float operations are the same
+// intrinsics in the same order as det_at(): identical bits (tests/test_gpu_kernels.py::test_surf_detect_equals_oracle).
+// dlc_surf_detect uses it when the runtime plan equals the compile-time tables (surf_fast_ok), else the generic kernel.
+constexpr int kFastLayers = 5;                       // n_layers = 3 (+ 2)
+constexpr int kFastMaxMargin = 16;                   // margin of the widest layer (size 33 << o): (33 / 2)
+constexpr int kFastPD = 67;                          // plane dimension: ((33 + 33) * step + 1 pixels) / step, rounded up
+__host__ __device__ constexpr int fast_cr(int x, int size) { return (2 * x * size + 9) / 18; }   // cvRound(size / 9.f * x): never a tie
+__host__ __device__ constexpr int fast_size(int step, int l) { return (9 + 6 * l) * step; }
+__host__ __device__ constexpr int fast_margin(int step, int l) { return (fast_size(step, l) / 2) / step; }
+// word offset (relative to the cell's base word) of the integral-image pixel (dy, dx) of layer l's filter window
+template <int STEP, int LAYER>
+__device__ __forceinline__ constexpr int fast_off(int dy, int dx) {
+  constexpr int add = kFastMaxMargin - fast_margin(STEP, LAYER);
+  return (((dy % STEP) * STEP + (dx % STEP)) * kFastPD + (add + dy / STEP)) * kFastPD + (add + dx / STEP);
+}
+template <int STEP, int LAYER>
+__device__ __forceinline__ float det_fast(const int32_t* __restrict__ cell, const SurfLayer& L) {
+  constexpr int S = fast_size(STEP, LAYER);
+  constexpr int e0 = fast_cr(0, S), e3 = fast_cr(3, S), e6 = fast_cr(6, S), e9 = fast_cr(9, S);   // lobe edges
+  constexpr int b2 = fast_cr(2, S), b7 = fast_cr(7, S);                                           // band edges
+  constexpr int g1 = fast_cr(1, S), g4 = fast_cr(4, S), g5 = fast_cr(5, S), g8 = fast_cr(8, S);   // Dxy grid
+#define SURF_F(dy, dx) cell[fast_off<STEP, LAYER>(dy, dx)]
+  int box[4];
+  float w[4];
+  {
+    // int32 arithmetic is exact (and wraps like the reference's): regrouped as column differences, 7 subtractions
+    const int d[4] = {SURF_F(b7, e0) - SURF_F(b2, e0), SURF_F(b7, e3) - SURF_F(b2, e3), SURF_F(b7, e6) - SURF_F(b2, e6),
+                      SURF_F(b7, e9) - SURF_F(b2, e9)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      box[k] = d[k + 1] - d[k];
+      w[k] = L.dx[k].w;
+    }
+  }
+  const float dx = haar_acc(box, w, 3);
+  {
+    const int d[4] = {SURF_F(e0, b7) - SURF_F(e0, b2), SURF_F(e3, b7) - SURF_F(e3, b2), SURF_F(e6, b7) - SURF_F(e6, b2),
+                      SURF_F(e9, b7) - SURF_F(e9, b2)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      box[k] = d[k + 1] - d[k];
+      w[k] = L.dy[k].w;
+    }
+  }
+  const float dy = haar_acc(box, w, 3);
+  {
+    const int g[4][4] = {{SURF_F(g1, g1), SURF_F(g1, g4), SURF_F(g1, g5), SURF_F(g1, g8)},
+                         {SURF_F(g4, g1), SURF_F(g4, g4), SURF_F(g4, g5), SURF_F(g4, g8)},
+                         {SURF_F(g5, g1), SURF_F(g5, g4), SURF_F(g5, g5), SURF_F(g5, g8)},
+                         {SURF_F(g8, g1), SURF_F(g8, g4), SURF_F(g8, g5), SURF_F(g8, g8)}};
+    box[0] = (g[1][1] - g[1][0]) - (g[0][1] - g[0][0]);
+    box[1] = (g[1][3] - g[1][2]) - (g[0][3] - g[0][2]);
+    box[2] = (g[3][1] - g[3][0]) - (g[2][1] - g[2][0]);
+    box[3] = (g[3][3] - g[3][2]) - (g[2][3] - g[2][2]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = L.dxy[k].w;
+  }
+  const float dxy = haar_acc(box, w, 4);
+#undef SURF_F
+  return __fsub_rn(__fmul_rn(dx, dy), __fmul_rn(__fmul_rn(0.81f, dxy), dxy));
+}
+template <int STEP, int LAYER>
+__device__ __forceinline__ void det_fast_cell(const int32_t* __restrict__ cell, const SurfOctave& oc, int i_halo, int j_halo,
+                                              float* __restrict__ out) {
+  const SurfLayer& L = oc.layer[LAYER];
+  const int i = i_halo - fast_margin(STEP, LAYER), j = j_halo - fast_margin(STEP, LAYER);   // filter origin (samples)
+  float v = 0.0f;
+  if (i >= 0 && i < L.ni && j >= 0 && j < L.nj) v = det_fast<STEP, LAYER>(cell, L);
+  out[LAYER * kSurfHalo * kSurfHalo] = v;
+}
+
+template <int STEP>
+__global__ void __launch_bounds__(256, 2)
+surf_octave_fast_kernel(const int32_t* __restrict__ sum, int H, int W, const __grid_constant__ SurfOctave oc, int octave,
+                        float thr, float4* __restrict__ cand, unsigned long long* __restrict__ keys,
+                        int* __restrict__ count) {
+  extern __shared__ float s_det[];   // [kFastLayers][kSurfHalo][kSurfHalo], then the integral-image planes
+  constexpr int kCells = kSurfHalo * kSurfHalo;
+  constexpr int kLog = STEP == 1 ? 0 : 1;
+  static_assert(STEP == 1 || STEP == 2, "octaves 0 and 1");
+  int32_t* s_int = reinterpret_cast<int32_t*>(s_det + kFastLayers * kCells);   // [STEP * STEP][kFastPD][kFastPD]
+  const int b = blockIdx.z;
+  const int tiles_x = (oc.cols + kSurfTile - 1) / kSurfTile;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int i0 = ty * kSurfTile - 1, j0 = tx * kSurfTile - 1;   // sample coordinates of the halo's corner
+  const int pitch = W + 1;
+  const int32_t* frame = sum + static_cast<int64_t>(b) * (H + 1) * pitch;
+  // ---- the region: pixels [yb, yb + E) x [xb, xb + E), E = 66 * STEP + 1 (zeros outside the integral image)
+  constexpr int E = 66 * STEP + 1;
+  const int yb = (i0 - kFastMaxMargin) * STEP, xb = (j0 - kFastMaxMargin) * STEP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // two rows x all column groups per pass: 2 * kColIters independent loads in flight per thread
+  constexpr int kColIters = (E + 31) / 32;
+  for (int yr0 = 2 * warp; yr0 < E; yr0 += 16) {
+    int v[2][kColIters];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int yr = yr0 + dy, y = yb + yr;
+      const bool y_ok = yr < E && y >= 0 && y <= H;
+      const int32_t* src = frame + static_cast<int64_t>(y) * pitch + xb;
+#pragma unroll
+      for (int k = 0; k < kColIters; ++k) {
+        const int xr = k * 32 + lane, x = xb + xr;
+        v[dy][k] = (y_ok && xr < E && x >= 0 && x <= W) ? __ldg(src + xr) : 0;
+      }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int yr = yr0 + dy;
+      int32_t* dst = s_int + (((yr & (STEP - 1)) * STEP) * kFastPD + (yr >> kLog)) * kFastPD;
+#pragma unroll
+      for (int k = 0; k < kColIters; ++k) {
+        const int xr = k * 32 + lane;
+        if (yr < E && xr < E) dst[(xr & (STEP - 1)) * (kFastPD * kFastPD) + (xr >> kLog)] = v[dy][k];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- determinants of the five layers on the 34 x 34 halo grid. A warp pass is one halo row, lanes = columns 0..31
+  // (consecutive words: no bank conflict whatever the pitch); the last two columns are done with lanes = rows
+  // (word stride kFastPD = 67 = 3 mod 32: conflict-free as well). 34 + 3 passes over 8 warps, 5 each at most.
+  for (int it = 0; it < 5; ++it) {
+    const int idx = warp + 8 * it;
+    int r, c;
+    if (idx < kSurfHalo) {
+      r = idx;
+      c = lane;
+    } else {
+      const int q = (idx - kSurfHalo) * 32 + lane;
+      if (idx >= kSurfHalo + 3 || q >= 2 * kSurfHalo) continue;
+      r = q % kSurfHalo;
+      c = 32 + q / kSurfHalo;
+    }
+    const int32_t* cell = s_int + r * kFastPD + c;
+    float* out = s_det + r * kSurfHalo + c;
+    det_fast_cell<STEP, 0>(cell, oc, i0 + r, j0 + c, out);
+    det_fast_cell<STEP, 1>(cell, oc, i0 + r, j0 + c, out);
+    det_fast_cell<STEP, 2>(cell, oc, i0 + r, j0 + c, out);
+    det_fast_cell<STEP, 3>(cell, oc, i0 + r, j0 + c, out);
+    det_fast_cell<STEP, 4>(cell, oc, i0 + r, j0 + c, out);
+  }
+  __syncthreads();
+  surf_tile_maxima(s_det, oc, i0, j0, b, octave, thr, H, W, cand, keys, count);
+}
+constexpr size_t surf_fast_smem(int step) {
+  return sizeof(float) * kFastLayers * kSurfHalo * kSurfHalo + sizeof(int32_t) * step * step * kFastPD * kFastPD;
 }
 
 // ---------------------------------------------------------------- n best per frame
@@ -459,6 +624,30 @@ static SurfPlan surf_plan(int B, int H, int W, int n_octaves, int n_layers) {
   return p;
 }
 
+// The compile-time tables of surf_octave_fast_kernel describe this octave of the runtime plan?
+static bool surf_fast_ok(const SurfOctave& oc, int octave) {
+  if (octave > 1 || oc.n != kFastLayers || oc.step != (1 << octave)) return false;
+  for (int l = 0; l < kFastLayers; ++l) {
+    const SurfLayer& L = oc.layer[l];
+    const int S = fast_size(oc.step, l);
+    if (L.size != S || L.margin != fast_margin(oc.step, l) || L.margin > kFastMaxMargin) return false;
+    const int e[4] = {fast_cr(0, S), fast_cr(3, S), fast_cr(6, S), fast_cr(9, S)};
+    const int b2 = fast_cr(2, S), b7 = fast_cr(7, S);
+    const int g[4] = {fast_cr(1, S), fast_cr(4, S), fast_cr(5, S), fast_cr(8, S)};
+    for (int k = 0; k < 3; ++k) {
+      if (L.dx[k].x1 != e[k] || L.dx[k].x2 != e[k + 1] || L.dx[k].y1 != b2 || L.dx[k].y2 != b7) return false;
+      if (L.dy[k].y1 != e[k] || L.dy[k].y2 != e[k + 1] || L.dy[k].x1 != b2 || L.dy[k].x2 != b7) return false;
+    }
+    for (int k = 0; k < 4; ++k) {
+      const int gx = (k & 1) * 2, gy = (k >> 1) * 2;
+      if (L.dxy[k].x1 != g[gx] || L.dxy[k].x2 != g[gx + 1] || L.dxy[k].y1 != g[gy] || L.dxy[k].y2 != g[gy + 1]) return false;
+    }
+    if (e[3] != S) return false;
+  }
+  return true;
+}
+std::atomic<int> g_surf_fast{1};  // dlc_debug_set key 10: 0 = always the generic octave kernel (developer A/B, tests)
+
 }  // namespace dlc
 
 using namespace dlc;
@@ -501,6 +690,24 @@ extern "C" int dlc_surf_detect(const uint8_t* img_dev, int B, int H, int W, floa
     const int cells = oc.rows * oc.cols;
     if (cells == 0) continue;
     const int tiles = ceil_div(oc.rows, kSurfTile) * ceil_div(oc.cols, kSurfTile);
+    if (g_surf_fast.load() && surf_fast_ok(oc, o)) {   // compile-time box tables + shared-memory lookups
+      if (o == 0) {
+        surf_octave_fast_kernel<1><<<dim3(tiles, 1, B), 256, surf_fast_smem(1), s>>>(sum, H, W, oc, o, hessian_threshold,
+                                                                                      cand, keys, count);
+      } else {
+        static std::atomic<bool> attr_set[64] = {};
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (!attr_set[dev].load(std::memory_order_acquire)) {
+          DLC_CUDA(cudaFuncSetAttribute(surf_octave_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(surf_fast_smem(2))));
+          attr_set[dev].store(true, std::memory_order_release);
+        }
+        surf_octave_fast_kernel<2><<<dim3(tiles, 1, B), 256, surf_fast_smem(2), s>>>(sum, H, W, oc, o, hessian_threshold,
+                                                                                      cand, keys, count);
+      }
+      continue;
+    }
     surf_octave_kernel<<<dim3(tiles, 1, B), 256, sizeof(float) * oc.n * kSurfHalo * kSurfHalo, s>>>(
         sum, H, W, oc, o, hessian_threshold, cand, keys, count);
   }

@@ -734,16 +734,22 @@ def _surf_frames(kind, B, H, W, seed):
 
 @pytest.mark.parametrize("kind,B,H,W", [("blobs", 3, 192, 240), ("noise", 2, 192, 240), ("blobs", 2, 101, 135),
                                         ("noise", 1, 50, 61), ("blobs", 1, 480, 640)])
-def test_surf_detect_equals_oracle(cuda, kind, B, H, W):
+@pytest.mark.parametrize("fast", [1, 0])
+def test_surf_detect_equals_oracle(cuda, kind, B, H, W, fast):
     """dlc_surf_detect == oracle/surf.py bit for bit: positions, sizes, responses, order and the keypoint count, for
     blob and noise frames, sizes that are not multiples of the sampling steps and frames too small for the upper
-    octaves."""
-    from deeploopcloser_b200 import ops
+    octaves. fast = 1: octaves 0 and 1 run the shared-memory kernel with compile-time box tables (the default);
+    fast = 0: every octave runs the generic kernel."""
+    from deeploopcloser_b200 import _lib, ops
     from oracle import surf
     frames = _surf_frames(kind, B, H, W, seed=H + B)
     n = 30
-    xy, info, found = ops.surf_detect(torch.from_numpy(frames).cuda(), top_n=n)
-    xy, info, found = xy.cpu().numpy(), info.cpu().numpy(), found.cpu().numpy()
+    _lib.call("dlc_debug_set", 10, fast)
+    try:
+        xy, info, found = ops.surf_detect(torch.from_numpy(frames).cuda(), top_n=n)
+        xy, info, found = xy.cpu().numpy(), info.cpu().numpy(), found.cpu().numpy()
+    finally:
+        _lib.call("dlc_debug_set", 10, 1)
     for b in range(B):
         all_kp = surf.detect(frames[b])
         ref = surf.top_n(all_kp, n)

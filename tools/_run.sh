@@ -1,8 +1,12 @@
-for i in 1 2; do
-for L in "" "/root/repo/deeploopcloser_b200/libdlc_ab.so"; do
-echo "== lib=$L"
-DLC_LIB_PATH=$L timeout 300 python bench.py --headline-only --one-arm --no-cpu-baseline 2>/dev/null | python -c "
-import sys,json
-d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print(round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages_ms'].items()})"
-DLC_LIB_PATH=$L timeout 200 python tools/bench_cnnvtl.py 2>&1 | tail -1 | cut -c1-130
-done; done
+timeout 900 python -m pytest tests -x -q -m gpu -k "surf" 2>&1 | tail -6
+timeout 300 python tools/bench_surf.py 2>&1 | tail -3 | cut -c1-200
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum --clock-control none -k regex:surf_octave -s 8 -c 4 --csv --log-file /tmp/l.csv python tools/bench_surf.py > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open('/tmp/l.csv')) if len(r)>10]
+h=rows[0]; i_k=h.index('Kernel Name'); i_m=h.index('Metric Name'); i_v=h.index('Metric Value'); i_id=h.index('ID')
+d={}
+for r in rows[1:]:
+    d.setdefault((r[i_id], r[i_k][:40]),{})[r[i_m][:34]]=r[i_v]
+for k,v in d.items(): print(k, v)
+PY
