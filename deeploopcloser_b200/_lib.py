@@ -35,6 +35,7 @@ PROTOTYPES = {
     "dlc_device_check": (_i, []),
     "dlc_sm_count": (_i, []),
     "dlc_debug_set": (_i, [_i, _i]),
+    "dlc_set_sm_reserve": (_i, [_i]),
     "dlc_sdav_debug_gram_only": (_i, [_i]),
     "dlc_plane_ld": (_i, [_i]),
     "dlc_split_planes": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),

@@ -647,7 +647,12 @@ inline cudaError_t launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, con
   return cudaGetLastError();
 }
 
-inline int sm_count() {  // of the CURRENT device (cached per device)
+// SMs the persistent kernels of this library size their grids for: the CURRENT device's count (cached per device)
+// minus dlc_set_sm_reserve(). A sequence split over GPUs reserves a few SMs so that the NCCL kernels of the exchange
+// stage - launched on another stream while a persistent tensor kernel holds every SM - start at once instead of
+// waiting for the running layer to end.
+extern std::atomic<int> g_sm_reserve;  // planes.cu
+inline int sm_count() {
   static std::atomic<int> cache[kMaxDevices] = {};
   const int dev = current_device();
   int n = cache[dev].load(std::memory_order_relaxed);
@@ -655,7 +660,8 @@ inline int sm_count() {  // of the CURRENT device (cached per device)
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cache[dev].store(n, std::memory_order_relaxed);
   }
-  return n;
+  const int keep = n - g_sm_reserve.load(std::memory_order_relaxed);
+  return keep < 2 ? 2 : keep & ~1;
 }
 
 }  // namespace dlc

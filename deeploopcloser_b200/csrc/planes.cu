@@ -92,6 +92,8 @@ thread_local int g_gemm_k_valid = 0;
 thread_local float g_gemm_alpha = 1.0f;
 std::atomic<int> g_tma_store{1};
 std::atomic<int> g_cta_pair{1};
+std::atomic<int> g_sm_reserve{0};   // dlc_set_sm_reserve
+std::atomic<int> g_wave_pad{1};     // dlc_debug_set key 11: the encoder picks its GEMM width per call (sda.cu gemm_pad)
 std::atomic<int> g_gram_pair{1};  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
 extern std::atomic<int> g_sim_mgroup;  // sdav_sim.cu
 extern std::atomic<int> g_refine_cap;  // sdav_sim.cu
@@ -156,6 +158,7 @@ static int run_bias_act(const void* a_hi, const void* a_lo, const void* b_hi, co
 // for translation units that do not include the GEMM headers (sda.cu)
 int device_sm_count() { return sm_count(); }
 bool gemm_pairs_enabled() { return g_cta_pair.load() != 0; }
+bool encoder_wave_pad_enabled() { return g_wave_pad.load() != 0; }
 int gemm_debug_flags() { return g_dbg_flags.load(); }  // developer A/B switches of the epilogue (dlc_debug_set key 3)
 
 }  // namespace dlc
@@ -167,6 +170,12 @@ extern std::atomic<int> g_surf_fast;  // surf.cu
 }
 
 extern "C" int dlc_plane_ld(int cols) { return cols <= 0 ? 0 : (cols + 63) / 64 * 64; }
+
+extern "C" int dlc_set_sm_reserve(int sms) {
+  DLC_CHECK_ARG(sms >= 0 && sms <= 64);
+  g_sm_reserve = sms;
+  return DLC_OK;
+}
 
 extern "C" int dlc_debug_set(int key, int value) {
   if (key == 0 && (value == 32 || value == 64)) {
@@ -199,6 +208,10 @@ extern "C" int dlc_debug_set(int key, int value) {
   }
   if (key == 9) {  // 0: the similarity precision probe runs on the caller's stream instead of its side stream
     g_probe_side_stream = value ? 1 : 0;
+    return DLC_OK;
+  }
+  if (key == 11) {  // 0: the encoder keeps its default GEMM width whatever the row count
+    g_wave_pad = value ? 1 : 0;
     return DLC_OK;
   }
   if (key == 10) {  // 0: the keypoint detector always uses its generic octave kernel

@@ -33,6 +33,7 @@ extern thread_local int g_gemm_k_valid;  // planes.cu
 extern thread_local float g_gemm_alpha;  // planes.cu
 int device_sm_count();                   // planes.cu
 bool gemm_pairs_enabled();               // planes.cu
+bool encoder_wave_pad_enabled();         // planes.cu (dlc_debug_set key 11)
 }
 
 namespace {
@@ -70,7 +71,7 @@ constexpr int kPadTiles[] = {256, 224, 192};  // accumulator widths tried per ca
 int gemm_pad(const dlc_sda* h, int l, int rows) {
   const int n = h->dims[l + 1], sms = device_sm_count();
   int best = h->n_pad[l];
-  if (n <= 256 || !gemm_pairs_enabled() || (static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (best / tile_of_pad(best))) < sms / 2) return best;
+  if (n <= 256 || !gemm_pairs_enabled() || !encoder_wave_pad_enabled() || (static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (best / tile_of_pad(best))) < sms / 2) return best;
   int64_t best_cost = pair_cost(rows, best, sms);
   for (int t : kPadTiles) {
     const int cand = ceil_div(n, t) * t;

@@ -5,7 +5,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 # NVTX ranges around the stages of a step (tracing row of SURVEY 5): visible in an Nsight Systems / ncu --nvtx
 # timeline. Off unless DLC_NVTX=1 - range pushes are host calls on the launch path.
@@ -162,6 +162,25 @@ class LoopClosurePipeline:
         return outs
 
 
+SM_RESERVE_DEFAULT = 0
+
+
+class _SmReserve:
+    """Context manager: dlc_set_sm_reserve(n) for the duration of a sharded step (process-wide knob, restored to 0)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        if self.n:
+            _lib.call("dlc_set_sm_reserve", int(self.n))
+
+    def __exit__(self, *exc):
+        if self.n:
+            _lib.call("dlc_set_sm_reserve", 0)
+        return False
+
+
 class ShardedSequencePipeline(LoopClosurePipeline):
     """ONE sequence over the GPUs of a box (strong scaling of BASELINE config 2): one process per
     GPU (torch.distributed, NCCL). Frames are dealt in contiguous blocks of `per = ceil(N / world)`; every rank gathers
@@ -192,6 +211,10 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         # + score stages of step i; 3 = encoder, exchange and score each on a stream of their own (steps i+2, i+1, i).
         # Measured on 8 GPUs, see DESIGN.md 6.
         self.pipeline_stages = 2
+        # SMs the library's persistent kernels leave free while this pipeline runs (dlc_set_sm_reserve), so that NCCL's
+        # kernels of the exchange stage start at once next to a running encoder layer. None: leave the process-wide
+        # setting alone. Measured on 8 GPUs, see DESIGN.md 6.
+        self.sm_reserve = int(os.environ.get("DLC_SM_RESERVE", SM_RESERVE_DEFAULT)) if self.world > 1 else None
 
     @staticmethod
     def frame_block(n_frames, rank, world):
@@ -275,9 +298,10 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         P = P or (xy_local.shape[1] if xy_local is not None else 30)
         b = self._buffers(n, P)
         slot = b["slots"][0]
-        self._encode_block(frames_local, xy_local, n, P, slot["desc"])
-        self._exchange_block(slot, n, P)
-        return self._score_block(b, slot, n, P, k, exclude_band)
+        with _SmReserve(getattr(self, "sm_reserve", None)):
+            self._encode_block(frames_local, xy_local, n, P, slot["desc"])
+            self._exchange_block(slot, n, P)
+            return self._score_block(b, slot, n, P, k, exclude_band)
 
     def _encode_block(self, frames_local, xy_local, n, P, desc_all):
         """Stage A (rank-local, no collective): patch gather + encoder of this rank's frames into its slice of the
@@ -338,6 +362,10 @@ class ShardedSequencePipeline(LoopClosurePipeline):
             cand = ops.topk_rows(S, min(k, max(n - 1, 1)), largest=True, exclude_band=exclude_band)
         return {"descriptors": slot["desc"][:n * P], "similarity": S, "candidates": cand}
 
+    def _pipelined(self, sequences, k, exclude_band, host):
+        with _SmReserve(getattr(self, "sm_reserve", None)):
+            return self._pipelined_steps(sequences, k, exclude_band, host)
+
     def run_many(self, sequences, k=10, exclude_band=0):
         """A stream of sequences [(frames uint8 [N,H,W], xy float32 [N,P,2]), ...] resident on the device (every rank
         holds them; each reads its block) -> [(scores [N,k], idx [N,k]), ...]. Successive sequences are PIPELINED: the
@@ -353,7 +381,7 @@ class ShardedSequencePipeline(LoopClosurePipeline):
         into pinned buffers owned by the pipeline (valid until the next call); one synchronisation at the end."""
         return self._pipelined(list(batches), k, exclude_band, host=True)
 
-    def _pipelined(self, sequences, k, exclude_band, host):
+    def _pipelined_steps(self, sequences, k, exclude_band, host):
         """Three stages per step: A = upload + encode (rank-local), B = exchange (collectives), C = score matrix +
         candidates. A of step i+1 runs on a side stream, into slot (i+1) & 1, while B and C of step i run on the
         caller's stream (pipeline_stages = 2) or B has a stream of its own as well (3). Collectives are issued in one

@@ -81,6 +81,10 @@ int dlc_version(void);
  *   7: SDAV Gram kernels on CTA pairs [1]
  *   8: capacity of the deferred-refinement list of the SDAV score kernel; 0 = refine inside the epilogue [-1: default]
  *   9: SDAV precision probe on its side stream [1] */
+/* SMs left free by the library's persistent kernels (tensor-core contractions, second pass): their grids are sized for
+ * (SM count - sms). 0 (default) on a single GPU. A sequence split over GPUs sets a few (ShardedSequencePipeline: 8) so
+ * that NCCL's kernels, launched on another stream during a persistent kernel, find SMs at once. Process-wide. */
+int dlc_set_sm_reserve(int sms);
 int dlc_debug_set(int key, int value);
 /* Timing aid: 1 = dlc_sdav_similarity launches only the Gram / score kernels (+ refinement pass) on the operand
  * planes, statistics and tile list a previous full call left in the workspace; 2 = without the refinement pass

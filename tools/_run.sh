@@ -1,12 +1,11 @@
-timeout 900 python -m pytest tests -x -q -m gpu -k "surf" 2>&1 | tail -6
-timeout 300 python tools/bench_surf.py 2>&1 | tail -3 | cut -c1-200
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum --clock-control none -k regex:surf_octave -s 8 -c 4 --csv --log-file /tmp/l.csv python tools/bench_surf.py > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('/tmp/l.csv')) if len(r)>10]
-h=rows[0]; i_k=h.index('Kernel Name'); i_m=h.index('Metric Name'); i_v=h.index('Metric Value'); i_id=h.index('ID')
-d={}
-for r in rows[1:]:
-    d.setdefault((r[i_id], r[i_k][:40]),{})[r[i_m][:34]]=r[i_v]
-for k,v in d.items(): print(k, v)
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513"
+timeout 300 $TR tools/ab_sharded_seq.py > gpurun_out/r2_ab_sharded_8gpu.log 2>&1; grep '^{' gpurun_out/r2_ab_sharded_8gpu.log > gpurun_out/r2_ab_sharded_8gpu.jsonl; cut -c48-230 gpurun_out/r2_ab_sharded_8gpu.jsonl; grep -E "Error|Traceback" gpurun_out/r2_ab_sharded_8gpu.log | head -3
+BEST=$(python - <<'PY'
+import json
+rows=[json.loads(l) for l in open('gpurun_out/r2_ab_sharded_8gpu.jsonl')]
+rows=[r for r in rows if r['weights']=='normal' and r['wave_pad']==1 and r['pipeline_stages']==2]
+print(min(rows,key=lambda r:r['ms_per_sequence'])['sm_reserve'] if rows else 0)
 PY
+)
+echo "best reserve $BEST"
+DLC_SM_RESERVE=$BEST timeout 400 $TR bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2_bench_8gpu_b.log 2>&1; echo "exit $?"; tail -1 gpurun_out/r2_bench_8gpu_b.log > gpurun_out/r2_bench_8gpu_b.json; cut -c1-400 gpurun_out/r2_bench_8gpu_b.json
