@@ -9,6 +9,8 @@ Every contraction is a tcgen05 GEMM through the C ABI (`dlc_gemm_planes`, fp16 h
 gradients, the bias sums, the transposes and the SGD update are the `dlc_train_*` kernels. This module only sequences
 those calls - as the reference's Python sequences TensorFlow ops - and owns the device buffers (torch tensors).
 There is no CPU path."""
+import gc
+
 import numpy as np
 import torch
 
@@ -253,8 +255,18 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         step0 = trainer.global_step
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = trainer.step(self.x, top, self.keep, self.add, apply_update=True, **args)
+        # No garbage collection while the stream is capturing: an earlier trainer's cached graphs are cyclic garbage
+        # (trainer -> cache -> GraphedStep -> trainer), and a collector run inside the capture would destroy their
+        # CUDA graphs there - "operation not permitted when stream is capturing" - and invalidate this capture.
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = trainer.step(self.x, top, self.keep, self.add, apply_update=True, **args)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
         trainer.global_step = step0          # capturing executes nothing
 
     @staticmethod
