@@ -82,9 +82,16 @@ int dlc_version(void);
  *   8: capacity of the deferred-refinement list of the SDAV score kernel; 0 = refine inside the epilogue [-1: default]
  *   9: SDAV precision probe on its side stream [1] */
 /* SMs left free by the library's persistent kernels (tensor-core contractions, second pass): their grids are sized for
- * (SM count - sms). 0 (default) on a single GPU. A sequence split over GPUs sets a few (ShardedSequencePipeline: 8) so
- * that NCCL's kernels, launched on another stream during a persistent kernel, find SMs at once. Process-wide. */
+ * (SM count - sms), 0 <= sms <= 64; 0 is the default. Meant for a sequence split over GPUs, so that NCCL's kernels,
+ * launched on another stream during a persistent kernel, find SMs at once (measured on 8 GPUs: no gain beyond the
+ * run-to-run noise, DESIGN.md 6 - hence off by default; ShardedSequencePipeline.sm_reserve / DLC_SM_RESERVE set it).
+ * Process-wide. */
 int dlc_set_sm_reserve(int sms);
+/* Developer A/B switches (key: value): 0 K block of split-precision GEMMs (32 | 64); 2 K elements accumulated in TMEM
+ * before promotion; 3 epilogue flags (1 skip stores, 2 skip activation, 4 skip TMA store issue, 8 skip min/max);
+ * 4 Gram M-group; 5 TMA plane stores on/off; 6 CTA pairs (0 never, 1 auto, 2 always); 7 Gram pairs; 8 capacity of
+ * the deferred-refinement list; 9 (no-op); 10 keypoint detector: shared-memory octave kernel on/off; 11 encoder:
+ * per-call GEMM width on/off. */
 int dlc_debug_set(int key, int value);
 /* Timing aid: 1 = dlc_sdav_similarity launches only the Gram / score kernels (+ refinement pass) on the operand
  * planes, statistics and tile list a previous full call left in the workspace; 2 = without the refinement pass
