@@ -505,7 +505,24 @@ def run_config2(ctx, args):
         st["similarity_total"] = t_loop(sim, reps)
         st["gram_kernel"] = gram
         st["gram_plus_refinement_pass"] = gram_total
-        st["similarity_preparation"] = st["similarity_total"] - gram_total
+        # the preparation kernels on their own, through the staged ABI (the same kernels on one part): a difference of
+        # the two loops above would mix two power states
+        D_ = DIMS[-1]
+        colsums = torch.empty((1, 2 * D_), dtype=torch.float64, device="cuda")
+        w_d = torch.empty(D_, dtype=torch.float64, device="cuda")
+        c_d = torch.empty(D_, dtype=torch.float32, device="cuda")
+        plane = torch.empty((N_FRAMES * P, ops.plane_ld(D_)), dtype=torch.float16, device="cuda")
+        stats = torch.empty(ops.sdav_stage_stats_bytes(N_FRAMES), dtype=torch.uint8, device="cuda")
+        prep_prec = "fp16r" if args.sim_precision == "auto" else args.sim_precision
+        plane_lo = torch.empty_like(plane) if prep_prec == "fp16x2" else None
+
+        def prep():
+            ops.sdav_stage_colsum(desc, colsums[0])
+            ops.sdav_stage_weights(colsums, N_FRAMES * P, w_d, c_d, pipe.sim_args["mu"], pipe.sim_args["sigma"])
+            ops.sdav_stage_prepare(desc, N_FRAMES, N_FRAMES, P, w_d, c_d, prep_prec, plane, plane_lo, stats)
+
+        st["similarity_preparation"] = t_loop(prep, reps)
+        del plane, plane_lo, stats
         st["topk"] = t_loop(lambda: ops.topk_rows(pipe.last_similarity, K_CAND, largest=True, exclude_band=0), reps)
         enc_flop = N_FRAMES * ENC_FLOP_PER_FRAME
         layer_ms = st["encoder_layers"] / (len(DIMS) - 1)

@@ -636,10 +636,7 @@ int run_conv(const dlc_cnnvtl* h, int l, int n, const void* a_hi, const void* a_
   // ncu: tensor pipe 46 %); a pair stages each half of the weight tile once for 256 pixels.
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int pair_mode = g_cta_pair.load();
-  // conv1 stays on the single-CTA kernel: its short K (576) makes it epilogue-bound, and there the alternate-tile
-  // epilogue (two warp groups, one tile each) beats the pair's column split (0.67 vs 0.71 ms per 1063 frames)
-  const bool pairs = split && pair_mode && p.n_tile % 32 == 0 &&
-                     ((pair_tiles >= sm_count() / 2 && g.k_ld > 1024) || pair_mode == 2);
+  const bool pairs = split && pair_mode && p.n_tile % 32 == 0 && (pair_tiles >= sm_count() / 2 || pair_mode == 2);
   const int b_rows = pairs ? p.n_tile / 2 : p.n_tile;
   if (ok) ok = make_tmap_k_major(&tb0, h->w_hi[l], 0, g.k_ld, s.cout, g.k_ld, BK, b_rows);
   tb1 = tb0;

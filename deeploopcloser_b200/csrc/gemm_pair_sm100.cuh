@@ -58,6 +58,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   int S = ring_bytes<Policy>() / stage_bytes;
   S = S < SMAX ? S : SMAX;
 
+  // Alternate-tile epilogue (policies with kAltTiles; narrow accumulator, K in one chunk - cnn_vtl conv1): warp group g
+  // of each CTA drains the tiles that accumulate in TMEM buffer g, all of their (<= 4) column chunks, instead of
+  // splitting the columns of every tile - two tile times per tile for an epilogue-bound contraction.
+  bool alt_tiles = false;
+  if constexpr (Policy::kPromote && policy_alt_tiles<Policy>::value)
+    alt_tiles = p.n_tile <= 128 && (p.kc <= 0 || p.kc >= p.k_blocks);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -81,7 +87,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull[a], 1);
-        mbar_init(&tempty[a], 2 * kEpiWarps);  // the epilogue warps of both CTAs
+        mbar_init(&tempty[a], alt_tiles ? kEpiWarps : 2 * kEpiWarps);  // the epilogue warps of both CTAs that read it
       }
       fence_mbar_init();
     }
@@ -229,11 +235,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     typename Policy::Epilogue epi(p, quarter, half, lane, scratch);
     // this warp group's chunks [c_first, c_first + c_count), at most 4
     const int c_split = kConv ? min(n_cchunks, 2 * ((n_cchunks + 3) / 4)) : min(n_cchunks, 4);
-    const int c_first = half ? c_split : 0;
-    const int c_count = half ? n_cchunks - c_split : c_split;
+    const int c_first = alt_tiles ? 0 : (half ? c_split : 0);
+    const int c_count = alt_tiles ? n_cchunks : (half ? n_cchunks - c_split : c_split);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int i = 0; i < my_tiles; ++i) {
+      if (alt_tiles) {
+        if ((i & 1) != half) continue;            // the other group's tile
+        acc = half;                               // one K chunk per tile: tile i accumulates in buffer i & 1
+        acc_phase = static_cast<uint32_t>(i >> 1) & 1u;
+      }
       TileCoord tc = Policy::tile_pair(p, cluster, nclusters, i);
       tc.mt += static_cast<int>(rank);
       float sums[128];

@@ -138,7 +138,7 @@ weights_centre_kernel(const double* __restrict__ part, int slabs, int64_t rows, 
 // candidates. h - c is ONE float32 subtraction (exact when h and c are within a factor two, Sterbenz - the case that
 // matters - and good to 6e-8 relative otherwise). The planes are stored P rows per frame: both sides of the Gram
 // kernel read them (the M side through a 3-D tensor map whose 32-row boxes zero-fill rows P..31).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double* __restrict__ w,
                  const float* __restrict__ centre, __half* __restrict__ b_hi, __half* __restrict__ b_lo, int ld,
                  float* __restrict__ sqn, double* __restrict__ pw, unsigned int* __restrict__ nmax_bits,
@@ -161,7 +161,7 @@ prep_rows_kernel(const float* __restrict__ H, int N, int P, int D, const double*
   const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
   const bool wvec = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(centre) & 15) == 0;
   double n2 = 0.0, pr = 0.0;
-#pragma unroll 2
+#pragma unroll 4
   for (int c0 = lane * 8; c0 < ld; c0 += 256) {
     float x[8];
 #pragma unroll
