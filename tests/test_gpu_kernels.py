@@ -704,6 +704,36 @@ def test_encoder_wave_aware_width_gives_the_same_bits(cuda, precision):
     enc.close()
 
 
+def test_sm_reserve_leaves_results_unchanged(cuda):
+    """dlc_set_sm_reserve(n): the persistent kernels size their grids for (SM count - n) - fewer CTAs walk the same
+    tiles, so encoder descriptors and similarity scores keep their bits."""
+    from deeploopcloser_b200 import _lib, ops
+    dims = [1681, 2500, 2500]
+    ws, bs = o_sda.make_weights(dims, seed=6, scale="xavier")
+    rng = np.random.default_rng(8)
+    rows = 40 * 30
+    x = torch.from_numpy(rng.integers(0, 256, (rows, 1728)).astype(np.float16))
+    x[:, 1681:] = 0
+    x = x.cuda()
+    enc = ops.SdaEncoder(dims, "fp16x2", input_u8=True)
+    for l, (w, b) in enumerate(zip(ws, bs)):
+        enc.set_layer(l, w, b)
+    want = enc.encode_planes(x, None, rows).clone()
+    s_want = ops.sdav_similarity(want.view(40, 30, -1), precision="fp16r").clone()
+    try:
+        for n in (8, 24, 64):
+            _lib.call("dlc_set_sm_reserve", n)
+            assert _lib.call("dlc_sm_count") >= 2
+            got = enc.encode_planes(x, None, rows)
+            assert torch.equal(got, want), n
+            assert torch.equal(ops.sdav_similarity(got.view(40, 30, -1), precision="fp16r"), s_want), n
+    finally:
+        _lib.call("dlc_set_sm_reserve", 0)
+    with pytest.raises(RuntimeError):
+        _lib.call("dlc_set_sm_reserve", 65)
+    enc.close()
+
+
 def test_encoder_raw_pixel_mode_needs_layer0_again(cuda):
     from deeploopcloser_b200 import _lib, ops
     enc = ops.SdaEncoder([1681, 64], "fp16x2")
