@@ -1,8 +1,2 @@
-for i in 1 2; do
-for L in "" "/root/repo/deeploopcloser_b200/libdlc_old.so"; do
-echo "== lib=$L"
-DLC_LIB_PATH=$L timeout 200 python tools/bench_matcher.py --batches 1024 --reps 8 2>&1 | grep '^{' | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print({k:(round(v,3) if isinstance(v,float) else v) for k,v in d.items() if k in ('B','ms','tflops','batch')})"
-done; done
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29516"
+timeout 400 $TR bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2_bench_4gpu_final.log 2>&1; echo "exit $?"; tail -1 gpurun_out/r2_bench_4gpu_final.log > gpurun_out/r2_bench_4gpu_final.json; cut -c1-330 gpurun_out/r2_bench_4gpu_final.json
