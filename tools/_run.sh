@@ -1,2 +1,6 @@
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29516"
-timeout 400 $TR bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r2_bench_4gpu_final.log 2>&1; echo "exit $?"; tail -1 gpurun_out/r2_bench_4gpu_final.log > gpurun_out/r2_bench_4gpu_final.json; cut -c1-330 gpurun_out/r2_bench_4gpu_final.json
+for A in normal xavier; do
+python bench.py --steps 1 --warmup 1 --headline-only --one-arm --no-cpu-baseline --weights $A > gpurun_out/r2_plain_$A.log 2>&1 || exit 1
+timeout 500 ncu --set full --clock-control none --import-source on -c 40 -o /tmp/full_$A python bench.py --steps 1 --warmup 1 --headline-only --one-arm --no-cpu-baseline --weights $A > gpurun_out/r2_ncu_full_$A.log 2>&1
+ncu -i /tmp/full_$A.ncu-rep --page raw --csv > gpurun_out/r2_full_raw_$A.csv 2>/dev/null
+ls -la /tmp/full_$A.ncu-rep gpurun_out/r2_full_raw_$A.csv
+done
