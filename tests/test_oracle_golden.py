@@ -266,3 +266,31 @@ def test_parity_report_classes(golden_dir):
         wrong[2, 5] = np.sum(10.0 - 10.0 * np.log(np.abs((dev[2] - dev[5][idx]) @ w_dev)))
     rep3 = pr.report(wrong, dev[:n], desc[:n])
     assert rep3["unexplained"] == 1 and rep3["unexplained_detail"][0][0] == (2, 5)
+
+
+def test_surf_compile_time_box_tables_match_the_oracle_patterns():
+    """csrc/surf.cu surf_octave_fast_kernel hard-codes the box corners of the default pyramid as
+    fast_cr(x, size) = (2 x size + 9) / 18 (integer division) and fast_margin = (size / 2) / step; dlc_surf_detect
+    compares them with the runtime plan before using the kernel (surf_fast_ok). The same rule, restated here, must
+    reproduce oracle/surf.py's float32 resize_pattern for every layer the fast kernel serves (octaves 0 and 1) - and,
+    as it happens, for the whole default pyramid."""
+    from oracle import surf
+
+    def cr(x, size):
+        return (2 * x * size + 9) // 18
+
+    for octave, sizes in enumerate(surf.layer_sizes(4, 3)):
+        for size in sizes:
+            for name, src in (("dx", surf.DX), ("dy", surf.DY), ("dxy", surf.DXY)):
+                want = [box[:4] for box in surf.resize_pattern(src, size)]
+                got = [tuple(cr(v, size) for v in box[:4]) for box in src]
+                assert got == want, (octave, size, name)
+            lobes = [cr(x, size) for x in (0, 3, 6, 9)]
+            assert lobes[0] == 0 and lobes[3] == size and len({b - a for a, b in zip(lobes, lobes[1:])}) == 1
+    # region bookkeeping of the kernel: 34 halo samples, widest margin 16, plane dimension 67 for both steps
+    for step in (1, 2):
+        sizes = [(9 + 6 * l) * step for l in range(5)]
+        margins = [(s // 2) // step for s in sizes]
+        assert margins == [4, 7, 10, 13, 16]
+        extent = max((33 - m + 16) * step + s for m, s in zip(margins, sizes)) + 1
+        assert extent == 66 * step + 1 and -(-extent // step) == 67
