@@ -337,3 +337,26 @@ def test_frame_blocks_cover_the_sequence():
             assert start == min(r * per, n)
             seen += list(range(start, end))
         assert seen == list(range(n))
+
+
+def test_sm_reserve_is_scoped_to_the_sharded_step(monkeypatch):
+    """ShardedSequencePipeline.sm_reserve: the process-wide dlc_set_sm_reserve knob is set for the duration of a step and
+    restored to 0 afterwards, also when the step raises; 0 / None never touch it; DLC_SM_RESERVE sets the default of a
+    multi-rank pipeline (host logic only - no library call is made here)."""
+    from deeploopcloser_b200 import pipeline
+    calls = []
+    monkeypatch.setattr(pipeline._lib, "call", lambda name, *a: calls.append((name,) + a))
+    with pipeline._SmReserve(8):
+        assert calls == [("dlc_set_sm_reserve", 8)]
+    assert calls == [("dlc_set_sm_reserve", 8), ("dlc_set_sm_reserve", 0)]
+    calls.clear()
+    with pytest.raises(ValueError):
+        with pipeline._SmReserve(4):
+            raise ValueError("step failed")
+    assert calls[-1] == ("dlc_set_sm_reserve", 0)
+    calls.clear()
+    for n in (0, None):
+        with pipeline._SmReserve(n):
+            pass
+    assert calls == []
+    assert pipeline.SM_RESERVE_DEFAULT == 0      # measured on 8 GPUs: no gain beyond the noise (DESIGN.md 6)
