@@ -19,7 +19,8 @@ namespace dlc {
 // ------------------------------------------------------------------------------------------------
 struct BiasActParams {
   int n_tile, k_blocks, ab_fmt, kc;
-  int dbg;  // developer switches for kernel experiments: 1 = skip stores, 2 = skip activation math
+  int dbg;  // developer switches for kernel experiments: 1 skip stores, 2 skip activation math, 4 skip the TMA store
+            // instructions (values still staged), 8 skip the conv min/max
   int m_tiles, n_tiles;
   int M, N;
   const float* bias;

@@ -83,21 +83,21 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int k, int n, int n_
 }
 
 static std::atomic<int> g_split_bk{32};  // smem ring of the 3-product kernel: BK=32 -> 4 stages, BK=64 -> 2 stages
-std::atomic<int> g_promote_k{256};
+std::atomic<int> g_promote_k{256};  // K elements accumulated inside the tensor core before promotion to fp32 registers
 // Valid K of the next dlc_gemm_planes call on this thread (0 = the whole ld). Callers that know their operands are zero
 // beyond K (the SDA encoder: 2500 of 2560, 1681 of 1728) set it so that all-zero K blocks are not loaded or multiplied.
 thread_local int g_gemm_k_valid = 0;
 // Scale of the accumulator before the bias of the next dlc_gemm_planes call on this thread (z = alpha * acc + bias;
 // reset to 1 by the call). The SDA encoder's first layer on raw 8-bit pixels uses 1/256 (see dlc_sda_set_input_u8).
 thread_local float g_gemm_alpha = 1.0f;
-std::atomic<int> g_tma_store{1};
-std::atomic<int> g_cta_pair{1};
-std::atomic<int> g_sm_reserve{0};   // dlc_set_sm_reserve
-std::atomic<int> g_wave_pad{1};     // dlc_debug_set key 11: the encoder picks its GEMM width per call (sda.cu gemm_pad)
-std::atomic<int> g_gram_pair{1};  // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)  // large 3-product contractions on the CTA-pair kernel (dlc_debug_set key 6 = 0: single CTA)  // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
+std::atomic<int> g_tma_store{1};   // plane outputs through staged TMA stores (dlc_debug_set key 5 = 0: direct 16-byte stores)
+std::atomic<int> g_cta_pair{1};    // contractions on the CTA-pair kernel (dlc_debug_set key 6: 0 never, 1 auto, 2 always)
+std::atomic<int> g_sm_reserve{0};  // dlc_set_sm_reserve
+std::atomic<int> g_wave_pad{1};    // dlc_debug_set key 11: the encoder picks its GEMM width per call (sda.cu gemm_pad)
+std::atomic<int> g_gram_pair{1};   // the SDAV Gram kernel on CTA pairs (dlc_debug_set key 7)
 extern std::atomic<int> g_sim_mgroup;  // sdav_sim.cu
 extern std::atomic<int> g_refine_cap;  // sdav_sim.cu
-static std::atomic<int> g_dbg_flags{0};       // K elements accumulated inside the tensor core before promotion to fp32 registers
+static std::atomic<int> g_dbg_flags{0};  // epilogue A/B flags (dlc_debug_set key 3, see BiasActParams::dbg)
 
 template <class Policy>
 static cudaError_t launch_gemm_pair_if(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,

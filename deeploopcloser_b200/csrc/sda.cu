@@ -71,7 +71,9 @@ constexpr int kPadTiles[] = {256, 224, 192};  // accumulator widths tried per ca
 int gemm_pad(const dlc_sda* h, int l, int rows) {
   const int n = h->dims[l + 1], sms = device_sm_count();
   int best = h->n_pad[l];
-  if (n <= 256 || !gemm_pairs_enabled() || !encoder_wave_pad_enabled() || (static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (best / tile_of_pad(best))) < sms / 2) return best;
+  const int64_t default_tiles = static_cast<int64_t>((ceil_div(rows, 128) + 1) / 2) * (best / tile_of_pad(best));
+  // narrow layers, pairs switched off, or too few tiles for the pair kernel (dlc_gemm_planes then runs single CTAs)
+  if (n <= 256 || !gemm_pairs_enabled() || !encoder_wave_pad_enabled() || default_tiles < sms / 2) return best;
   int64_t best_cost = pair_cost(rows, best, sms);
   for (int t : kPadTiles) {
     const int cand = ceil_div(n, t) * t;
